@@ -1,0 +1,99 @@
+"""ctypes binding of ``csrc/libavdn.so`` (the C ABI of ``include/avdn.h``).
+
+Fails loudly: a missing library, a missing symbol or a non-zero status raises;
+nothing here ever falls back to a CPU or torch implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libavdn.so")
+
+_lib = None
+
+c_void_p, c_int, c_i64, c_f32, c_f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+
+
+class TileDesc(C.Structure):
+    """``avdn_tile_desc`` of include/avdn.h."""
+    _fields_ = [("tile4", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+# name -> argtypes ; every function returns int (avdn_status) unless noted
+_SIGNATURES = {
+    "avdn_pack_tile": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "avdn_gps_to_pixels": [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "avdn_homography_from_corners": [c_void_p, c_int, c_void_p, c_void_p],
+    "avdn_render_views": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p, c_void_p],
+}
+
+
+def exported_symbols():
+    """Every symbol ``include/avdn.h`` declares (used by the CPU-side ABI test)."""
+    return ["avdn_last_error_string", "avdn_abi_version", "avdn_device_supported"] + list(_SIGNATURES)
+
+
+def register(name, argtypes):
+    _SIGNATURES[name] = argtypes
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the library is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        h = C.CDLL(LIB_PATH)
+        h.avdn_last_error_string.restype = C.c_char_p
+        h.avdn_last_error_string.argtypes = []
+        h.avdn_abi_version.restype = C.c_int
+        h.avdn_device_supported.restype = C.c_int
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(h, name)          # AttributeError if the symbol is missing
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = h
+    return _lib
+
+
+def last_error() -> str:
+    return lib().avdn_last_error_string().decode()
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        raise RuntimeError(f"libavdn {what} failed (status {status}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (``None`` -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    """Invoke an ABI function on torch's current stream; raise on error."""
+    fn = getattr(lib(), name)
+    check(fn(*args, stream_ptr()), name)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("libavdn ops take CUDA tensors only (no CPU fallback)")

@@ -1,0 +1,376 @@
+// Stage 1 of the AVDN hot path: batched view rendering (src/env.py:254-332).
+//
+// Replaces, per pose, cv2.getPerspectiveTransform + two cv2.warpPerspective
+// calls (map and attention map) + the agent's image normalisation
+// (src/xview_et/agent.py:586-592) with three kernels:
+//
+//   pack_tile_kernel     one-off per map: BGR u8 HWC (+ attention) -> u32/pixel
+//                        B|G<<8|R<<16|ATT<<24 with a 1-px zero border
+//   homography_kernel    one thread per pose: OpenCV's 8x8 LU + 3x3 adjugate
+//                        inverse in float64, same operation order, no FMA
+//   render_kernel        one CTA per (pose, 32-row band): fixed-point bilinear
+//                        gather (INTER_BITS=5), bit-exact with OpenCV
+//
+// The warp is a gather: every output pixel reads a 2x2 footprint of the source
+// at a data-dependent position.  It is bound by L2->SM sector traffic, not by
+// tensor cores; the design rules that matter are (i) one aligned 32-bit load
+// per tap (all four channels at once), (ii) lanes of a warp arranged as an 8x4
+// output patch so that a warp's footprint stays compact under any rotation,
+// (iii) the band is staged in shared memory and leaves the SM as full 16-byte
+// coalesced stores (a 32-row band of a 224x224x3 view is one contiguous
+// 21 504-byte range of HBM).
+//
+// Exactness: OpenCV evaluates, in float64 and per 64-pixel-wide block,
+//   X0 = (M0*xb + M1*y) + M2 ... W = W0 + M6*x1 ; W = W ? 32/W : 0
+//   X  = rint((X0 + M0*x1) * W)                                   
+// A correctly rounded f64 division per pixel is the most expensive part, so the
+// fast path uses a Newton reciprocal (error ~1e-15 relative) and extracts
+// floor/fraction with a magic-number add; whenever the fractional part is
+// within 2^-17 of a rounding tie (or anything is out of range) the lane
+// re-evaluates with exactly OpenCV's sequence (__dmul_rn/__dadd_rn/__ddiv_rn,
+// rint).  The fast path can therefore never round differently from OpenCV.
+//
+// This file is compiled with -fmad=false.
+#include "common.cuh"
+
+namespace {
+
+constexpr int VIEW = AVDN_VIEW;       // 224
+constexpr int BAND = 32;              // rows per CTA
+constexpr int NBAND = VIEW / BAND;    // 7
+constexpr int THREADS = 256;
+constexpr int INTER_BITS = 5;
+constexpr int INTER_TAB = 1 << INTER_BITS;
+
+// ---------------------------------------------------------------- pack tile
+__global__ void pack_tile_kernel(const uint8_t* __restrict__ map_bgr,
+                                 const uint8_t* __restrict__ att, int att_ch,
+                                 int H, int W, uint32_t* __restrict__ tile4) {
+  const int pitch = W + 2;
+  const long long n = (long long)(H + 2) * pitch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int yy = (int)(i / pitch), xx = (int)(i - (long long)yy * pitch);
+    uint32_t v = 0;
+    if (yy >= 1 && yy <= H && xx >= 1 && xx <= W) {
+      const long long s = (long long)(yy - 1) * W + (xx - 1);
+      const uint8_t* p = map_bgr + s * 3;
+      v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+      if (att) v |= (uint32_t)att[s * att_ch] << 24;
+    }
+    tile4[i] = v;
+  }
+}
+
+// ------------------------------------------------------------ gps -> pixels
+__global__ void gps_to_pixels_kernel(const double* __restrict__ corners_gps,
+                                     const double* __restrict__ geo, int P,
+                                     int32_t* __restrict__ corners_px) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // corner index
+  if (i >= P * 4) return;
+  const int p = i >> 2;
+  const double lat = corners_gps[2 * i], lng = corners_gps[2 * i + 1];
+  const double bl_lng = geo[5 * p + 1], tr_lat = geo[5 * p + 2], ratio = geo[5 * p + 4];
+  // src/env.py:196 — both axes use lat_ratio; round() is half-to-even
+  corners_px[2 * i]     = __double2int_rn(__ddiv_rn(__dsub_rn(lng, bl_lng), ratio));
+  corners_px[2 * i + 1] = __double2int_rn(__ddiv_rn(__dsub_rn(tr_lat, lat), ratio));
+}
+
+// --------------------------------------------------------------- homography
+__global__ void homography_kernel(const int32_t* __restrict__ corners_px, int P,
+                                  double* __restrict__ minv) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double a[8][8], b[8];
+  const double dstx[4] = {0.0, VIEW - 1.0, VIEW - 1.0, 0.0};   // src/env.py:275-278
+  const double dsty[4] = {0.0, 0.0, VIEW - 1.0, VIEW - 1.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    // int corners -> float32 (src/env.py:284) -> float64 inside OpenCV
+    const double sx = (double)(float)corners_px[p * 8 + 2 * i];
+    const double sy = (double)(float)corners_px[p * 8 + 2 * i + 1];
+    a[i][0] = a[i + 4][3] = sx;
+    a[i][1] = a[i + 4][4] = sy;
+    a[i][2] = a[i + 4][5] = 1.0;
+    a[i][3] = a[i][4] = a[i][5] = a[i + 4][0] = a[i + 4][1] = a[i + 4][2] = 0.0;
+    a[i][6] = __dmul_rn(-sx, dstx[i]);
+    a[i][7] = __dmul_rn(-sy, dstx[i]);
+    a[i + 4][6] = __dmul_rn(-sx, dsty[i]);
+    a[i + 4][7] = __dmul_rn(-sy, dsty[i]);
+    b[i] = dstx[i];
+    b[i + 4] = dsty[i];
+  }
+  bool singular = false;
+  const double eps = 2.220446049250313e-16 * 100;
+  for (int i = 0; i < 8 && !singular; ++i) {
+    int k = i;
+    for (int j = i + 1; j < 8; ++j)
+      if (fabs(a[j][i]) > fabs(a[k][i])) k = j;
+    if (fabs(a[k][i]) < eps) { singular = true; break; }
+    if (k != i) {
+      for (int j = i; j < 8; ++j) { double t = a[i][j]; a[i][j] = a[k][j]; a[k][j] = t; }
+      double t = b[i]; b[i] = b[k]; b[k] = t;
+    }
+    const double d = __ddiv_rn(-1.0, a[i][i]);
+    for (int j = i + 1; j < 8; ++j) {
+      const double alpha = __dmul_rn(a[j][i], d);
+      for (int kk = i + 1; kk < 8; ++kk)
+        a[j][kk] = __dadd_rn(a[j][kk], __dmul_rn(alpha, a[i][kk]));
+      b[j] = __dadd_rn(b[j], __dmul_rn(alpha, b[i]));
+    }
+  }
+  double m[9];
+  if (!singular) {
+    for (int i = 7; i >= 0; --i) {
+      double s = b[i];
+      for (int kk = i + 1; kk < 8; ++kk) s = __dsub_rn(s, __dmul_rn(a[i][kk], b[kk]));
+      b[i] = __ddiv_rn(s, a[i][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = b[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = 0.0;     // cv::solve failure -> zero solution
+  }
+  m[8] = 1.0;
+  // cv::invert, n == 3 closed form
+#define MUL(x, y) __dmul_rn((x), (y))
+#define SUB(x, y) __dsub_rn((x), (y))
+  const double c0 = SUB(MUL(m[4], m[8]), MUL(m[5], m[7]));
+  const double c1 = SUB(MUL(m[3], m[8]), MUL(m[5], m[6]));
+  const double c2 = SUB(MUL(m[3], m[7]), MUL(m[4], m[6]));
+  const double det = __dadd_rn(SUB(MUL(m[0], c0), MUL(m[1], c1)), MUL(m[2], c2));
+  double* o = minv + (size_t)p * 9;
+  if (det != 0.0) {
+    const double d = __ddiv_rn(1.0, det);
+    o[0] = MUL(SUB(MUL(m[4], m[8]), MUL(m[5], m[7])), d);
+    o[1] = MUL(SUB(MUL(m[2], m[7]), MUL(m[1], m[8])), d);
+    o[2] = MUL(SUB(MUL(m[1], m[5]), MUL(m[2], m[4])), d);
+    o[3] = MUL(SUB(MUL(m[5], m[6]), MUL(m[3], m[8])), d);
+    o[4] = MUL(SUB(MUL(m[0], m[8]), MUL(m[2], m[6])), d);
+    o[5] = MUL(SUB(MUL(m[2], m[3]), MUL(m[0], m[5])), d);
+    o[6] = MUL(SUB(MUL(m[3], m[7]), MUL(m[4], m[6])), d);
+    o[7] = MUL(SUB(MUL(m[1], m[6]), MUL(m[0], m[7])), d);
+    o[8] = MUL(SUB(MUL(m[0], m[4]), MUL(m[1], m[3])), d);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = 0.0;     // cv::invert failure -> zero matrix
+  }
+#undef MUL
+#undef SUB
+}
+
+// ------------------------------------------------------------------- render
+// Exactly OpenCV's per-pixel sequence (WarpPerspectiveInvoker), used by the
+// rare lanes whose fast-path result sits next to a rounding tie.
+__device__ __noinline__ void exact_coords(const double* __restrict__ m, int xb, int x1,
+                                          int y, int* X, int* Y) {
+  const double dxb = (double)xb, dx1 = (double)x1, dy = (double)y;
+  const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dxb), __dmul_rn(m[1], dy)), m[2]);
+  const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dxb), __dmul_rn(m[4], dy)), m[5]);
+  const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m[6], dxb), __dmul_rn(m[7], dy)), m[8]);
+  double W = __dadd_rn(W0, __dmul_rn(m[6], dx1));
+  W = (W != 0.0) ? __ddiv_rn((double)INTER_TAB, W) : 0.0;
+  double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(m[0], dx1)), W);
+  double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(m[3], dx1)), W);
+  fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
+  fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+  *X = __double2int_rn(fX);
+  *Y = __double2int_rn(fY);
+}
+
+__device__ __forceinline__ double rcp_seed(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
+// v = f + 1.5*2^32 ; returns true when the fast result is trustworthy.
+__device__ __forceinline__ bool fast_round(double f, int* out) {
+  const double v = __dadd_rn(f, 6442450944.0);
+  const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+  const uint32_t fl = __funnelshift_r(lo, hi, 20) ^ 0x80000000u;   // floor(f)
+  const int frac = (int)(lo & 0xFFFFFu);                              // 20-bit fraction
+  *out = (int)fl + (frac > 0x80000 ? 1 : 0);
+  const int d = frac - 0x80000;
+  // exponent of v must be that of [2^32, 2^33): rejects NaN/inf/|f| >= 2^31
+  return ((hi >> 20) == 0x41Fu) && (d > 8 || d < -8);
+}
+
+__global__ void __launch_bounds__(THREADS, 3)
+render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restrict__ tile_idx,
+              const double* __restrict__ minv, int P,
+              uint8_t* __restrict__ views, uint8_t* __restrict__ att,
+              float* __restrict__ norm_nchw, __nv_bfloat16* __restrict__ norm_nhwc,
+              const float* __restrict__ norm_lut) {
+  __shared__ double s_m[9];
+  __shared__ double s_tab[4][BAND][3];                       // 32*X0, 32*Y0, W0
+  __shared__ __align__(16) uint8_t s_view[BAND * VIEW * 3];  // 21504 B
+  __shared__ __align__(16) uint8_t s_att[BAND * VIEW];       // 7168 B
+  __shared__ float s_lut[3 * 256];
+
+  const int p = blockIdx.x / NBAND, band = blockIdx.x - p * NBAND;
+  const int t = threadIdx.x;
+  if (t < 9) s_m[t] = minv[(size_t)p * 9 + t];
+  const bool want_norm = (norm_nchw != nullptr) || (norm_nhwc != nullptr);
+  if (want_norm)
+    for (int i = t; i < 768; i += THREADS) s_lut[i] = norm_lut[i];
+  const avdn_tile_desc td = tiles[tile_idx ? tile_idx[p] : 0];
+  __syncthreads();
+  if (t < 4 * BAND) {
+    const int xbi = t >> 5, r = t & 31;
+    const double dxb = (double)(xbi * 64), dy = (double)(band * BAND + r);
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(s_m[0], dxb), __dmul_rn(s_m[1], dy)), s_m[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(s_m[3], dxb), __dmul_rn(s_m[4], dy)), s_m[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(s_m[6], dxb), __dmul_rn(s_m[7], dy)), s_m[8]);
+    s_tab[xbi][r][0] = X0 * 32.0;     // exact power-of-two scaling
+    s_tab[xbi][r][1] = Y0 * 32.0;
+    s_tab[xbi][r][2] = W0;
+  }
+  __syncthreads();
+
+  const int warp = t >> 5, lane = t & 31;
+  const int x1 = warp * 8 + (lane & 7);           // column inside the 64-wide block
+  const int ly = lane >> 3;                       // 0..3
+  const double dx1 = (double)x1;
+  const double c0s = __dmul_rn(s_m[0], dx1) * 32.0;
+  const double c3s = __dmul_rn(s_m[3], dx1) * 32.0;
+  const double c6 = __dmul_rn(s_m[6], dx1);
+  const int pitch = td.W + 2;
+  const uint32_t* __restrict__ tile = td.tile4;
+
+  const int n_xb = (x1 < 32) ? 4 : 3;             // 224 = 3*64 + 32 (warp-uniform)
+  for (int xbi = 0; xbi < n_xb; ++xbi) {
+    const int x = xbi * 64 + x1;
+#pragma unroll 2
+    for (int rg = 0; rg < BAND / 4; ++rg) {
+      const int r = rg * 4 + ly;
+      const double X0s = s_tab[xbi][r][0], Y0s = s_tab[xbi][r][1], W0 = s_tab[xbi][r][2];
+      const double W = __dadd_rn(W0, c6);
+      double rr = rcp_seed(W);
+      rr = fma(rr, fma(-W, rr, 1.0), rr);
+      rr = fma(rr, fma(-W, rr, 1.0), rr);
+      const double fX = __dmul_rn(__dadd_rn(X0s, c0s), rr);
+      const double fY = __dmul_rn(__dadd_rn(Y0s, c3s), rr);
+      int X, Y;
+      const bool okx = fast_round(fX, &X);
+      const bool oky = fast_round(fY, &Y);
+      if (!(okx && oky)) exact_coords(s_m, xbi * 64, x1, band * BAND + r, &X, &Y);
+      const int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
+      const int ax = X & (INTER_TAB - 1), ay = Y & (INTER_TAB - 1);
+      uint32_t p00 = 0, p01 = 0, p10 = 0, p11 = 0;
+      if ((unsigned)(sx + 1) <= (unsigned)td.W && (unsigned)(sy + 1) <= (unsigned)td.H) {
+        const uint32_t* q = tile + (size_t)(sy + 1) * pitch + (sx + 1);
+        p00 = __ldg(q);
+        p01 = __ldg(q + 1);
+        p10 = __ldg(q + pitch);
+        p11 = __ldg(q + pitch + 1);
+      }
+      const int w00 = (INTER_TAB - ay) * (INTER_TAB - ax), w01 = (INTER_TAB - ay) * ax;
+      const int w10 = ay * (INTER_TAB - ax), w11 = ay * ax;
+      const int o = r * VIEW + x;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int sh = 8 * c;
+        const int v = (int)((p00 >> sh) & 255u) * w00 + (int)((p01 >> sh) & 255u) * w01 +
+                      (int)((p10 >> sh) & 255u) * w10 + (int)((p11 >> sh) & 255u) * w11;
+        const uint8_t b = (uint8_t)((v + 512) >> 10);
+        if (c < 3) s_view[o * 3 + c] = b; else s_att[o] = b;
+      }
+    }
+  }
+  __syncthreads();
+
+  const size_t band_px = (size_t)p * VIEW * VIEW + (size_t)band * BAND * VIEW;
+  if (views) {
+    uint4* dst = reinterpret_cast<uint4*>(views + band_px * 3);
+    const uint4* src = reinterpret_cast<const uint4*>(s_view);
+    for (int i = t; i < BAND * VIEW * 3 / 16; i += THREADS) dst[i] = src[i];
+  }
+  if (att) {
+    uint4* dst = reinterpret_cast<uint4*>(att + band_px);
+    const uint4* src = reinterpret_cast<const uint4*>(s_att);
+    for (int i = t; i < BAND * VIEW / 16; i += THREADS) dst[i] = src[i];
+  }
+  if (norm_nhwc) {
+    // [P,224,224,4] bf16: R,G,B,0 -> one 8-byte store per pixel, coalesced
+    uint2* dst = reinterpret_cast<uint2*>(norm_nhwc) + band_px;
+    for (int i = t; i < BAND * VIEW; i += THREADS) {
+      const float r_ = s_lut[s_view[i * 3 + 2]];
+      const float g_ = s_lut[256 + s_view[i * 3 + 1]];
+      const float b_ = s_lut[512 + s_view[i * 3 + 0]];
+      const __nv_bfloat162 rg = __floats2bfloat162_rn(r_, g_);
+      const __nv_bfloat162 b0 = __floats2bfloat162_rn(b_, 0.f);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&rg);
+      o.y = *reinterpret_cast<const uint32_t*>(&b0);
+      dst[i] = o;
+    }
+  }
+  if (norm_nchw) {
+    // [P,3,224,224] f32, channel c = RGB -> BGR byte 2-c; 4 pixels per store
+    for (int i = t; i < 3 * BAND * VIEW / 4; i += THREADS) {
+      const int c = i / (BAND * VIEW / 4);
+      const int j = (i - c * (BAND * VIEW / 4)) * 4;     // pixel index inside the band
+      float4 o;
+      o.x = s_lut[c * 256 + s_view[(j + 0) * 3 + 2 - c]];
+      o.y = s_lut[c * 256 + s_view[(j + 1) * 3 + 2 - c]];
+      o.z = s_lut[c * 256 + s_view[(j + 2) * 3 + 2 - c]];
+      o.w = s_lut[c * 256 + s_view[(j + 3) * 3 + 2 - c]];
+      float* base = norm_nchw + ((size_t)p * 3 + c) * VIEW * VIEW + (size_t)band * BAND * VIEW + j;
+      *reinterpret_cast<float4*>(base) = o;
+    }
+  }
+}
+
+}  // namespace
+
+// ===================================================================== C ABI
+extern "C" int avdn_pack_tile(const uint8_t* map_bgr, const uint8_t* att, int att_ch, int H,
+                              int W, uint32_t* tile4, avdn_stream_t stream) {
+  AVDN_REQUIRE(map_bgr && tile4, "avdn_pack_tile: null pointer");
+  AVDN_REQUIRE(H > 0 && W > 0 && H <= 32766 && W <= 32766, "avdn_pack_tile: bad size %dx%d", H, W);
+  AVDN_REQUIRE(!att || att_ch >= 1, "avdn_pack_tile: att_ch must be >= 1");
+  const long long n = (long long)(H + 2) * (W + 2);
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  pack_tile_kernel<<<blocks, 256, 0, avdn::to_cuda(stream)>>>(map_bgr, att, att_ch, H, W, tile4);
+  return avdn::check_launch("avdn_pack_tile");
+}
+
+extern "C" int avdn_gps_to_pixels(const double* corners_gps, const double* geo, int P,
+                                  int32_t* corners_px, avdn_stream_t stream) {
+  AVDN_REQUIRE(P >= 0, "avdn_gps_to_pixels: P < 0");
+  if (P == 0) return AVDN_OK;
+  AVDN_REQUIRE(corners_gps && geo && corners_px, "avdn_gps_to_pixels: null pointer");
+  gps_to_pixels_kernel<<<(P * 4 + 127) / 128, 128, 0, avdn::to_cuda(stream)>>>(corners_gps, geo, P,
+                                                                                corners_px);
+  return avdn::check_launch("avdn_gps_to_pixels");
+}
+
+extern "C" int avdn_homography_from_corners(const int32_t* corners_px, int P, double* minv,
+                                            avdn_stream_t stream) {
+  AVDN_REQUIRE(P >= 0, "avdn_homography_from_corners: P < 0");
+  if (P == 0) return AVDN_OK;
+  AVDN_REQUIRE(corners_px && minv, "avdn_homography_from_corners: null pointer");
+  homography_kernel<<<(P + 63) / 64, 64, 0, avdn::to_cuda(stream)>>>(corners_px, P, minv);
+  return avdn::check_launch("avdn_homography_from_corners");
+}
+
+extern "C" int avdn_render_views(const avdn_tile_desc* tiles, int n_tiles, const int32_t* tile_idx,
+                                 const double* minv, int P, uint8_t* views, uint8_t* att,
+                                 float* norm_nchw, void* norm_nhwc, const float* norm_lut,
+                                 avdn_stream_t stream) {
+  AVDN_REQUIRE(P >= 0, "avdn_render_views: P < 0");
+  if (P == 0) return AVDN_OK;
+  AVDN_REQUIRE(tiles && n_tiles >= 1 && minv, "avdn_render_views: null tiles/minv");
+  AVDN_REQUIRE(views || att || norm_nchw || norm_nhwc, "avdn_render_views: no output requested");
+  AVDN_REQUIRE(!(norm_nchw || norm_nhwc) || norm_lut, "avdn_render_views: norm output needs norm_lut");
+  AVDN_REQUIRE(((uintptr_t)views & 15) == 0 && ((uintptr_t)att & 15) == 0 &&
+                   ((uintptr_t)norm_nchw & 15) == 0 && ((uintptr_t)norm_nhwc & 15) == 0,
+               "avdn_render_views: outputs must be 16-byte aligned");
+  AVDN_REQUIRE((long long)P * NBAND < 2147483647LL, "avdn_render_views: too many poses");
+  render_kernel<<<P * NBAND, THREADS, 0, avdn::to_cuda(stream)>>>(
+      tiles, tile_idx, minv, P, views, att, norm_nchw,
+      reinterpret_cast<__nv_bfloat16*>(norm_nhwc), norm_lut);
+  return avdn::check_launch("avdn_render_views");
+}

@@ -1,0 +1,109 @@
+/*
+ * avdn.h — C ABI of libavdn.so, the sm_100a device library behind the AVDN
+ * (Aerial Vision-and-Dialog Navigation) HAA-Transformer hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name ends in `_host`;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is
+ *     allocated, retained or freed by the library;
+ *   - work is enqueued on `stream`; the library never synchronises the device;
+ *   - return 0 on success, a negative avdn_status on failure;
+ *     avdn_last_error_string() gives the reason (thread-local);
+ *   - there is no CPU fallback: on a machine without an sm_100 device every
+ *     compute entry point returns AVDN_ERR_NO_DEVICE / AVDN_ERR_LAUNCH.
+ *
+ * Each declaration cites the reference code (file:line under /root/reference)
+ * that it replaces.
+ */
+#ifndef AVDN_H_
+#define AVDN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* avdn_stream_t; /* == cudaStream_t */
+
+typedef enum avdn_status {
+  AVDN_OK = 0,
+  AVDN_ERR_BAD_ARG = -1,    /* null pointer, bad shape, bad alignment */
+  AVDN_ERR_UNSUPPORTED = -2,/* shape / mode outside what the kernels implement */
+  AVDN_ERR_LAUNCH = -3,     /* cudaGetLastError() after a launch */
+  AVDN_ERR_NO_DEVICE = -4,  /* no CUDA device / not sm_100 */
+  AVDN_ERR_DRIVER = -5      /* driver entry point (tensor-map encode) failed */
+} avdn_status;
+
+const char* avdn_last_error_string(void);
+/* ABI version; bumped whenever a signature changes. */
+int avdn_abi_version(void);
+/* 1 if device 0 is compute capability 10.x, 0 otherwise (no exception). */
+int avdn_device_supported(void);
+
+#define AVDN_VIEW 224 /* src/env.py:273-274 */
+
+/* ------------------------------------------------------------------------
+ * Stage 1 — view renderer (src/env.py:254-332)
+ * ---------------------------------------------------------------------- */
+
+/* Map preparation: packs a BGR u8 HWC satellite tile and (optionally) its
+ * human-attention map into the renderer's HBM layout: one u32 per pixel
+ * (B | G<<8 | R<<16 | ATT<<24) with a 1-pixel zero border, row pitch W+2.
+ * The zero border implements BORDER_CONSTANT(0) of cv2.warpPerspective
+ * (src/env.py:290,292) without per-tap predicates.
+ *   map_bgr  [H,W,3] u8      (self.map_batch[name],           src/env.py:217-221)
+ *   att      [H,W,att_ch] u8 or NULL; channel 0 is taken
+ *                            (self.attention_map_batch[name], src/env.py:224-231)
+ *   tile4    [(H+2)*(W+2)] u32 (out)                                            */
+int avdn_pack_tile(const uint8_t* map_bgr, const uint8_t* att, int att_ch,
+                   int H, int W, uint32_t* tile4, avdn_stream_t stream);
+
+/* gps_to_img_coords (src/env.py:189-196), batched and bit-exact:
+ *   x = rint((lng - bl_lng) / lat_ratio), y = rint((tr_lat - lat) / lat_ratio)
+ * in float64 with round-half-even.
+ *   corners_gps [P,4,2] f64 (lat,lng);  geo [P,5] f64 = (bl_lat, bl_lng,
+ *   tr_lat, tr_lng, lat_ratio) per pose;  corners_px [P,4,2] i32 (x,y) (out)   */
+int avdn_gps_to_pixels(const double* corners_gps, const double* geo, int P,
+                       int32_t* corners_px, avdn_stream_t stream);
+
+/* cv2.getPerspectiveTransform (src/env.py:287) followed by the matrix
+ * inversion cv2.warpPerspective performs internally (src/env.py:290):
+ *   corners_px [P,4,2] i32 (FL,FR,BR,BL; x,y)  ->  minv [P,9] f64 row-major.
+ * float64, same elimination / rounding order as OpenCV (no FMA contraction);
+ * a singular system yields the all-zero matrix, as OpenCV does.                */
+int avdn_homography_from_corners(const int32_t* corners_px, int P, double* minv,
+                                 avdn_stream_t stream);
+
+/* One packed tile as the renderer sees it. */
+typedef struct avdn_tile_desc {
+  const uint32_t* tile4; /* avdn_pack_tile output */
+  int32_t H, W;          /* un-padded size */
+} avdn_tile_desc;
+
+/* cv2.warpPerspective(map, M, (224,224)) and the same warp of the attention
+ * map (src/env.py:290-293), fixed-point bilinear, bit-exact, for P poses.
+ *   tiles     [n_tiles] avdn_tile_desc (device array)
+ *   tile_idx  [P] i32 or NULL (all poses use tiles[0])
+ *   minv      [P,9] f64 from avdn_homography_from_corners
+ * Outputs, each may be NULL:
+ *   views     [P,224,224,3] u8 BGR HWC     = obs['current_view']  (env.py:308)
+ *   att       [P,224,224]   u8             = 255 * obs['gt_saliency'] (env.py:293)
+ *   norm_nchw [P,3,224,224] f32 RGB, (x-mean)/std (src/xview_et/agent.py:586-592)
+ *   norm_nhwc [P,224,224,4] bf16 RGB0, same normalisation rounded to bf16
+ *             (channel 3 is zero; this is the trunk's input layout)
+ *   norm_lut  [3,256] f32, lut[c][v] = (float(v) - mean[c]) / std[c] for RGB
+ *             channel c, computed on the host in float32 exactly as the
+ *             reference does; required when norm_nchw or norm_nhwc is given.  */
+int avdn_render_views(const avdn_tile_desc* tiles, int n_tiles,
+                      const int32_t* tile_idx, const double* minv, int P,
+                      uint8_t* views, uint8_t* att, float* norm_nchw,
+                      void* norm_nhwc, const float* norm_lut,
+                      avdn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVDN_H_ */
