@@ -30,12 +30,17 @@ _SIGNATURES = {
     "avdn_homography_from_corners": [c_void_p, c_int, c_void_p, c_void_p],
     "avdn_render_views": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_void_p],
+    # struct pointers are passed with ctypes.byref(...)
+    "avdn_gemm_plan": [c_void_p, c_void_p, C.c_size_t],
+    "avdn_gemm_run": [c_void_p, c_void_p],
 }
+_SIZE_T_FUNCS = ["avdn_gemm_plan_bytes"]
 
 
 def exported_symbols():
     """Every symbol ``include/avdn.h`` declares (used by the CPU-side ABI test)."""
-    return ["avdn_last_error_string", "avdn_abi_version", "avdn_device_supported"] + list(_SIGNATURES)
+    return (["avdn_last_error_string", "avdn_abi_version", "avdn_device_supported"] + _SIZE_T_FUNCS
+            + list(_SIGNATURES))
 
 
 def register(name, argtypes):
@@ -59,6 +64,9 @@ def lib():
         h.avdn_last_error_string.argtypes = []
         h.avdn_abi_version.restype = C.c_int
         h.avdn_device_supported.restype = C.c_int
+        for name in _SIZE_T_FUNCS:
+            getattr(h, name).restype = C.c_size_t
+            getattr(h, name).argtypes = []
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(h, name)          # AttributeError if the symbol is missing
             fn.argtypes = argtypes

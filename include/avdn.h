@@ -103,6 +103,73 @@ int avdn_render_views(const avdn_tile_desc* tiles, int n_tiles,
                       void* norm_nhwc, const float* norm_lut,
                       avdn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Tensor-core primitive (tcgen05 / TMEM / TMA): every dense contraction of
+ * the path runs through one planned kernel.  It replaces the cuDNN / cuBLAS
+ * library calls behind
+ *   nn.Conv2d fwd/dgrad/wgrad        src/models/dark_net.py:22-28
+ *   nn.Linear / MHA projections      src/models/enc_vl.py:16-22,68
+ *   QK^T, PV and their backward      (inside nn.TransformerEncoderLayer)
+ *   ET heads / fc2                   src/models/ET_haa.py:98-119,144-167
+ * A plan is a caller-owned HOST blob (avdn_gemm_plan_bytes() bytes) holding the
+ * encoded TMA descriptors and launch geometry for fixed device pointers; it can
+ * be re-run any number of times (and captured in a CUDA graph).
+ * ---------------------------------------------------------------------- */
+enum { AVDN_GEMM_PLAIN = 0, AVDN_GEMM_CONV = 1, AVDN_GEMM_WGRAD = 2 };
+enum { AVDN_DT_BF16 = 0, AVDN_DT_F32 = 1 };
+
+/* One k-step source of a convolution: which A (CONV) / B (WGRAD) view, the
+ * offset added to the box's W and H coordinates, and the operand-B k offset
+ * (CONV) or the output column offset (WGRAD) of this filter tap. */
+typedef struct avdn_tap { int32_t map, d1, d2, bk; } avdn_tap;
+
+/* A bf16 operand as a rank-4 strided tensor; dim[0] is contiguous.  Strides in
+ * elements.  box = TMA box (box[0] must be 64). */
+typedef struct avdn_operand {
+  const void* ptr;
+  int64_t dim[4];
+  int64_t stride[4];
+  int32_t box[4];
+} avdn_operand;
+
+typedef struct avdn_gemm_core {
+  int32_t mode;               /* AVDN_GEMM_* */
+  int32_t M, N;               /* logical output extent per batch (PLAIN/WGRAD); N only (CONV) */
+  int32_t num_kb;             /* k-steps of 64: ceil(K/64) | taps*cblocks | pixel tiles */
+  int32_t split_k;            /* >1 only with accumulate == 2 */
+  int32_t batch0, batch1;     /* PLAIN: grid.z = batch0*batch1*split_k -> coords 2,3 */
+  int32_t b_batched;          /* PLAIN: 1 if operand B has the batch dims too */
+  int32_t cblocks, n_taps;    /* CONV: channel blocks per tap */
+  avdn_tap taps[9];
+  int32_t tiles_w, tiles_h, tiles_n;   /* spatial tiling of the box over (W,H,N) */
+  int32_t box_w, box_h, box_n;
+  int32_t valid_w, valid_h, valid_n;   /* CONV: extent of valid output coords */
+  int32_t out_H, out_W, out_sh, out_sw, out_oh, out_ow; /* CONV: out pixel (n, h*sh+oh, w*sw+ow) */
+  int32_t out_dtype;          /* AVDN_DT_* */
+  int32_t accumulate;         /* 0 store, 1 out += (read-modify-write), 2 atomicAdd (fp32) */
+  int32_t relu;
+  float alpha;
+  uint32_t tx_bytes;          /* filled by avdn_gemm_plan */
+  int32_t pad_;
+  int64_t ldc, out_bs0, out_bs1;       /* output row pitch / batch strides, elements */
+  void* out;
+  const float* bias;          /* [N] fp32 or NULL */
+} avdn_gemm_core;
+
+typedef struct avdn_gemm_desc {
+  avdn_gemm_core core;
+  int32_t bn;                 /* N tile: 64, 128 or 256 */
+  int32_t a_mn, b_mn;         /* 0 = K-major operand, 1 = MN-major operand */
+  int32_t n_a, n_b;           /* number of A / B views (parity views of stride-2 convs) */
+  int32_t grid_m, grid_n, grid_z;
+  avdn_operand a[4];
+  avdn_operand b[4];
+} avdn_gemm_desc;
+
+size_t avdn_gemm_plan_bytes(void);
+int avdn_gemm_plan(const avdn_gemm_desc* desc, void* plan_host, size_t plan_bytes);
+int avdn_gemm_run(const void* plan_host, avdn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,145 @@
+"""GPU: the tcgen05 GEMM / implicit-GEMM conv primitive against fp32 torch
+references on the same bf16-rounded inputs (tolerance: bf16 output rounding,
+fp32 accumulation => 1e-2 relative as north_star states for bf16)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G(built_lib):
+    from avdn_b200 import gemm
+    return gemm
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def _close(out, ref, rtol=1e-2):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs().max().item()
+    tol = rtol * ref.abs().max().item() + 1e-6
+    assert err <= tol, f"max err {err} > tol {tol}"
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(300, 200, 520, 128), (128, 64, 64, 64), (1000, 512, 768, 256),
+                                      (77, 270, 64, 128), (256, 2304, 768, 256)])
+def test_plain_kmajor(G, M, N, K, bn):
+    a, b = _rand(M, K, seed=1), _rand(N, K, seed=2)
+    out = G.gemm(a, b, bn=bn, out_dtype=torch.float32)
+    _close(out, a.float() @ b.float().t(), rtol=2e-3)
+    out16 = G.gemm(a, b, bn=bn)
+    _close(out16, a.float() @ b.float().t())
+
+
+def test_plain_epilogues(G):
+    M, N, K = 260, 200, 192
+    a, b = _rand(M, K, seed=3), _rand(N, K, seed=4)
+    bias = torch.randn(N, device="cuda")
+    ref = torch.relu(0.5 * (a.float() @ b.float().t()) + bias)
+    _close(G.gemm(a, b, bias=bias, relu=True, alpha=0.5, out_dtype=torch.float32), ref, rtol=2e-3)
+    base = torch.randn(M, N, device="cuda")
+    out = base.clone()
+    G.gemm(a, b, out=out, accumulate=1)
+    _close(out, base + a.float() @ b.float().t(), rtol=2e-3)
+    base16 = _rand(M, N, seed=9)
+    out16 = base16.clone()
+    G.gemm(a, b, out=out16, accumulate=1)
+    _close(out16, base16.float() + a.float() @ b.float().t())
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_plain_mn_major(G, a_mn, b_mn, bn):
+    M, N, K = 200, 320, 333 + 3        # K multiple of 8 for the pitch; ragged tiles
+    K = 336
+    a, b = _rand(M, K, seed=5), _rand(N, K, seed=6)
+    A = a.t().contiguous() if a_mn else a
+    B = b.t().contiguous() if b_mn else b
+    out = G.gemm(A, B, a_mn=a_mn, b_mn=b_mn, bn=bn, out_dtype=torch.float32)
+    _close(out, a.float() @ b.float().t(), rtol=2e-3)
+
+
+def test_split_k_atomic(G):
+    M, N, K = 130, 100, 4096
+    a, b = _rand(M, K, seed=7), _rand(N, K, seed=8)
+    out = G.gemm(a.t().contiguous(), b.t().contiguous(), a_mn=True, b_mn=True, split_k=7, accumulate=2,
+                 out_dtype=torch.float32)
+    _close(out, a.float() @ b.float().t(), rtol=2e-3)
+
+
+def test_batched_attention_shapes(G):
+    """QK^T and PV with the ET strides: qkv [B,S,3*768], heads of 64, S=270."""
+    B, S, H, dh = 2, 270, 12, 64
+    qkv = _rand(B, S, 3 * H * dh, seed=11)
+    Sp = 272
+    scores = torch.zeros(B, H, S, Sp, device="cuda", dtype=torch.float32)
+    p = G.plan_plain(M=S, N=S, K=dh, a_ptr=qkv.data_ptr(), lda=3 * H * dh, a_mn=False,
+                     b_ptr=qkv.data_ptr() + H * dh * 2, ldb=3 * H * dh, b_mn=False, out=scores, ldc=Sp,
+                     alpha=0.125, batch0=H, batch1=B, a_bs=(dh, S * 3 * H * dh), b_bs=(dh, S * 3 * H * dh),
+                     out_bs=(S * Sp, H * S * Sp), keep=(qkv,))
+    p.run()
+    q = qkv[:, :, :H * dh].view(B, S, H, dh).permute(0, 2, 1, 3).float()
+    k = qkv[:, :, H * dh:2 * H * dh].view(B, S, H, dh).permute(0, 2, 1, 3).float()
+    v = qkv[:, :, 2 * H * dh:].view(B, S, H, dh).permute(0, 2, 1, 3).float()
+    ref = 0.125 * q @ k.transpose(-1, -2)
+    _close(scores[..., :S], ref, rtol=2e-3)
+    assert (scores[..., S:] == 0).all()
+    # PV: P [B,H,S,Sp] bf16 (K-major over keys), V MN-major
+    P = torch.softmax(ref, -1).to(torch.bfloat16)
+    Pp = torch.zeros(B, H, S, Sp, device="cuda", dtype=torch.bfloat16)
+    Pp[..., :S] = P
+    o = torch.zeros(B, S, H * dh, device="cuda", dtype=torch.bfloat16)
+    p2 = G.plan_plain(M=S, N=dh, K=S, a_ptr=Pp.data_ptr(), lda=Sp, a_mn=False,
+                      b_ptr=qkv.data_ptr() + 2 * H * dh * 2, ldb=3 * H * dh, b_mn=True, out=o, ldc=H * dh,
+                      batch0=H, batch1=B, a_bs=(S * Sp, H * S * Sp), b_bs=(dh, S * 3 * H * dh),
+                      out_bs=(dh, S * H * dh), bn=64, keep=(Pp, qkv))
+    p2.run()
+    ref_o = (P.float() @ v).permute(0, 2, 1, 3).reshape(B, S, H * dh)
+    _close(o, ref_o)
+
+
+def _conv_ref(x_nhwc, w, stride):
+    k = w.shape[-1]
+    return torch.nn.functional.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w.float(), stride=stride,
+                                      padding=(k - 1) // 2)
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,k,stride", [
+    (4, 14, 128, 256, 3, 1), (3, 28, 64, 128, 3, 2), (5, 7, 256, 128, 1, 1), (2, 56, 64, 64, 3, 1),
+    (20, 7, 128, 256, 3, 1), (2, 14, 256, 512, 3, 2), (1, 112, 64, 64, 3, 2)])
+def test_conv_fwd_dgrad_wgrad(G, N, H, Cin, Cout, k, stride):
+    W = H
+    x = _rand(N, H, W, Cin, seed=21)
+    w = _rand(Cout, Cin, k, k, seed=22, scale=0.05)
+    Ho, Wo = H // stride, W // stride
+    # forward
+    w_f = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous()
+    z = torch.empty(N, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
+    G.plan_conv_fwd(x, w_f, z, N=N, H=H, W=W, Cin=Cin, Cout=Cout, k=k, stride=stride).run()
+    ref = _conv_ref(x, w, stride)
+    _close(z.permute(0, 3, 1, 2), ref)
+    # dgrad
+    dz = _rand(N, Ho, Wo, Cout, seed=23)
+    w_d = w.permute(1, 2, 3, 0).reshape(Cin, k * k * Cout).contiguous()
+    dx = torch.full((N, H, W, Cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    for p in G.plan_conv_dgrad(dz, w_d, dx, N=N, H=H, W=W, Cin=Cin, Cout=Cout, k=k, stride=stride):
+        p.run()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    out = torch.nn.functional.conv2d(xr, wr, stride=stride, padding=(k - 1) // 2)
+    out.backward(dz.float().permute(0, 3, 1, 2))
+    _close(dx.permute(0, 3, 1, 2), xr.grad)
+    # dgrad accumulate
+    dx2 = dx.clone()
+    for p in G.plan_conv_dgrad(dz, w_d, dx2, N=N, H=H, W=W, Cin=Cin, Cout=Cout, k=k, stride=stride, accumulate=1):
+        p.run()
+    _close(dx2.permute(0, 3, 1, 2), 2 * xr.grad, rtol=2e-2)
+    # wgrad
+    dw = torch.zeros(Cout, k * k * Cin, device="cuda", dtype=torch.float32)
+    G.plan_conv_wgrad(dz, x, dw, N=N, H=H, W=W, Cin=Cin, Cout=Cout, k=k, stride=stride).run()
+    ref_dw = wr.grad.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)
+    _close(dw, ref_dw, rtol=3e-3)
