@@ -150,6 +150,21 @@ def conv_box(W, H, N, rows):
     return best[1]
 
 
+def wgrad_box(W, H, N):
+    """Box of EXACTLY 64 pixels for a wgrad k-step (the unused part of a k-step would
+    otherwise multiply stale shared memory).  Box dims may exceed the tensor extent:
+    TMA zero-fills out-of-bounds elements of both operands."""
+    best = None
+    for lw in range(7):
+        for lh in range(7 - lw):
+            bw, bh, bnn = 1 << lw, 1 << lh, 1 << (6 - lw - lh)
+            tiles = _cdiv(W, bw) * _cdiv(H, bh) * _cdiv(N, bnn)
+            key = (tiles, -bw, -bh)
+            if best is None or key < best[0]:
+                best = (key, (bw, bh, bnn))
+    return best[1]
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None, relu=False,
          alpha=1.0, accumulate=0, split_k=1, bn=None):
     """Convenience one-shot 2-D GEMM on contiguous bf16 matrices (tests, small ops).
@@ -296,8 +311,7 @@ def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, b
     assert Cin % 64 == 0 and Cout % 64 == 0 and dw.dtype == torch.float32
     Ho, Wo = H // stride, W // stride
     bn = bn or pick_bn(Cin)
-    bw, bh, bnn = conv_box(Wo, Ho, N, 64)
-    assert bw * bh * bnn == 64, f"wgrad k-step must be exactly 64 pixels, got box {(bw, bh, bnn)}"
+    bw, bh, bnn = wgrad_box(Wo, Ho, N)
     d = GemmDesc()
     c = d.core
     c.mode, c.M, c.N = WGRAD, Cout, Cin

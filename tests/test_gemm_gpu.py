@@ -64,7 +64,7 @@ def test_plain_mn_major(G, a_mn, b_mn, bn):
 
 
 def test_split_k_atomic(G):
-    M, N, K = 130, 100, 4096
+    M, N, K = 136, 104, 4096
     a, b = _rand(M, K, seed=7), _rand(N, K, seed=8)
     out = G.gemm(a.t().contiguous(), b.t().contiguous(), a_mn=True, b_mn=True, split_k=7, accumulate=2,
                  out_dtype=torch.float32)
