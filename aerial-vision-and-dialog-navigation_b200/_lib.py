@@ -33,6 +33,20 @@ _SIGNATURES = {
     # struct pointers are passed with ctypes.byref(...)
     "avdn_gemm_plan": [c_void_p, c_void_p, C.c_size_t],
     "avdn_gemm_run": [c_void_p, c_void_p],
+    "avdn_conv0_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "avdn_conv0_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "avdn_bn_stats": [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_f32,
+                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "avdn_bn_eval_coeffs": [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_void_p, c_void_p,
+                            c_void_p],
+    "avdn_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_f32, c_void_p],
+    "avdn_bn_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_f32,
+                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "avdn_pack_conv_weight": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "avdn_unpack_conv_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "avdn_cast_f32_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
+    "avdn_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "avdn_nchw_f32_to_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
 }
 _SIZE_T_FUNCS = ["avdn_gemm_plan_bytes"]
 

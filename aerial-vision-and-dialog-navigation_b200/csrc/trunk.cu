@@ -1,0 +1,495 @@
+// Stage 2 of the AVDN hot path: the xview-yolov3 Darknet trunk
+// (src/models/dark_net.py:7-64,212-240) around the tensor-core convolutions.
+//
+// CUDA-core kernels that are HBM-bound by nature: the 3->32 first convolution
+// (K = 27, too thin for a tensor-core tile), train-mode BatchNorm statistics and
+// application fused with LeakyReLU(0.01) and the shortcut add, their backward
+// counterparts, and the weight (un)packing between the reference's
+// [Cout,Cin,kh,kw] fp32 parameters and the bf16 GEMM operand layouts.
+//
+// Activations are NHWC bf16 with channels padded to a multiple of 64; a tensor
+// is addressed as rows x C (rows = N*H*W).  Every elementwise kernel moves 16
+// bytes (8 channels) per thread per access.
+#include "common.cuh"
+
+namespace {
+
+constexpr int C0_OUT = 32;     // first conv: 3 -> 32 channels
+constexpr int C0_PAD = 64;     // stored padded to 64
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    f[2 * i] = __low2float(b);
+    f[2 * i + 1] = __high2float(b);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------- conv0 forward
+// x: [N,H,W,4] bf16 (R,G,B,0); w: [32][3][3][3] fp32 (co, ci, kh, kw); z: [N,H,W,64] bf16.
+// One thread per output pixel; the 27-value patch sits in registers, weights in smem.
+__global__ void __launch_bounds__(256) conv0_fwd_kernel(const uint2* __restrict__ x, const float* __restrict__ w,
+                                                        uint4* __restrict__ z, int N, int H, int W) {
+  __shared__ float sw[27 * C0_OUT];          // [tap*3+ci][co]
+  for (int i = threadIdx.x; i < 27 * C0_OUT; i += blockDim.x) {
+    const int co = i % C0_OUT, r = i / C0_OUT, ci = r % 3, tap = r / 3;
+    sw[i] = w[(co * 3 + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const long long total = (long long)N * H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int wx = (int)(p % W), hy = (int)((p / W) % H);
+    const long long nbase = (p / ((long long)W * H)) * (long long)W * H;
+    float patch[27];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int yy = hy + kh - 1, xx = wx + kw - 1;
+        float r = 0.f, g = 0.f, b = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const uint2 v = __ldg(x + nbase + (long long)yy * W + xx);
+          const __nv_bfloat162 rg = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+          const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+          r = __low2float(rg); g = __high2float(rg); b = __low2float(b0);
+        }
+        patch[(kh * 3 + kw) * 3 + 0] = r;
+        patch[(kh * 3 + kw) * 3 + 1] = g;
+        patch[(kh * 3 + kw) * 3 + 2] = b;
+      }
+    uint4* o = z + p * (C0_PAD / 8);
+#pragma unroll
+    for (int g8 = 0; g8 < C0_OUT / 8; ++g8) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int t = 0; t < 27; ++t) {
+        const float xv = patch[t];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, sw[t * C0_OUT + g8 * 8 + j], acc[j]);
+      }
+      o[g8] = pack8(acc);
+    }
+#pragma unroll
+    for (int g8 = C0_OUT / 8; g8 < C0_PAD / 8; ++g8) o[g8] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// --------------------------------------------------------------- conv0 wgrad
+// dw[co][ci][kh][kw] += sum_p dz[p][co] * x[p + tap][ci].  Block = 8 warps; each
+// warp streams pixels, lane = co, 27 accumulators per lane; block-reduce at the end.
+__global__ void __launch_bounds__(256) conv0_wgrad_kernel(const __nv_bfloat16* __restrict__ dz,
+                                                          const uint2* __restrict__ x, float* __restrict__ dw,
+                                                          int N, int H, int W) {
+  __shared__ float red[27 * C0_OUT];
+  for (int i = threadIdx.x; i < 27 * C0_OUT; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total = (long long)N * H * W;
+  float acc[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+  for (long long p = (long long)blockIdx.x * 8 + warp; p < total; p += (long long)gridDim.x * 8) {
+    const int wx = (int)(p % W), hy = (int)((p / W) % H);
+    const long long nbase = (p / ((long long)W * H)) * (long long)W * H;
+    const float g = __bfloat162float(dz[p * C0_PAD + lane]);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int yy = hy + kh - 1, xx = wx + kw - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {      // warp-uniform
+          const uint2 v = __ldg(x + nbase + (long long)yy * W + xx);
+          const __nv_bfloat162 rg = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+          const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+          acc[(kh * 3 + kw) * 3 + 0] = fmaf(g, __low2float(rg), acc[(kh * 3 + kw) * 3 + 0]);
+          acc[(kh * 3 + kw) * 3 + 1] = fmaf(g, __high2float(rg), acc[(kh * 3 + kw) * 3 + 1]);
+          acc[(kh * 3 + kw) * 3 + 2] = fmaf(g, __low2float(b0), acc[(kh * 3 + kw) * 3 + 2]);
+        }
+      }
+  }
+#pragma unroll
+  for (int t = 0; t < 27; ++t) atomicAdd(&red[t * C0_OUT + lane], acc[t]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * C0_OUT; i += blockDim.x) {
+    const int co = i % C0_OUT, r = i / C0_OUT, ci = r % 3, tap = r / 3;
+    atomicAdd(&dw[(co * 3 + ci) * 9 + tap], red[i]);
+  }
+}
+
+// ------------------------------------------------------------ BN statistics
+// sums[0][c] = sum z, sums[1][c] = sum z^2 over R rows (fp64 accumulators).
+// Thread layout: threadIdx.x -> group of 8 channels, threadIdx.y -> row lane.
+template <bool BWD>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ shift,
+                                                        const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, float slope, long long R,
+                                                        int C, double* __restrict__ sums, int rows_per_block) {
+  extern __shared__ float sred[];           // [2][ty][C8*8]
+  const int C8 = C >> 3;
+  const int cx = threadIdx.x % C8;           // channel group
+  const int ry = threadIdx.x / C8;           // row lane inside the block
+  const int RY = blockDim.x / C8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  float sc[8], sh[8], mu[8], rs[8];
+  if (BWD) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = scale[cx * 8 + j]; sh[j] = shift[cx * 8 + j]; mu[j] = mean[cx * 8 + j]; rs[j] = rstd[cx * 8 + j];
+    }
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  if (ry < RY) {
+    for (long long r = r0 + ry; r < r1; r += RY) {
+      float f[8];
+      unpack8(__ldg(z + r * C8 + cx), f);
+      if (!BWD) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+      } else {
+        float g[8];
+        unpack8(__ldg(da + r * C8 + cx), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf(f[j], sc[j], sh[j]);
+          const float gg = y > 0.f ? g[j] : g[j] * slope;
+          s1[j] += gg;
+          s2[j] = fmaf(gg, (f[j] - mu[j]) * rs[j], s2[j]);
+        }
+      }
+    }
+  }
+  float* a1 = sred;
+  float* a2 = sred + RY * C;
+  if (ry < RY) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a1[ry * C + cx * 8 + j] = s1[j]; a2[ry * C + cx * 8 + j] = s2[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int y = 0; y < RY; ++y) { t1 += a1[y * C + c]; t2 += a2[y * C + c]; }
+    atomicAdd(&sums[c], (double)t1);
+    atomicAdd(&sums[C + c], (double)t2);
+  }
+}
+
+// mean/var -> per-channel affine (scale, shift); running statistics update
+// (nn.BatchNorm2d: momentum 0.1, eps 1e-5, unbiased variance for the running buffer).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long R, int C, int C_real,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float momentum, float eps, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (c >= C_real) { scale[c] = 0.f; shift[c] = 0.f; mean[c] = 0.f; rstd[c] = 0.f; return; }
+  const double m = sums[c] / (double)R;
+  double var = sums[C + c] / (double)R - m * m;
+  if (var < 0.0) var = 0.0;
+  const float rs = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * rs;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  mean[c] = (float)m;
+  rstd[c] = rs;
+  if (running_mean) {
+    const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval mode: affine from the running statistics
+__global__ void bn_eval_coeffs_kernel(int C, int C_real, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ running_mean,
+                                      const float* __restrict__ running_var, float eps, float* __restrict__ scale,
+                                      float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (c >= C_real) { scale[c] = 0.f; shift[c] = 0.f; return; }
+  const float rs = 1.f / sqrtf(running_var[c] + eps);
+  scale[c] = gamma[c] * rs;
+  shift[c] = beta[c] - running_mean[c] * gamma[c] * rs;
+}
+
+// a = leaky(z*scale + shift) (+ residual)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift,
+                                                       const uint4* __restrict__ residual, uint4* __restrict__ a,
+                                                       long long n8, int C8, float slope) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % C8);
+    float f[8], r[8];
+    unpack8(__ldg(z + i), f);
+    if (residual) unpack8(__ldg(residual + i), r);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + cx * 2);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale) + cx * 2 + 1);
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + cx * 2);
+    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift) + cx * 2 + 1);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(f[j], sc[j], sh[j]);
+      y = y > 0.f ? y : y * slope;
+      f[j] = residual ? y + r[j] : y;
+    }
+    a[i] = pack8(f);
+  }
+}
+
+// dz = scale * (g - S1/R - xhat * S2/R),  g = da * leaky'(y)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ z,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd,
+                                                           const double* __restrict__ sums, double invR,
+                                                           uint4* __restrict__ dz, long long n8, int C, float slope) {
+  const int C8 = C >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cx = (int)(i % C8);
+    float f[8], g[8];
+    unpack8(__ldg(z + i), f);
+    unpack8(__ldg(da + i), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cx * 8 + j;
+      const float sc = __ldg(scale + c), sh = __ldg(shift + c), mu = __ldg(mean + c), rs = __ldg(rstd + c);
+      const float m1 = (float)(sums[c] * invR), m2 = (float)(sums[C + c] * invR);
+      const float y = fmaf(f[j], sc, sh);
+      const float gg = y > 0.f ? g[j] : g[j] * slope;
+      const float xh = (f[j] - mu) * rs;
+      f[j] = sc * (gg - m1 - xh * m2);
+    }
+    dz[i] = pack8(f);
+  }
+}
+
+// eval-mode backward is not needed (the trunk is only differentiated in train mode).
+
+// dgamma += S2, dbeta += S1 for the real channels
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, int C_real, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C_real) return;
+  dbeta[c] += (float)sums[c];
+  dgamma[c] += (float)sums[C + c];
+}
+
+// ------------------------------------------------------- weight (un)packing
+// w [Cout,Cin,k,k] fp32 -> wf [Cout_p][k*k][Cin_p] bf16 and wd [Cin_p][k*k][Cout_p] bf16 (zero padded)
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cout_p, int Cin_p,
+                                        __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const int kk = k * k;
+  const long long n = (long long)Cout_p * kk * Cin_p;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin_p), t = (int)((i / Cin_p) % kk), co = (int)(i / ((long long)Cin_p * kk));
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * kk + t];
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    wf[i] = b;
+    wd[((long long)ci * kk + t) * Cout_p + co] = b;
+  }
+}
+
+// grad [Cout,Cin,k,k] += dwf [Cout_p][k*k][Cin_p]
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwf, int Cout, int Cin, int k, int Cin_p,
+                                         float* __restrict__ grad) {
+  const int kk = k * k;
+  const long long n = (long long)Cout * Cin * kk;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % kk), ci = (int)((i / kk) % Cin), co = (int)(i / ((long long)kk * Cin));
+    grad[i] += dwf[((long long)co * kk + t) * Cin_p + ci];
+  }
+}
+
+// fp32 -> bf16 cast (linear-layer weights, features)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// NHWC bf16 [N,HW,C] -> NCHW-flattened fp32 [N,C,HW] (trunk output -> ET `frames`) and its adjoint
+__global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int N, int HW,
+                                        int C) {
+  const long long n = (long long)N * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW), c = (int)((i / HW) % C);
+    const long long b = i / ((long long)HW * C);
+    out[i] = __bfloat162float(in[(b * HW + p) * C + c]);
+  }
+}
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int HW,
+                                        int C) {
+  const long long n = (long long)N * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), p = (int)((i / C) % HW);
+    const long long b = i / ((long long)HW * C);
+    out[i] = __float2bfloat16_rn(in[(b * C + c) * HW + p]);
+  }
+}
+
+inline int grid_for(long long n, int block = 256, int waves = 8) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)avdn::sm_count() * waves;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+// ===================================================================== C ABI
+extern "C" int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W,
+                              avdn_stream_t stream) {
+  AVDN_REQUIRE(x_nhwc4 && w && z && N > 0 && H > 0 && W > 0, "avdn_conv0_fwd: bad argument");
+  const long long total = (long long)N * H * W;
+  conv0_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, avdn::to_cuda(stream)>>>(
+      reinterpret_cast<const uint2*>(x_nhwc4), w, reinterpret_cast<uint4*>(z), N, H, W);
+  return avdn::check_launch("avdn_conv0_fwd");
+}
+
+extern "C" int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int H, int W,
+                                avdn_stream_t stream) {
+  AVDN_REQUIRE(dz && x_nhwc4 && dw && N > 0 && H > 0 && W > 0, "avdn_conv0_wgrad: bad argument");
+  const int blocks = avdn::sm_count() * 8;
+  conv0_wgrad_kernel<<<blocks, 256, 0, avdn::to_cuda(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dz),
+                                                               reinterpret_cast<const uint2*>(x_nhwc4), dw, N, H, W);
+  return avdn::check_launch("avdn_conv0_wgrad");
+}
+
+static int bn_reduce_launch(bool bwd, const void* z, const void* da, const float* scale, const float* shift,
+                            const float* mean, const float* rstd, float slope, long long R, int C, double* sums,
+                            cudaStream_t s) {
+  AVDN_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, "bn reduce: C=%d must be a multiple of 8 in [8,2048]", C);
+  const int C8 = C / 8;
+  int threads = 256;
+  if (C8 > 256) threads = C8;            // C up to 2048 -> one row lane
+  threads = (threads / C8) * C8;
+  const int RY = threads / C8;
+  // enough blocks to fill the machine, at least 64 rows per block
+  long long blocks = (long long)avdn::sm_count() * 8;
+  long long rpb = (R + blocks - 1) / blocks;
+  if (rpb < 64) rpb = 64;
+  blocks = (R + rpb - 1) / rpb;
+  const size_t smem = (size_t)2 * RY * C * sizeof(float);
+  if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s) != cudaSuccess) return avdn::check_launch("bn reduce memset");
+  if (bwd)
+    bn_reduce_kernel<true><<<(unsigned)blocks, threads, smem, s>>>(
+        reinterpret_cast<const uint4*>(z), reinterpret_cast<const uint4*>(da), scale, shift, mean, rstd, slope, R, C,
+        sums, (int)rpb);
+  else
+    bn_reduce_kernel<false><<<(unsigned)blocks, threads, smem, s>>>(reinterpret_cast<const uint4*>(z), nullptr,
+                                                                    nullptr, nullptr, nullptr, nullptr, slope, R, C,
+                                                                    sums, (int)rpb);
+  return avdn::check_launch("bn_reduce_kernel");
+}
+
+extern "C" int avdn_bn_stats(const void* z, long long R, int C, int C_real, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, float momentum, float eps, double* sums,
+                             float* scale, float* shift, float* mean, float* rstd, avdn_stream_t stream) {
+  AVDN_REQUIRE(z && gamma && beta && sums && scale && shift && mean && rstd && R > 0, "avdn_bn_stats: bad argument");
+  cudaStream_t s = avdn::to_cuda(stream);
+  int r = bn_reduce_launch(false, z, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, R, C, sums, s);
+  if (r) return r;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, C_real, gamma, beta, running_mean, running_var,
+                                                     momentum, eps, scale, shift, mean, rstd);
+  return avdn::check_launch("bn_finalize_kernel");
+}
+
+extern "C" int avdn_bn_eval_coeffs(int C, int C_real, const float* gamma, const float* beta,
+                                   const float* running_mean, const float* running_var, float eps, float* scale,
+                                   float* shift, avdn_stream_t stream) {
+  AVDN_REQUIRE(gamma && beta && running_mean && running_var && scale && shift, "avdn_bn_eval_coeffs: null pointer");
+  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, avdn::to_cuda(stream)>>>(C, C_real, gamma, beta, running_mean,
+                                                                           running_var, eps, scale, shift);
+  return avdn::check_launch("bn_eval_coeffs_kernel");
+}
+
+extern "C" int avdn_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* a,
+                             long long R, int C, float slope, avdn_stream_t stream) {
+  AVDN_REQUIRE(z && scale && shift && a && R > 0 && C % 8 == 0, "avdn_bn_apply: bad argument");
+  const long long n8 = R * (C / 8);
+  bn_apply_kernel<<<grid_for(n8, 256, 16), 256, 0, avdn::to_cuda(stream)>>>(
+      reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<const uint4*>(residual),
+      reinterpret_cast<uint4*>(a), n8, C / 8, slope);
+  return avdn::check_launch("avdn_bn_apply");
+}
+
+extern "C" int avdn_bn_backward(const void* da, const void* z, const float* scale, const float* shift,
+                                const float* mean, const float* rstd, long long R, int C, int C_real, float slope,
+                                double* sums, void* dz, float* dgamma, float* dbeta, avdn_stream_t stream) {
+  AVDN_REQUIRE(da && z && scale && shift && mean && rstd && sums && dz && R > 0, "avdn_bn_backward: bad argument");
+  cudaStream_t s = avdn::to_cuda(stream);
+  int r = bn_reduce_launch(true, z, da, scale, shift, mean, rstd, slope, R, C, sums, s);
+  if (r) return r;
+  const long long n8 = R * (C / 8);
+  bn_bwd_apply_kernel<<<grid_for(n8, 256, 16), 256, 0, s>>>(reinterpret_cast<const uint4*>(da),
+                                                            reinterpret_cast<const uint4*>(z), scale, shift, mean,
+                                                            rstd, sums, 1.0 / (double)R, reinterpret_cast<uint4*>(dz),
+                                                            n8, C, slope);
+  r = avdn::check_launch("bn_bwd_apply_kernel");
+  if (r) return r;
+  if (dgamma && dbeta) {
+    bn_param_grad_kernel<<<(C_real + 127) / 128, 128, 0, s>>>(sums, C, C_real, dgamma, dbeta);
+    r = avdn::check_launch("bn_param_grad_kernel");
+  }
+  return r;
+}
+
+extern "C" int avdn_pack_conv_weight(const float* w, int Cout, int Cin, int k, int Cout_p, int Cin_p, void* wf,
+                                     void* wd, avdn_stream_t stream) {
+  AVDN_REQUIRE(w && wf && wd && Cout_p >= Cout && Cin_p >= Cin, "avdn_pack_conv_weight: bad argument");
+  const long long n = (long long)Cout_p * k * k * Cin_p;
+  pack_conv_weight_kernel<<<grid_for(n), 256, 0, avdn::to_cuda(stream)>>>(
+      w, Cout, Cin, k, Cout_p, Cin_p, reinterpret_cast<__nv_bfloat16*>(wf), reinterpret_cast<__nv_bfloat16*>(wd));
+  return avdn::check_launch("avdn_pack_conv_weight");
+}
+
+extern "C" int avdn_unpack_conv_wgrad(const float* dwf, int Cout, int Cin, int k, int Cin_p, float* grad,
+                                      avdn_stream_t stream) {
+  AVDN_REQUIRE(dwf && grad, "avdn_unpack_conv_wgrad: null pointer");
+  const long long n = (long long)Cout * Cin * k * k;
+  unpack_conv_wgrad_kernel<<<grid_for(n), 256, 0, avdn::to_cuda(stream)>>>(dwf, Cout, Cin, k, Cin_p, grad);
+  return avdn::check_launch("avdn_unpack_conv_wgrad");
+}
+
+extern "C" int avdn_cast_f32_bf16(const float* in, void* out, long long n, avdn_stream_t stream) {
+  AVDN_REQUIRE(n >= 0, "avdn_cast_f32_bf16: n < 0");
+  if (n == 0) return AVDN_OK;
+  AVDN_REQUIRE(in && out, "avdn_cast_f32_bf16: null pointer");
+  cast_f32_bf16_kernel<<<grid_for(n), 256, 0, avdn::to_cuda(stream)>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  return avdn::check_launch("avdn_cast_f32_bf16");
+}
+
+extern "C" int avdn_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, avdn_stream_t stream) {
+  AVDN_REQUIRE(in && out && N > 0, "avdn_nhwc_to_nchw_f32: bad argument");
+  nhwc_to_nchw_f32_kernel<<<grid_for((long long)N * HW * C), 256, 0, avdn::to_cuda(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), out, N, HW, C);
+  return avdn::check_launch("avdn_nhwc_to_nchw_f32");
+}
+
+extern "C" int avdn_nchw_f32_to_nhwc(const float* in, void* out, int N, int HW, int C, avdn_stream_t stream) {
+  AVDN_REQUIRE(in && out && N > 0, "avdn_nchw_f32_to_nhwc: bad argument");
+  nchw_f32_to_nhwc_kernel<<<grid_for((long long)N * HW * C), 256, 0, avdn::to_cuda(stream)>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out), N, HW, C);
+  return avdn::check_launch("avdn_nchw_f32_to_nhwc");
+}

@@ -1,0 +1,320 @@
+"""B200-native ``Darknet`` trunk — host-side mirror of the reference class
+(``/root/reference/src/models/dark_net.py``): same constructor, same cfg format,
+same ``state_dict`` keys (``module_list.{i}.conv_{i}.weight``,
+``module_list.{i}.batch_norm_{i}.{weight,bias,running_mean,running_var,num_batches_tracked}``),
+``forward`` returns the last layer's output ``[N, C, H/32, W/32]`` float32.
+
+Device work: every 3x3 / 1x1 convolution (forward, dgrad, wgrad) is the tcgen05
+implicit-GEMM kernel (``avdn_gemm_*``); BatchNorm(train) + LeakyReLU(0.01) +
+shortcut add and their backward are the fused elementwise kernels of
+``csrc/trunk.cu``.  Activations live in NHWC bf16 with channels padded to 64.
+The nn.Conv2d / nn.BatchNorm2d sub-modules are parameter containers only (so
+that reference checkpoints load); their ``forward`` is never called.
+
+Scope: the layer types the truncated xview-yolov3 trunk contains
+(``convolutional`` with batch_normalize=1 + leaky, ``shortcut``).  ``route``,
+``upsample`` and ``yolo`` blocks are outside the hot path and
+raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .. import gemm as G
+
+LEAKY_SLOPE = 0.01      # nn.LeakyReLU() default, dark_net.py:33
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def parse_model_config(path):
+    """Same cfg grammar as the reference parser (dark_net.py:243-261): ``[type]``
+    headers, ``key=value`` lines, ``#`` comments; conv blocks default
+    ``batch_normalize`` to 0."""
+    defs = []
+    with open(path, "r") as f:
+        for raw in f.read().split("\n"):
+            line = raw.strip()
+            if not line or line.startswith("#"):
+                continue
+            if line.startswith("["):
+                d = {"type": line[1:-1].rstrip()}
+                if d["type"] == "convolutional":
+                    d["batch_normalize"] = 0
+                defs.append(d)
+            else:
+                k, v = line.split("=")
+                defs[-1][k.rstrip()] = v.strip()
+    return defs
+
+
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+class EmptyLayer(nn.Module):
+    """Placeholder for 'shortcut' blocks (keeps module indices aligned with the cfg)."""
+
+
+def create_modules(module_defs):
+    hyper = module_defs.pop(0)
+    filters_out = [int(hyper["channels"])]
+    mods = nn.ModuleList()
+    for i, d in enumerate(module_defs):
+        seq = nn.Sequential()
+        if d["type"] == "convolutional":
+            bn = int(d["batch_normalize"])
+            filters = int(d["filters"])
+            k = int(d["size"])
+            pad = (k - 1) // 2 if int(d["pad"]) else 0
+            seq.add_module("conv_%d" % i, nn.Conv2d(filters_out[-1], filters, k, int(d["stride"]), pad, bias=not bn))
+            if bn:
+                seq.add_module("batch_norm_%d" % i, nn.BatchNorm2d(filters))
+            if d["activation"] == "leaky":
+                seq.add_module("leaky_%d" % i, nn.LeakyReLU())
+        elif d["type"] == "shortcut":
+            filters = filters_out[int(d["from"])]
+            seq.add_module("shortcut_%d" % i, EmptyLayer())
+        else:
+            raise NotImplementedError(f"darknet block '{d['type']}' is outside the AVDN hot path")
+        mods.append(seq)
+        filters_out.append(filters)
+    return hyper, mods
+
+
+class _Layer:
+    """Static description + device buffers of one convolutional block."""
+    pass
+
+
+class _Engine:
+    """Per-batch-size execution state: activation / gradient buffers and GEMM plans."""
+
+    def __init__(self, net: "Darknet", N: int, H: int, W: int, device):
+        self.N, self.H, self.W, self.device = N, H, W, device
+        bf, f32 = torch.bfloat16, torch.float32
+        dev = device
+        self.layers = []
+        defs = net.module_defs
+        out_of = {}                    # module index -> layer object producing that output
+        cur = dict(C=3, Cp=4, H=H, W=W, layer=None)
+        shapes = {}                    # module index -> (C, H, W)
+        max_elems = 0
+        for i, d in enumerate(defs):
+            if d["type"] == "convolutional":
+                conv = net.module_list[i][0]
+                if int(d["batch_normalize"]) != 1 or d["activation"] != "leaky":
+                    raise NotImplementedError("only conv+BN+leaky blocks are on the hot path")
+                k, s = conv.kernel_size[0], conv.stride[0]
+                if k not in (1, 3) or s not in (1, 2) or (k == 1 and s != 1) or conv.padding[0] != (k - 1) // 2:
+                    raise NotImplementedError(f"conv k={k} s={s} pad={conv.padding[0]} is not supported")
+                L = _Layer()
+                L.idx, L.k, L.s = i, k, s
+                L.Cin, L.Cout = conv.in_channels, conv.out_channels
+                L.Cin_p = 4 if len(self.layers) == 0 else _pad64(L.Cin)
+                L.Cout_p = _pad64(L.Cout)
+                L.Hin, L.Win = cur["H"], cur["W"]
+                L.Hout, L.Wout = L.Hin // s, L.Win // s
+                L.src = cur["layer"]           # producing layer of the input (None = image)
+                L.res = None                   # residual source layer (fused shortcut)
+                L.first = len(self.layers) == 0
+                if L.first and not (L.Cin == 3 and L.Cout == 32 and k == 3 and s == 1):
+                    raise NotImplementedError("first layer must be the 3->32 3x3 stride-1 conv of yolov3")
+                L.R = N * L.Hout * L.Wout
+                self.layers.append(L)
+                out_of[i] = L
+                shapes[i] = (L.Cout, L.Hout, L.Wout)
+                cur = dict(C=L.Cout, Cp=L.Cout_p, H=L.Hout, W=L.Wout, layer=L)
+            elif d["type"] == "shortcut":
+                frm = i + int(d["from"]) if int(d["from"]) < 0 else int(d["from"])
+                prev = out_of.get(i - 1)
+                srcl = out_of.get(frm)
+                if prev is None or srcl is None or prev.idx != i - 1 or prev.res is not None:
+                    raise NotImplementedError("shortcut must directly follow a convolutional block")
+                if shapes[frm] != shapes[i - 1]:
+                    raise ValueError("shortcut operands differ in shape")
+                prev.res = srcl                # fuse: out[i] = leaky(bn(conv)) + out[frm]
+                out_of[i] = prev
+                shapes[i] = shapes[i - 1]
+        self.last = self.layers[-1]
+        # ---- buffers ----
+        for L in self.layers:
+            n_el = L.R * L.Cout_p
+            max_elems = max(max_elems, n_el)
+            L.z = torch.empty((N, L.Hout, L.Wout, L.Cout_p), dtype=bf, device=dev)
+            L.a = torch.empty((N, L.Hout, L.Wout, L.Cout_p), dtype=bf, device=dev)
+            L.scale = torch.zeros(L.Cout_p, dtype=f32, device=dev)
+            L.shift = torch.zeros(L.Cout_p, dtype=f32, device=dev)
+            L.mean = torch.zeros(L.Cout_p, dtype=f32, device=dev)
+            L.rstd = torch.zeros(L.Cout_p, dtype=f32, device=dev)
+            L.sums = torch.zeros(2 * L.Cout_p, dtype=torch.float64, device=dev)
+            if not L.first:
+                L.wf = torch.empty((L.Cout_p, L.k * L.k * L.Cin_p), dtype=bf, device=dev)
+                L.wd = torch.empty((L.Cin_p, L.k * L.k * L.Cout_p), dtype=bf, device=dev)
+            L.g = None                 # gradient buffer of L.a (allocated on first backward)
+        self.x_in = None
+        self.dz = None
+        self._max_elems = max_elems
+        self._fwd_plans = False
+        self._bwd_plans = False
+
+    # plans bake device pointers, so they are created once the buffers exist
+    def build_fwd(self, x_nhwc4):
+        if self._fwd_plans and self.x_in is x_nhwc4:
+            return
+        self.x_in = x_nhwc4
+        if not self._fwd_plans:
+            for L in self.layers:
+                if L.first:
+                    continue
+                L.p_fwd = G.plan_conv_fwd(L.src.a, L.wf, L.z, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
+                                          Cout=L.Cout_p, k=L.k, stride=L.s)
+            self._fwd_plans = True
+
+    def build_bwd(self):
+        if self._bwd_plans:
+            return
+        bf, f32, dev = torch.bfloat16, torch.float32, self.device
+        self.dz = torch.empty(self._max_elems, dtype=bf, device=dev)
+        # gradient buffers: a fused-shortcut output shares its buffer with the residual source
+        for L in reversed(self.layers):
+            if L.g is None:
+                L.g = torch.empty((self.N, L.Hout, L.Wout, L.Cout_p), dtype=bf, device=dev)
+            if L.res is not None:
+                assert L.res.g is None
+                L.res.g = L.g
+        seen_as_input = set()
+        for L in reversed(self.layers):
+            dz = self.dz[: L.R * L.Cout_p].view(self.N, L.Hout, L.Wout, L.Cout_p)
+            L.dz = dz
+            L.dgamma = torch.zeros(L.Cout, dtype=f32, device=dev)
+            L.dbeta = torch.zeros(L.Cout, dtype=f32, device=dev)
+            L.dw = torch.zeros((L.Cout, L.Cin, L.k, L.k), dtype=f32, device=dev)
+            if L.first:
+                continue
+            L.dwf = torch.zeros((L.Cout_p, L.k * L.k * L.Cin_p), dtype=f32, device=dev)
+            L.p_wgrad = G.plan_conv_wgrad(dz, L.src.a, L.dwf, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
+                                          Cout=L.Cout_p, k=L.k, stride=L.s)
+            # the input's gradient buffer already holds the skip gradient iff the input is a
+            # residual source whose consumer (a later fused shortcut) was processed before
+            acc = 1 if id(L.src) in seen_as_input else 0
+            L.p_dgrad = G.plan_conv_dgrad(dz, L.wd, L.src.g, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
+                                          Cout=L.Cout_p, k=L.k, stride=L.s, accumulate=acc)
+            seen_as_input.add(id(L.src))
+            if L.res is not None:
+                seen_as_input.add(id(L.res))
+        self._bwd_plans = True
+
+
+class _TrunkFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, eng, x_nhwc4, train, *params):
+        call = _lib.call
+        ptr = _lib.ptr
+        eng.build_fwd(x_nhwc4)
+        for li, L in enumerate(eng.layers):
+            conv = net.module_list[L.idx][0]
+            bn = net.module_list[L.idx][1]
+            if L.first:
+                call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win)
+            else:
+                call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
+                     ptr(L.wd))
+                L.p_fwd.run()
+            if train:
+                call("avdn_bn_stats", ptr(L.z), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
+                     ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.sums), ptr(L.scale),
+                     ptr(L.shift), ptr(L.mean), ptr(L.rstd))
+                bn.num_batches_tracked += 1
+            else:
+                call("avdn_bn_eval_coeffs", L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+                     ptr(bn.running_var), BN_EPS, ptr(L.scale), ptr(L.shift))
+            call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.res.a) if L.res is not None else None,
+                 ptr(L.a), L.R, L.Cout_p, LEAKY_SLOPE)
+        last = eng.last
+        out = torch.empty((eng.N, last.Cout, last.Hout, last.Wout), dtype=torch.float32, device=eng.device)
+        call("avdn_nhwc_to_nchw_f32", ptr(last.a), ptr(out), eng.N, last.Hout * last.Wout, last.Cout_p)
+        ctx.net, ctx.eng, ctx.train = net, eng, train
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        net, eng = ctx.net, ctx.eng
+        if not ctx.train:
+            raise RuntimeError("Darknet backward is implemented for train mode (batch statistics) only")
+        call, ptr = _lib.call, _lib.ptr
+        eng.build_bwd()
+        last = eng.last
+        dout = dout.contiguous().float()
+        call("avdn_nchw_f32_to_nhwc", ptr(dout), ptr(last.g), eng.N, last.Hout * last.Wout, last.Cout_p)
+        grads = []
+        for L in reversed(eng.layers):
+            conv = net.module_list[L.idx][0]
+            L.dgamma.zero_()
+            L.dbeta.zero_()
+            L.dw.zero_()
+            call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
+                 L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
+            if L.first:
+                call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
+            else:
+                L.dwf.zero_()
+                L.p_wgrad.run()
+                call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
+                for p in L.p_dgrad:
+                    p.run()
+            grads.append((L.dw, L.dgamma, L.dbeta))
+        flat = []
+        for dw, dg, db in reversed(grads):
+            flat += [dw, dg, db]
+        return (None, None, None, None, *flat)
+
+
+class Darknet(nn.Module):
+    """YOLOv3 trunk used as the 512x7x7 feature extractor (src/xview_et/agent.py:134-141,593)."""
+
+    def __init__(self, config_path, img_size=416):
+        super().__init__()
+        self.module_defs = parse_model_config(config_path)
+        self.module_defs[0]["height"] = img_size            # dark_net.py:207
+        self.hyperparams, self.module_list = create_modules(self.module_defs)
+        self.img_size = img_size
+        self.loss_names = ["loss", "x", "y", "w", "h", "conf", "cls", "nGT", "TP", "FP", "FPe", "FN", "TC"]
+        self._engines = {}
+
+    def _params(self):
+        ps = []
+        for i, d in enumerate(self.module_defs):
+            if d["type"] == "convolutional":
+                ps += [self.module_list[i][0].weight, self.module_list[i][1].weight, self.module_list[i][1].bias]
+        return ps
+
+    def _engine(self, N, H, W, device):
+        key = (N, H, W, str(device))
+        e = self._engines.get(key)
+        if e is None:
+            e = _Engine(self, N, H, W, device)
+            self._engines[key] = e
+        return e
+
+    def forward_nhwc4(self, x_nhwc4):
+        """Fast path: ``x`` is the renderer's ``norm_nhwc`` output ``[N,H,W,4]`` bf16
+        (R,G,B,0).  Returns ``[N, C_last, H/32, W/32]`` float32."""
+        _lib.require_cuda(x_nhwc4)
+        assert x_nhwc4.dtype == torch.bfloat16 and x_nhwc4.shape[-1] == 4 and x_nhwc4.is_contiguous()
+        N, H, W, _ = x_nhwc4.shape
+        eng = self._engine(N, H, W, x_nhwc4.device)
+        return _TrunkFn.apply(self, eng, x_nhwc4, self.training, *self._params())
+
+    def forward(self, x, targets=None, requestPrecision=False, weight=None, epoch=None):
+        """Reference signature (dark_net.py:212): ``x`` is ``[N,3,H,W]`` float32 NCHW."""
+        if targets is not None:
+            raise NotImplementedError("detection losses (YOLOLayer) are outside the AVDN hot path")
+        _lib.require_cuda(x)
+        N, C, H, W = x.shape
+        assert C == 3
+        x4 = torch.zeros((N, H, W, 4), dtype=torch.bfloat16, device=x.device)
+        x4[..., :3] = x.permute(0, 2, 3, 1)          # layout glue of the compatibility entry point
+        return self.forward_nhwc4(x4)

@@ -170,6 +170,52 @@ size_t avdn_gemm_plan_bytes(void);
 int avdn_gemm_plan(const avdn_gemm_desc* desc, void* plan_host, size_t plan_bytes);
 int avdn_gemm_run(const void* plan_host, avdn_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Stage 2 — Darknet trunk (src/models/dark_net.py).  Activations are NHWC
+ * bf16, channels padded to a multiple of 64, addressed as R rows x C.
+ * ---------------------------------------------------------------------- */
+
+/* First convolution 3->32, 3x3, pad 1 (module_list.0.conv_0; K = 27 is too thin
+ * for a tensor-core tile).  x [N,H,W,4] bf16 (R,G,B,0: avdn_render_views'
+ * norm_nhwc), w [32,3,3,3] fp32 (nn.Conv2d layout), z [N,H,W,64] bf16 (ch 32..63 = 0). */
+int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W, avdn_stream_t stream);
+/* dw [32,3,3,3] fp32 += sum_pixels dz * x (weight gradient of the same layer). */
+int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int H, int W, avdn_stream_t stream);
+
+/* nn.BatchNorm2d in train mode (dark_net.py:31; eps 1e-5, momentum 0.1): batch
+ * statistics of z [R,C] bf16 -> per-channel affine scale = gamma*rstd,
+ * shift = beta - mean*scale, plus mean/rstd for the backward pass; updates the
+ * running buffers (NULL to skip).  sums [2,C] f64 is scratch.  Channels >= C_real
+ * are padding (scale = shift = 0).                                            */
+int avdn_bn_stats(const void* z, long long R, int C, int C_real, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float momentum, float eps, double* sums,
+                  float* scale, float* shift, float* mean, float* rstd, avdn_stream_t stream);
+/* eval mode: the same affine from the running statistics. */
+int avdn_bn_eval_coeffs(int C, int C_real, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* scale, float* shift, avdn_stream_t stream);
+/* a = LeakyReLU_slope(z*scale + shift) (+ residual): BN apply + nn.LeakyReLU()
+ * (dark_net.py:33, slope 0.01) + the shortcut add (dark_net.py:224-226).       */
+int avdn_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* a,
+                  long long R, int C, float slope, avdn_stream_t stream);
+/* Backward of the above (train mode): dz [R,C] bf16 from da; dgamma/dbeta (+=, the
+ * C_real real channels).  The residual branch receives da unchanged (caller).   */
+int avdn_bn_backward(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
+                     const float* rstd, long long R, int C, int C_real, float slope, double* sums, void* dz,
+                     float* dgamma, float* dbeta, avdn_stream_t stream);
+
+/* nn.Conv2d weight [Cout,Cin,k,k] fp32 -> GEMM operands (bf16, zero padded):
+ * wf [Cout_p][k*k][Cin_p] (forward / wgrad layout), wd [Cin_p][k*k][Cout_p] (dgrad). */
+int avdn_pack_conv_weight(const float* w, int Cout, int Cin, int k, int Cout_p, int Cin_p, void* wf, void* wd,
+                          avdn_stream_t stream);
+/* grad [Cout,Cin,k,k] fp32 += dwf [Cout_p][k*k][Cin_p] fp32 (WGRAD output layout). */
+int avdn_unpack_conv_wgrad(const float* dwf, int Cout, int Cin, int k, int Cin_p, float* grad,
+                           avdn_stream_t stream);
+int avdn_cast_f32_bf16(const float* in, void* out, long long n, avdn_stream_t stream);
+/* Trunk output [N,HW,C] bf16 NHWC -> `frames` [N,C,HW] fp32 (the .view at
+ * src/xview_et/agent.py:594) and its adjoint for the backward pass.           */
+int avdn_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, avdn_stream_t stream);
+int avdn_nchw_f32_to_nhwc(const float* in, void* out, int N, int HW, int C, avdn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

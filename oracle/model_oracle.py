@@ -1,0 +1,311 @@
+"""CPU (torch fp32 / fp64) restatement of stages 2 and 3 of the AVDN hot path.
+
+TEST INFRASTRUCTURE ONLY — never imported by the product package.
+
+Every function takes the reference's ``state_dict`` tensors by their reference
+names, so the same random-init weights drive the reference modules, this oracle
+and the CUDA path.  Reference ``file:line`` (relative to /root/reference):
+
+* ``darknet_forward``            src/models/dark_net.py:17-33, 212-240
+* ``soft_dot_attention``         src/models/ET_haa.py:54-74
+* ``pos_encoding_table``         src/models/encodings.py:12-20
+* ``mask_pad`` / ``attention_mask``  src/models/enc_vl.py:44-55, src/models/model_util.py:204-241
+* ``encoder_vl_forward``         src/models/enc_vl.py:34-83 + torch ``nn.TransformerEncoderLayer``
+                                 (post-norm, relu, eps 1e-5; third-party: torch, README.md:78)
+* ``et_forward``                 src/models/ET_haa.py:121-184
+* ``et_loss``                    src/xview_et/agent.py:663-681, 256-270, 883-885
+* ``postprocess_waypoints``      src/xview_et/agent.py:637-653, 745-752
+
+Parity pin: the reference has no tests or golden vectors.  This
+restatement is pinned by executing the reference's own modules in the build
+container on shared seeds/state_dicts (``tests/golden/make_model_golden.py``,
+which also wrote the committed fixtures ``tests/golden/model_golden.pt``).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+PI_REF = 3.14159          # the reference's pi (agent.py:606,666,745)
+
+
+# --------------------------------------------------------------------------
+# Darknet
+# --------------------------------------------------------------------------
+def yolov3_trunk_cfg(truncate_after=None):
+    """Text of the (inferred) truncated xview-yolov3 cfg: Darknet-53 + 5 head
+    convs, ending at the 512-channel stride-32 layer."""
+    out = ["[net]", "channels=3", "height=416", ""]
+
+    def conv(f, k, s):
+        out.extend(["[convolutional]", "batch_normalize=1", f"filters={f}", f"size={k}", f"stride={s}",
+                    "pad=1", "activation=leaky", ""])
+
+    def res(f, n):
+        for _ in range(n):
+            conv(f // 2, 1, 1)
+            conv(f, 3, 1)
+            out.extend(["[shortcut]", "from=-3", "activation=linear", ""])
+
+    conv(32, 3, 1)
+    conv(64, 3, 2); res(64, 1)
+    conv(128, 3, 2); res(128, 2)
+    conv(256, 3, 2); res(256, 8)
+    conv(512, 3, 2); res(512, 8)
+    conv(1024, 3, 2); res(1024, 4)
+    conv(512, 1, 1); conv(1024, 3, 1); conv(512, 1, 1); conv(1024, 3, 1); conv(512, 1, 1)
+    return "\n".join(out)
+
+
+def tiny_trunk_cfg():
+    """A small cfg with the same block types (stride-1/2 3x3, 1x1, shortcuts) for fast tests."""
+    out = ["[net]", "channels=3", "height=64", ""]
+
+    def conv(f, k, s):
+        out.extend(["[convolutional]", "batch_normalize=1", f"filters={f}", f"size={k}", f"stride={s}",
+                    "pad=1", "activation=leaky", ""])
+
+    conv(32, 3, 1)
+    conv(64, 3, 2)
+    conv(32, 1, 1); conv(64, 3, 1); out.extend(["[shortcut]", "from=-3", "activation=linear", ""])
+    conv(128, 3, 2)
+    conv(64, 1, 1); conv(128, 3, 1); out.extend(["[shortcut]", "from=-3", "activation=linear", ""])
+    conv(64, 1, 1); conv(128, 3, 1); out.extend(["[shortcut]", "from=-3", "activation=linear", ""])
+    conv(64, 1, 1)
+    return "\n".join(out)
+
+
+def parse_cfg_text(text):
+    defs = []
+    for line in text.split("\n"):
+        line = line.strip()
+        if not line or line.startswith("#"):
+            continue
+        if line.startswith("["):
+            defs.append({"type": line[1:-1].strip()})
+            if defs[-1]["type"] == "convolutional":
+                defs[-1]["batch_normalize"] = 0
+        else:
+            k, v = line.split("=")
+            defs[-1][k.strip()] = v.strip()
+    return defs
+
+
+def darknet_forward(x, sd, cfg_text, train=True, update_running=False, eps=1e-5, momentum=0.1):
+    """dark_net.py:212-240 for conv(+BN+leaky) / shortcut blocks.  ``sd`` maps the
+    reference state_dict names to tensors (requires_grad leaves for gradient
+    parity).  Train mode uses batch statistics (agent.py:214)."""
+    defs = parse_cfg_text(cfg_text)[1:]
+    outs = []
+    for i, d in enumerate(defs):
+        if d["type"] == "convolutional":
+            w = sd[f"module_list.{i}.conv_{i}.weight"]
+            k = int(d["size"])
+            pad = (k - 1) // 2 if int(d["pad"]) else 0
+            x = F.conv2d(x, w, None, stride=int(d["stride"]), padding=pad)
+            g, b = sd[f"module_list.{i}.batch_norm_{i}.weight"], sd[f"module_list.{i}.batch_norm_{i}.bias"]
+            rm, rv = sd[f"module_list.{i}.batch_norm_{i}.running_mean"], sd[f"module_list.{i}.batch_norm_{i}.running_var"]
+            if train:
+                x = F.batch_norm(x, rm if update_running else None, rv if update_running else None, g, b,
+                                 True, momentum, eps)
+            else:
+                x = F.batch_norm(x, rm, rv, g, b, False, momentum, eps)
+            x = F.leaky_relu(x, 0.01)                      # nn.LeakyReLU() default slope
+        elif d["type"] == "shortcut":
+            x = outs[-1] + outs[int(d["from"])]
+        else:
+            raise NotImplementedError(d["type"])
+        outs.append(x)
+    return outs[-1]
+
+
+# --------------------------------------------------------------------------
+# ET (HAA-Transformer)
+# --------------------------------------------------------------------------
+def soft_dot_attention(h, context, w_in, w_out):
+    """ET_haa.py:54-74.  h [B,49]; context [B,512,49]; softmax over the 512 channels."""
+    target = h @ w_in.t()                                      # [B,49]
+    attn = torch.softmax(torch.bmm(context, target.unsqueeze(2)).squeeze(2), dim=1)   # [B,512]
+    weighted = torch.bmm(attn.unsqueeze(1), context).squeeze(1)                      # [B,49]
+    return torch.tanh(torch.cat((weighted, h), 1) @ w_out.t()), attn
+
+
+def pos_encoding_table(d_model=768, max_len=1250):
+    """encodings.py:12-20 (float32 table, then /sqrt(d_model) at use)."""
+    pe = torch.zeros(max_len, d_model)
+    position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def mask_pad(lengths, len_lang):
+    """enc_vl.py:44-55: True = padded key.  [B, L + 2*Tmax] bool."""
+    tmax = int(np.max(lengths))
+    m = torch.zeros((len(lengths), len_lang + 2 * tmax), dtype=torch.bool)
+    for i, l in enumerate(lengths):
+        m[i, len_lang + l: len_lang + tmax] = True
+        m[i, len_lang + tmax + l:] = True
+    return m
+
+
+def attention_mask(len_lang, len_frames):
+    """model_util.py:213-241: additive float mask [(L+2T),(L+2T)], 0 = may attend, -inf = may not."""
+    S = len_lang + 2 * len_frames
+    m = torch.full((S, S), float("-inf"))
+    m[:, :len_lang] = 0.0                       # everyone sees language ...
+    m[:len_lang, len_lang:] = float("-inf")     # ... language sees only language
+    tri = torch.triu(torch.ones(len_frames, len_frames), diagonal=1) == 1      # True above the diagonal
+    block = torch.zeros(len_frames, len_frames).masked_fill(tri, float("-inf"))
+    for r0 in (len_lang, len_lang + len_frames):
+        for c0 in (len_lang, len_lang + len_frames):
+            m[r0:r0 + len_frames, c0:c0 + len_frames] = block
+    return m
+
+
+def _layer_norm(x, w, b, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+def transformer_layer(x, sd, prefix, n_heads, mask_attn, mask_padding):
+    """One post-norm nn.TransformerEncoderLayer(d, h, ff, dropout, relu) in eval
+    arithmetic (dropout inactive), batch-first here."""
+    B, S, E = x.shape
+    dh = E // n_heads
+    qkv = x @ sd[prefix + "self_attn.in_proj_weight"].t() + sd[prefix + "self_attn.in_proj_bias"]
+    q, k, v = qkv.split(E, dim=-1)
+    q = q.view(B, S, n_heads, dh).transpose(1, 2)
+    k = k.view(B, S, n_heads, dh).transpose(1, 2)
+    v = v.view(B, S, n_heads, dh).transpose(1, 2)
+    scores = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    scores = scores + mask_attn[None, None]
+    scores = scores.masked_fill(mask_padding[:, None, None, :], float("-inf"))
+    p = torch.softmax(scores, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(B, S, E)
+    o = o @ sd[prefix + "self_attn.out_proj.weight"].t() + sd[prefix + "self_attn.out_proj.bias"]
+    x = _layer_norm(x + o, sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"])
+    ff = torch.relu(x @ sd[prefix + "linear1.weight"].t() + sd[prefix + "linear1.bias"])
+    ff = ff @ sd[prefix + "linear2.weight"].t() + sd[prefix + "linear2.bias"]
+    return _layer_norm(x + ff, sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"])
+
+
+def encoder_vl_forward(emb_lang, emb_frames, emb_dirs, lengths, sd, n_heads=12, n_layers=2,
+                       prefix="encoder_vl."):
+    """enc_vl.py:34-83."""
+    B, L, E = emb_lang.shape
+    T = emb_frames.shape[1]
+    assert T == int(np.max(lengths))
+    pe = pos_encoding_table(E)[: L + T] / math.sqrt(E)
+    lang = emb_lang + pe[None, :L]
+    frames = emb_frames + pe[None, L:L + T]
+    dirs = emb_dirs + pe[None, L:L + T]                 # same positions as the frames
+    x = torch.cat((lang, frames, dirs), dim=1)
+    x = _layer_norm(x, sd[prefix + "enc_layernorm.weight"], sd[prefix + "enc_layernorm.bias"])
+    mp = mask_pad(lengths, L)
+    ma = attention_mask(L, T)
+    for l in range(n_layers):
+        x = transformer_layer(x, sd, f"{prefix}enc_transformer.layers.{l}.", n_heads, ma, mp)
+    return x, mp
+
+
+def et_forward(sd, directions, frames, lenths, lang, lang_cls, n_heads=12, n_layers=2):
+    """ET_haa.py:121-184 (eval arithmetic: dropout inactive).
+    Returns (output [B,4], pred_saliency [B,1,224,224], h_sali [B,64])."""
+    B, T = frames.shape[:2]
+    L = lang.shape[1]
+    att = []
+    for i in range(T):
+        a, _ = soft_dot_attention(lang_cls, frames[:, i], sd["attention_layer_vision.linear_in.weight"],
+                                  sd["attention_layer_vision.linear_out.weight"])
+        att.append(a.unsqueeze(1))
+    att = torch.cat(att, dim=1)                                          # [B,T,49]
+    emb_frames = att.reshape(-1, 49) @ sd["fc2.weight"].t() + sd["fc2.bias"]
+    emb_frames = emb_frames.view(B, T, -1)
+    emb_dirs = directions.reshape(-1, 2) @ sd["direction_embedding.weight"].t() + sd["direction_embedding.bias"]
+    emb_dirs = emb_dirs.view(B, T, -1)
+    enc, _ = encoder_vl_forward(lang, emb_frames, emb_dirs, lenths, sd, n_heads, n_layers)
+    tmax = int(np.max(lenths))
+    vis = enc[:, L + tmax - 1]
+    dire = enc[:, L + 2 * tmax - 1]
+    h = torch.relu(dire @ sd["decoder_2_action_full.0.weight"].t() + sd["decoder_2_action_full.0.bias"])
+    h = torch.relu(h @ sd["decoder_2_action_full.3.weight"].t() + sd["decoder_2_action_full.3.bias"])
+    output = h @ sd["decoder_2_action_full.6.weight"].t() + sd["decoder_2_action_full.6.bias"]
+    h_sali = torch.relu(vis @ sd["fc.0.weight"].t() + sd["fc.0.bias"])       # Linear -> Dropout -> ReLU
+    pred = F.interpolate(h_sali.view(-1, 1, 8, 8), size=(224, 224), mode="bilinear", align_corners=False)
+    return output, pred, h_sali
+
+
+# --------------------------------------------------------------------------
+# agent slice: loss and waypoint post-processing
+# --------------------------------------------------------------------------
+def nss(sal, fix, nss_r=0):
+    """agent.py:256-270 (unbiased std)."""
+    m = torch.mean(sal.view(-1, 224 * 224), 1).view(-1, 1, 1)
+    std = torch.std(sal.view(-1, 224 * 224), 1).view(-1, 1, 1)
+    n_sal = (sal - m) / std
+    if nss_r == 1:
+        n_sal = n_sal / 2 + 1
+    elif nss_r == -1:
+        n_sal = n_sal / 2 - 1
+    s_fix = torch.sum(fix.view(-1, 224 * 224), 1) + 0.001
+    s_ns = torch.sum((n_sal * fix).view(-1, 224 * 224), 1)
+    return -torch.mean(s_ns / s_fix)
+
+
+def _ang(v0, v1):
+    return ((torch.atan2(v0, v1) / PI_REF + 2) / 2) % 1
+
+
+def et_loss(output, pred_saliency, gt_xy, gt_alt, gt_prog, gt_saliency, nss_w=0.1, nss_r=0, jitter=None):
+    """agent.py:663-681 for one time step: sum over ALL samples of the four
+    MSE-sum terms + the angular term, plus ``nss_w * NSS`` for samples with
+    attention.  ``jitter`` [B] stands for ``1e-5*np.random.rand()`` (agent.py:666;
+    zeros = deterministic).  ``gt_saliency`` float64 [B,224,224] -> float64 loss."""
+    B = output.shape[0]
+    ml = 0
+    for i in range(B):
+        p_xy = output[i, 0:2]
+        ml = ml + torch.sum((p_xy - gt_xy[i]) ** 2)
+        j = 0.0 if jitter is None else float(jitter[i])
+        ml = ml + (_ang(p_xy[0], p_xy[1] + j) - _ang(gt_xy[i, 0], gt_xy[i, 1])) ** 2
+        ml = ml + (output[i, 2] - gt_alt[i]) ** 2
+        ml = ml + (output[i, 3] - gt_prog[i]) ** 2
+    for i in range(B):
+        if float(gt_saliency[i].sum()) > 0:
+            v = nss(pred_saliency[i], gt_saliency[i], nss_r)
+            if not torch.isnan(v):
+                ml = ml + nss_w * v
+    return ml
+
+
+def step_loss(ml_loss, train_ml, batch_size):
+    """agent.py:883-885: ``loss += ml_loss * train_ml / batch_size``."""
+    return ml_loss * train_ml / batch_size
+
+
+def postprocess_waypoints(output, edge_len, stop_threshold=0.5):
+    """agent.py:637-653,738,745-752 on host float32/float64 exactly as numpy does.
+    ``output`` [B,4] float32; ``edge_len`` [B] float64 = ||c0 - c1||.
+    Returns (angle_deg int, dist f64, altitude_m int, stop bool) arrays."""
+    o = np.asarray(output, dtype=np.float32).copy()
+    B = o.shape[0]
+    ang = np.zeros(B, dtype=np.int64)
+    dist = np.zeros(B, dtype=np.float64)
+    alt = np.zeros(B, dtype=np.int64)
+    stop = np.zeros(B, dtype=bool)
+    for i in range(B):
+        x, y = o[i, 0], o[i, 1]
+        m = max(abs(x), abs(y), 1)
+        x, y = x / m, y / m                                   # float32 divides (numpy array elements)
+        a = min(1.0, max(0.0, o[i, 2]))
+        p = min(1.0, max(0.0, o[i, 3]))
+        a_dir = ((np.arctan2(x, y) / PI_REF + 2) / 2) % 1      # float32 atan2 promoted by the f64 constant
+        ang[i] = int(round(float(a_dir) * 360))
+        dist[i] = float(np.linalg.norm(np.array([x, y]))) * (float(edge_len[i]) / 2)
+        alt[i] = int(round(float(a) * 360)) + 40
+        stop[i] = bool(p > stop_threshold)
+    return ang, dist, alt, stop
