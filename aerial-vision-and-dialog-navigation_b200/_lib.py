@@ -47,6 +47,26 @@ _SIGNATURES = {
     "avdn_cast_f32_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "avdn_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "avdn_nchw_f32_to_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    # ---- stage 3: ET
+    "avdn_frame_attn_fwd": [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 4 + [c_void_p],
+    "avdn_frame_attn_bwd": [c_void_p] * 5 + [c_int, c_int] + [c_void_p] * 9 + [c_void_p],
+    "avdn_embed_fwd": [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_void_p],
+    "avdn_embed_dir_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "avdn_ln_fwd": [c_void_p] * 4 + [c_i64, c_int, c_f32] + [c_void_p] * 5 + [c_void_p],
+    "avdn_ln_bwd": [c_void_p] * 6 + [c_i64, c_int] + [c_void_p] * 4 + [c_void_p],
+    "avdn_softmax_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "avdn_softmax_bwd": [c_void_p, c_void_p, c_i64, c_int, c_int, c_f32, c_void_p, c_void_p],
+    "avdn_build_masks": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "avdn_colsum": [c_void_p, c_int, c_i64, c_int, c_i64, c_void_p, c_void_p],
+    "avdn_heads_fwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 + [c_void_p],
+    "avdn_heads_bwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 18 + [c_void_p],
+    # ---- agent slice
+    "avdn_loss": [c_void_p] * 7 + [c_int, c_f32, c_int, c_f64] + [c_void_p] * 4 + [c_void_p],
+    "avdn_upsample_saliency": [c_void_p, c_int, c_void_p, c_void_p],
+    "avdn_upsample_saliency_bwd": [c_void_p, c_int, c_void_p, c_void_p],
+    "avdn_postprocess_waypoints": [c_void_p, c_void_p, c_int, c_f32] + [c_void_p] * 5 + [c_void_p],
+    "avdn_sumsq": [c_void_p, c_i64, c_void_p, c_void_p],
+    "avdn_adamw": [c_void_p] * 4 + [c_i64] + [c_f32] * 5 + [c_int, c_void_p, c_f32, c_f32, c_void_p],
 }
 _SIZE_T_FUNCS = ["avdn_gemm_plan_bytes"]
 
@@ -109,9 +129,27 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# When set to a list, every kernel launch made through call() / GemmPlan.run() is bracketed by
+# CUDA events on the launching stream and (name, ev0, ev1, flops, bytes) is appended: the live
+# per-kernel breakdown bench.py reports.  None (default) = no instrumentation.
+PROFILE = None
+
+
+def profile_record(name, fn, flops=0, nbytes=0):
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    fn()
+    ev1.record()
+    PROFILE.append((name, ev0, ev1, flops, nbytes))
+
+
 def call(name, *args):
     """Invoke an ABI function on torch's current stream; raise on error."""
     fn = getattr(lib(), name)
+    if PROFILE is not None:
+        profile_record(name, lambda: check(fn(*args, stream_ptr()), name))
+        return
     check(fn(*args, stream_ptr()), name)
 
 

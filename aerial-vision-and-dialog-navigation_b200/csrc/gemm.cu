@@ -289,6 +289,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
         if (c.relu) x = fmaxf(x, 0.f);
         f[j] = x;
       }
+      if (c.relu_mask) {
+        const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(c.relu_mask) + row_off + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if ((col0 + j) < c.N && !(__bfloat162float(mk[j]) > 0.f)) f[j] = 0.f;
+      }
       const bool full = (col0 + 32) <= c.N;
       if (c.out_dtype == AVDN_DT_BF16) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(c.out) + row_off + col0;

@@ -38,7 +38,7 @@ class GemmCore(C.Structure):
                 ("out_dtype", i32), ("accumulate", i32), ("relu", i32), ("alpha", f32),
                 ("tx_bytes", u32), ("pad_", i32),
                 ("ldc", i64), ("out_bs0", i64), ("out_bs1", i64),
-                ("out", C.c_void_p), ("bias", C.c_void_p)]
+                ("out", C.c_void_p), ("bias", C.c_void_p), ("relu_mask", C.c_void_p)]
 
 
 class GemmDesc(C.Structure):
@@ -69,8 +69,9 @@ def _dt(t):
 
 
 class GemmPlan:
-    def __init__(self, desc: GemmDesc, keep=()):
+    def __init__(self, desc: GemmDesc, keep=(), flops=0, tag="gemm"):
         h = _lib.lib()
+        self.flops, self.tag = flops, tag
         n = h.avdn_gemm_plan_bytes()
         self.desc = desc
         self.buf = C.create_string_buffer(n)
@@ -79,6 +80,10 @@ class GemmPlan:
         self._run = h.avdn_gemm_run
 
     def run(self):
+        if _lib.PROFILE is not None:
+            _lib.profile_record(self.tag, lambda: _lib.check(self._run(self.buf, _lib.stream_ptr()), "avdn_gemm_run"),
+                                self.flops)
+            return
         _lib.check(self._run(self.buf, _lib.stream_ptr()), "avdn_gemm_run")
 
 
@@ -92,7 +97,7 @@ def pick_bn(N):
 
 def plan_plain(*, M, N, K, a_ptr, lda, a_mn, b_ptr, ldb, b_mn, out, ldc, bias=None, relu=False, alpha=1.0,
                accumulate=0, batch0=1, batch1=1, a_bs=(0, 0), b_bs=None, out_bs=(0, 0), split_k=1, bn=None,
-               keep=()):
+               relu_mask=None, out_ptr=None, keep=(), tag="gemm_plain"):
     """D[M,N] = alpha * A.B^T (+bias)(relu).  Operands are bf16.
 
     K-major operand: stored ``[rows][K]`` with row pitch ``ld``; MN-major operand:
@@ -109,8 +114,9 @@ def plan_plain(*, M, N, K, a_ptr, lda, a_mn, b_ptr, ldb, b_mn, out, ldc, bias=No
     c.b_batched = 0 if b_bs is None else 1
     c.out_dtype, c.accumulate, c.relu, c.alpha = _dt(out), accumulate, int(relu), alpha
     c.ldc, c.out_bs0, c.out_bs1 = ldc, out_bs[0], out_bs[1]
-    c.out = out.data_ptr()
+    c.out = out_ptr if out_ptr is not None else out.data_ptr()
     c.bias = bias.data_ptr() if bias is not None else None
+    c.relu_mask = relu_mask.data_ptr() if relu_mask is not None else None
     d.bn, d.a_mn, d.b_mn, d.n_a, d.n_b = bn, int(a_mn), int(b_mn), 1, 1
     safe = lambda s, fallback: s if s else fallback
     fa = lda * (K if a_mn else M)
@@ -126,7 +132,7 @@ def plan_plain(*, M, N, K, a_ptr, lda, a_mn, b_ptr, ldb, b_mn, out, ldc, bias=No
     else:
         d.b[0] = operand(b_ptr, (K, N, nb0, nb1), (1, ldb, safe(bb[0], fb), safe(bb[1], fb)), (64, bn, 1, 1))
     d.grid_m, d.grid_n, d.grid_z = _cdiv(M, 128), _cdiv(N, bn), batch0 * batch1 * split_k
-    return GemmPlan(d, keep=keep + (out, bias))
+    return GemmPlan(d, keep=keep + (out, bias, relu_mask), flops=2 * M * N * K * batch0 * batch1, tag=tag)
 
 
 def conv_box(W, H, N, rows):
@@ -227,7 +233,7 @@ def _x_views(x, Cin, W, H, N, stride, box):
     return views
 
 
-def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None):
+def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=None):
     """z[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) ; ``w_f`` is ``[Cout, k*k*Cin]`` bf16
     (tap-major, channel-minor).  Channels are multiples of 64."""
     assert Cin % 64 == 0 and Cout % 64 == 0
@@ -257,10 +263,11 @@ def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None):
     Kt = k * k * Cin
     d.b[0] = operand(w_f.data_ptr(), (Kt, Cout, 1, 1), (1, Kt, Kt * Cout, Kt * Cout), (64, bn, 1, 1))
     d.grid_m, d.grid_n, d.grid_z = c.tiles_w * c.tiles_h * c.tiles_n, _cdiv(Cout, bn), 1
-    return GemmPlan(d, keep=(x, w_f, z))
+    return GemmPlan(d, keep=(x, w_f, z), flops=flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin,
+                    tag="gemm_conv_fwd")
 
 
-def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0, bn=None):
+def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0, bn=None, flops=None):
     """dx[N,H,W,Cin] (+)= conv_transpose(dz[N,Ho,Wo,Cout], w); ``w_d`` is
     ``[Cin, k*k*Cout]`` bf16 (tap-major, out-channel-minor).  Returns a list of plans
     (4 output-parity plans for stride 2)."""
@@ -301,11 +308,12 @@ def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0,
         d.a[0] = _act_operand(dz.data_ptr(), Cout, Wo, Ho, N, (64, bw, bh, bnn))
         d.b[0] = operand(w_d.data_ptr(), (Kt, Cin, 1, 1), (1, Kt, Kt * Cin, Kt * Cin), (64, bn, 1, 1))
         d.grid_m, d.grid_n, d.grid_z = c.tiles_w * c.tiles_h * c.tiles_n, _cdiv(Cin, bn), 1
-        plans.append(GemmPlan(d, keep=(dz, w_d, dx)))
+        fl = flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin
+        plans.append(GemmPlan(d, keep=(dz, w_d, dx), flops=fl // len(parities), tag="gemm_conv_dgrad"))
     return plans
 
 
-def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, bn=None, sms=148):
+def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, bn=None, sms=148, flops=None):
     """dw[Cout, k*k*Cin] (fp32, atomically accumulated -- zero it first) +=
     sum_pixels dz[pix, co] * x[pix + tap, ci]."""
     assert Cin % 64 == 0 and Cout % 64 == 0 and dw.dtype == torch.float32
@@ -334,4 +342,5 @@ def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, b
     for i, v in enumerate(views):
         d.b[i] = v
     d.grid_m, d.grid_n, d.grid_z = gm, gn, len(taps) * split_k
-    return GemmPlan(d, keep=(dz, x, dw))
+    return GemmPlan(d, keep=(dz, x, dw), flops=flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin,
+                    tag="gemm_conv_wgrad")

@@ -123,6 +123,7 @@ class _Engine:
                 if L.first and not (L.Cin == 3 and L.Cout == 32 and k == 3 and s == 1):
                     raise NotImplementedError("first layer must be the 3->32 3x3 stride-1 conv of yolov3")
                 L.R = N * L.Hout * L.Wout
+                L.flops = 2 * L.R * L.Cout * L.Cin * k * k          # algorithmic (un-padded) FLOPs
                 self.layers.append(L)
                 out_of[i] = L
                 shapes[i] = (L.Cout, L.Hout, L.Wout)
@@ -159,6 +160,7 @@ class _Engine:
         self._max_elems = max_elems
         self._fwd_plans = False
         self._bwd_plans = False
+        self.launches = 0
 
     # plans bake device pointers, so they are created once the buffers exist
     def build_fwd(self, x_nhwc4):
@@ -170,12 +172,13 @@ class _Engine:
                 if L.first:
                     continue
                 L.p_fwd = G.plan_conv_fwd(L.src.a, L.wf, L.z, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
-                                          Cout=L.Cout_p, k=L.k, stride=L.s)
+                                          Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
             self._fwd_plans = True
 
-    def build_bwd(self):
+    def build_bwd(self, net=None):
         if self._bwd_plans:
             return
+        arena = getattr(net, "_grad_arena", None) if net is not None else None
         bf, f32, dev = torch.bfloat16, torch.float32, self.device
         self.dz = torch.empty(self._max_elems, dtype=bf, device=dev)
         # gradient buffers: a fused-shortcut output shares its buffer with the residual source
@@ -189,53 +192,105 @@ class _Engine:
         for L in reversed(self.layers):
             dz = self.dz[: L.R * L.Cout_p].view(self.N, L.Hout, L.Wout, L.Cout_p)
             L.dz = dz
-            L.dgamma = torch.zeros(L.Cout, dtype=f32, device=dev)
-            L.dbeta = torch.zeros(L.Cout, dtype=f32, device=dev)
-            L.dw = torch.zeros((L.Cout, L.Cin, L.k, L.k), dtype=f32, device=dev)
+            if arena is not None:
+                i = L.idx
+                L.dgamma = arena[f"module_list.{i}.batch_norm_{i}.weight"]
+                L.dbeta = arena[f"module_list.{i}.batch_norm_{i}.bias"]
+                L.dw = arena[f"module_list.{i}.conv_{i}.weight"]
+            else:
+                L.dgamma = torch.zeros(L.Cout, dtype=f32, device=dev)
+                L.dbeta = torch.zeros(L.Cout, dtype=f32, device=dev)
+                L.dw = torch.zeros((L.Cout, L.Cin, L.k, L.k), dtype=f32, device=dev)
             if L.first:
                 continue
             L.dwf = torch.zeros((L.Cout_p, L.k * L.k * L.Cin_p), dtype=f32, device=dev)
             L.p_wgrad = G.plan_conv_wgrad(dz, L.src.a, L.dwf, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
-                                          Cout=L.Cout_p, k=L.k, stride=L.s)
+                                          Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
             # the input's gradient buffer already holds the skip gradient iff the input is a
             # residual source whose consumer (a later fused shortcut) was processed before
             acc = 1 if id(L.src) in seen_as_input else 0
             L.p_dgrad = G.plan_conv_dgrad(dz, L.wd, L.src.g, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
-                                          Cout=L.Cout_p, k=L.k, stride=L.s, accumulate=acc)
+                                          Cout=L.Cout_p, k=L.k, stride=L.s, accumulate=acc, flops=L.flops)
             seen_as_input.add(id(L.src))
             if L.res is not None:
                 seen_as_input.add(id(L.res))
         self._bwd_plans = True
 
 
+def _trunk_forward(net, eng, x_nhwc4, train, out=None):
+    """Forward of every block on libavdn kernels.  Returns ``[N, C_last, h, w]`` fp32."""
+    call = _lib.call
+    ptr = _lib.ptr
+    eng.build_fwd(x_nhwc4)
+    n = 0
+    for li, L in enumerate(eng.layers):
+        conv = net.module_list[L.idx][0]
+        bn = net.module_list[L.idx][1]
+        if L.first:
+            call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win)
+            n += 1
+        else:
+            call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
+                 ptr(L.wd))
+            L.p_fwd.run()
+            n += 2
+        if train:
+            call("avdn_bn_stats", ptr(L.z), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
+                 ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.sums), ptr(L.scale),
+                 ptr(L.shift), ptr(L.mean), ptr(L.rstd))
+            n += 3
+        else:
+            call("avdn_bn_eval_coeffs", L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+                 ptr(bn.running_var), BN_EPS, ptr(L.scale), ptr(L.shift))
+            n += 1
+        call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.res.a) if L.res is not None else None,
+             ptr(L.a), L.R, L.Cout_p, LEAKY_SLOPE)
+        n += 1
+    if train:
+        net._bump_batches_tracked()
+    last = eng.last
+    if out is None:
+        out = torch.empty((eng.N, last.Cout, last.Hout, last.Wout), dtype=torch.float32, device=eng.device)
+    call("avdn_nhwc_to_nchw_f32", ptr(last.a), ptr(out), eng.N, last.Hout * last.Wout, last.Cout_p)
+    eng.launches += n + 1
+    return out
+
+
+def _trunk_backward(net, eng, dout, after_layer=None):
+    """Backward of every block; parameter gradients are ACCUMULATED into the
+    engine's gradient tensors (``L.dw / L.dgamma / L.dbeta``: views of the optimiser
+    arena when one is attached, engine-owned buffers otherwise).
+    ``after_layer(i)`` is called once the gradients of conv block ``i`` (counted from
+    the input) are complete -- the hook the data-parallel bucketing uses."""
+    call, ptr = _lib.call, _lib.ptr
+    eng.build_bwd(net)
+    last = eng.last
+    n = 1
+    call("avdn_nchw_f32_to_nhwc", ptr(dout), ptr(last.g), eng.N, last.Hout * last.Wout, last.Cout_p)
+    for li in reversed(range(len(eng.layers))):
+        L = eng.layers[li]
+        call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
+             L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
+        n += 4
+        if L.first:
+            call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
+            n += 1
+        else:
+            L.dwf.zero_()
+            L.p_wgrad.run()
+            call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
+            for p in L.p_dgrad:
+                p.run()
+            n += 3 + len(L.p_dgrad)
+        if after_layer is not None:
+            after_layer(li)
+    eng.launches += n
+
+
 class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, eng, x_nhwc4, train, *params):
-        call = _lib.call
-        ptr = _lib.ptr
-        eng.build_fwd(x_nhwc4)
-        for li, L in enumerate(eng.layers):
-            conv = net.module_list[L.idx][0]
-            bn = net.module_list[L.idx][1]
-            if L.first:
-                call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win)
-            else:
-                call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
-                     ptr(L.wd))
-                L.p_fwd.run()
-            if train:
-                call("avdn_bn_stats", ptr(L.z), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
-                     ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.sums), ptr(L.scale),
-                     ptr(L.shift), ptr(L.mean), ptr(L.rstd))
-                bn.num_batches_tracked += 1
-            else:
-                call("avdn_bn_eval_coeffs", L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
-                     ptr(bn.running_var), BN_EPS, ptr(L.scale), ptr(L.shift))
-            call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.res.a) if L.res is not None else None,
-                 ptr(L.a), L.R, L.Cout_p, LEAKY_SLOPE)
-        last = eng.last
-        out = torch.empty((eng.N, last.Cout, last.Hout, last.Wout), dtype=torch.float32, device=eng.device)
-        call("avdn_nhwc_to_nchw_f32", ptr(last.a), ptr(out), eng.N, last.Hout * last.Wout, last.Cout_p)
+        out = _trunk_forward(net, eng, x_nhwc4, train)
         ctx.net, ctx.eng, ctx.train = net, eng, train
         return out
 
@@ -244,31 +299,15 @@ class _TrunkFn(torch.autograd.Function):
         net, eng = ctx.net, ctx.eng
         if not ctx.train:
             raise RuntimeError("Darknet backward is implemented for train mode (batch statistics) only")
-        call, ptr = _lib.call, _lib.ptr
-        eng.build_bwd()
-        last = eng.last
-        dout = dout.contiguous().float()
-        call("avdn_nchw_f32_to_nhwc", ptr(dout), ptr(last.g), eng.N, last.Hout * last.Wout, last.Cout_p)
-        grads = []
-        for L in reversed(eng.layers):
-            conv = net.module_list[L.idx][0]
-            L.dgamma.zero_()
-            L.dbeta.zero_()
-            L.dw.zero_()
-            call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
-                 L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
-            if L.first:
-                call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
-            else:
-                L.dwf.zero_()
-                L.p_wgrad.run()
-                call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
-                for p in L.p_dgrad:
-                    p.run()
-            grads.append((L.dw, L.dgamma, L.dbeta))
+        eng.build_bwd(net)
+        own = net._grad_arena is None
+        if own:
+            for L in eng.layers:
+                L.dw.zero_(); L.dgamma.zero_(); L.dbeta.zero_()
+        _trunk_backward(net, eng, dout.contiguous().float())
         flat = []
-        for dw, dg, db in reversed(grads):
-            flat += [dw, dg, db]
+        for L in eng.layers:
+            flat += [L.dw.clone(), L.dgamma.clone(), L.dbeta.clone()] if own else [None, None, None]
         return (None, None, None, None, *flat)
 
 
@@ -283,6 +322,24 @@ class Darknet(nn.Module):
         self.img_size = img_size
         self.loss_names = ["loss", "x", "y", "w", "h", "conf", "cls", "nGT", "TP", "FP", "FPe", "FN", "TC"]
         self._engines = {}
+        self._grad_arena = None          # name -> tensor, set by the optimiser arena (xview_et.agent)
+        self._pending_batches = 0
+        self.register_state_dict_pre_hook(lambda m, prefix, keep_vars: m._flush_batches_tracked())
+
+    def _bump_batches_tracked(self):
+        # nn.BatchNorm2d.num_batches_tracked: counted on the host, written to the 57 buffers only
+        # when somebody looks (state_dict), instead of 57 one-element kernels per step
+        self._pending_batches += 1
+
+    def _flush_batches_tracked(self, *a, **k):
+        if self._pending_batches:
+            for i, d in enumerate(self.module_defs):
+                if d["type"] == "convolutional":
+                    self.module_list[i][1].num_batches_tracked += self._pending_batches
+            self._pending_batches = 0
+
+    def engine(self, N, H, W, device):
+        return self._engine(N, H, W, device)
 
     def _params(self):
         ps = []

@@ -1,0 +1,47 @@
+"""Host-side data-parallel plumbing (device-agnostic: the same code runs under
+``gloo`` on CPU tensors in the tests and under ``nccl`` on the B200s).
+
+The reference has no distributed training (``utils/distributed.py`` is never
+called and DDP is commented out, src/xview_lstm/agent.py:144-150); the semantics
+here are torch-DDP defaults: replicas start from rank 0's parameters, every rank
+processes its own shard of episodes / poses, gradients are summed across ranks
+and divided by the world size, BatchNorm statistics stay per-rank.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous, balanced shard ``[lo, hi)`` of ``n_total`` independent units
+    (episodes for training, poses for rendering)."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def bucket_edges(first_offsets, total, cut_fracs=(0.75, 0.45, 0.0)):
+    """Split a flat gradient arena laid out in FORWARD layer order into buckets that
+    complete in BACKWARD order.  ``first_offsets[i]`` is the arena offset of the first
+    parameter of layer ``i``.  Returns ``[(layer_pos, lo, hi), ...]``: once the backward
+    pass has finished layer ``layer_pos``, ``flat[lo:hi]`` is final and can be reduced."""
+    nl = len(first_offsets)
+    cuts = sorted({min(nl - 1, max(0, int(nl * f))) for f in cut_fracs} | {0}, reverse=True)
+    edges, hi = [], total
+    for c in cuts:
+        lo = first_offsets[c]
+        if hi > lo:
+            edges.append((c, lo, hi))
+        hi = lo
+    return edges
+
+
+def allreduce_sum_(flat: torch.Tensor, lo: int, hi: int, group=None):
+    import torch.distributed as dist
+    dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+
+
+def broadcast_(tensors, src=0, group=None):
+    import torch.distributed as dist
+    for t in tensors:
+        dist.broadcast(t, src, group=group)

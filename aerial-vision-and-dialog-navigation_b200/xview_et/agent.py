@@ -1,0 +1,341 @@
+"""``NavCMTAgent`` -- the training / inference agent of the HAA-Transformer
+(mirror of src/xview_et/agent.py, hot-path subset).
+
+What is here
+------------
+* ``train_step``: ONE fused, device-resident training iteration of BASELINE
+  configs[1]: render the B*T views of the batch (stage 1) -> Darknet trunk in
+  train mode (stage 2) -> ET forward, loss, backward (stage 3) -> Darknet
+  backward -> (data-parallel gradient all-reduce) -> clip + AdamW.  No autograd
+  graph, no host round trip besides the final loss read.
+* ``forward_loss``: the same forward + loss without backward (validation).
+* ``NSS`` (agent.py:256-270), ``postprocess_waypoints`` (agent.py:637-653,745-752),
+  ``move_view_corners`` / ``get_direction`` (agent.py:83-101,285-384: host float64,
+  restated because the reference evaluates them on the host per sample),
+  ``save`` / ``load`` (agent.py:899-940; ``lang_model`` is outside the path).
+
+What is not here: the dataset-driven ``rollout`` with the shapely teacher
+(``teacher_action``, agent.py:386-507) -- SURVEY.md §8f N3 ("next").
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..env import ViewRenderer
+from ..models.ET_haa import ET
+from ..models import dark_net as DN
+from ..models.dark_net import Darknet
+from ..optim import FusedAdamW
+from .. import parallel
+
+PI_REF = 3.14159
+
+
+def get_direction(start, end):
+    """src/xview_et/agent.py:83-101 (host float64)."""
+    vec = np.array(end) - np.array(start)
+    if vec[1] > 0:
+        ang = np.arctan(vec[0] / vec[1]) / 1.57 * 90
+    elif vec[1] < 0:
+        ang = np.arctan(vec[0] / vec[1]) / 1.57 * 90 + 180
+    else:
+        ang = 90 if np.sign(vec[0]) == 1 else 270
+    return (360 - ang + 90) % 360
+
+
+class NavCMTAgent:
+    def __init__(self, args, rank=0, world_size=1, device=None, process_group=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("NavCMTAgent needs a CUDA device (sm_100); there is no CPU fallback")
+        _lib.lib()
+        self.args = args
+        self.rank, self.world = rank, world_size
+        self.pg = process_group
+        self.device = torch.device(device if device is not None else "cuda")
+        self.results = {}
+        self.losses = []
+        self.logs = {"IL_loss": []}
+        self.env = []
+        self.vision_model = Darknet(args.darknet_model_file, 224).to(self.device)
+        wf = getattr(args, "darknet_weight_file", None)
+        if wf and os.path.exists(wf):                           # agent.py:136-141
+            new_state = torch.load(wf, map_location=self.device)
+            state = self.vision_model.state_dict()
+            state.update({k: v for k, v in new_state["model"].items() if k in state})
+            self.vision_model.load_state_dict(state)
+        self.vln_model = ET(args).to(self.device)
+        lr = getattr(args, "lr", 1e-5)
+        # agent.py:153-156: one AdamW per model, default weight decay; only ET is clipped (agent.py:247)
+        self.et_optimizer = FusedAdamW(self.vln_model.used_parameters(), lr=lr, max_norm=40.0)
+        self.vision_model_optimizer = FusedAdamW(dict(self.vision_model.named_parameters()), lr=lr)
+        self.vln_model._grad_arena = self.et_optimizer.grads
+        self.vision_model._grad_arena = self.vision_model_optimizer.grads
+        self.optimizers = (self.et_optimizer, self.vision_model_optimizer)
+        self.renderer = ViewRenderer(self.device)
+        self.loss_total = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._bufs = {}
+        self.launches = 0
+        self._comm_stream = torch.cuda.Stream(self.device) if world_size > 1 else None
+        self._buckets = None
+        if world_size > 1:
+            self.broadcast_parameters()
+
+    # ------------------------------------------------------------ distributed
+    def broadcast_parameters(self):
+        """Replicas start identical (DDP semantics): rank 0's arenas and BN buffers."""
+        parallel.broadcast_([opt.p for opt in self.optimizers], 0, self.pg)
+        parallel.broadcast_(list(self.vision_model.buffers()), 0, self.pg)
+
+    def _trunk_buckets(self, eng):
+        """Slices of the trunk's gradient arena in backward-completion order.  The deep
+        7x7 / 14x14 blocks hold most parameters and finish first; the shallow blocks
+        hold most of the time: 3 buckets let NCCL run under the rest of the backward."""
+        if self._buckets is None:
+            offs = self.vision_model_optimizer.offsets
+            first = [offs[f"module_list.{L.idx}.conv_{L.idx}.weight"][0] for L in eng.layers]
+            self._buckets = parallel.bucket_edges(first, self.vision_model_optimizer.n)
+        return self._buckets
+
+    def _allreduce_async(self, flat, lo, hi):
+        cs = self._comm_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            parallel.allreduce_sum_(flat, lo, hi, self.pg)
+
+    # ----------------------------------------------------------------- buffers
+    def _get_bufs(self, B, T):
+        key = (B, T)
+        b = self._bufs.get(key)
+        if b is None:
+            dev = self.device
+            b = dict(
+                x=torch.empty((B * T, 224, 224, 4), dtype=torch.bfloat16, device=dev),
+                att=torch.empty((B, 224, 224), dtype=torch.uint8, device=dev),
+                frames=torch.empty((B * T, 512, 7, 7), dtype=torch.float32, device=dev),
+                d_frames=torch.empty((B * T, 512, 49), dtype=torch.float32, device=dev),
+                d_output=torch.empty((B, 4), dtype=torch.float32, device=dev),
+                d_h_sali=torch.empty((B, 64), dtype=torch.float32, device=dev),
+                loss_i=torch.empty(B, dtype=torch.float64, device=dev),
+            )
+            self._bufs[key] = b
+        return b
+
+    # ------------------------------------------------------------------- steps
+    def _forward(self, batch, train):
+        """Stages 1-3 forward + loss.  ``batch`` (device tensors unless noted):
+        ``corners_px`` i32 [B,T,4,2] pose corners (FL,FR,BR,BL; pixel x,y) or ``images``
+        bf16 [B*T,224,224,4] (pre-rendered, normalised NHWC); ``tile_idx`` i32 [B,T] or None;
+        ``lang`` f32 [B,L,768]; ``lang_cls`` f32 [B,49]; ``directions`` f32 [B,T,2];
+        ``lenths`` host list[int]; ``gt_xy`` [B,2], ``gt_alt`` [B], ``gt_prog`` [B] f32;
+        optional ``att`` u8 [B,224,224], ``jitter`` f32 [B]."""
+        ptr = _lib.ptr
+        lang, lang_cls, dirs = batch["lang"], batch["lang_cls"], batch["directions"]
+        B, T = dirs.shape[0], dirs.shape[1]
+        L = lang.shape[1]
+        bufs = self._get_bufs(B, T)
+        n = 0
+        att = batch.get("att")
+        if "images" in batch:
+            x = batch["images"]
+        else:
+            r = self.renderer
+            c = batch["corners_px"].view(B * T, 4, 2)
+            ti = batch.get("tile_idx")
+            minv = r.homography(c)
+            r.render(None, None if ti is None else ti.view(-1), views=False, norm_nhwc=True, minv=minv,
+                     out={"norm_nhwc": bufs["x"]})
+            n += 2
+            x = bufs["x"]
+            if att is None and self.nss_w != 0:
+                # human-attention target of the current (last) step of every episode (env.py:292-293)
+                last = minv.view(B, T, 3, 3)[:, -1].contiguous()
+                r.render(None, None if ti is None else ti.view(B, T)[:, -1].contiguous(), views=False, att=True,
+                         minv=last, out={"att": bufs["att"]})
+                att = bufs["att"]
+                n += 2
+        vm = self.vision_model
+        teng = vm.engine(B * T, 224, 224, self.device)
+        l0 = teng.launches
+        DN._trunk_forward(vm, teng, x, train, out=bufs["frames"])
+        et = self.vln_model
+        eng = et.engine(B, L, T, self.device)
+        e0 = eng.launches
+        output, h_sali = eng.forward(bufs["frames"].view(B * T, 512, 49), lang, lang_cls, dirs, batch["lenths"],
+                                     et.encoder_vl.enc_pos.pe[0])
+        self.loss_total.zero_()
+        scale = float(self.train_ml) / B                               # agent.py:883-885
+        _lib.call("avdn_loss", ptr(output), ptr(h_sali), ptr(batch["gt_xy"]), ptr(batch["gt_alt"]),
+                  ptr(batch["gt_prog"]), ptr(att), ptr(batch.get("jitter")), B, float(self.nss_w),
+                  int(getattr(self.args, "nss_r", 0)), scale, ptr(self.loss_total), ptr(bufs["loss_i"]),
+                  ptr(bufs["d_output"]), ptr(bufs["d_h_sali"]))
+        n += 2
+        self._ctx = (teng, eng, bufs, l0, e0)
+        self.launches += n
+        return output, h_sali
+
+    @property
+    def nss_w(self):
+        return float(getattr(self.args, "nss_w", 0.1))
+
+    @property
+    def train_ml(self):
+        return float(getattr(self.args, "ml_weight", 0.2))
+
+    def forward_loss(self, batch):
+        """Validation: forward + loss (trunk in eval mode).  Returns (loss, output, h_sali)."""
+        self.vision_model.eval()
+        output, h_sali = self._forward(batch, False)
+        return self.loss_total, output, h_sali
+
+    def train_step(self, batch, sync_loss=False):
+        """One training iteration (see the module docstring).  Returns the device
+        tensor holding the step loss (float64 [1]); ``sync_loss=True`` returns a host float."""
+        self.vision_model.train()
+        for opt in self.optimizers:
+            opt.zero_grad()
+        self.launches += 2
+        self._forward(batch, True)
+        teng, eng, bufs, l0, e0 = self._ctx
+        eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=bufs["d_frames"])
+        dp = self.world > 1
+        if dp:
+            self._allreduce_async(self.et_optimizer.g, 0, self.et_optimizer.n)
+            buckets = {c: (lo, hi) for c, lo, hi in self._trunk_buckets(teng)}
+            hook = lambda li: (self._allreduce_async(self.vision_model_optimizer.g, *buckets[li])
+                               if li in buckets else None)
+        else:
+            hook = None
+        DN._trunk_backward(self.vision_model, teng, bufs["d_frames"].view(-1, 512, 7, 7), after_layer=hook)
+        if dp:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        gs = 1.0 / self.world
+        for opt in self.optimizers:
+            self.launches += opt.step(grad_scale=gs)
+        self.launches += (teng.launches - l0) + (eng.launches - e0)
+        self.logs["IL_loss"].append(self.loss_total)
+        if sync_loss:
+            return float(self.loss_total.item())
+        return self.loss_total
+
+    # ------------------------------------------------------------ API helpers
+    def NSS(self, sal, fix):
+        """src/xview_et/agent.py:256-270 on device tensors (torch elementwise; off the hot
+        path -- the training step uses the fused ``avdn_loss`` kernel instead)."""
+        nss_r = int(getattr(self.args, "nss_r", 0))
+        m = torch.mean(sal.view(-1, 224 * 224), 1).view(-1, 1, 1)
+        std = torch.std(sal.view(-1, 224 * 224), 1).view(-1, 1, 1)
+        n_sal = (sal - m) / std
+        if nss_r == 1:
+            n_sal = n_sal / 2 + 1
+        elif nss_r == -1:
+            n_sal = n_sal / 2 - 1
+        s_fix = torch.sum(fix.view(-1, 224 * 224), 1) + 0.001
+        s_ns = torch.sum((n_sal * fix).view(-1, 224 * 224), 1)
+        return -torch.mean(s_ns / s_fix)
+
+    def postprocess_waypoints(self, output, edge_len, stop_threshold=0.5):
+        """agent.py:637-653,738,745-752 for the whole batch in one kernel.
+        ``output`` [B,4] f32, ``edge_len`` [B] f64 -> dict of device tensors."""
+        B = output.shape[0]
+        dev = output.device
+        res = dict(angle=torch.empty(B, dtype=torch.int32, device=dev),
+                   dist=torch.empty(B, dtype=torch.float64, device=dev),
+                   altitude=torch.empty(B, dtype=torch.int32, device=dev),
+                   stop=torch.empty(B, dtype=torch.uint8, device=dev),
+                   xy=torch.empty((B, 2), dtype=torch.float32, device=dev))
+        el = torch.as_tensor(edge_len, dtype=torch.float64, device=dev).contiguous()
+        _lib.call("avdn_postprocess_waypoints", _lib.ptr(output.contiguous()), _lib.ptr(el), B, float(stop_threshold),
+                  _lib.ptr(res["angle"]), _lib.ptr(res["dist"]), _lib.ptr(res["altitude"]), _lib.ptr(res["stop"]),
+                  _lib.ptr(res["xy"]))
+        return res
+
+    def gps_to_img_coords(self, gps, ob):
+        """agent.py:508-509 (twin of env.py:189-196)."""
+        return (int(round((gps[1] - ob["gps_botm_left"][1]) / ob["lat_ratio"])),
+                int(round((ob["gps_top_right"][0] - gps[0]) / ob["lat_ratio"])))
+
+    def move_view_corners(self, corners, angle, distance, altitude, gps_botm_left, gps_top_right,
+                          input_current_direction=None):
+        """agent.py:285-384: zoom to ``altitude``, rotate by ``-angle`` about the centre, move
+        forward by ``distance``; each stage is rejected if a corner leaves the map.  Host
+        float64, evaluated in the reference's operation order."""
+        corners = np.asarray(corners, dtype=np.float64)
+        norm = np.linalg.norm
+
+        def inside(p):
+            return gps_botm_left[0] < p[0] < gps_top_right[0] and gps_botm_left[1] < p[1] < gps_top_right[1]
+
+        def rot(theta, p):
+            t = theta / 180 * PI_REF
+            M = np.array([[np.cos(t), np.sin(t)], [-np.sin(t), np.cos(t)]])
+            return np.matmul(M, np.array([p[0], p[1]]))
+
+        def zoom(cs, ch):
+            o = np.zeros((4, 2))
+            o[0] = cs[0] + (cs[0] - cs[1]) / norm(cs[1] - cs[0]) * ch
+            o[0] += (cs[0] - cs[3]) / norm(cs[3] - cs[0]) * ch
+            o[1] = cs[1] + (cs[1] - cs[0]) / norm(cs[1] - cs[0]) * ch
+            o[1] += (cs[1] - cs[2]) / norm(cs[2] - cs[1]) * ch
+            o[2] = cs[2] + (cs[2] - cs[3]) / norm(cs[2] - cs[3]) * ch
+            o[2] += (cs[2] - cs[1]) / norm(cs[2] - cs[1]) * ch
+            o[3] = cs[3] + (cs[3] - cs[2]) / norm(cs[2] - cs[3]) * ch
+            o[3] += (cs[3] - cs[0]) / norm(cs[3] - cs[0]) * ch
+            return o
+
+        def forward(cs, ch):
+            o = np.zeros((4, 2))
+            o[0] = cs[0] + (cs[0] - cs[3]) / norm(cs[3] - cs[0]) * ch
+            o[1] = cs[1] + (cs[1] - cs[2]) / norm(cs[2] - cs[1]) * ch
+            o[2] = cs[2] + (cs[1] - cs[2]) / norm(cs[2] - cs[1]) * ch
+            o[3] = cs[3] + (cs[0] - cs[3]) / norm(cs[3] - cs[0]) * ch
+            return o
+
+        cur = round(get_direction(np.mean(corners, axis=0), (corners[0] + corners[1]) / 2)) % 360
+        if input_current_direction is not None and abs(input_current_direction - cur) > 2:
+            angle += input_current_direction
+        edge = norm(corners[1] - corners[0]) * 11.13 * 1e4
+        zoomed = zoom(corners, 0.5 * (altitude - edge) / 11.13 / 1e4)
+        if not all(inside(p) for p in zoomed):
+            return np.array(corners), cur
+        corners = zoomed
+        centre = np.mean(corners, axis=0)
+        rotated = [centre + rot(-angle, corners[i] - centre) for i in range(4)]
+        if not all(inside(p) for p in rotated):
+            return np.array(corners), cur
+        moved = forward(np.array(rotated), distance)
+        if not all(inside(p) for p in moved):
+            return np.array(rotated), (cur + angle) % 360
+        return np.array(moved), (cur + angle) % 360
+
+    # ------------------------------------------------------------- checkpoints
+    def save(self, epoch, path):
+        """agent.py:899-916 (vision_model and vln_model; lang_model is outside the path)."""
+        d = os.path.dirname(path)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        states = {}
+        for name, model, opt in (("vision_model", self.vision_model, self.vision_model_optimizer),
+                                 ("vln_model", self.vln_model, self.et_optimizer)):
+            states[name] = {"epoch": epoch + 1, "state_dict": model.state_dict(),
+                            "optimizer": {"m": opt.m.clone(), "v": opt.v.clone(), "step": opt.step_count}}
+        torch.save(states, path)
+
+    def load(self, path):
+        """agent.py:918-940: parameters (and optimiser moments when ``args.resume_optimizer``)."""
+        states = torch.load(path, map_location=self.device)
+        for name, model, opt in (("vision_model", self.vision_model, self.vision_model_optimizer),
+                                 ("vln_model", self.vln_model, self.et_optimizer)):
+            if name not in states:
+                continue
+            state = model.state_dict()
+            state.update({k: v for k, v in states[name]["state_dict"].items() if k in state})
+            for k, v in state.items():                       # copy IN PLACE: parameters live in the arena
+                model.state_dict()[k].copy_(v)
+            if getattr(self.args, "resume_optimizer", False) and "m" in states[name].get("optimizer", {}):
+                o = states[name]["optimizer"]
+                opt.m.copy_(o["m"]); opt.v.copy_(o["v"]); opt.step_count = int(o["step"])
+        return states.get("vln_model", {}).get("epoch", 0) - 1

@@ -307,7 +307,7 @@ def main():
                 "gpu_launches": launches, "clocks": clk.summary(), "wall_s_timed_region": t_wall}
         extra = getattr(wl, "extra", None)
         if extra:
-            line.update(extra())
+            line.update(extra(ms / args.steps))
         print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()

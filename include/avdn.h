@@ -154,6 +154,8 @@ typedef struct avdn_gemm_core {
   int64_t ldc, out_bs0, out_bs1;       /* output row pitch / batch strides, elements */
   void* out;
   const float* bias;          /* [N] fp32 or NULL */
+  const void* relu_mask;      /* bf16, addressed like `out`: result is zeroed where mask <= 0
+                                 (backward of the ReLU whose forward output is `relu_mask`) */
 } avdn_gemm_core;
 
 typedef struct avdn_gemm_desc {
@@ -215,6 +217,122 @@ int avdn_cast_f32_bf16(const float* in, void* out, long long n, avdn_stream_t st
  * src/xview_et/agent.py:594) and its adjoint for the backward pass.           */
 int avdn_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, avdn_stream_t stream);
 int avdn_nchw_f32_to_nhwc(const float* in, void* out, int N, int HW, int C, avdn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Stage 3 — episodic cross-modal transformer "ET" (src/models/ET_haa.py,
+ * enc_vl.py, encodings.py, model_util.py).  d_model is 768 (hard-coded by the
+ * reference: ET_haa.py:98-119).  The dense contractions run through
+ * avdn_gemm_*; these are the warp-level kernels around them.  fp32 tensors
+ * unless stated.
+ * ---------------------------------------------------------------------- */
+
+/* SoftDotAttention(49) over the 512 channels of every frame, T frames per
+ * sample, followed by fc2 (ET_haa.py:54-74,138-144):
+ *   frames [B*T,512,49], lang_cls [B,49], w_in [49,49], w_out [49,98],
+ *   fc2_w [768,49], fc2_b [768]
+ *   -> attn [B*T,512], wc [B*T,49], e49 [B*T,49] (saved for backward),
+ *      emb [B*T,768] = emb_frames.                                          */
+int avdn_frame_attn_fwd(const float* frames, const float* lang_cls, const float* w_in, const float* w_out,
+                        const float* fc2_w, const float* fc2_b, int B, int T, float* attn, float* wc, float* e49,
+                        float* emb, avdn_stream_t stream);
+/* Backward: d_frames [B*T,512,49] is overwritten; the parameter gradients are
+ * accumulated (+=).  lang_cls receives no gradient (it is a detached input of
+ * the path, src/xview_et/agent.py:527-538 feeds BERT's output).             */
+int avdn_frame_attn_bwd(const float* frames, const float* lang_cls, const float* w_in, const float* w_out,
+                        const float* fc2_w, int B, int T, const float* attn, const float* wc, const float* e49,
+                        const float* d_emb, float* d_frames, float* d_w_in, float* d_w_out, float* d_fc2_w,
+                        float* d_fc2_b, avdn_stream_t stream);
+
+/* PosEncoding + concat + direction embedding (encodings.py:22-49,
+ * enc_vl.py:71-83, ET_haa.py:147):
+ *   v[b] = [lang[b] + pe[:L] ; emb_frames[b] + pe[L:L+T] ; (W_d dirs[b] + b_d) + pe[L:L+T]] / with
+ *   pe scaled by 1/sqrt(768).  lang [B,L,768], emb_frames [B,T,768], dirs [B,T,2],
+ *   wd [768,2], bd [768], pe [>=L+T,768] -> v [B,L+2T,768].
+ *   wd == NULL: `dirs` is the already embedded [B,T,768] (EncoderVL.forward's
+ *   emb_directions, enc_vl.py:34-40).                                        */
+int avdn_embed_fwd(const float* lang, const float* emb_frames, const float* dirs, const float* wd, const float* bd,
+                   const float* pe, int B, int L, int T, float* v, avdn_stream_t stream);
+/* d_wd [768,2] += , d_bd [768] += from dv [B,L+2T,768] (direction rows). */
+int avdn_embed_dir_bwd(const float* dv, const float* dirs, int B, int L, int T, float* d_wd, float* d_bd,
+                       avdn_stream_t stream);
+
+/* (residual add +) nn.LayerNorm(768, eps): v = a (+ b); y = LN(v)*gamma + beta.
+ * Outputs (each may be NULL except mean/rstd): v_out (the sum, kept for backward),
+ * y fp32, y16 bf16 (the next GEMM's operand), mean/rstd [M].                 */
+int avdn_ln_fwd(const float* a, const float* b, const float* gamma, const float* beta, long long M, int D, float eps,
+                float* v_out, float* y, void* y16, float* mean, float* rstd, avdn_stream_t stream);
+/* dy = dy1 (+ dy2) -> dv fp32 and/or dv16 bf16; dgamma/dbeta [768] += .      */
+int avdn_ln_bwd(const float* dy1, const float* dy2, const float* v, const float* mean, const float* rstd,
+                const float* gamma, long long M, int D, float* dv, void* dv16, float* dgamma, float* dbeta,
+                avdn_stream_t stream);
+
+/* Masked softmax of the attention scores.  The block-causal attention mask
+ * (model_util.py:213-241) and the key-padding mask (enc_vl.py:44-55) are
+ * evaluated as a predicate of (q, k, L, T, lens[b]) — never materialised.
+ *   scores [B,H,S,Sp] fp32 (S = L+2T, Sp >= S row pitch) -> P [B,H,S,Sp] bf16,
+ *   zero where masked and in the pitch padding.                              */
+int avdn_softmax_fwd(const float* scores, const int* lens, int B, int H, int L, int T, int Sp, void* P,
+                     avdn_stream_t stream);
+/* dS = alpha * P * (dP - sum_k P*dP), bf16, zero in the padding. */
+int avdn_softmax_bwd(const void* P, const float* dP, long long rows, int S, int Sp, float alpha, void* dS,
+                     avdn_stream_t stream);
+/* The two masks materialised exactly as the reference builds them (bit-exact
+ * parity tests): mask_pad [B,S] u8 (1 = padded key), mask_attn [S,S] f32 (0 / -inf). */
+int avdn_build_masks(const int* lens, int B, int L, int T, uint8_t* mask_pad, float* mask_attn,
+                     avdn_stream_t stream);
+/* out[n] += sum_m in[m][n] (bias gradients); in is bf16 (AVDN_DT_BF16) or fp32. */
+int avdn_colsum(const void* in, int in_dtype, long long M, int N, long long ld, float* out, avdn_stream_t stream);
+
+/* Row gather + waypoint MLP + saliency FC (ET_haa.py:157-166):
+ *   x [B,S,768]; dir row -> 768->256 ReLU ->32 ReLU ->4 = output [B,4];
+ *   vis row -> 768->64 ReLU = h_sali [B,64] (the 8x8 map before the upsample).
+ *   h0 [B,256], h1 [B,32] are saved for the backward pass.                    */
+int avdn_heads_fwd(const float* x, int B, int S, int row_vis, int row_dir, const float* w0, const float* b0,
+                   const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
+                   const float* bf, float* h0, float* h1, float* output, float* h_sali, avdn_stream_t stream);
+/* dx [B,S,768] must be zero-filled by the caller; only the two gathered rows are
+ * written.  Parameter gradients are accumulated (+=).                          */
+int avdn_heads_bwd(const float* x, int B, int S, int row_vis, int row_dir, const float* w0, const float* w1,
+                   const float* w2, const float* wf, const float* h0, const float* h1, const float* h_sali,
+                   const float* d_output, const float* d_h_sali, float* dx, float* dw0, float* db0, float* dw1,
+                   float* db1, float* dw2, float* db2, float* dwf, float* dbf, avdn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Agent slice (src/xview_et/agent.py): loss, waypoint post-processing, optimiser
+ * ---------------------------------------------------------------------- */
+
+/* Per-step loss and its gradient in one kernel (agent.py:663-681,883-885):
+ *   loss_i = |p_xy-g_xy|^2 + (ang(p)-ang(g))^2 + (alt-g_alt)^2 + (prog-g_prog)^2
+ *            [+ nss_w * NSS(upsample(h_sali_i), att_i/255) if sum(att_i) > 0]
+ *   *loss_total += scale * sum_i loss_i   (scale = train_ml / batch_size)
+ *   d_output [B,4], d_h_sali [B,64] = scale * d loss_i / d(...)
+ * att [B,224,224] u8 is avdn_render_views' attention output (NULL: no NSS term);
+ * jitter [B] stands for 1e-5*np.random.rand() of agent.py:666 (NULL: 0).
+ * The F.interpolate(8x8 -> 224x224, bilinear, align_corners=False) of
+ * ET_haa.py:166-167 and its adjoint are fused in.  float64 accumulation as the
+ * reference's promotion through gt_saliency (env.py:293).                      */
+int avdn_loss(const float* output, const float* h_sali, const float* gt_xy, const float* gt_alt,
+              const float* gt_prog, const uint8_t* att, const float* jitter, int B, float nss_w, int nss_r,
+              double scale, double* loss_total, double* loss_i, float* d_output, float* d_h_sali,
+              avdn_stream_t stream);
+/* pred_saliency [B,1,224,224] = F.interpolate(h_sali.view(B,1,8,8)) (ET_haa.py:166-167). */
+int avdn_upsample_saliency(const float* h_sali, int B, float* pred, avdn_stream_t stream);
+/* adjoint: d_h_sali [B,64] = upsample^T d_pred [B,1,224,224] (overwrites). */
+int avdn_upsample_saliency_bwd(const float* d_pred, int B, float* d_h_sali, avdn_stream_t stream);
+/* agent.py:637-653,738,745-752: normalise xy, clamp altitude / progress, discretise.
+ *   output [B,4] f32, edge_len [B] f64 (= |c0-c1|) -> angle_deg [B] i32,
+ *   dist [B] f64, altitude_m [B] i32, stop [B] u8, xy_norm [B,2] f32 (or NULL). */
+int avdn_postprocess_waypoints(const float* output, const double* edge_len, int B, float stop_threshold,
+                               int* angle_deg, double* dist, int* altitude_m, uint8_t* stop, float* xy_norm,
+                               avdn_stream_t stream);
+/* *out += sum g^2 (float64) — torch.nn.utils.clip_grad_norm_ (agent.py:247). */
+int avdn_sumsq(const float* g, long long n, double* out, avdn_stream_t stream);
+/* torch.optim.AdamW step over a flat arena (agent.py:153-156,249-251).  When
+ * sumsq != NULL the gradient is first scaled by min(1, max_norm/(grad_scale*sqrt(*sumsq)+1e-6));
+ * grad_scale multiplies every gradient (1/world_size for data-parallel means). */
+int avdn_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+               float eps, float wd, int step, const double* sumsq, float max_norm, float grad_scale,
+               avdn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,49 @@ def parse_cfg_text(text):
     return defs
 
 
+def random_trunk_state(cfg_text, seed=0):
+    """Random-init state_dict with the reference's names/shapes (nn.Conv2d / nn.BatchNorm2d
+    default initialisers, dark_net.py:17-31) for synthetic-weight runs."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    defs = parse_cfg_text(cfg_text)
+    cin = [int(defs[0]["channels"])]
+    sd = {}
+    for i, d in enumerate(defs[1:]):
+        if d["type"] == "convolutional":
+            f, k = int(d["filters"]), int(d["size"])
+            sd[f"module_list.{i}.conv_{i}.weight"] = nn.Conv2d(cin[-1], f, k, bias=False).weight.detach().clone()
+            sd[f"module_list.{i}.batch_norm_{i}.weight"] = torch.ones(f)
+            sd[f"module_list.{i}.batch_norm_{i}.bias"] = torch.zeros(f)
+            sd[f"module_list.{i}.batch_norm_{i}.running_mean"] = torch.zeros(f)
+            sd[f"module_list.{i}.batch_norm_{i}.running_var"] = torch.ones(f)
+            cin.append(f)
+        else:
+            cin.append(cin[int(d["from"])])
+    return sd
+
+
+def random_et_state(seed=0, d=768, heads=12, layers=2):
+    """Random-init ET state_dict (reference parameter names, ET_haa.py:77-119 / enc_vl.py:8-33)
+    built from stock torch modules of the same shapes."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    sd = {}
+    enc = nn.TransformerEncoder(nn.TransformerEncoderLayer(d, heads, d, 0.1), layers, enable_nested_tensor=False)
+    for k, v in enc.state_dict().items():
+        sd["encoder_vl.enc_transformer." + k] = v.detach().clone()
+    ln = nn.LayerNorm(d)
+    sd["encoder_vl.enc_layernorm.weight"], sd["encoder_vl.enc_layernorm.bias"] = ln.weight.detach().clone(), ln.bias.detach().clone()
+    for name, mod in (("decoder_2_action_full.0", nn.Linear(d, 256)), ("decoder_2_action_full.3", nn.Linear(256, 32)),
+                      ("decoder_2_action_full.6", nn.Linear(32, 4)), ("fc.0", nn.Linear(d, 64)),
+                      ("direction_embedding", nn.Linear(2, d)), ("fc2", nn.Linear(49, d)),
+                      ("attention_layer_vision.linear_in", nn.Linear(49, 49, bias=False)),
+                      ("attention_layer_vision.linear_out", nn.Linear(98, 49, bias=False))):
+        for k, v in mod.state_dict().items():
+            sd[f"{name}.{k}"] = v.detach().clone()
+    return sd
+
+
 def darknet_forward(x, sd, cfg_text, train=True, update_running=False, eps=1e-5, momentum=0.1):
     """dark_net.py:212-240 for conv(+BN+leaky) / shortcut blocks.  ``sd`` maps the
     reference state_dict names to tensors (requires_grad leaves for gradient
