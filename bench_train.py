@@ -152,6 +152,7 @@ class TrainWorkload:
         tot = sum(v[1] for v in self.profile.values())
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms else None
         peak = peaks["bf16_sustained"]
+        self._peak = peak
         top = sorted(self.profile.items(), key=lambda kv: -kv[1][1])[:14]
         return {"kernel": "gemm_kernel (tcgen05 implicit-GEMM conv fwd/dgrad/wgrad + transformer GEMMs)",
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
@@ -166,7 +167,8 @@ class TrainWorkload:
         if ms_per_step:
             fl = self.flops_per_step()
             out["step_tflops_algorithmic"] = fl / 1e12
-            out["mfu_vs_sustained_bf16"] = fl / (ms_per_step * 1e-3) / 1e12
+            out["step_tflops_per_s"] = fl / (ms_per_step * 1e-3) / 1e12
+            out["mfu_vs_sustained_bf16"] = out["step_tflops_per_s"] / self._peak if getattr(self, "_peak", None) else None
         return out
 
     # --------------------------------------------------------------------- CPU

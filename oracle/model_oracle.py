@@ -137,18 +137,62 @@ def random_et_state(seed=0, d=768, heads=12, layers=2):
     return sd
 
 
-def darknet_forward(x, sd, cfg_text, train=True, update_running=False, eps=1e-5, momentum=0.1):
+class _RoundBF16(torch.autograd.Function):
+    """Value AND gradient pass through bf16 storage (round-to-nearest-even), fp32 arithmetic
+    around it: models a tensor the product keeps in HBM as bf16 (activations, their gradients)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+class _RoundBF16Fwd(torch.autograd.Function):
+    """Forward value rounded to bf16, gradient untouched: models a bf16 copy of an fp32 master
+    parameter whose gradient is accumulated in fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def darknet_forward(x, sd, cfg_text, train=True, update_running=False, eps=1e-5, momentum=0.1, storage=None):
     """dark_net.py:212-240 for conv(+BN+leaky) / shortcut blocks.  ``sd`` maps the
     reference state_dict names to tensors (requires_grad leaves for gradient
-    parity).  Train mode uses batch statistics (agent.py:214)."""
+    parity).  Train mode uses batch statistics (agent.py:214).
+
+    ``storage=None``   the reference arithmetic, float32 end to end.
+    ``storage="bf16"`` the SAME arithmetic (float32 products and sums) with every tensor the
+    bf16 pipeline stores -- the input image, conv weights (except the 3->32 first conv, which
+    the product evaluates from the fp32 master), conv outputs, block outputs, and the matching
+    gradients -- rounded to bf16 at the point of storage.  This is what "the reference PyTorch
+    path in bf16" computes; the random-init 57-block trunk amplifies a perturbation ~100x
+    (conditioning), so bf16 parity is checked against this mode and the distance of
+    both from the float32 mode is reported beside it."""
+    q = _RoundBF16.apply if storage == "bf16" else (lambda t: t)
+    qw = _RoundBF16Fwd.apply if storage == "bf16" else (lambda t: t)
+    if storage not in (None, "bf16"):
+        raise ValueError(storage)
     defs = parse_cfg_text(cfg_text)[1:]
     outs = []
+    x = q(x)
+    n_conv = 0
     for i, d in enumerate(defs):
         if d["type"] == "convolutional":
             w = sd[f"module_list.{i}.conv_{i}.weight"]
+            if n_conv > 0:
+                w = qw(w)
+            n_conv += 1
             k = int(d["size"])
             pad = (k - 1) // 2 if int(d["pad"]) else 0
-            x = F.conv2d(x, w, None, stride=int(d["stride"]), padding=pad)
+            x = q(F.conv2d(x, w, None, stride=int(d["stride"]), padding=pad))
             g, b = sd[f"module_list.{i}.batch_norm_{i}.weight"], sd[f"module_list.{i}.batch_norm_{i}.bias"]
             rm, rv = sd[f"module_list.{i}.batch_norm_{i}.running_mean"], sd[f"module_list.{i}.batch_norm_{i}.running_var"]
             if train:
@@ -157,8 +201,11 @@ def darknet_forward(x, sd, cfg_text, train=True, update_running=False, eps=1e-5,
             else:
                 x = F.batch_norm(x, rm, rv, g, b, False, momentum, eps)
             x = F.leaky_relu(x, 0.01)                      # nn.LeakyReLU() default slope
+            nxt = defs[i + 1] if i + 1 < len(defs) else None
+            if not (nxt is not None and nxt["type"] == "shortcut"):
+                x = q(x)                                   # a fused shortcut stores only the sum
         elif d["type"] == "shortcut":
-            x = outs[-1] + outs[int(d["from"])]
+            x = q(outs[-1] + outs[int(d["from"])])
         else:
             raise NotImplementedError(d["type"])
         outs.append(x)

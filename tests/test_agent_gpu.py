@@ -139,6 +139,14 @@ def agent(built_lib):
         f.write(mo.yolov3_trunk_cfg())
     torch.manual_seed(0)
     a = NavCMTAgent(_args(f.name), device="cuda")
+    # conditioned synthetic weights: the reference's default init with the BN gamma of every
+    # residual branch scaled by 0.1 (perturbation gain ~7x instead of ~100x through the 57
+    # blocks -- DESIGN.md, conditioning), so that end-to-end comparisons carry information
+    defs = mo.parse_cfg_text(mo.yolov3_trunk_cfg())[1:]
+    with torch.no_grad():
+        for i, d in enumerate(defs):
+            if d["type"] == "shortcut":
+                a.vision_model.module_list[i - 1][1].weight.mul_(0.1)
     tile = wo.synthetic_tile(seed=2, size=1024)
     att = wo.synthetic_attention_tile(seed=2, size=1024)
     a.renderer.add_map("m", tile, att)
@@ -192,14 +200,12 @@ def test_train_step_loss_matches_oracle_and_learns(agent):
 
 
 def test_step_gradients_vs_oracle(agent):
-    """Gradients the fused step leaves in the arenas vs fp32 autograd of the oracle pipeline."""
+    """Gradients the fused step leaves in the arenas vs autograd of the oracle pipeline, run twice:
+    float32 end to end (the reference arithmetic) and with the trunk's tensors stored in bf16
+    (``storage="bf16"``).  We must be as close to the fp32 reference as bf16 storage allows."""
     B, T, L = 2, 2, 24
     hb = _small_batch(B, T, L, 12)
     batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in hb.items()}
-    sd_t = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point() and "running" not in k)
-            for k, v in agent.vision_model.state_dict().items()}
-    sd_e = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point())
-            for k, v in agent.vln_model.state_dict().items()}
     views, atts = [], []
     for b in range(B):
         for t in range(T):
@@ -208,25 +214,40 @@ def test_step_gradients_vs_oracle(agent):
             if t == T - 1:
                 atts.append(wo.warp_fixed_point(agent._att, Mi)[:, :, 0])
     x = torch.from_numpy(wo.normalise_views(np.stack(views)))
-    feats = mo.darknet_forward(x, sd_t, mo.yolov3_trunk_cfg(), train=True).view(B, T, 512, 49)
-    out, sal, _ = mo.et_forward(sd_e, hb["directions"], feats, hb["lenths"], hb["lang"], hb["lang_cls"])
     gt_sal = torch.from_numpy(np.stack(atts).astype(np.float64) / 255)
-    mo.step_loss(mo.et_loss(out, sal, hb["gt_xy"], hb["gt_alt"], hb["gt_prog"], gt_sal, 0.1), 0.2, B).backward()
+    refs = []
+    for storage in (None, "bf16"):
+        sd_t = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point() and "running" not in k)
+                for k, v in agent.vision_model.state_dict().items()}
+        sd_e = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point())
+                for k, v in agent.vln_model.state_dict().items()}
+        feats = mo.darknet_forward(x, sd_t, mo.yolov3_trunk_cfg(), train=True, storage=storage).view(B, T, 512, 49)
+        out, sal, _ = mo.et_forward(sd_e, hb["directions"], feats, hb["lenths"], hb["lang"], hb["lang_cls"])
+        loss = mo.step_loss(mo.et_loss(out, sal, hb["gt_xy"], hb["gt_alt"], hb["gt_prog"], gt_sal, 0.1), 0.2, B)
+        loss.backward()
+        refs.append((float(loss.detach()), sd_t, sd_e))
     for opt in agent.optimizers:
         opt.lr = 0.0                               # keep the weights: we only look at the gradients
         opt.wd = 0.0
-    agent.train_step(batch, sync_loss=True)
+    ours = agent.train_step(batch, sync_loss=True)
+    assert abs(ours - refs[0][0]) <= 1e-2 * abs(refs[0][0]), (ours, refs[0][0])
 
     def rel2(a, b):
         a, b = a.detach().double().cpu(), b.detach().double().cpu()
         return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
+    report = {}
     for n in ("fc2.weight", "encoder_vl.enc_transformer.layers.0.self_attn.in_proj_weight",
               "encoder_vl.enc_transformer.layers.1.linear2.weight", "decoder_2_action_full.0.weight", "fc.0.weight"):
-        r = rel2(agent.et_optimizer.grads[n], sd_e[n].grad)
-        assert r < 5e-2, (n, r)
-    # trunk: the last blocks see one bf16 stage of error, the first block all 57
-    for i, tol in ((79, 5e-2), (78, 5e-2), (40, 0.15), (0, 0.3)):
+        e = rel2(agent.et_optimizer.grads[n], refs[0][2][n].grad)
+        e16 = rel2(refs[1][2][n].grad, refs[0][2][n].grad)
+        report[n] = (e, e16)
+        # + the ET's own bf16 GEMM rounding (checked at 5e-2 on exact frames in test_et_gpu)
+        assert e <= 1.5 * e16 + 8e-2, (n, e, e16)
+    for i in (79, 78, 62, 41, 12, 1, 0):
         n = f"module_list.{i}.conv_{i}.weight"
-        r = rel2(agent.vision_model_optimizer.grads[n], sd_t[n].grad)
-        assert r < tol, (n, r)
+        e = rel2(agent.vision_model_optimizer.grads[n], refs[0][1][n].grad)
+        e16 = rel2(refs[1][1][n].grad, refs[0][1][n].grad)
+        report[n] = (e, e16)
+        assert e <= 1.5 * e16 + 8e-2, (n, e, e16)
+    print({k: (round(a, 4), round(b, 4)) for k, (a, b) in report.items()})

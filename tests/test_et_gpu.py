@@ -93,9 +93,11 @@ def test_loss_and_gradients_vs_reference_golden(et, golden):
     d_out = torch.zeros(B, 4, device="cuda")
     d_hs = torch.zeros(B, 64, device="cuda")
     ptr = _lib.ptr
-    _lib.call("avdn_loss", ptr(out.detach()), ptr(hs.detach()), ptr(g["gt_xy"].cuda()), ptr(g["gt_alt"].cuda()),
-              ptr(g["gt_prog"].cuda()), ptr(att), None, B, 0.1, 0, 0.2 / B, ptr(loss), ptr(loss_i), ptr(d_out),
-              ptr(d_hs))
+    # keep the device copies alive across the call: ptr() of a temporary would dangle
+    o_d, h_d = out.detach().contiguous(), hs.detach().contiguous()
+    xy_d, alt_d, prog_d = g["gt_xy"].cuda(), g["gt_alt"].cuda(), g["gt_prog"].cuda()
+    _lib.call("avdn_loss", ptr(o_d), ptr(h_d), ptr(xy_d), ptr(alt_d), ptr(prog_d), ptr(att), None, B, 0.1, 0,
+              0.2 / B, ptr(loss), ptr(loss_i), ptr(d_out), ptr(d_hs))
     assert abs(loss.item() - g["loss"].item()) <= 1e-2 * abs(g["loss"].item()), (loss.item(), g["loss"].item())
     et.zero_grad()
     torch.autograd.backward([out, hs], [d_out, d_hs])
