@@ -129,60 +129,76 @@ __global__ void __launch_bounds__(256) conv0_wgrad_kernel(const __nv_bfloat16* _
 }
 
 // ------------------------------------------------------------ BN statistics
-// sums[0][c] = sum z, sums[1][c] = sum z^2 over R rows (fp64 accumulators).
-// Thread layout: threadIdx.x -> group of 8 channels, threadIdx.y -> row lane.
+// Per-channel reductions over the R rows of a [R,C] bf16 tensor.  Every thread owns ONE group of
+// 8 channels for its whole life (the grid stride is a multiple of C/8), so the per-channel
+// constants sit in registers; UNROLL independent 16-byte loads per tensor are in flight per
+// thread.  Partial sums are fp32 per thread, reduced through shared memory per block and
+// committed with one fp64 atomic per channel per block.
+//   forward : sums[0][c] = sum z          sums[1][c] = sum z^2
+//   backward: sums[0][c] = sum g          sums[1][c] = sum g * (z - mean)     g = da * leaky'(y)
+constexpr int BN_THREADS = 256;
+constexpr int BN_UNROLL = 4;
+
 template <bool BWD>
-__global__ void __launch_bounds__(256) bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da,
-                                                        const float* __restrict__ scale,
-                                                        const float* __restrict__ shift,
-                                                        const float* __restrict__ mean,
-                                                        const float* __restrict__ rstd, float slope, long long R,
-                                                        int C, double* __restrict__ sums, int rows_per_block) {
-  extern __shared__ float sred[];           // [2][ty][C8*8]
+__global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da,
+                                                               const float* __restrict__ scale,
+                                                               const float* __restrict__ shift,
+                                                               const float* __restrict__ mean, float slope,
+                                                               long long n8, int C, double* __restrict__ sums) {
+  extern __shared__ float sred[];           // [2][RY][C]
   const int C8 = C >> 3;
-  const int cx = threadIdx.x % C8;           // channel group
-  const int ry = threadIdx.x / C8;           // row lane inside the block
-  const int RY = blockDim.x / C8;
+  const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
+  const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8 (host guarantees)
+  const int cx = (int)(tid % C8);
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  float sc[8], sh[8], mu[8], rs[8];
+  float sc[8], sh[8], mu[8];
   if (BWD) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = scale[cx * 8 + j]; sh[j] = shift[cx * 8 + j]; mu[j] = mean[cx * 8 + j]; rs[j] = rstd[cx * 8 + j];
-    }
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[cx * 8 + j]; sh[j] = shift[cx * 8 + j]; mu[j] = mean[cx * 8 + j]; }
   }
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(R, r0 + rows_per_block);
-  if (ry < RY) {
-    for (long long r = r0 + ry; r < r1; r += RY) {
-      float f[8];
-      unpack8(__ldg(z + r * C8 + cx), f);
-      if (!BWD) {
+  for (long long i = tid; i < n8; i += stride * BN_UNROLL) {
+    uint4 zv[BN_UNROLL], gv[BN_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
-      } else {
-        float g[8];
-        unpack8(__ldg(da + r * C8 + cx), g);
+    for (int u = 0; u < BN_UNROLL; ++u) {
+      const long long k = i + u * stride;
+      if (k < n8) {
+        zv[u] = __ldg(z + k);
+        if (BWD) gv[u] = __ldg(da + k);
+      }
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float y = fmaf(f[j], sc[j], sh[j]);
-          const float gg = y > 0.f ? g[j] : g[j] * slope;
-          s1[j] += gg;
-          s2[j] = fmaf(gg, (f[j] - mu[j]) * rs[j], s2[j]);
+    for (int u = 0; u < BN_UNROLL; ++u) {
+      if (i + u * stride < n8) {
+        float f[8];
+        unpack8(zv[u], f);
+        if (!BWD) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+        } else {
+          float g[8];
+          unpack8(gv[u], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float y = fmaf(f[j], sc[j], sh[j]);
+            const float gg = y > 0.f ? g[j] : g[j] * slope;
+            s1[j] += gg;
+            s2[j] = fmaf(gg, f[j] - mu[j], s2[j]);
+          }
         }
       }
     }
   }
+  // block reduction: threads with the same cx are BN_THREADS/C8 "row lanes" apart
+  const int RY = BN_THREADS / C8, ry = threadIdx.x / C8;
   float* a1 = sred;
   float* a2 = sred + RY * C;
-  if (ry < RY) {
+  // note: threadIdx.x % C8 == cx because BN_THREADS % C8 == 0
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a1[ry * C + cx * 8 + j] = s1[j]; a2[ry * C + cx * 8 + j] = s2[j]; }
-  }
+  for (int j = 0; j < 8; ++j) { a1[ry * C + cx * 8 + j] = s1[j]; a2[ry * C + cx * 8 + j] = s2[j]; }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
     float t1 = 0.f, t2 = 0.f;
     for (int y = 0; y < RY; ++y) { t1 += a1[y * C + c]; t2 += a2[y * C + c]; }
     atomicAdd(&sums[c], (double)t1);
@@ -230,71 +246,110 @@ __global__ void bn_eval_coeffs_kernel(int C, int C_real, const float* __restrict
 }
 
 // a = leaky(z*scale + shift) (+ residual)
-__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift,
-                                                       const uint4* __restrict__ residual, uint4* __restrict__ a,
-                                                       long long n8, int C8, float slope) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cx = (int)(i % C8);
-    float f[8], r[8];
-    unpack8(__ldg(z + i), f);
-    if (residual) unpack8(__ldg(residual + i), r);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + cx * 2);
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale) + cx * 2 + 1);
-    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + cx * 2);
-    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift) + cx * 2 + 1);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const uint4* __restrict__ residual, uint4* __restrict__ a,
+                                                              long long n8, int C8, float slope) {
+  const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
+  const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8
+  const int cx = (int)(tid % C8);
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = fmaf(f[j], sc[j], sh[j]);
-      y = y > 0.f ? y : y * slope;
-      f[j] = residual ? y + r[j] : y;
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[cx * 8 + j]; sh[j] = shift[cx * 8 + j]; }
+  const bool has_res = residual != nullptr;
+  for (long long i = tid; i < n8; i += stride * BN_UNROLL) {
+    uint4 zv[BN_UNROLL], rv[BN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BN_UNROLL; ++u) {
+      const long long k = i + u * stride;
+      if (k < n8) {
+        zv[u] = __ldg(z + k);
+        if (has_res) rv[u] = __ldg(residual + k);
+      }
     }
-    a[i] = pack8(f);
+#pragma unroll
+    for (int u = 0; u < BN_UNROLL; ++u) {
+      const long long k = i + u * stride;
+      if (k < n8) {
+        float f[8], r[8];
+        unpack8(zv[u], f);
+        if (has_res) unpack8(rv[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = fmaf(f[j], sc[j], sh[j]);
+          y = y > 0.f ? y : y * slope;
+          f[j] = has_res ? y + r[j] : y;
+        }
+        a[k] = pack8(f);
+      }
+    }
   }
 }
 
-// dz = scale * (g - S1/R - xhat * S2/R),  g = da * leaky'(y)
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ z,
-                                                           const float* __restrict__ scale,
-                                                           const float* __restrict__ shift,
-                                                           const float* __restrict__ mean,
-                                                           const float* __restrict__ rstd,
-                                                           const double* __restrict__ sums, double invR,
-                                                           uint4* __restrict__ dz, long long n8, int C, float slope) {
+// per-channel coefficients of the backward apply pass:
+//   dz = scale*(g - S1/R - xhat*S2/R),  xhat = (z-mean)*rstd,  S2 = rstd * sum g*(z-mean)
+//      = scale*g + A*z + B,   A = -scale*rstd^2*sums1/R,   B = -scale*sums0/R - A*mean
+// coef [4][C]: scale, shift, A, B.  Also dgamma += S2, dbeta += S1 for the real channels.
+__global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double invR, int C, int C_real,
+                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                   float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double sc = scale[c], rs = rstd[c], mu = mean[c];
+  const double A = -sc * rs * rs * sums[C + c] * invR;
+  const double B = -sc * sums[c] * invR - A * mu;
+  coef[c] = scale[c];
+  coef[C + c] = shift[c];
+  coef[2 * C + c] = (float)A;
+  coef[3 * C + c] = (float)B;
+  if (c < C_real && dgamma && dbeta) {
+    dbeta[c] += (float)sums[c];
+    dgamma[c] += (float)(rs * sums[C + c]);
+  }
+}
+
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ z,
+                                                                  const float* __restrict__ coef,
+                                                                  uint4* __restrict__ dz, long long n8, int C,
+                                                                  float slope) {
   const int C8 = C >> 3;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cx = (int)(i % C8);
-    float f[8], g[8];
-    unpack8(__ldg(z + i), f);
-    unpack8(__ldg(da + i), g);
+  const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
+  const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8
+  const int cx = (int)(tid % C8);
+  float sc[8], sh[8], cA[8], cB[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cx * 8 + j;
-      const float sc = __ldg(scale + c), sh = __ldg(shift + c), mu = __ldg(mean + c), rs = __ldg(rstd + c);
-      const float m1 = (float)(sums[c] * invR), m2 = (float)(sums[C + c] * invR);
-      const float y = fmaf(f[j], sc, sh);
-      const float gg = y > 0.f ? g[j] : g[j] * slope;
-      const float xh = (f[j] - mu) * rs;
-      f[j] = sc * (gg - m1 - xh * m2);
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = coef[cx * 8 + j]; sh[j] = coef[C + cx * 8 + j];
+    cA[j] = coef[2 * C + cx * 8 + j]; cB[j] = coef[3 * C + cx * 8 + j];
+  }
+  for (long long i = tid; i < n8; i += stride * BN_UNROLL) {
+    uint4 zv[BN_UNROLL], gv[BN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BN_UNROLL; ++u) {
+      const long long k = i + u * stride;
+      if (k < n8) { zv[u] = __ldg(z + k); gv[u] = __ldg(da + k); }
     }
-    dz[i] = pack8(f);
+#pragma unroll
+    for (int u = 0; u < BN_UNROLL; ++u) {
+      const long long k = i + u * stride;
+      if (k < n8) {
+        float f[8], g[8];
+        unpack8(zv[u], f);
+        unpack8(gv[u], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf(f[j], sc[j], sh[j]);
+          const float gg = y > 0.f ? g[j] : g[j] * slope;
+          f[j] = fmaf(sc[j], gg, fmaf(cA[j], f[j], cB[j]));
+        }
+        dz[k] = pack8(f);
+      }
+    }
   }
 }
 
 // eval-mode backward is not needed (the trunk is only differentiated in train mode).
-
-// dgamma += S2, dbeta += S1 for the real channels
-__global__ void bn_param_grad_kernel(const double* __restrict__ sums, int C, int C_real, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C_real) return;
-  dbeta[c] += (float)sums[c];
-  dgamma[c] += (float)sums[C + c];
-}
 
 // ------------------------------------------------------- weight (un)packing
 // w [Cout,Cin,k,k] fp32 -> wf [Cout_p][k*k][Cin_p] bf16 and wd [Cin_p][k*k][Cout_p] bf16 (zero padded)
@@ -376,30 +431,32 @@ extern "C" int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, 
   return avdn::check_launch("avdn_conv0_wgrad");
 }
 
+// grid of BN_THREADS-wide blocks whose total thread count is a multiple of C/8 (so that every
+// thread keeps its channel group) and that fills the machine without exceeding the work
+static int bn_grid(long long n8, int waves) {
+  long long blocks = (n8 + (long long)BN_THREADS * BN_UNROLL - 1) / ((long long)BN_THREADS * BN_UNROLL);
+  const long long cap = (long long)avdn::sm_count() * waves;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
 static int bn_reduce_launch(bool bwd, const void* z, const void* da, const float* scale, const float* shift,
-                            const float* mean, const float* rstd, float slope, long long R, int C, double* sums,
-                            cudaStream_t s) {
-  AVDN_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048, "bn reduce: C=%d must be a multiple of 8 in [8,2048]", C);
+                            const float* mean, float slope, long long R, int C, double* sums, cudaStream_t s) {
+  AVDN_REQUIRE(C % 8 == 0 && C >= 8 && BN_THREADS % (C / 8) == 0,
+               "bn reduce: C=%d must be 8 * (a divisor of %d)", C, BN_THREADS);
   const int C8 = C / 8;
-  int threads = 256;
-  if (C8 > 256) threads = C8;            // C up to 2048 -> one row lane
-  threads = (threads / C8) * C8;
-  const int RY = threads / C8;
-  // enough blocks to fill the machine, at least 64 rows per block
-  long long blocks = (long long)avdn::sm_count() * 8;
-  long long rpb = (R + blocks - 1) / blocks;
-  if (rpb < 64) rpb = 64;
-  blocks = (R + rpb - 1) / rpb;
-  const size_t smem = (size_t)2 * RY * C * sizeof(float);
+  const int RY = BN_THREADS / C8;
+  const long long n8 = R * C8;
+  const int blocks = bn_grid(n8, 8);
+  const size_t smem = (size_t)2 * RY * C * sizeof(float);      // = 2 * 256 * 8 * 4 = 16 KB
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s) != cudaSuccess) return avdn::check_launch("bn reduce memset");
   if (bwd)
-    bn_reduce_kernel<true><<<(unsigned)blocks, threads, smem, s>>>(
-        reinterpret_cast<const uint4*>(z), reinterpret_cast<const uint4*>(da), scale, shift, mean, rstd, slope, R, C,
-        sums, (int)rpb);
+    bn_reduce_kernel<true><<<blocks, BN_THREADS, smem, s>>>(reinterpret_cast<const uint4*>(z),
+                                                            reinterpret_cast<const uint4*>(da), scale, shift, mean,
+                                                            slope, n8, C, sums);
   else
-    bn_reduce_kernel<false><<<(unsigned)blocks, threads, smem, s>>>(reinterpret_cast<const uint4*>(z), nullptr,
-                                                                    nullptr, nullptr, nullptr, nullptr, slope, R, C,
-                                                                    sums, (int)rpb);
+    bn_reduce_kernel<false><<<blocks, BN_THREADS, smem, s>>>(reinterpret_cast<const uint4*>(z), nullptr, nullptr,
+                                                             nullptr, nullptr, slope, n8, C, sums);
   return avdn::check_launch("bn_reduce_kernel");
 }
 
@@ -408,7 +465,7 @@ extern "C" int avdn_bn_stats(const void* z, long long R, int C, int C_real, cons
                              float* scale, float* shift, float* mean, float* rstd, avdn_stream_t stream) {
   AVDN_REQUIRE(z && gamma && beta && sums && scale && shift && mean && rstd && R > 0, "avdn_bn_stats: bad argument");
   cudaStream_t s = avdn::to_cuda(stream);
-  int r = bn_reduce_launch(false, z, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, R, C, sums, s);
+  int r = bn_reduce_launch(false, z, nullptr, nullptr, nullptr, nullptr, 0.f, R, C, sums, s);
   if (r) return r;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, C_real, gamma, beta, running_mean, running_var,
                                                      momentum, eps, scale, shift, mean, rstd);
@@ -426,9 +483,10 @@ extern "C" int avdn_bn_eval_coeffs(int C, int C_real, const float* gamma, const 
 
 extern "C" int avdn_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* a,
                              long long R, int C, float slope, avdn_stream_t stream) {
-  AVDN_REQUIRE(z && scale && shift && a && R > 0 && C % 8 == 0, "avdn_bn_apply: bad argument");
+  AVDN_REQUIRE(z && scale && shift && a && R > 0 && C % 8 == 0 && BN_THREADS % (C / 8) == 0,
+               "avdn_bn_apply: bad argument (C=%d)", C);
   const long long n8 = R * (C / 8);
-  bn_apply_kernel<<<grid_for(n8, 256, 16), 256, 0, avdn::to_cuda(stream)>>>(
+  bn_apply_kernel<<<bn_grid(n8, 16), BN_THREADS, 0, avdn::to_cuda(stream)>>>(
       reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<const uint4*>(residual),
       reinterpret_cast<uint4*>(a), n8, C / 8, slope);
   return avdn::check_launch("avdn_bn_apply");
@@ -439,20 +497,18 @@ extern "C" int avdn_bn_backward(const void* da, const void* z, const float* scal
                                 double* sums, void* dz, float* dgamma, float* dbeta, avdn_stream_t stream) {
   AVDN_REQUIRE(da && z && scale && shift && mean && rstd && sums && dz && R > 0, "avdn_bn_backward: bad argument");
   cudaStream_t s = avdn::to_cuda(stream);
-  int r = bn_reduce_launch(true, z, da, scale, shift, mean, rstd, slope, R, C, sums, s);
+  int r = bn_reduce_launch(true, z, da, scale, shift, mean, slope, R, C, sums, s);
+  if (r) return r;
+  float* coef = reinterpret_cast<float*>(sums + 2 * C);         // second half of the [4,C] f64 scratch
+  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, 1.0 / (double)R, C, C_real, scale, shift, mean, rstd, coef,
+                                                     dgamma, dbeta);
+  r = avdn::check_launch("bn_bwd_coef_kernel");
   if (r) return r;
   const long long n8 = R * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for(n8, 256, 16), 256, 0, s>>>(reinterpret_cast<const uint4*>(da),
-                                                            reinterpret_cast<const uint4*>(z), scale, shift, mean,
-                                                            rstd, sums, 1.0 / (double)R, reinterpret_cast<uint4*>(dz),
-                                                            n8, C, slope);
-  r = avdn::check_launch("bn_bwd_apply_kernel");
-  if (r) return r;
-  if (dgamma && dbeta) {
-    bn_param_grad_kernel<<<(C_real + 127) / 128, 128, 0, s>>>(sums, C, C_real, dgamma, dbeta);
-    r = avdn::check_launch("bn_param_grad_kernel");
-  }
-  return r;
+  bn_bwd_apply_kernel<<<bn_grid(n8, 16), BN_THREADS, 0, s>>>(reinterpret_cast<const uint4*>(da),
+                                                            reinterpret_cast<const uint4*>(z), coef,
+                                                            reinterpret_cast<uint4*>(dz), n8, C, slope);
+  return avdn::check_launch("bn_bwd_apply_kernel");
 }
 
 extern "C" int avdn_pack_conv_weight(const float* w, int Cout, int Cin, int k, int Cout_p, int Cin_p, void* wf,

@@ -150,7 +150,7 @@ class _Engine:
             L.shift = torch.zeros(L.Cout_p, dtype=f32, device=dev)
             L.mean = torch.zeros(L.Cout_p, dtype=f32, device=dev)
             L.rstd = torch.zeros(L.Cout_p, dtype=f32, device=dev)
-            L.sums = torch.zeros(2 * L.Cout_p, dtype=torch.float64, device=dev)
+            L.sums = torch.zeros(4 * L.Cout_p, dtype=torch.float64, device=dev)
             if not L.first:
                 L.wf = torch.empty((L.Cout_p, L.k * L.k * L.Cin_p), dtype=bf, device=dev)
                 L.wd = torch.empty((L.Cin_p, L.k * L.k * L.Cout_p), dtype=bf, device=dev)

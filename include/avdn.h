@@ -187,8 +187,9 @@ int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int 
 /* nn.BatchNorm2d in train mode (dark_net.py:31; eps 1e-5, momentum 0.1): batch
  * statistics of z [R,C] bf16 -> per-channel affine scale = gamma*rstd,
  * shift = beta - mean*scale, plus mean/rstd for the backward pass; updates the
- * running buffers (NULL to skip).  sums [2,C] f64 is scratch.  Channels >= C_real
- * are padding (scale = shift = 0).                                            */
+ * running buffers (NULL to skip).  sums [4,C] f64 is scratch (shared with
+ * avdn_bn_backward).  Channels >= C_real are padding (scale = shift = 0).
+ * C must be 8 * (a divisor of 256).                                           */
 int avdn_bn_stats(const void* z, long long R, int C, int C_real, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, double* sums,
                   float* scale, float* shift, float* mean, float* rstd, avdn_stream_t stream);
@@ -200,7 +201,9 @@ int avdn_bn_eval_coeffs(int C, int C_real, const float* gamma, const float* beta
 int avdn_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* a,
                   long long R, int C, float slope, avdn_stream_t stream);
 /* Backward of the above (train mode): dz [R,C] bf16 from da; dgamma/dbeta (+=, the
- * C_real real channels).  The residual branch receives da unchanged (caller).   */
+ * C_real real channels).  The residual branch receives da unchanged (caller).
+ * sums [4,C] f64 scratch: two reduction rows, then the per-channel coefficients
+ * of the apply pass.                                                           */
 int avdn_bn_backward(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
                      const float* rstd, long long R, int C, int C_real, float slope, double* sums, void* dz,
                      float* dgamma, float* dbeta, avdn_stream_t stream);
