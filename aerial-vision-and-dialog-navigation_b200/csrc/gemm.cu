@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / TMA tensor-core primitive of libavdn.so (sm_100a).
 //
-// One warp-specialised kernel covers every dense contraction of the hot path:
+// One persistent, warp-specialised kernel covers every dense contraction of the hot path:
 //
 //   PLAIN  D[M,N] = alpha * op(A) . op(B)^T (+bias)(relu)   batched over 2 extra dims
 //          -> nn.Linear fwd / dgrad (src/models/enc_vl.py:16-22, ET_haa.py:98-119),
@@ -11,16 +11,23 @@
 //          fill IS the padding.  Stride-2 layers read one of four parity views.
 //          -> nn.Conv2d fwd and dgrad (src/models/dark_net.py:22-28)
 //   WGRAD  D[Cout,Cin] += sum_pixels dZ[pix,co] * X[pix+tap,ci]: both operands
-//          MN-major 4-D boxes, split-K over pixel tiles, fp32 atomic epilogue
+//          MN-major 4-D boxes, split-K over pixel tiles, fp32 reduce-add epilogue
 //          -> nn.Conv2d / nn.Linear weight gradients
 //
-// Pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (single elected lane,
-// tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM), warps 2..5 = epilogue
-// (tcgen05.ld 32x32b, one TMEM lane quarter each).  smem ring of STAGES x
-// (A 16 KB + B BN*128 B), 128-byte swizzle, mbarrier full/empty pairs,
-// tcgen05.commit releases a stage and finally signals the epilogue.  Two CTAs
-// fit per SM (<= 100 KB smem, <= 256 TMEM columns each) so one CTA's epilogue
-// overlaps the other's main loop.
+// Structure (one CTA -- or one CTA pair, cta_group::2 -- per SM, looping over tiles):
+//   warp 0      TMA producer: fills a ring of STAGES x (A 16 KB + B) smem stages, 128-byte swizzle,
+//               running ahead across tile boundaries
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma kind::f16 (bf16 x bf16 -> fp32)
+//               into one of TWO TMEM accumulators; tcgen05.commit frees smem stages and hands
+//               the finished accumulator to the epilogue
+//   warps 2..5  epilogue: tcgen05.ld (one TMEM lane quarter each) -> alpha/bias/ReLU -> bf16|fp32
+//               -> 128-byte-swizzled smem slab -> TMA store (or TMA reduce-add for the
+//               accumulating modes); the epilogue of tile i overlaps the main loop of tile i+1.
+//               Optional fused BatchNorm statistics: per-channel sum / sum of squares of the
+//               rounded outputs, accumulated per CTA and committed with fp64 atomics
+//               (nn.BatchNorm2d batch statistics, dark_net.py:31).
+//   cta_group::2: the pair computes a 256 x BN tile; each CTA loads its own 128 rows of A and
+//               HALF of B, so the L2->SM operand traffic per FLOP drops by a third.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -29,10 +36,12 @@
 
 namespace {
 
-constexpr int BM = 128;         // UMMA M (cta_group::1)
+constexpr int BM = 128;         // rows per CTA (UMMA M = 128 * CTAS)
 constexpr int BK = 64;          // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr int SLAB_BYTES = BM * 128;      // one epilogue slab: 128 rows x 128 bytes
 
 // ------------------------------------------------------------------ PTX glue
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -43,6 +52,23 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 remote;\n\t"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
+      "}" ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -55,17 +81,65 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+template <int CTAS>
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2, int c3) {
+  if (CTAS == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+        : "memory");
+  } else {      // `bar` is a shared::cluster address in the leader CTA
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
-      "r"(c3)
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src),
+      "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+      "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+template <int CTAS>
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
+  if (CTAS == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+  } else {      // arrive on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            bar),
+        "h"((uint16_t)3)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -73,15 +147,26 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
+template <int CTAS>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (CTAS == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -114,250 +199,420 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 struct alignas(64) KernelParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB[4];
-  avdn_gemm_core c;     // plain-data description shared with the host (gemm.h)
+  CUtensorMap tmC;      // output map (out_tma == 1)
+  avdn_gemm_core c;     // plain-data description shared with the host (avdn.h)
+  int32_t grid_m, grid_n, grid_z;   // tile space (grid_m counts 128-row tiles)
+  int32_t out_tma;      // 1: epilogue goes through smem slabs + TMA store / reduce-add
+  int32_t rows_in_box;  // rows of a tile that exist (CONV: bw*bh*bn <= 128; otherwise 128)
+  int32_t pad_;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS>
 struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
+  static constexpr int B_BYTES = (BN / CTAS) * BK * 2;         // this CTA's part of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int SLAB_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STAT_OFF = SLAB_OFF + 2 * SLAB_BYTES;   // float [2][BN]
+  static constexpr int BAR_OFF = STAT_OFF + 2 * BN * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ KernelParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, CTAS>;
+  constexpr int BNH = BN / CTAS;                                // B columns this CTA loads
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + L::BAR_OFF;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFF + 8 * (2 * STAGES + 1));
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFF + 8 * L::NUM_BARS);
+  float* s_stat = reinterpret_cast<float*>(smem_gen + L::STAT_OFF);
 
   const avdn_gemm_core& c = p.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
 
-  // ---- tile coordinates -------------------------------------------------
-  const int mt = blockIdx.x, nt = blockIdx.y;
-  int z = blockIdx.z;
-  const int split = z % c.split_k;  z /= c.split_k;
-  int z0 = 0, z1 = 0, tap_fixed = 0;
-  if (c.mode == AVDN_GEMM_WGRAD) tap_fixed = z;
-  else { z0 = z % c.batch0; z1 = z / c.batch0; }
-  const int n0 = nt * BN;
-  // conv modes: spatial tile of this CTA's rows (CONV) -- WGRAD walks tiles in the k loop
-  int w0 = 0, h0 = 0, i0 = 0;
-  if (c.mode == AVDN_GEMM_CONV) {
-    w0 = (mt % c.tiles_w) * c.box_w;
-    h0 = ((mt / c.tiles_w) % c.tiles_h) * c.box_h;
-    i0 = (mt / (c.tiles_w * c.tiles_h)) * c.box_n;
-  }
-  const int m0 = mt * BM;
-  // k range of this split
+  // ---- tile space: pair-tiles when CTAS == 2 (two adjacent 128-row tiles share one B) -----
+  const int pm = (p.grid_m + CTAS - 1) / CTAS;
+  const long long total = (long long)pm * p.grid_n * p.grid_z;
+  const long long t_begin = blockIdx.x / CTAS, t_step = gridDim.x / CTAS;
   const int kb_per = (c.num_kb + c.split_k - 1) / c.split_k;
-  const int kb_begin = split * kb_per;
-  const int kb_end = min(c.num_kb, kb_begin + kb_per);
-  const int my_kb = max(0, kb_end - kb_begin);
+
+  struct Tile { int mt, nt, z0, z1, tap, kb_begin, my_kb; };
+  auto decode = [&](long long t) {
+    Tile T;
+    T.nt = (int)(t % p.grid_n);
+    const long long r = t / p.grid_n;
+    T.mt = (int)(r % pm) * CTAS + (int)rank;
+    int z = (int)(r / pm);
+    const int split = z % c.split_k;  z /= c.split_k;
+    T.z0 = T.z1 = T.tap = 0;
+    if (c.mode == AVDN_GEMM_WGRAD) T.tap = z;
+    else { T.z0 = z % c.batch0; T.z1 = z / c.batch0; }
+    T.kb_begin = split * kb_per;
+    const int kb_end = min(c.num_kb, T.kb_begin + kb_per);
+    T.my_kb = max(0, kb_end - T.kb_begin);
+    return T;
+  };
 
   // ---- one-time setup -----------------------------------------------------
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32((const void*)tmem_slot)),
-                 "r"((uint32_t)(BN < 32 ? 32 : BN))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32((const void*)tmem_slot)),
+                   "r"((uint32_t)(2 * BN))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32((const void*)tmem_slot)),
+                   "r"((uint32_t)(2 * BN))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < 2 * BN; i += EPI_THREADS) s_stat[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();          // peer barriers initialised before anyone signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // =========================== TMA producer ===============================
-    if (lane == 0 && my_kb > 0) {
+    if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-        const uint32_t sb = sa + L::A_BYTES;
-        mbar_expect_tx(full_bar(stage), c.tx_bytes);
-        if (c.mode == AVDN_GEMM_PLAIN) {
-          const int k0 = kb * BK;
-          if (!A_MN) tma_load_4d(sa, &p.tmA[0], full_bar(stage), k0, m0, z0, z1);
-          else {
-            tma_load_4d(sa, &p.tmA[0], full_bar(stage), m0, k0, z0, z1);
-            tma_load_4d(sa + 8192, &p.tmA[0], full_bar(stage), m0 + 64, k0, z0, z1);
-          }
-          if (!B_MN) tma_load_4d(sb, &p.tmB[0], full_bar(stage), k0, n0, z0 * c.b_batched, z1 * c.b_batched);
-          else {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sb + j * 8192, &p.tmB[0], full_bar(stage), n0 + 64 * j, k0, z0 * c.b_batched,
-                          z1 * c.b_batched);
-          }
-        } else if (c.mode == AVDN_GEMM_CONV) {
-          const int t = kb / c.cblocks, cb = kb - t * c.cblocks;
-          const avdn_tap tp = c.taps[t];
-          tma_load_4d(sa, &p.tmA[tp.map], full_bar(stage), cb * BK, w0 + tp.d1, h0 + tp.d2, i0);
-          tma_load_4d(sb, &p.tmB[0], full_bar(stage), tp.bk + cb * BK, n0, 0, 0);
-        } else {  // WGRAD: k-step = one pixel tile (box_w*box_h*box_n == 64 pixels)
-          const avdn_tap tp = c.taps[tap_fixed];
-          const int pw = (kb % c.tiles_w) * c.box_w;
-          const int ph = ((kb / c.tiles_w) % c.tiles_h) * c.box_h;
-          const int pn = (kb / (c.tiles_w * c.tiles_h)) * c.box_n;
-          tma_load_4d(sa, &p.tmA[0], full_bar(stage), m0, pw, ph, pn);
-          tma_load_4d(sa + 8192, &p.tmA[0], full_bar(stage), m0 + 64, pw, ph, pn);
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(sb + j * 8192, &p.tmB[tp.map], full_bar(stage), n0 + 64 * j, pw + tp.d1, ph + tp.d2, pn);
+      const uint32_t tx_total = c.tx_bytes;                 // bytes both CTAs deposit per k-step
+      for (long long t = t_begin; t < total; t += t_step) {
+        const Tile T = decode(t);
+        const int n0 = T.nt * BN + (int)rank * BNH;         // this CTA's slice of B
+        const int m0 = T.mt * BM;
+        int w0 = 0, h0 = 0, i0 = 0;
+        if (c.mode == AVDN_GEMM_CONV) {
+          w0 = (T.mt % c.tiles_w) * c.box_w;
+          h0 = ((T.mt / c.tiles_w) % c.tiles_h) * c.box_h;
+          i0 = (T.mt / (c.tiles_w * c.tiles_h)) * c.box_n;  // phantom tile of an odd pair: out of bounds -> zeros
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int kb = T.kb_begin; kb < T.kb_begin + T.my_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
+          uint32_t fb = full_bar(stage);
+          if (CTAS == 2) fb = mapa_rank(fb, 0);
+          if (leader) mbar_expect_tx(full_bar(stage), tx_total);
+          if (c.mode == AVDN_GEMM_PLAIN) {
+            const int k0 = kb * BK;
+            if (!A_MN) tma_load_4d<CTAS>(sa, &p.tmA[0], fb, k0, m0, T.z0, T.z1);
+            else {
+              tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, k0, T.z0, T.z1);
+              tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, k0, T.z0, T.z1);
+            }
+            if (!B_MN) tma_load_4d<CTAS>(sb, &p.tmB[0], fb, k0, n0, T.z0 * c.b_batched, T.z1 * c.b_batched);
+            else {
+#pragma unroll
+              for (int j = 0; j < BNH / 64; ++j)
+                tma_load_4d<CTAS>(sb + j * 8192, &p.tmB[0], fb, n0 + 64 * j, k0, T.z0 * c.b_batched,
+                                  T.z1 * c.b_batched);
+            }
+          } else if (c.mode == AVDN_GEMM_CONV) {
+            const int tp_i = kb / c.cblocks, cb = kb - tp_i * c.cblocks;
+            const avdn_tap tp = c.taps[tp_i];
+            tma_load_4d<CTAS>(sa, &p.tmA[tp.map], fb, cb * BK, w0 + tp.d1, h0 + tp.d2, i0);
+            tma_load_4d<CTAS>(sb, &p.tmB[0], fb, tp.bk + cb * BK, n0, 0, 0);
+          } else {  // WGRAD: k-step = one pixel tile (box_w*box_h*box_n == 64 pixels)
+            const avdn_tap tp = c.taps[T.tap];
+            const int pw = (kb % c.tiles_w) * c.box_w;
+            const int ph = ((kb / c.tiles_w) % c.tiles_h) * c.box_h;
+            const int pn = (kb / (c.tiles_w * c.tiles_h)) * c.box_n;
+            tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, pw, ph, pn);
+            tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, pw, ph, pn);
+#pragma unroll
+            for (int j = 0; j < BNH / 64; ++j)
+              tma_load_4d<CTAS>(sb + j * 8192, &p.tmB[tp.map], fb, n0 + 64 * j, pw + tp.d1, ph + tp.d2, pn);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ================================
-    if (lane == 0 && my_kb > 0) {
+    if (lane == 0 && leader) {
       // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((BM * CTAS) >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < my_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      uint32_t it = 0;
+      for (long long t = t_begin; t < total; t += t_step) {
+        const Tile T = decode(t);
+        if (T.my_kb == 0) continue;
+        const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+        ++it;
+        mbar_wait(tempty_bar(as), aphase ^ 1);              // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-        const uint32_t sb = sa + L::A_BYTES;
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < T.my_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t ad = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), 8192, 1024)
-                                   : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024)
-                                   : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), 8192, 1024)
+                                     : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bd = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024)
+                                     : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16<CTAS>(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit<CTAS>(empty_bar(stage));           // frees the smem stage when the MMAs retire
+          if (kb == T.my_kb - 1) tcgen05_commit<CTAS>(tfull_bar(as));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(empty_bar(stage));            // frees the smem stage when the MMAs retire
-        if (kb == my_kb - 1) tcgen05_commit(tmem_full_bar);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
     // ============================== epilogue ================================
     const int q = warp & 3;                      // TMEM lane quarter of this warp
     const int row = q * 32 + lane;               // row of the 128-row tile
-    if (my_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tcgen05_fence_after();
-    }
-    // ---- where does this row go? ----
-    bool row_ok;
-    size_t row_off;                              // element offset of (row, col 0)
-    if (c.mode == AVDN_GEMM_CONV) {
-      const int dw = row % c.box_w, dh = (row / c.box_w) % c.box_h, dn = row / (c.box_w * c.box_h);
-      const int w = w0 + dw, h = h0 + dh, n = i0 + dn;
-      row_ok = (dn < c.box_n) && (w < c.valid_w) && (h < c.valid_h) && (n < c.valid_n);
-      row_off = (((size_t)n * c.out_H + (size_t)h * c.out_sh + c.out_oh) * c.out_W + (size_t)w * c.out_sw +
-                 c.out_ow) * (size_t)c.ldc;
-    } else {
-      row_ok = (m0 + row) < c.M;
-      row_off = (size_t)(m0 + row) * (size_t)c.ldc + (size_t)z0 * c.out_bs0 + (size_t)z1 * c.out_bs1;
-      if (c.mode == AVDN_GEMM_WGRAD) row_off += (size_t)c.taps[tap_fixed].bk;
-    }
+    const int et = threadIdx.x - 64;             // 0..127
+    const bool is_bf16 = (c.out_dtype == AVDN_DT_BF16);
     const float alpha = c.alpha;
+    uint32_t it = 0, slab_ctr = 0;
+    int stat_nt = -1;
+    auto flush_stats = [&]() {
+      // all epilogue threads: commit the CTA's running column sums of tile column `stat_nt`
+      epi_bar_sync();
+      for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+        const int j = i % BN, which = i / BN;
+        const int col = stat_nt * BN + j;
+        if (col < c.N) atomicAdd(c.stats + (size_t)which * c.N + col, (double)s_stat[i]);
+        s_stat[i] = 0.f;
+      }
+      epi_bar_sync();
+    };
+    for (long long t = t_begin; t < total; t += t_step) {
+      const Tile T = decode(t);
+      if (T.my_kb == 0) continue;
+      const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
+      ++it;
+      const int n0 = T.nt * BN, m0 = T.mt * BM;
+      int w0 = 0, h0 = 0, i0 = 0;
+      if (c.mode == AVDN_GEMM_CONV) {
+        w0 = (T.mt % c.tiles_w) * c.box_w;
+        h0 = ((T.mt / c.tiles_w) % c.tiles_h) * c.box_h;
+        i0 = (T.mt / (c.tiles_w * c.tiles_h)) * c.box_n;
+      }
+      if (c.stats && stat_nt != T.nt) {
+        if (stat_nt >= 0) flush_stats();
+        stat_nt = T.nt;
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tcgen05_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+
+      if (p.out_tma) {
+        // ---- TMEM -> registers -> swizzled smem slab -> TMA store / reduce-add ----
+        const int cols_per_slab = is_bf16 ? 64 : 32;
+        const bool row_live = row < p.rows_in_box;
 #pragma unroll 1
-    for (int cc = 0; cc < BN; cc += 32) {
-      uint32_t v[32];
-      if (my_kb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-      else {
+        for (int cc = 0; cc < BN; cc += 32) {
+          const int col0 = n0 + cc;
+          if (col0 >= c.N) break;                                   // uniform: whole slab out of range
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + (uint32_t)cc, v);
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      const int col0 = n0 + cc;
-      if (!row_ok || col0 >= c.N) continue;
-      float f[32];
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) * alpha;
+            if (c.bias && (col0 + j) < c.N) x += __ldg(c.bias + col0 + j);
+            if (c.relu) x = fmaxf(x, 0.f);
+            f[j] = row_live ? x : 0.f;
+          }
+          const bool slab_first = is_bf16 ? ((cc & 32) == 0) : true;
+          const bool slab_last = is_bf16 ? ((cc & 32) != 0 || col0 + 32 >= c.N) : true;
+          uint8_t* slab = smem_gen + L::SLAB_OFF + (slab_ctr & 1u) * SLAB_BYTES;
+          if (slab_first) {
+            // the TMA store that read this buffer two slabs ago must have finished reading it
+            if (et == 0) tma_wait_group_read<1>();
+            epi_bar_sync();
+          }
+          uint8_t* rowp = slab + row * 128;
+          const int sw = row & 7;
+          if (is_bf16) {
+            const int cbase = (cc & 32) ? 4 : 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]) * alpha;
-        if (c.bias && (col0 + j) < c.N) x += __ldg(c.bias + col0 + j);
-        if (c.relu) x = fmaxf(x, 0.f);
-        f[j] = x;
-      }
-      if (c.relu_mask) {
-        const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(c.relu_mask) + row_off + col0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if ((col0 + j) < c.N && !(__bfloat162float(mk[j]) > 0.f)) f[j] = 0.f;
-      }
-      const bool full = (col0 + 32) <= c.N;
-      if (c.out_dtype == AVDN_DT_BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(c.out) + row_off + col0;
-        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-          uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t w[4];
-            if (c.accumulate == 1) {
-              const uint4 old = o4[g];
-              const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&ow[j]);
-                f[g * 8 + 2 * j] += __low2float(ob);
-                f[g * 8 + 2 * j + 1] += __high2float(ob);
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&b2);
               }
+              *reinterpret_cast<uint4*>(rowp + (((cbase + g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
+            if (slab_first && slab_last) {                          // N tail: zero the unused half
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
-              w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+              for (int g = 4; g < 8; ++g) *reinterpret_cast<uint4*>(rowp + ((g ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
             }
-            o4[g] = make_uint4(w[0], w[1], w[2], w[3]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(rowp + ((g ^ sw) << 4)) =
+                  make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
           }
-        } else {
-          for (int j = 0; j < 32 && (col0 + j) < c.N; ++j) {
-            float x = f[j];
-            if (c.accumulate == 1) x += __bfloat162float(o[j]);
-            o[j] = __float2bfloat16_rn(x);
+          if (slab_last) {
+            fence_proxy_async_smem();
+            epi_bar_sync();
+            const int scol = n0 + (is_bf16 ? (cc & ~32) : cc);      // first column of this slab
+            if (et == 0) {
+              const uint32_t src = smem_u32(slab);
+              int c0 = scol, c1, c2, c3;
+              if (c.mode == AVDN_GEMM_CONV) { c1 = w0; c2 = h0; c3 = i0; }
+              else if (c.mode == AVDN_GEMM_WGRAD) { c0 = scol + c.taps[T.tap].bk; c1 = m0; c2 = 0; c3 = 0; }
+              else { c1 = m0; c2 = T.z0; c3 = T.z1; }
+              if (c.accumulate) tma_reduce_add_4d(&p.tmC, src, c0, c1, c2, c3);
+              else tma_store_4d(&p.tmC, src, c0, c1, c2, c3);
+              tma_commit_group();
+            }
+            if (c.stats) {
+              // fused BatchNorm statistics of the ROUNDED outputs: thread -> (column, row half)
+              const int j = et & 63, half = et >> 6;
+              const int r0 = half * 64, r1 = min(p.rows_in_box, r0 + 64);
+              float s1 = 0.f, s2 = 0.f;
+              for (int r = r0; r < r1; ++r) {
+                const __nv_bfloat16 b =
+                    *reinterpret_cast<const __nv_bfloat16*>(slab + r * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2);
+                const float x = __bfloat162float(b);
+                s1 += x;
+                s2 = fmaf(x, x, s2);
+              }
+              const int jj = (scol - n0) + j;
+              atomicAdd(&s_stat[jj], s1);
+              atomicAdd(&s_stat[BN + jj], s2);
+            }
+            ++slab_ctr;
           }
         }
+        tcgen05_fence_before();
+        if (lane == 0) {
+          if (CTAS == 1) mbar_arrive(tempty_bar(as));
+          else mbar_arrive_cluster(tempty_bar(as), 0);
+        }
       } else {
-        float* o = reinterpret_cast<float*>(c.out) + row_off + col0;
-        if (c.accumulate == 2) {
-          for (int j = 0; j < 32 && (col0 + j) < c.N; ++j) atomicAdd(o + j, f[j]);
-        } else if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-          float4* o4 = reinterpret_cast<float4*>(o);
+        // ---- direct path: each thread stores its own row (relu_mask, unaligned or tiny outputs) ----
+        const bool row_ok = (m0 + row) < c.M;
+        size_t row_off = (size_t)(m0 + row) * (size_t)c.ldc + (size_t)T.z0 * c.out_bs0 + (size_t)T.z1 * c.out_bs1;
+        if (c.mode == AVDN_GEMM_WGRAD) row_off += (size_t)c.taps[T.tap].bk;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 32) {
+          const int col0 = n0 + cc;
+          if (col0 >= c.N) break;
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + (uint32_t)cc, v);
+          if (!row_ok) continue;
+          float f[32];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 x = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
-            if (c.accumulate == 1) { const float4 old = o4[g]; x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w; }
-            o4[g] = x;
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) * alpha;
+            if (c.bias && (col0 + j) < c.N) x += __ldg(c.bias + col0 + j);
+            if (c.relu) x = fmaxf(x, 0.f);
+            f[j] = x;
           }
-        } else {
-          for (int j = 0; j < 32 && (col0 + j) < c.N; ++j) {
-            float x = f[j];
-            if (c.accumulate == 1) x += o[j];
-            o[j] = x;
+          if (c.relu_mask) {
+            const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(c.relu_mask) + row_off + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((col0 + j) < c.N && !(__bfloat162float(mk[j]) > 0.f)) f[j] = 0.f;
           }
+          const bool full = (col0 + 32) <= c.N;
+          if (is_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(c.out) + row_off + col0;
+            if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint32_t w[4];
+                if (c.accumulate == 1) {
+                  const uint4 old = o4[g];
+                  const uint32_t ow[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&ow[j]);
+                    f[g * 8 + 2 * j] += __low2float(ob);
+                    f[g * 8 + 2 * j + 1] += __high2float(ob);
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
+                  w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                o4[g] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            } else {
+              for (int j = 0; j < 32 && (col0 + j) < c.N; ++j) {
+                float x = f[j];
+                if (c.accumulate == 1) x += __bfloat162float(o[j]);
+                o[j] = __float2bfloat16_rn(x);
+              }
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(c.out) + row_off + col0;
+            if (c.accumulate == 2) {
+              for (int j = 0; j < 32 && (col0 + j) < c.N; ++j) atomicAdd(o + j, f[j]);
+            } else if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float4 x = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                if (c.accumulate == 1) { const float4 old = o4[g]; x.x += old.x; x.y += old.y; x.z += old.z; x.w += old.w; }
+                o4[g] = x;
+              }
+            } else {
+              for (int j = 0; j < 32 && (col0 + j) < c.N; ++j) {
+                float x = f[j];
+                if (c.accumulate == 1) x += o[j];
+                o[j] = x;
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        if (lane == 0) {
+          if (CTAS == 1) mbar_arrive(tempty_bar(as));
+          else mbar_arrive_cluster(tempty_bar(as), 0);
         }
       }
     }
+    if (c.stats && stat_nt >= 0) flush_stats();
+    if (et == 0) tma_wait_group_read<0>();       // smem slabs must outlive the bulk stores reading them
   }
 
   // ---- teardown -------------------------------------------------------------
   tcgen05_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();             // the peer may still be signalling our barriers / reading our smem
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)(BN < 32 ? 32 : BN))
-                 : "memory");
+    if (CTAS == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN))
+                   : "memory");
   }
 }
 
@@ -379,63 +634,83 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int encode_operand(const avdn_operand& o, CUtensorMap* out) {
+// rank-4 tensor map with a 128-byte-swizzled box whose inner extent is exactly 128 bytes
+int encode_map(const void* ptr, int elem_bytes, const int64_t* dim, const int64_t* stride, const int32_t* boxdim,
+               CUtensorMap* out, bool check_only = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return avdn::set_err(AVDN_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
-  if (o.stride[0] != 1) return avdn::set_err(AVDN_ERR_BAD_ARG, "operand dim 0 must be contiguous");
-  if ((reinterpret_cast<uintptr_t>(o.ptr) & 15) != 0)
+  if (stride[0] != 1) return avdn::set_err(AVDN_ERR_BAD_ARG, "operand dim 0 must be contiguous");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0)
     return avdn::set_err(AVDN_ERR_BAD_ARG, "operand pointer must be 16-byte aligned");
   cuuint64_t dims[4], strides[3];
   cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   for (int i = 0; i < 4; ++i) {
-    dims[i] = (cuuint64_t)o.dim[i];
-    box[i] = (cuuint32_t)o.box[i];
-    if (o.dim[i] < 1) return avdn::set_err(AVDN_ERR_BAD_ARG, "operand dim %d < 1", i);
+    dims[i] = (cuuint64_t)dim[i];
+    box[i] = (cuuint32_t)boxdim[i];
+    if (dim[i] < 1) return avdn::set_err(AVDN_ERR_BAD_ARG, "operand dim %d < 1", i);
     if (box[i] < 1 || box[i] > 256) return avdn::set_err(AVDN_ERR_BAD_ARG, "TMA box dim %d = %u out of range", i, box[i]);
   }
-  if (box[0] != 64) return avdn::set_err(AVDN_ERR_BAD_ARG, "TMA box dim 0 must be 64 bf16 (128-byte swizzle)");
+  if ((int)box[0] * elem_bytes != 128)
+    return avdn::set_err(AVDN_ERR_BAD_ARG, "TMA box dim 0 must span 128 bytes (128-byte swizzle)");
   for (int i = 1; i < 4; ++i) {
-    const cuuint64_t s = (cuuint64_t)o.stride[i] * 2;
+    const cuuint64_t s = (cuuint64_t)stride[i] * (cuuint64_t)elem_bytes;
     if (s % 16 != 0 || s == 0)
       return avdn::set_err(AVDN_ERR_BAD_ARG, "operand stride %d (%llu B) must be a non-zero multiple of 16", i, (unsigned long long)s);
     strides[i - 1] = s;
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(o.ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (check_only) return AVDN_OK;
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return avdn::set_err(AVDN_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return AVDN_OK;
 }
 
+int encode_operand(const avdn_operand& o, CUtensorMap* out) {
+  return encode_map(o.ptr, 2, o.dim, o.stride, o.box, out);
+}
+
 struct Plan {
   uint32_t magic;
-  int32_t bn, stages, a_mn, b_mn;
-  dim3 grid;
+  int32_t bn, stages, a_mn, b_mn, ctas;
+  int32_t grid;
   int smem;
   KernelParams kp;
 };
-constexpr uint32_t PLAN_MAGIC = 0xA7D17C05u;
+constexpr uint32_t PLAN_MAGIC = 0xA7D17C06u;
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS>
 int launch_t(const Plan& pl, cudaStream_t s) {
-  auto kfn = gemm_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kfn = gemm_kernel<BN, STAGES, A_MN, B_MN, CTAS>;
+  using L = SmemLayout<BN, STAGES, CTAS>;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BN, STAGES>::TOTAL) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
       return avdn::check_launch("cudaFuncSetAttribute(gemm_kernel)");
     attr_done = true;
   }
-  kfn<<<pl.grid, NUM_THREADS, SmemLayout<BN, STAGES>::TOTAL, s>>>(pl.kp);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)pl.grid, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kfn, pl.kp) != cudaSuccess) return avdn::check_launch("gemm_kernel launch");
   return avdn::check_launch("gemm_kernel");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS>
 int launch_bn(const Plan& pl, cudaStream_t s) {
-  if (!pl.a_mn && !pl.b_mn) return launch_t<BN, STAGES, false, false>(pl, s);
-  if (!pl.a_mn && pl.b_mn) return launch_t<BN, STAGES, false, true>(pl, s);
-  if (pl.a_mn && !pl.b_mn) return launch_t<BN, STAGES, true, false>(pl, s);
-  return launch_t<BN, STAGES, true, true>(pl, s);
+  if (!pl.a_mn && !pl.b_mn) return launch_t<BN, STAGES, false, false, CTAS>(pl, s);
+  if (!pl.a_mn && pl.b_mn) return launch_t<BN, STAGES, false, true, CTAS>(pl, s);
+  if (pl.a_mn && !pl.b_mn) return launch_t<BN, STAGES, true, false, CTAS>(pl, s);
+  return launch_t<BN, STAGES, true, true, CTAS>(pl, s);
 }
 
 }  // namespace
@@ -449,24 +724,35 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   AVDN_REQUIRE(d->bn == 64 || d->bn == 128 || d->bn == 256, "avdn_gemm_plan: bn must be 64/128/256");
   AVDN_REQUIRE(d->n_a >= 1 && d->n_a <= 4 && d->n_b >= 1 && d->n_b <= 4, "avdn_gemm_plan: 1..4 operand maps");
   AVDN_REQUIRE(d->core.out, "avdn_gemm_plan: null output");
-  AVDN_REQUIRE(d->core.split_k >= 1 && d->core.num_kb >= 0, "avdn_gemm_plan: bad k split");
+  AVDN_REQUIRE(d->core.split_k >= 1 && d->core.num_kb >= 1, "avdn_gemm_plan: bad k split");
   AVDN_REQUIRE(d->core.split_k == 1 || d->core.accumulate == 2, "avdn_gemm_plan: split-K needs the atomic epilogue");
   AVDN_REQUIRE(d->core.accumulate != 2 || d->core.out_dtype == AVDN_DT_F32, "avdn_gemm_plan: atomic epilogue is fp32 only");
+  AVDN_REQUIRE(d->ctas == 1 || d->ctas == 2, "avdn_gemm_plan: ctas must be 1 or 2");
+  AVDN_REQUIRE(d->ctas == 1 || d->bn >= 128, "avdn_gemm_plan: cta pairs need bn >= 128");
+  AVDN_REQUIRE(!d->core.stats || (d->core.out_dtype == AVDN_DT_BF16 && d->core.accumulate == 0),
+               "avdn_gemm_plan: fused statistics need a plain bf16 store");
   Plan* pl = reinterpret_cast<Plan*>(plan_host);
   memset(pl, 0, sizeof(Plan));
   pl->bn = d->bn;
   pl->a_mn = d->a_mn;
   pl->b_mn = d->b_mn;
+  pl->ctas = d->ctas;
   pl->kp.c = d->core;
+  const avdn_gemm_core& c = d->core;
   for (int i = 0; i < d->n_a; ++i) {
     int r = encode_operand(d->a[i], &pl->kp.tmA[i]);
     if (r) return r;
   }
   for (int i = 0; i < d->n_b; ++i) {
-    int r = encode_operand(d->b[i], &pl->kp.tmB[i]);
+    avdn_operand b = d->b[i];
+    if (d->ctas == 2) {            // each CTA of a pair loads half of the B tile
+      if (!d->b_mn) b.box[1] = d->bn / 2;
+    }
+    int r = encode_operand(b, &pl->kp.tmB[i]);
     if (r) return r;
   }
-  // bytes one k-step deposits in a stage: full boxes, OOB elements are zero-filled and counted
+  // bytes one k-step deposits in a stage (both CTAs of a pair): full boxes, OOB elements are
+  // zero-filled and counted
   auto box_bytes = [](const avdn_operand& o) {
     long long b = 2;
     for (int i = 0; i < 4; ++i) b *= o.box[i];
@@ -475,13 +761,60 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   const long long a_bytes = box_bytes(d->a[0]) * (d->a_mn ? 2 : 1);
   const long long b_bytes = box_bytes(d->b[0]) * (d->b_mn ? d->bn / 64 : 1);
   AVDN_REQUIRE(a_bytes <= BM * BK * 2 && b_bytes <= (long long)d->bn * BK * 2, "avdn_gemm_plan: boxes exceed the stage");
-  pl->kp.c.tx_bytes = (uint32_t)(a_bytes + b_bytes);
-  // stages: keep two CTAs per SM where the tile allows it
-  pl->stages = (d->bn == 256) ? 4 : (d->bn == 128 ? 3 : 4);
-  pl->smem = 0;
-  pl->grid = dim3((unsigned)d->grid_m, (unsigned)d->grid_n, (unsigned)d->grid_z);
-  AVDN_REQUIRE(d->grid_m >= 1 && d->grid_n >= 1 && d->grid_z >= 1 && d->grid_n <= 65535 && d->grid_z <= 65535,
-               "avdn_gemm_plan: bad grid %d x %d x %d", d->grid_m, d->grid_n, d->grid_z);
+  pl->kp.c.tx_bytes = (uint32_t)(a_bytes * d->ctas + b_bytes);
+  pl->kp.grid_m = d->grid_m;
+  pl->kp.grid_n = d->grid_n;
+  pl->kp.grid_z = d->grid_z;
+  AVDN_REQUIRE(d->grid_m >= 1 && d->grid_n >= 1 && d->grid_z >= 1, "avdn_gemm_plan: bad tile space %d x %d x %d",
+               d->grid_m, d->grid_n, d->grid_z);
+  pl->kp.rows_in_box = BM;
+  if (c.mode == AVDN_GEMM_CONV) {
+    pl->kp.rows_in_box = c.box_w * c.box_h * c.box_n;
+    AVDN_REQUIRE(pl->kp.rows_in_box >= 1 && pl->kp.rows_in_box <= BM, "avdn_gemm_plan: conv box of %d rows", pl->kp.rows_in_box);
+  }
+  // ---- output tensor map: the TMA epilogue is used whenever the output can be described ----
+  pl->kp.out_tma = 0;
+  if (!c.relu_mask) {
+    const int eb = (c.out_dtype == AVDN_DT_BF16) ? 2 : 4;
+    const int slab_cols = 128 / eb;
+    int64_t dim[4], str[4];
+    int32_t box[4];
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(c.out);
+    bool ok = true;
+    if (c.mode == AVDN_GEMM_CONV) {
+      // out pixel (n, h*sh+oh, w*sw+ow), channel-contiguous rows of pitch ldc
+      base += ((int64_t)c.out_oh * c.out_W + c.out_ow) * c.ldc * eb;
+      dim[0] = c.N; dim[1] = c.valid_w; dim[2] = c.valid_h; dim[3] = c.valid_n;
+      str[0] = 1; str[1] = (int64_t)c.out_sw * c.ldc; str[2] = (int64_t)c.out_sh * c.out_W * c.ldc;
+      str[3] = (int64_t)c.out_H * c.out_W * c.ldc;
+      box[0] = slab_cols; box[1] = c.box_w; box[2] = c.box_h; box[3] = c.box_n;
+    } else if (c.mode == AVDN_GEMM_WGRAD) {
+      dim[0] = c.ldc; dim[1] = c.M; dim[2] = 1; dim[3] = 1;
+      str[0] = 1; str[1] = c.ldc; str[2] = (int64_t)c.ldc * c.M; str[3] = str[2];
+      box[0] = slab_cols; box[1] = BM; box[2] = 1; box[3] = 1;
+      // a tap's columns [bk, bk+N) must not spill into the next tap: N must fill whole slabs
+      ok = (c.N % slab_cols) == 0;
+    } else {
+      dim[0] = c.N; dim[1] = c.M; dim[2] = c.batch0; dim[3] = c.batch1;
+      str[0] = 1; str[1] = c.ldc;
+      str[2] = c.out_bs0 ? c.out_bs0 : (int64_t)c.ldc * c.M;
+      str[3] = c.out_bs1 ? c.out_bs1 : str[2] * c.batch0;
+      box[0] = slab_cols; box[1] = BM; box[2] = 1; box[3] = 1;
+    }
+    if (ok && encode_map(base, eb, dim, str, box, nullptr, true) == AVDN_OK) {
+      int r = encode_map(base, eb, dim, str, box, &pl->kp.tmC);
+      if (r) return r;
+      pl->kp.out_tma = 1;
+    }
+  }
+  AVDN_REQUIRE(!c.stats || pl->kp.out_tma, "avdn_gemm_plan: fused statistics need the TMA epilogue");
+  AVDN_REQUIRE(pl->kp.out_tma || c.mode != AVDN_GEMM_CONV, "avdn_gemm_plan: conv output cannot be described to TMA");
+  // ---- launch geometry: persistent, one CTA (pair) per SM ----
+  pl->stages = 0;
+  const long long pm = (d->grid_m + d->ctas - 1) / d->ctas;
+  const long long tiles = pm * d->grid_n * d->grid_z;
+  const long long slots = avdn::sm_count() / d->ctas;
+  pl->grid = (int)((tiles < slots ? tiles : slots) * d->ctas);
   pl->magic = PLAN_MAGIC;
   return AVDN_OK;
 }
@@ -490,10 +823,21 @@ extern "C" int avdn_gemm_run(const void* plan_host, avdn_stream_t stream) {
   const Plan* pl = reinterpret_cast<const Plan*>(plan_host);
   AVDN_REQUIRE(pl && pl->magic == PLAN_MAGIC, "avdn_gemm_run: not a plan");
   cudaStream_t s = avdn::to_cuda(stream);
-  switch (pl->bn) {
-    case 64: return launch_bn<64, 4>(*pl, s);
-    case 128: return launch_bn<128, 3>(*pl, s);
-    case 256: return launch_bn<256, 4>(*pl, s);
+  if (pl->kp.c.stats) {
+    if (cudaMemsetAsync(pl->kp.c.stats, 0, sizeof(double) * 2 * pl->kp.c.N, s) != cudaSuccess)
+      return avdn::check_launch("gemm stats memset");
   }
-  return avdn::set_err(AVDN_ERR_UNSUPPORTED, "avdn_gemm_run: bn %d", pl->bn);
+  if (pl->ctas == 2) {
+    switch (pl->bn) {
+      case 128: return launch_bn<128, 6, 2>(*pl, s);
+      case 256: return launch_bn<256, 5, 2>(*pl, s);
+    }
+  } else {
+    switch (pl->bn) {
+      case 64: return launch_bn<64, 6, 1>(*pl, s);
+      case 128: return launch_bn<128, 5, 1>(*pl, s);
+      case 256: return launch_bn<256, 3, 1>(*pl, s);
+    }
+  }
+  return avdn::set_err(AVDN_ERR_UNSUPPORTED, "avdn_gemm_run: bn %d ctas %d", pl->bn, pl->ctas);
 }

@@ -8,6 +8,7 @@ shape) and re-run every step; nothing here touches the data.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -38,18 +39,30 @@ class GemmCore(C.Structure):
                 ("out_dtype", i32), ("accumulate", i32), ("relu", i32), ("alpha", f32),
                 ("tx_bytes", u32), ("pad_", i32),
                 ("ldc", i64), ("out_bs0", i64), ("out_bs1", i64),
-                ("out", C.c_void_p), ("bias", C.c_void_p), ("relu_mask", C.c_void_p)]
+                ("out", C.c_void_p), ("bias", C.c_void_p), ("relu_mask", C.c_void_p), ("stats", C.c_void_p)]
 
 
 class GemmDesc(C.Structure):
     _fields_ = [("core", GemmCore), ("bn", i32), ("a_mn", i32), ("b_mn", i32), ("n_a", i32), ("n_b", i32),
-                ("grid_m", i32), ("grid_n", i32), ("grid_z", i32), ("a", Operand * 4), ("b", Operand * 4)]
+                ("grid_m", i32), ("grid_n", i32), ("grid_z", i32), ("ctas", i32),
+                ("a", Operand * 4), ("b", Operand * 4)]
 
 
 
 
 def _cdiv(a, b):
     return (a + b - 1) // b
+
+
+# CTA pairs (tcgen05 cta_group::2) wherever the tile shape allows it; AVDN_GEMM_CTAS=1 forces
+# single-CTA tiles (A/B comparison in the benchmarks).
+PAIR_DEFAULT = int(os.environ.get("AVDN_GEMM_CTAS", "2"))
+
+
+def pick_ctas(bn, grid_m, ctas=None):
+    if ctas is None:
+        ctas = PAIR_DEFAULT
+    return 2 if (ctas == 2 and bn >= 128 and grid_m >= 2) else 1
 
 
 def operand(ptr, dims, strides, box):
@@ -97,7 +110,7 @@ def pick_bn(N):
 
 def plan_plain(*, M, N, K, a_ptr, lda, a_mn, b_ptr, ldb, b_mn, out, ldc, bias=None, relu=False, alpha=1.0,
                accumulate=0, batch0=1, batch1=1, a_bs=(0, 0), b_bs=None, out_bs=(0, 0), split_k=1, bn=None,
-               relu_mask=None, out_ptr=None, keep=(), tag="gemm_plain"):
+               relu_mask=None, out_ptr=None, keep=(), tag="gemm_plain", ctas=None):
     """D[M,N] = alpha * A.B^T (+bias)(relu).  Operands are bf16.
 
     K-major operand: stored ``[rows][K]`` with row pitch ``ld``; MN-major operand:
@@ -132,6 +145,7 @@ def plan_plain(*, M, N, K, a_ptr, lda, a_mn, b_ptr, ldb, b_mn, out, ldc, bias=No
     else:
         d.b[0] = operand(b_ptr, (K, N, nb0, nb1), (1, ldb, safe(bb[0], fb), safe(bb[1], fb)), (64, bn, 1, 1))
     d.grid_m, d.grid_n, d.grid_z = _cdiv(M, 128), _cdiv(N, bn), batch0 * batch1 * split_k
+    d.ctas = pick_ctas(bn, d.grid_m, ctas)
     return GemmPlan(d, keep=keep + (out, bias, relu_mask), flops=2 * M * N * K * batch0 * batch1, tag=tag)
 
 
@@ -233,7 +247,7 @@ def _x_views(x, Cin, W, H, N, stride, box):
     return views
 
 
-def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=None):
+def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=None, stats=None, ctas=None):
     """z[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) ; ``w_f`` is ``[Cout, k*k*Cin]`` bf16
     (tap-major, channel-minor).  Channels are multiples of 64."""
     assert Cin % 64 == 0 and Cout % 64 == 0
@@ -263,11 +277,15 @@ def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=No
     Kt = k * k * Cin
     d.b[0] = operand(w_f.data_ptr(), (Kt, Cout, 1, 1), (1, Kt, Kt * Cout, Kt * Cout), (64, bn, 1, 1))
     d.grid_m, d.grid_n, d.grid_z = c.tiles_w * c.tiles_h * c.tiles_n, _cdiv(Cout, bn), 1
-    return GemmPlan(d, keep=(x, w_f, z), flops=flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin,
+    d.ctas = pick_ctas(bn, d.grid_m, ctas)
+    if stats is not None:        # fused BatchNorm statistics: f64 [2, Cout]
+        assert stats.dtype == torch.float64 and stats.numel() >= 2 * Cout
+        c.stats = stats.data_ptr()
+    return GemmPlan(d, keep=(x, w_f, z, stats), flops=flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin,
                     tag="gemm_conv_fwd")
 
 
-def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0, bn=None, flops=None):
+def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0, bn=None, flops=None, ctas=None):
     """dx[N,H,W,Cin] (+)= conv_transpose(dz[N,Ho,Wo,Cout], w); ``w_d`` is
     ``[Cin, k*k*Cout]`` bf16 (tap-major, out-channel-minor).  Returns a list of plans
     (4 output-parity plans for stride 2)."""
@@ -308,12 +326,14 @@ def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0,
         d.a[0] = _act_operand(dz.data_ptr(), Cout, Wo, Ho, N, (64, bw, bh, bnn))
         d.b[0] = operand(w_d.data_ptr(), (Kt, Cin, 1, 1), (1, Kt, Kt * Cin, Kt * Cin), (64, bn, 1, 1))
         d.grid_m, d.grid_n, d.grid_z = c.tiles_w * c.tiles_h * c.tiles_n, _cdiv(Cin, bn), 1
+        d.ctas = pick_ctas(bn, d.grid_m, ctas)
         fl = flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin
         plans.append(GemmPlan(d, keep=(dz, w_d, dx), flops=fl // len(parities), tag="gemm_conv_dgrad"))
     return plans
 
 
-def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, bn=None, sms=148, flops=None):
+def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, bn=None, sms=148, flops=None,
+                    ctas=None):
     """dw[Cout, k*k*Cin] (fp32, atomically accumulated -- zero it first) +=
     sum_pixels dz[pix, co] * x[pix + tap, ci]."""
     assert Cin % 64 == 0 and Cout % 64 == 0 and dw.dtype == torch.float32
@@ -342,5 +362,6 @@ def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, b
     for i, v in enumerate(views):
         d.b[i] = v
     d.grid_m, d.grid_n, d.grid_z = gm, gn, len(taps) * split_k
+    d.ctas = pick_ctas(bn, gm, ctas)
     return GemmPlan(d, keep=(dz, x, dw), flops=flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin,
                     tag="gemm_conv_wgrad")

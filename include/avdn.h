@@ -113,7 +113,10 @@ int avdn_render_views(const avdn_tile_desc* tiles, int n_tiles,
  *   ET heads / fc2                   src/models/ET_haa.py:98-119,144-167
  * A plan is a caller-owned HOST blob (avdn_gemm_plan_bytes() bytes) holding the
  * encoded TMA descriptors and launch geometry for fixed device pointers; it can
- * be re-run any number of times (and captured in a CUDA graph).
+ * be re-run any number of times (and captured in a CUDA graph).  The kernel is
+ * persistent (one CTA or CTA pair per SM walks the tile space); outputs leave
+ * through TMA stores (reduce-adds for the accumulating modes: `out += ` on a
+ * bf16 tensor adds the bf16-rounded tile in bf16).
  * ---------------------------------------------------------------------- */
 enum { AVDN_GEMM_PLAIN = 0, AVDN_GEMM_CONV = 1, AVDN_GEMM_WGRAD = 2 };
 enum { AVDN_DT_BF16 = 0, AVDN_DT_F32 = 1 };
@@ -146,7 +149,7 @@ typedef struct avdn_gemm_core {
   int32_t valid_w, valid_h, valid_n;   /* CONV: extent of valid output coords */
   int32_t out_H, out_W, out_sh, out_sw, out_oh, out_ow; /* CONV: out pixel (n, h*sh+oh, w*sw+ow) */
   int32_t out_dtype;          /* AVDN_DT_* */
-  int32_t accumulate;         /* 0 store, 1 out += (read-modify-write), 2 atomicAdd (fp32) */
+  int32_t accumulate;         /* 0 store, 1 out += (bf16 / fp32 reduce-add), 2 fp32 reduce-add with split-K */
   int32_t relu;
   float alpha;
   uint32_t tx_bytes;          /* filled by avdn_gemm_plan */
@@ -156,6 +159,9 @@ typedef struct avdn_gemm_core {
   const float* bias;          /* [N] fp32 or NULL */
   const void* relu_mask;      /* bf16, addressed like `out`: result is zeroed where mask <= 0
                                  (backward of the ReLU whose forward output is `relu_mask`) */
+  double* stats;              /* NULL, or [2][N] f64: fused BatchNorm statistics -- per output column the
+                                 sum and the sum of squares of the (bf16-rounded) outputs; zeroed by
+                                 avdn_gemm_run before the launch (bf16 store epilogue only) */
 } avdn_gemm_core;
 
 typedef struct avdn_gemm_desc {
@@ -163,7 +169,9 @@ typedef struct avdn_gemm_desc {
   int32_t bn;                 /* N tile: 64, 128 or 256 */
   int32_t a_mn, b_mn;         /* 0 = K-major operand, 1 = MN-major operand */
   int32_t n_a, n_b;           /* number of A / B views (parity views of stride-2 convs) */
-  int32_t grid_m, grid_n, grid_z;
+  int32_t grid_m, grid_n, grid_z;  /* tile space: 128-row tiles x bn-column tiles x (batch | taps*split_k) */
+  int32_t ctas;               /* 1, or 2 = CTA pairs (tcgen05 cta_group::2): a pair computes 256 x bn and
+                                 each CTA loads half of B; needs bn >= 128 */
   avdn_operand a[4];
   avdn_operand b[4];
 } avdn_gemm_desc;
