@@ -33,10 +33,12 @@ _SIGNATURES = {
     # struct pointers are passed with ctypes.byref(...)
     "avdn_gemm_plan": [c_void_p, c_void_p, C.c_size_t],
     "avdn_gemm_run": [c_void_p, c_void_p],
-    "avdn_conv0_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "avdn_conv0_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "avdn_conv0_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "avdn_bn_stats": [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_f32,
                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "avdn_bn_finalize": [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_f32,
+                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "avdn_bn_eval_coeffs": [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_void_p, c_void_p,
                             c_void_p],
     "avdn_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_f32, c_void_p],

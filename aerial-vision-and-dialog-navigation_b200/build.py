@@ -29,6 +29,7 @@ SOURCES = {
     "render.cu": ["-fmad=false"],
     "gemm.cu": [],
     "trunk.cu": [],
+    "conv0.cu": [],
     "encoder.cu": [],
     "agent.cu": [],
 }

@@ -252,10 +252,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     const long long r = t / p.grid_n;
     T.mt = (int)(r % pm) * CTAS + (int)rank;
     int z = (int)(r / pm);
-    const int split = z % c.split_k;  z /= c.split_k;
+    int split;
     T.z0 = T.z1 = T.tap = 0;
-    if (c.mode == AVDN_GEMM_WGRAD) T.tap = z;
-    else { T.z0 = z % c.batch0; T.z1 = z / c.batch0; }
+    if (c.mode == AVDN_GEMM_WGRAD) {
+      // taps fastest: the CTAs running side by side sweep the SAME pixel range for all filter
+      // taps, so dZ and X are fetched from HBM once and re-read from L2 by the other taps
+      T.tap = z % c.n_taps;
+      split = z / c.n_taps;
+    } else {
+      split = z % c.split_k;  z /= c.split_k;
+      T.z0 = z % c.batch0; T.z1 = z / c.batch0;
+    }
     T.kb_begin = split * kb_per;
     const int kb_end = min(c.num_kb, T.kb_begin + kb_per);
     T.my_kb = max(0, kb_end - T.kb_begin);

@@ -1,8 +1,7 @@
 // Stage 2 of the AVDN hot path: the xview-yolov3 Darknet trunk
 // (src/models/dark_net.py:7-64,212-240) around the tensor-core convolutions.
 //
-// CUDA-core kernels that are HBM-bound by nature: the 3->32 first convolution
-// (K = 27, too thin for a tensor-core tile), train-mode BatchNorm statistics and
+// CUDA-core kernels that are HBM-bound by nature: train-mode BatchNorm statistics and
 // application fused with LeakyReLU(0.01) and the shortcut add, their backward
 // counterparts, and the weight (un)packing between the reference's
 // [Cout,Cin,kh,kw] fp32 parameters and the bf16 GEMM operand layouts.
@@ -13,9 +12,6 @@
 #include "common.cuh"
 
 namespace {
-
-constexpr int C0_OUT = 32;     // first conv: 3 -> 32 channels
-constexpr int C0_PAD = 64;     // stored padded to 64
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -34,98 +30,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     w[i] = *reinterpret_cast<const uint32_t*>(&b);
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// ------------------------------------------------------------- conv0 forward
-// x: [N,H,W,4] bf16 (R,G,B,0); w: [32][3][3][3] fp32 (co, ci, kh, kw); z: [N,H,W,64] bf16.
-// One thread per output pixel; the 27-value patch sits in registers, weights in smem.
-__global__ void __launch_bounds__(256) conv0_fwd_kernel(const uint2* __restrict__ x, const float* __restrict__ w,
-                                                        uint4* __restrict__ z, int N, int H, int W) {
-  __shared__ float sw[27 * C0_OUT];          // [tap*3+ci][co]
-  for (int i = threadIdx.x; i < 27 * C0_OUT; i += blockDim.x) {
-    const int co = i % C0_OUT, r = i / C0_OUT, ci = r % 3, tap = r / 3;
-    sw[i] = w[(co * 3 + ci) * 9 + tap];
-  }
-  __syncthreads();
-  const long long total = (long long)N * H * W;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
-       p += (long long)gridDim.x * blockDim.x) {
-    const int wx = (int)(p % W), hy = (int)((p / W) % H);
-    const long long nbase = (p / ((long long)W * H)) * (long long)W * H;
-    float patch[27];
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int yy = hy + kh - 1, xx = wx + kw - 1;
-        float r = 0.f, g = 0.f, b = 0.f;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          const uint2 v = __ldg(x + nbase + (long long)yy * W + xx);
-          const __nv_bfloat162 rg = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
-          const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
-          r = __low2float(rg); g = __high2float(rg); b = __low2float(b0);
-        }
-        patch[(kh * 3 + kw) * 3 + 0] = r;
-        patch[(kh * 3 + kw) * 3 + 1] = g;
-        patch[(kh * 3 + kw) * 3 + 2] = b;
-      }
-    uint4* o = z + p * (C0_PAD / 8);
-#pragma unroll
-    for (int g8 = 0; g8 < C0_OUT / 8; ++g8) {
-      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-      for (int t = 0; t < 27; ++t) {
-        const float xv = patch[t];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, sw[t * C0_OUT + g8 * 8 + j], acc[j]);
-      }
-      o[g8] = pack8(acc);
-    }
-#pragma unroll
-    for (int g8 = C0_OUT / 8; g8 < C0_PAD / 8; ++g8) o[g8] = make_uint4(0, 0, 0, 0);
-  }
-}
-
-// --------------------------------------------------------------- conv0 wgrad
-// dw[co][ci][kh][kw] += sum_p dz[p][co] * x[p + tap][ci].  Block = 8 warps; each
-// warp streams pixels, lane = co, 27 accumulators per lane; block-reduce at the end.
-__global__ void __launch_bounds__(256) conv0_wgrad_kernel(const __nv_bfloat16* __restrict__ dz,
-                                                          const uint2* __restrict__ x, float* __restrict__ dw,
-                                                          int N, int H, int W) {
-  __shared__ float red[27 * C0_OUT];
-  for (int i = threadIdx.x; i < 27 * C0_OUT; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long total = (long long)N * H * W;
-  float acc[27];
-#pragma unroll
-  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
-  for (long long p = (long long)blockIdx.x * 8 + warp; p < total; p += (long long)gridDim.x * 8) {
-    const int wx = (int)(p % W), hy = (int)((p / W) % H);
-    const long long nbase = (p / ((long long)W * H)) * (long long)W * H;
-    const float g = __bfloat162float(dz[p * C0_PAD + lane]);
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int yy = hy + kh - 1, xx = wx + kw - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {      // warp-uniform
-          const uint2 v = __ldg(x + nbase + (long long)yy * W + xx);
-          const __nv_bfloat162 rg = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
-          const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
-          acc[(kh * 3 + kw) * 3 + 0] = fmaf(g, __low2float(rg), acc[(kh * 3 + kw) * 3 + 0]);
-          acc[(kh * 3 + kw) * 3 + 1] = fmaf(g, __high2float(rg), acc[(kh * 3 + kw) * 3 + 1]);
-          acc[(kh * 3 + kw) * 3 + 2] = fmaf(g, __low2float(b0), acc[(kh * 3 + kw) * 3 + 2]);
-        }
-      }
-  }
-#pragma unroll
-  for (int t = 0; t < 27; ++t) atomicAdd(&red[t * C0_OUT + lane], acc[t]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 27 * C0_OUT; i += blockDim.x) {
-    const int co = i % C0_OUT, r = i / C0_OUT, ci = r % 3, tap = r / 3;
-    atomicAdd(&dw[(co * 3 + ci) * 9 + tap], red[i]);
-  }
 }
 
 // ------------------------------------------------------------ BN statistics
@@ -413,24 +317,6 @@ inline int grid_for(long long n, int block = 256, int waves = 8) {
 }  // namespace
 
 // ===================================================================== C ABI
-extern "C" int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W,
-                              avdn_stream_t stream) {
-  AVDN_REQUIRE(x_nhwc4 && w && z && N > 0 && H > 0 && W > 0, "avdn_conv0_fwd: bad argument");
-  const long long total = (long long)N * H * W;
-  conv0_fwd_kernel<<<grid_for(total, 256, 16), 256, 0, avdn::to_cuda(stream)>>>(
-      reinterpret_cast<const uint2*>(x_nhwc4), w, reinterpret_cast<uint4*>(z), N, H, W);
-  return avdn::check_launch("avdn_conv0_fwd");
-}
-
-extern "C" int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int H, int W,
-                                avdn_stream_t stream) {
-  AVDN_REQUIRE(dz && x_nhwc4 && dw && N > 0 && H > 0 && W > 0, "avdn_conv0_wgrad: bad argument");
-  const int blocks = avdn::sm_count() * 8;
-  conv0_wgrad_kernel<<<blocks, 256, 0, avdn::to_cuda(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(dz),
-                                                               reinterpret_cast<const uint2*>(x_nhwc4), dw, N, H, W);
-  return avdn::check_launch("avdn_conv0_wgrad");
-}
-
 // grid of BN_THREADS-wide blocks whose total thread count is a multiple of C/8 (so that every
 // thread keeps its channel group) and that fills the machine without exceeding the work
 static int bn_grid(long long n8, int waves) {
@@ -469,6 +355,17 @@ extern "C" int avdn_bn_stats(const void* z, long long R, int C, int C_real, cons
   if (r) return r;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, C_real, gamma, beta, running_mean, running_var,
                                                      momentum, eps, scale, shift, mean, rstd);
+  return avdn::check_launch("bn_finalize_kernel");
+}
+
+extern "C" int avdn_bn_finalize(const double* sums, long long R, int C, int C_real, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum,
+                                float eps, float* scale, float* shift, float* mean, float* rstd,
+                                avdn_stream_t stream) {
+  AVDN_REQUIRE(sums && gamma && beta && scale && shift && mean && rstd && R > 0, "avdn_bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, avdn::to_cuda(stream)>>>(sums, R, C, C_real, gamma, beta, running_mean,
+                                                                         running_var, momentum, eps, scale, shift,
+                                                                         mean, rstd);
   return avdn::check_launch("bn_finalize_kernel");
 }
 

@@ -171,8 +171,11 @@ class _Engine:
             for L in self.layers:
                 if L.first:
                     continue
+                # two plans: train mode accumulates the BatchNorm batch statistics in the epilogue
                 L.p_fwd = G.plan_conv_fwd(L.src.a, L.wf, L.z, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
                                           Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
+                L.p_fwd_stats = G.plan_conv_fwd(L.src.a, L.wf, L.z, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
+                                                Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops, stats=L.sums)
             self._fwd_plans = True
 
     def build_bwd(self, net=None):
@@ -227,18 +230,19 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None):
         conv = net.module_list[L.idx][0]
         bn = net.module_list[L.idx][1]
         if L.first:
-            call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win)
-            n += 1
+            call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win,
+                 ptr(L.sums) if train else None)
+            n += 2 if train else 1
         else:
             call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
                  ptr(L.wd))
-            L.p_fwd.run()
+            (L.p_fwd_stats if train else L.p_fwd).run()
             n += 2
         if train:
-            call("avdn_bn_stats", ptr(L.z), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
-                 ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.sums), ptr(L.scale),
+            call("avdn_bn_finalize", ptr(L.sums), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
+                 ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.scale),
                  ptr(L.shift), ptr(L.mean), ptr(L.rstd))
-            n += 3
+            n += 1 if L.first else 2    # finalize (+ the stats memset inside avdn_gemm_run)
         else:
             call("avdn_bn_eval_coeffs", L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
                  ptr(bn.running_var), BN_EPS, ptr(L.scale), ptr(L.shift))

@@ -186,9 +186,13 @@ int avdn_gemm_run(const void* plan_host, avdn_stream_t stream);
  * ---------------------------------------------------------------------- */
 
 /* First convolution 3->32, 3x3, pad 1 (module_list.0.conv_0; K = 27 is too thin
- * for a tensor-core tile).  x [N,H,W,4] bf16 (R,G,B,0: avdn_render_views'
- * norm_nhwc), w [32,3,3,3] fp32 (nn.Conv2d layout), z [N,H,W,64] bf16 (ch 32..63 = 0). */
-int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W, avdn_stream_t stream);
+ * for a tcgen05 tile: warp-level mma.sync).  x [N,H,W,4] bf16 (R,G,B,0:
+ * avdn_render_views' norm_nhwc), w [32,3,3,3] fp32 (nn.Conv2d layout, rounded to
+ * bf16 for the tensor cores), z [N,H,W,64] bf16 (ch 32..63 = 0).  stats: NULL or
+ * [2,64] f64 receiving the BatchNorm batch statistics of z (sum, sum of squares;
+ * zeroed by the call), to be finished by avdn_bn_finalize.  W % 16 == H % 4 == 0. */
+int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W, double* stats,
+                   avdn_stream_t stream);
 /* dw [32,3,3,3] fp32 += sum_pixels dz * x (weight gradient of the same layer). */
 int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int H, int W, avdn_stream_t stream);
 
@@ -201,6 +205,11 @@ int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int 
 int avdn_bn_stats(const void* z, long long R, int C, int C_real, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, double* sums,
                   float* scale, float* shift, float* mean, float* rstd, avdn_stream_t stream);
+/* The second half of avdn_bn_stats alone: sums [2,C] f64 (sum, sum of squares over R rows) were
+ * produced by the convolution's epilogue (avdn_gemm_core.stats).                              */
+int avdn_bn_finalize(const double* sums, long long R, int C, int C_real, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                     float* shift, float* mean, float* rstd, avdn_stream_t stream);
 /* eval mode: the same affine from the running statistics. */
 int avdn_bn_eval_coeffs(int C, int C_real, const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float* scale, float* shift, avdn_stream_t stream);

@@ -170,9 +170,9 @@ def darknet_forward(x, sd, cfg_text, train=True, update_running=False, eps=1e-5,
 
     ``storage=None``   the reference arithmetic, float32 end to end.
     ``storage="bf16"`` the SAME arithmetic (float32 products and sums) with every tensor the
-    bf16 pipeline stores -- the input image, conv weights (except the 3->32 first conv, which
-    the product evaluates from the fp32 master), conv outputs, block outputs, and the matching
-    gradients -- rounded to bf16 at the point of storage.  This is what "the reference PyTorch
+    bf16 pipeline stores -- the input image, the conv weights (bf16 copies of the fp32 masters),
+    conv outputs, block outputs, and the matching gradients -- rounded to bf16 at the point of
+    storage.  This is what "the reference PyTorch
     path in bf16" computes; the random-init 57-block trunk amplifies a perturbation ~100x
     (conditioning), so bf16 parity is checked against this mode and the distance of
     both from the float32 mode is reported beside it."""
@@ -183,13 +183,9 @@ def darknet_forward(x, sd, cfg_text, train=True, update_running=False, eps=1e-5,
     defs = parse_cfg_text(cfg_text)[1:]
     outs = []
     x = q(x)
-    n_conv = 0
     for i, d in enumerate(defs):
         if d["type"] == "convolutional":
-            w = sd[f"module_list.{i}.conv_{i}.weight"]
-            if n_conv > 0:
-                w = qw(w)
-            n_conv += 1
+            w = qw(sd[f"module_list.{i}.conv_{i}.weight"])
             k = int(d["size"])
             pad = (k - 1) // 2 if int(d["pad"]) else 0
             x = q(F.conv2d(x, w, None, stride=int(d["stride"]), padding=pad))
