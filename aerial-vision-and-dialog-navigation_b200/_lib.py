@@ -62,6 +62,14 @@ _SIGNATURES = {
     "avdn_colsum": [c_void_p, c_int, c_i64, c_int, c_i64, c_void_p, c_void_p],
     "avdn_heads_fwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 + [c_void_p],
     "avdn_heads_bwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 18 + [c_void_p],
+    # ---- config 5: ViT_LSTM step + simulator update
+    "avdn_linear_f32": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int,
+                        c_void_p],
+    "avdn_lstm_cell": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_int, c_int, c_void_p],
+    "avdn_direction_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "avdn_lang_attn_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_i64, c_void_p],
+    "avdn_waypoint_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_f32, c_int, c_void_p, c_void_p,
+                           c_void_p, c_void_p],
     # ---- agent slice
     "avdn_loss": [c_void_p] * 7 + [c_int, c_f32, c_int, c_f64] + [c_void_p] * 4 + [c_void_p],
     "avdn_upsample_saliency": [c_void_p, c_int, c_void_p, c_void_p],

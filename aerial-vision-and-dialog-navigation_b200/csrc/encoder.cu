@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256) frame_attn_fwd_kernel(
     e49_out[(size_t)bt * NSP + tid] = a;
   }
   __syncthreads();
+  if (fc2_w == nullptr) return;          // SoftDotAttention only (ViT_LSTM)
   for (int o = tid; o < E; o += 256) {
     float a = fc2_b[o];
     for (int j = 0; j < NSP; ++j) a = fmaf(fc2_w[o * NSP + j], s_e[j], a);
@@ -561,8 +562,8 @@ inline int rows_grid(long long rows) { return (int)((rows + 7) / 8); }
 extern "C" int avdn_frame_attn_fwd(const float* frames, const float* lang_cls, const float* w_in,
                                    const float* w_out, const float* fc2_w, const float* fc2_b, int B, int T,
                                    float* attn, float* wc, float* e49, float* emb, avdn_stream_t stream) {
-  AVDN_REQUIRE(frames && lang_cls && w_in && w_out && fc2_w && fc2_b && attn && wc && e49 && emb,
-               "avdn_frame_attn_fwd: null pointer");
+  AVDN_REQUIRE(frames && lang_cls && w_in && w_out && attn && wc && e49, "avdn_frame_attn_fwd: null pointer");
+  AVDN_REQUIRE(!fc2_w || (fc2_b && emb), "avdn_frame_attn_fwd: fc2 needs its bias and the emb output");
   if (B * T == 0) return AVDN_OK;
   frame_attn_fwd_kernel<<<B * T, 256, 0, avdn::to_cuda(stream)>>>(frames, lang_cls, w_in, w_out, fc2_w, fc2_b, T,
                                                                 attn, wc, e49, emb);

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
 // ------------------------------------------------------------------ lstm_cell
 // gates [B,4H] = W_ih x + b_ih + W_hh h + b_hh (order i,f,g,o); c_prev may be NULL (zero state).
 __global__ void lstm_cell_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
-                                 float* __restrict__ h_out, float* __restrict__ c_out, int B, int H) {
+                                 float* __restrict__ h_out, long long ldh, float* __restrict__ c_out, int B, int H) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int b = i / H, j = i - b * H;
@@ -91,7 +91,17 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gates, const float* _
   const float og = 1.f / (1.f + expf(-g[3 * H + j]));
   const float c = fg * (c_prev ? c_prev[i] : 0.f) + ig * gg;
   c_out[i] = c;
-  h_out[i] = og * tanhf(c);
+  h_out[(size_t)b * ldh + j] = og * tanhf(c);
+}
+
+// direction_embedding([sin, cos](d / 180 * 3.14159)) (vln_model.py:228-229), float32 as torch evaluates it
+__global__ void direction_embed_kernel(const float* __restrict__ deg, const float* __restrict__ w,
+                                       const float* __restrict__ b, float* __restrict__ out, int B, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int s = i / N, n = i - s * N;
+  const float a = __fmul_rn(__fdiv_rn(deg[s], 180.f), 3.14159f);
+  out[i] = __fadd_rn(__fadd_rn(__fmul_rn(w[n * 2], sinf(a)), __fmul_rn(w[n * 2 + 1], cosf(a))), b[n]);
 }
 
 // ------------------------------------------------------------------ lang_attn
@@ -99,7 +109,7 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gates, const float* _
 //   scores_l = ctx[b,l,:] . target[b,:] ; attn = softmax_l ; weighted = sum_l attn_l ctx[b,l,:]
 __global__ void __launch_bounds__(256) lang_attn_kernel(const float* __restrict__ ctx, const float* __restrict__ target,
                                                         int L, int D, float* __restrict__ attn_out,
-                                                        float* __restrict__ weighted) {
+                                                        float* __restrict__ weighted, long long ldw) {
   extern __shared__ float sm[];            // [D] target, [L] scores
   float* s_t = sm;
   float* s_s = sm + D;
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(256) lang_attn_kernel(const float* __restrict_
   for (int d = tid; d < D; d += 256) {
     float a = 0.f;
     for (int l = 0; l < L; ++l) a = fmaf(s_s[l], c[(size_t)l * D + d], a);
-    weighted[(size_t)b * D + d] = a;
+    weighted[(size_t)b * ldw + d] = a;
   }
 }
 
@@ -260,19 +270,26 @@ extern "C" int avdn_linear_f32(const float* x, long long ldx, const float* w, lo
   return avdn::check_launch("avdn_linear_f32");
 }
 
-extern "C" int avdn_lstm_cell(const float* gates, const float* c_prev, float* h_out, float* c_out, int B, int H,
-                              avdn_stream_t stream) {
-  AVDN_REQUIRE(gates && h_out && c_out && B > 0 && H > 0, "avdn_lstm_cell: bad argument");
-  lstm_cell_kernel<<<(B * H + 255) / 256, 256, 0, avdn::to_cuda(stream)>>>(gates, c_prev, h_out, c_out, B, H);
+extern "C" int avdn_lstm_cell(const float* gates, const float* c_prev, float* h_out, long long ldh, float* c_out,
+                              int B, int H, avdn_stream_t stream) {
+  AVDN_REQUIRE(gates && h_out && c_out && B > 0 && H > 0 && ldh >= H, "avdn_lstm_cell: bad argument");
+  lstm_cell_kernel<<<(B * H + 255) / 256, 256, 0, avdn::to_cuda(stream)>>>(gates, c_prev, h_out, ldh, c_out, B, H);
   return avdn::check_launch("avdn_lstm_cell");
 }
 
+extern "C" int avdn_direction_embed(const float* deg, const float* w, const float* b, float* out, int B, int N,
+                                    avdn_stream_t stream) {
+  AVDN_REQUIRE(deg && w && b && out && B > 0 && N > 0, "avdn_direction_embed: bad argument");
+  direction_embed_kernel<<<(B * N + 127) / 128, 128, 0, avdn::to_cuda(stream)>>>(deg, w, b, out, B, N);
+  return avdn::check_launch("avdn_direction_embed");
+}
+
 extern "C" int avdn_lang_attn_fwd(const float* ctx, const float* target, int B, int L, int D, float* attn,
-                                  float* weighted, avdn_stream_t stream) {
-  AVDN_REQUIRE(ctx && target && weighted && B > 0 && L > 0 && D > 0, "avdn_lang_attn_fwd: bad argument");
+                                  float* weighted, long long ldw, avdn_stream_t stream) {
+  AVDN_REQUIRE(ctx && target && weighted && B > 0 && L > 0 && D > 0 && ldw >= D, "avdn_lang_attn_fwd: bad argument");
   const size_t smem = (size_t)(D + L) * sizeof(float);
   AVDN_REQUIRE(smem <= 48 * 1024, "avdn_lang_attn_fwd: D + L = %d too large", D + L);
-  lang_attn_kernel<<<B, 256, smem, avdn::to_cuda(stream)>>>(ctx, target, L, D, attn, weighted);
+  lang_attn_kernel<<<B, 256, smem, avdn::to_cuda(stream)>>>(ctx, target, L, D, attn, weighted, ldw);
   return avdn::check_launch("avdn_lang_attn_fwd");
 }
 

@@ -220,12 +220,17 @@ class _Engine:
         self._bwd_plans = True
 
 
-def _trunk_forward(net, eng, x_nhwc4, train, out=None):
-    """Forward of every block on libavdn kernels.  Returns ``[N, C_last, h, w]`` fp32."""
+def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
+    """Forward of every block on libavdn kernels.  Returns ``[N, C_last, h, w]`` fp32.
+    ``frozen`` (eval mode only): the parameters and running statistics have not changed since
+    the previous call on this engine, so the bf16 weight operands and the BN affine
+    coefficients are reused (the rollout of config 5 runs 20 trunk passes on fixed weights)."""
     call = _lib.call
     ptr = _lib.ptr
     eng.build_fwd(x_nhwc4)
     n = 0
+    reuse = frozen and not train and getattr(eng, "_frozen_ready", False)
+    eng._frozen_ready = (not train)
     for li, L in enumerate(eng.layers):
         conv = net.module_list[L.idx][0]
         bn = net.module_list[L.idx][1]
@@ -234,16 +239,18 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None):
                  ptr(L.sums) if train else None)
             n += 2 if train else 1
         else:
-            call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
-                 ptr(L.wd))
+            if not reuse:
+                call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
+                     ptr(L.wd))
+                n += 1
             (L.p_fwd_stats if train else L.p_fwd).run()
-            n += 2
+            n += 1
         if train:
             call("avdn_bn_finalize", ptr(L.sums), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
                  ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.scale),
                  ptr(L.shift), ptr(L.mean), ptr(L.rstd))
             n += 1 if L.first else 2    # finalize (+ the stats memset inside avdn_gemm_run)
-        else:
+        elif not reuse:
             call("avdn_bn_eval_coeffs", L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
                  ptr(bn.running_var), BN_EPS, ptr(L.scale), ptr(L.shift))
             n += 1

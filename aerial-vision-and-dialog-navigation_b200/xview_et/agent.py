@@ -248,7 +248,8 @@ class NavCMTAgent:
                    stop=torch.empty(B, dtype=torch.uint8, device=dev),
                    xy=torch.empty((B, 2), dtype=torch.float32, device=dev))
         el = torch.as_tensor(edge_len, dtype=torch.float64, device=dev).contiguous()
-        _lib.call("avdn_postprocess_waypoints", _lib.ptr(output.contiguous()), _lib.ptr(el), B, float(stop_threshold),
+        out_c = output.contiguous()                  # named: a temporary inside ptr() would dangle
+        _lib.call("avdn_postprocess_waypoints", _lib.ptr(out_c), _lib.ptr(el), B, float(stop_threshold),
                   _lib.ptr(res["angle"]), _lib.ptr(res["dist"]), _lib.ptr(res["altitude"]), _lib.ptr(res["stop"]),
                   _lib.ptr(res["xy"]))
         return res

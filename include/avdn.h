@@ -252,6 +252,8 @@ int avdn_nchw_f32_to_nhwc(const float* in, void* out, int N, int HW, int C, avdn
  *   fc2_w [768,49], fc2_b [768]
  *   -> attn [B*T,512], wc [B*T,49], e49 [B*T,49] (saved for backward),
  *      emb [B*T,768] = emb_frames.                                          */
+/* fc2_w == NULL: SoftDotAttention only (ViT_LSTM's attention_layer_vision,
+ * vln_model.py:219); emb is then not written.                              */
 int avdn_frame_attn_fwd(const float* frames, const float* lang_cls, const float* w_in, const float* w_out,
                         const float* fc2_w, const float* fc2_b, int B, int T, float* attn, float* wc, float* e49,
                         float* emb, avdn_stream_t stream);
@@ -353,6 +355,42 @@ int avdn_sumsq(const float* g, long long n, double* out, avdn_stream_t stream);
 int avdn_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float wd, int step, const double* sumsq, float max_norm, float grad_scale,
                avdn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Config 5 — recurrent policy "ViT_LSTM" (src/models/vln_model.py:163-250) and the
+ * simulator update of the greedy rollout (src/xview_lstm/agent.py:592-602,700-730).
+ * fp32 CUDA-core kernels: ~3 MFLOP per sample and step next to 15.3 GFLOP of trunk.
+ * ---------------------------------------------------------------------- */
+
+/* y[M,N] (+)= act(x[M,K] w[N,K]^T + b[N]); ld* are row pitches in elements;
+ * act: 0 none, 1 ReLU, 2 tanh; b may be NULL.  nn.Linear / the two halves of
+ * nn.LSTMCell's gate pre-activations (vln_model.py:178-204,224-236).           */
+int avdn_linear_f32(const float* x, long long ldx, const float* w, long long ldw, const float* b, float* y,
+                    long long ldy, int M, int N, int K, int act, int accumulate, avdn_stream_t stream);
+/* nn.LSTMCell pointwise part: gates [B,4H] (order i,f,g,o, both bias vectors already added),
+ * c_prev [B,H] or NULL (zero state, vln_model.py:224-226) -> h [B,H] (row pitch ldh), c [B,H]. */
+int avdn_lstm_cell(const float* gates, const float* c_prev, float* h_out, long long ldh, float* c_out, int B, int H,
+                   avdn_stream_t stream);
+/* out[B,N] = W [N,2] . [sin, cos](deg / 180 * 3.14159) + b  (vln_model.py:228-229; float32). */
+int avdn_direction_embed(const float* deg, const float* w, const float* b, float* out, int B, int N,
+                         avdn_stream_t stream);
+/* SoftDotAttention between the two Linear layers (vln_model.py:33-42):
+ * attn = softmax_l(ctx[b,l,:] . target[b,:]); weighted[b,:] = sum_l attn_l ctx[b,l,:].
+ * ctx [B,L,D], target [B,D] -> attn [B,L] (may be NULL), weighted [B,D] (row pitch ldw). */
+int avdn_lang_attn_fwd(const float* ctx, const float* target, int B, int L, int D, float* attn, float* weighted,
+                       long long ldw, avdn_stream_t stream);
+/* One rollout step of the simulator for B samples (xview_lstm/agent.py:607-626,700-730 and
+ * move_view_corners, xview_et/agent.py:285-384), float64, one thread per sample:
+ *   output [B,4] f32 -> normalise / clamp / discretise (as avdn_postprocess_waypoints);
+ *   stop = progress > stop_threshold or last_step: ended[i] = 1 and the pose is kept;
+ *   otherwise zoom to the altitude, rotate by -angle about the centre, move forward by
+ *   dist; each stage is rejected when a corner leaves (gps_botm_left, gps_top_right).
+ * corners [B,4,2] f64 (lat,lng; FL,FR,BR,BL) in/out; bounds [B,4] f64 = (bl_lat, bl_lng,
+ * tr_lat, tr_lng); cur_dir [B] f64 in/out (current_directions); ended [B] u8 in/out (sticky).
+ * angle_deg / dist / altitude_m may be NULL.                                    */
+int avdn_waypoint_step(const float* output, double* corners, const double* bounds, double* cur_dir,
+                       uint8_t* ended, int B, float stop_threshold, int last_step, int* angle_deg, double* dist,
+                       int* altitude_m, avdn_stream_t stream);
 
 #ifdef __cplusplus
 }

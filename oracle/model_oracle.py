@@ -15,6 +15,9 @@ and the CUDA path.  Reference ``file:line`` (relative to /root/reference):
 * ``et_forward``                 src/models/ET_haa.py:121-184
 * ``et_loss``                    src/xview_et/agent.py:663-681, 256-270, 883-885
 * ``postprocess_waypoints``      src/xview_et/agent.py:637-653, 745-752
+* ``vit_lstm_step``              src/models/vln_model.py:213-250 (config 5)
+* ``move_view_corners`` / ``get_direction`` / ``waypoint_step``
+                                 src/xview_et/agent.py:83-101, 285-384; src/xview_lstm/agent.py:607-626, 700-730
 
 Parity pin: the reference has no tests or golden vectors.  This
 restatement is pinned by executing the reference's own modules in the build
@@ -395,3 +398,141 @@ def postprocess_waypoints(output, edge_len, stop_threshold=0.5):
         alt[i] = int(round(float(a) * 360)) + 40
         stop[i] = bool(p > stop_threshold)
     return ang, dist, alt, stop
+
+
+# --------------------------------------------------------------------------
+# config 5: ViT_LSTM step and the simulator update of the greedy rollout
+# --------------------------------------------------------------------------
+def _lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
+    """torch.nn.LSTMCell arithmetic (gate order i, f, g, o); zero state when h is None."""
+    gates = x @ w_ih.t() + b_ih + b_hh
+    if h is not None:
+        gates = gates + h @ w_hh.t()
+    H = w_hh.shape[1]
+    i, f, g, o = gates[:, :H], gates[:, H:2 * H], gates[:, 2 * H:3 * H], gates[:, 3 * H:]
+    c1 = torch.sigmoid(f) * (c if c is not None else 0) + torch.sigmoid(i) * torch.tanh(g)
+    return torch.sigmoid(o) * torch.tanh(c1), c1
+
+
+def vit_lstm_step(sd, im_feature, current_direct, cls_hidden, lang_feature, state=None):
+    """src/models/vln_model.py:213-250 after the vision model (eval arithmetic: dropout inactive).
+    ``im_feature`` [B,512,49]; ``current_direct`` [B,1] degrees (int64 in the reference loop);
+    ``state`` = (h, c, hh, cc) or None.  Returns (h1, c1, hh1, cc1, output [B,4], h_sali [B,64])."""
+    h0, c0, hh0, cc0 = state if state is not None else (None, None, None, None)
+    inp, _ = soft_dot_attention(cls_hidden, im_feature, sd["attention_layer_vision.linear_in.weight"],
+                                sd["attention_layer_vision.linear_out.weight"])
+    hh1, cc1 = _lstm_cell(inp, hh0, cc0, sd["vision_lstm.weight_ih"], sd["vision_lstm.weight_hh"],
+                          sd["vision_lstm.bias_ih"], sd["vision_lstm.bias_hh"])
+    cd = current_direct / 180 * PI_REF                       # int64 / int -> float32 (torch true division)
+    direction = torch.cat((torch.sin(cd), torch.cos(cd)), dim=1).float()
+    demb = direction @ sd["direction_embedding.weight"].t() + sd["direction_embedding.bias"]
+    h1, c1 = _lstm_cell(demb, h0, c0, sd["direct_lstm.weight_ih"], sd["direct_lstm.weight_hh"],
+                        sd["direct_lstm.bias_ih"], sd["direct_lstm.bias_hh"])
+    # SoftDotAttention(768) over the tokens (vln_model.py:26-46): softmax over seq_len
+    hcat = torch.cat((h1, hh1), 1)
+    target = hcat @ sd["attention_layer_lang.linear_in.weight"].t()
+    attn = torch.softmax(torch.bmm(lang_feature, target.unsqueeze(2)).squeeze(2), dim=1)
+    weighted = torch.bmm(attn.unsqueeze(1), lang_feature).squeeze(1)
+    act_in = torch.tanh(torch.cat((weighted, hcat), 1) @ sd["attention_layer_lang.linear_out.weight"].t())
+    h = torch.relu(act_in @ sd["decoder_2_action_full.0.weight"].t() + sd["decoder_2_action_full.0.bias"])
+    h = torch.relu(h @ sd["decoder_2_action_full.3.weight"].t() + sd["decoder_2_action_full.3.bias"])
+    output = h @ sd["decoder_2_action_full.6.weight"].t() + sd["decoder_2_action_full.6.bias"]
+    s = torch.relu(inp @ sd["fc.0.weight"].t() + sd["fc.0.bias"])
+    h_sali = torch.relu(s @ sd["fc.3.weight"].t() + sd["fc.3.bias"])
+    return h1, c1, hh1, cc1, output, h_sali
+
+
+def get_direction(start, end):
+    """src/xview_et/agent.py:83-101."""
+    vec = np.array(end) - np.array(start)
+    if vec[1] > 0:
+        ang = np.arctan(vec[0] / vec[1]) / 1.57 * 90
+    elif vec[1] < 0:
+        ang = np.arctan(vec[0] / vec[1]) / 1.57 * 90 + 180
+    else:
+        ang = 90 if np.sign(vec[0]) == 1 else 270
+    return (360 - ang + 90) % 360
+
+
+def move_view_corners(corners, angle, distance, altitude, gps_botm_left, gps_top_right, input_current_direction=None):
+    """src/xview_et/agent.py:285-384 (identical in src/xview_lstm/agent.py): zoom to the altitude,
+    rotate by -angle about the centre (pi = 3.14159), move forward; a stage whose corners leave the map
+    is rejected.  Host float64 in the reference's operation order."""
+    corners = np.asarray(corners, dtype=np.float64)
+    norm = np.linalg.norm
+
+    def inside(p):
+        return gps_botm_left[0] < p[0] < gps_top_right[0] and gps_botm_left[1] < p[1] < gps_top_right[1]
+
+    def rot(theta, p):
+        M = np.array([[np.cos(theta / 180 * PI_REF), np.sin(theta / 180 * PI_REF)],
+                      [-np.sin(theta / 180 * PI_REF), np.cos(theta / 180 * PI_REF)]])
+        return np.matmul(M, np.array([p[0], p[1]]))
+
+    def change_corner(cs, ch):
+        o = np.zeros((4, 2))
+        o[0] = cs[0] + (cs[0] - cs[1]) / norm(cs[1] - cs[0]) * ch
+        o[0] += (cs[0] - cs[3]) / norm(cs[3] - cs[0]) * ch
+        o[1] = cs[1] + (cs[1] - cs[0]) / norm(cs[1] - cs[0]) * ch
+        o[1] += (cs[1] - cs[2]) / norm(cs[2] - cs[1]) * ch
+        o[2] = cs[2] + (cs[2] - cs[3]) / norm(cs[2] - cs[3]) * ch
+        o[2] += (cs[2] - cs[1]) / norm(cs[2] - cs[1]) * ch
+        o[3] = cs[3] + (cs[3] - cs[2]) / norm(cs[2] - cs[3]) * ch
+        o[3] += (cs[3] - cs[0]) / norm(cs[3] - cs[0]) * ch
+        return o
+
+    def forward(cs, ch):
+        o = np.zeros((4, 2))
+        o[0] = cs[0] + (cs[0] - cs[3]) / norm(cs[3] - cs[0]) * ch
+        o[1] = cs[1] + (cs[1] - cs[2]) / norm(cs[2] - cs[1]) * ch
+        o[2] = cs[2] + (cs[1] - cs[2]) / norm(cs[2] - cs[1]) * ch
+        o[3] = cs[3] + (cs[0] - cs[3]) / norm(cs[3] - cs[0]) * ch
+        return o
+
+    cur = round(get_direction(np.mean(corners, axis=0), (corners[0] + corners[1]) / 2)) % 360
+    if input_current_direction is not None and abs(input_current_direction - cur) > 2:
+        angle += input_current_direction
+    edge = norm(corners[1] - corners[0]) * 11.13 * 1e4
+    zoomed = change_corner(corners, 0.5 * (altitude - edge) / 11.13 / 1e4)
+    if not all(inside(p) for p in zoomed):
+        return np.array(corners), cur
+    centre = np.mean(zoomed, axis=0)
+    rotated = [centre + rot(-angle, zoomed[i] - centre) for i in range(4)]
+    if not all(inside(p) for p in rotated):
+        return np.array(zoomed), cur
+    moved = forward(np.array(rotated), distance)
+    if not all(inside(p) for p in moved):
+        return np.array(rotated), (cur + angle) % 360
+    return np.array(moved), (cur + angle) % 360
+
+
+def waypoint_step(output, corners, bounds, cur_dir, ended, stop_threshold=0.25, last_step=False):
+    """One simulator step of the student rollout (src/xview_lstm/agent.py:607-626,700-730) for a batch.
+    ``output`` [B,4] f32; ``corners`` [B,4,2] f64; ``bounds`` [B,4] = (bl_lat, bl_lng, tr_lat, tr_lng);
+    ``cur_dir`` [B]; ``ended`` [B] bool.  Returns new (corners, cur_dir, ended, angle, altitude, dist)."""
+    import math
+    o = np.asarray(output, dtype=np.float32).copy()
+    B = o.shape[0]
+    corners = np.array(corners, dtype=np.float64)
+    cur_dir = np.array(cur_dir, dtype=np.float64)
+    ended = np.array(ended, dtype=bool)
+    ang = np.zeros(B, dtype=np.int64)
+    alt = np.zeros(B, dtype=np.int64)
+    dist = np.zeros(B, dtype=np.float64)
+    for i in range(B):
+        m = max(abs(o[i, 0]), abs(o[i, 1]), 1)
+        o[i, 0] /= m
+        o[i, 1] /= m
+        a = min(1., max(0., o[i, 2]))
+        p = min(1., max(0., o[i, 3]))
+        a_dir = (math.atan2(o[i, 0], o[i, 1]) / PI_REF + 2) / 2 % 1
+        ang[i] = round(a_dir * 360)
+        dist[i] = np.linalg.norm(o[i, 0:2]) * (np.linalg.norm(corners[i][0] - corners[i][1]) / 2)
+        alt[i] = round(a * 360) + 40
+        if p > stop_threshold or last_step:
+            ended[i] = True
+            continue
+        new_c, new_d = move_view_corners(corners[i], int(ang[i]), dist[i], int(alt[i]), bounds[i, 0:2], bounds[i, 2:4],
+                                         cur_dir[i])
+        corners[i], cur_dir[i] = new_c, new_d
+    return corners, cur_dir, ended, ang, alt, dist
