@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the AVDN hot path on B200 (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout]
     python bench.py --impl reference ...        # the reference's CPU path, same metric
 
 One JSON line on stdout (rank 0).  Under torchrun (N>1) every rank runs its shard
@@ -176,6 +176,13 @@ try:
     WORKLOADS["train"] = TrainWorkload
 except ImportError:
     TrainWorkload = None
+
+
+try:
+    from bench_rollout import RolloutWorkload      # noqa: E402
+    WORKLOADS["rollout"] = RolloutWorkload
+except ImportError:
+    RolloutWorkload = None
 
 
 def dist_env():
