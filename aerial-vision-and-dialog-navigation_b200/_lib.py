@@ -46,6 +46,7 @@ _SIGNATURES = {
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "avdn_pack_conv_weight": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "avdn_unpack_conv_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "avdn_unpack_conv_wgrad_pairs": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "avdn_cast_f32_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "avdn_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "avdn_nchw_f32_to_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -15,7 +15,7 @@
 namespace {
 
 constexpr int C0_OUT = 32;     // real output channels
-constexpr int C0_PAD = 64;     // stored padded to 64 (the tensor-core layers read 64-channel blocks)
+constexpr int C0_PAD = 32;     // stored as 32 channels (64-byte pixels; block 1 reads 32-element k-blocks)
 constexpr int WARPS = 7;       // 7 warps x 16 pixels = half a 224-pixel row
 constexpr int THREADS = WARPS * 32;
 
@@ -128,14 +128,12 @@ __global__ void __launch_bounds__(THREADS) conv0_fwd_kernel(const uint2* __restr
         }
       }
       __syncwarp();
-      // 16 pixels x 128 bytes (32 real channels + 32 zero channels), 512 contiguous bytes per instruction
+      // 16 pixels x 64 bytes, 512 contiguous bytes per instruction
       uint4* dst = z + (((size_t)n * H + h0 + hr) * W + w0) * (C0_PAD / 8);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int qd = i * 32 + lane, px = qd >> 3, part = qd & 7;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (part < 4) v = *reinterpret_cast<const uint4*>(my_out + px * OUT_PITCH + part * 16);
-        dst[qd] = v;
+      for (int i = 0; i < 2; ++i) {
+        const int qd = i * 32 + lane, px = qd >> 2, part = qd & 3;
+        dst[qd] = *reinterpret_cast<const uint4*>(my_out + px * OUT_PITCH + part * 16);
       }
       __syncwarp();
     }
@@ -186,7 +184,7 @@ __global__ void __launch_bounds__(THREADS) conv0_wgrad_kernel(const uint8_t* __r
   for (long long s = blockIdx.x; s < total; s += gridDim.x) {
     const int n = (int)(s / strips_per_img), h0 = (int)(s % strips_per_img) * G_ROWS;
     __syncthreads();
-    // dZ rows: the first 64 bytes (32 real channels) of every 128-byte pixel
+    // dZ rows: 64 bytes (32 channels) per pixel
     const uint8_t* src = dz + ((size_t)n * H + h0) * W * (C0_PAD * 2);
     for (int i = threadIdx.x; i < G_ROWS * W * 4; i += THREADS) {
       const int px = i >> 2, part = i & 3;

@@ -37,7 +37,8 @@
 namespace {
 
 constexpr int BM = 128;         // rows per CTA (UMMA M = 128 * CTAS)
-constexpr int BK = 64;          // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int BK = 64;          // default k-block: 64 bf16 = one 128-byte swizzle row (BKT = 32: 64-byte rows,
+                                // 64-byte swizzle, for the 32-channel activations of trunk blocks 0 and 2)
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_THREADS = 128;
@@ -186,13 +187,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 //   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused
 //   MN-major: 64 MN elements per 128-B row, one row per k; 8-k groups SBO apart,
 //             64-wide MN atoms LBO apart
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B (K-major rows of 64 B, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -207,10 +210,10 @@ struct alignas(64) KernelParams {
   int32_t pad_;
 };
 
-template <int BN, int STAGES, int CTAS>
+template <int BN, int STAGES, int CTAS, int BKT = BK>
 struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
-  static constexpr int B_BYTES = (BN / CTAS) * BK * 2;         // this CTA's part of B
+  static constexpr int A_BYTES = BM * BKT * 2;                 // 16 KB (8 KB for 32-element k-blocks)
+  static constexpr int B_BYTES = (BN / CTAS) * BKT * 2;        // this CTA's part of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLAB_OFF = STAGES * STAGE_BYTES;
   static constexpr int STAT_OFF = SLAB_OFF + 2 * SLAB_BYTES;   // float [2][BN]
@@ -219,9 +222,12 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;   // + alignment slack
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS, int BKT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ KernelParams p) {
-  using L = SmemLayout<BN, STAGES, CTAS>;
+  static_assert(BKT == 64 || (BKT == 32 && !A_MN && !B_MN), "32-element k-blocks: K-major operands only");
+  using L = SmemLayout<BN, STAGES, CTAS, BKT>;
+  constexpr uint32_t KLAYOUT = (BKT == 64) ? 2u : 4u;          // swizzle mode of the K-major operands
+  constexpr uint32_t KSBO = 8u * BKT * 2u;                     // 8 rows of BKT bf16
   constexpr int BNH = BN / CTAS;                                // B columns this CTA loads
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           if (CTAS == 2) fb = mapa_rank(fb, 0);
           if (leader) mbar_expect_tx(full_bar(stage), tx_total);
           if (c.mode == AVDN_GEMM_PLAIN) {
-            const int k0 = kb * BK;
+            const int k0 = kb * BKT;
             if (!A_MN) tma_load_4d<CTAS>(sa, &p.tmA[0], fb, k0, m0, T.z0, T.z1);
             else {
               tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, k0, T.z0, T.z1);
@@ -337,8 +343,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           } else if (c.mode == AVDN_GEMM_CONV) {
             const int tp_i = kb / c.cblocks, cb = kb - tp_i * c.cblocks;
             const avdn_tap tp = c.taps[tp_i];
-            tma_load_4d<CTAS>(sa, &p.tmA[tp.map], fb, cb * BK, w0 + tp.d1, h0 + tp.d2, i0);
-            tma_load_4d<CTAS>(sb, &p.tmB[0], fb, tp.bk + cb * BK, n0, 0, 0);
+            tma_load_4d<CTAS>(sa, &p.tmA[tp.map], fb, cb * BKT, w0 + tp.d1, h0 + tp.d2, i0);
+            tma_load_4d<CTAS>(sb, &p.tmB[0], fb, tp.bk + cb * BKT, n0, 0, 0);
           } else {  // WGRAD: k-step = one pixel tile (box_w*box_h*box_n == 64 pixels)
             const avdn_tap tp = c.taps[T.tap];
             const int pw = (kb % c.tiles_w) * c.box_w;
@@ -377,11 +383,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
+          for (int k = 0; k < BKT / UMMA_K; ++k) {
             const uint64_t ad = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), 8192, 1024)
-                                     : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+                                     : make_smem_desc(sa + k * (UMMA_K * 2), 16, KSBO, KLAYOUT);
             const uint64_t bd = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024)
-                                     : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+                                     : make_smem_desc(sb + k * (UMMA_K * 2), 16, KSBO, KLAYOUT);
             umma_bf16<CTAS>(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           tcgen05_commit<CTAS>(empty_bar(stage));           // frees the smem stage when the MMAs retire
@@ -432,8 +438,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
 
       if (p.out_tma) {
         // ---- TMEM -> registers -> swizzled smem slab -> TMA store / reduce-add ----
-        const int cols_per_slab = is_bf16 ? 64 : 32;
         const bool row_live = row < p.rows_in_box;
+        const bool slab64 = (BN == 32);           // bf16 tile of 32 columns: 64-byte slab rows, 64-byte swizzle
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += 32) {
           const int col0 = n0 + cc;
@@ -448,8 +454,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             if (c.relu) x = fmaxf(x, 0.f);
             f[j] = row_live ? x : 0.f;
           }
-          const bool slab_first = is_bf16 ? ((cc & 32) == 0) : true;
-          const bool slab_last = is_bf16 ? ((cc & 32) != 0 || col0 + 32 >= c.N) : true;
+          const bool slab_first = (is_bf16 && !slab64) ? ((cc & 32) == 0) : true;
+          const bool slab_last = (is_bf16 && !slab64) ? ((cc & 32) != 0 || col0 + 32 >= c.N) : true;
           uint8_t* slab = smem_gen + L::SLAB_OFF + (slab_ctr & 1u) * SLAB_BYTES;
           if (slab_first) {
             // the TMA store that read this buffer two slabs ago must have finished reading it
@@ -458,7 +464,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           }
           uint8_t* rowp = slab + row * 128;
           const int sw = row & 7;
-          if (is_bf16) {
+          if (slab64) {
+            uint8_t* rp = slab + row * 64;
+            const int s4 = (row >> 1) & 3;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+              }
+              *reinterpret_cast<uint4*>(rp + ((g ^ s4) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          } else if (is_bf16) {
             const int cbase = (cc & 32) ? 4 : 0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -483,7 +502,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           if (slab_last) {
             fence_proxy_async_smem();
             epi_bar_sync();
-            const int scol = n0 + (is_bf16 ? (cc & ~32) : cc);      // first column of this slab
+            const int scol = n0 + ((is_bf16 && !slab64) ? (cc & ~32) : cc);      // first column of this slab
             if (et == 0) {
               const uint32_t src = smem_u32(slab);
               int c0 = scol, c1, c2, c3;
@@ -495,14 +514,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
               tma_commit_group();
             }
             if (c.stats) {
-              // fused BatchNorm statistics of the ROUNDED outputs: thread -> (column, row half)
-              const int j = et & 63, half = et >> 6;
-              const int r0 = half * 64, r1 = min(p.rows_in_box, r0 + 64);
+              // fused BatchNorm statistics of the ROUNDED outputs: thread -> (column, row group)
+              const int ncol = slab64 ? 32 : 64, rows_per = slab64 ? 32 : 64;
+              const int j = et & (ncol - 1), grp = et / ncol;
+              const int r0 = grp * rows_per, r1 = min(p.rows_in_box, r0 + rows_per);
               float s1 = 0.f, s2 = 0.f;
               for (int r = r0; r < r1; ++r) {
-                const __nv_bfloat16 b =
-                    *reinterpret_cast<const __nv_bfloat16*>(slab + r * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2);
-                const float x = __bfloat162float(b);
+                const uint8_t* q = slab64 ? slab + r * 64 + (((j >> 3) ^ ((r >> 1) & 3)) << 4) + (j & 7) * 2
+                                          : slab + r * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2;
+                const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(q));
                 s1 += x;
                 s2 = fmaf(x, x, s2);
               }
@@ -641,7 +661,8 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// rank-4 tensor map with a 128-byte-swizzled box whose inner extent is exactly 128 bytes
+// rank-4 tensor map with a swizzled box whose inner extent is exactly 128 bytes (128-byte swizzle) or
+// 64 bytes (64-byte swizzle)
 int encode_map(const void* ptr, int elem_bytes, const int64_t* dim, const int64_t* stride, const int32_t* boxdim,
                CUtensorMap* out, bool check_only = false) {
   EncodeTiledFn enc = get_encode();
@@ -657,8 +678,9 @@ int encode_map(const void* ptr, int elem_bytes, const int64_t* dim, const int64_
     if (dim[i] < 1) return avdn::set_err(AVDN_ERR_BAD_ARG, "operand dim %d < 1", i);
     if (box[i] < 1 || box[i] > 256) return avdn::set_err(AVDN_ERR_BAD_ARG, "TMA box dim %d = %u out of range", i, box[i]);
   }
-  if ((int)box[0] * elem_bytes != 128)
-    return avdn::set_err(AVDN_ERR_BAD_ARG, "TMA box dim 0 must span 128 bytes (128-byte swizzle)");
+  const int inner = (int)box[0] * elem_bytes;
+  if (inner != 128 && inner != 64)
+    return avdn::set_err(AVDN_ERR_BAD_ARG, "TMA box dim 0 must span 128 or 64 bytes (swizzled rows)");
   for (int i = 1; i < 4; ++i) {
     const cuuint64_t s = (cuuint64_t)stride[i] * (cuuint64_t)elem_bytes;
     if (s % 16 != 0 || s == 0)
@@ -668,7 +690,8 @@ int encode_map(const void* ptr, int elem_bytes, const int64_t* dim, const int64_
   if (check_only) return AVDN_OK;
   CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   inner == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return avdn::set_err(AVDN_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return AVDN_OK;
 }
@@ -679,17 +702,17 @@ int encode_operand(const avdn_operand& o, CUtensorMap* out) {
 
 struct Plan {
   uint32_t magic;
-  int32_t bn, stages, a_mn, b_mn, ctas;
+  int32_t bn, stages, a_mn, b_mn, ctas, bk;
   int32_t grid;
   int smem;
   KernelParams kp;
 };
 constexpr uint32_t PLAN_MAGIC = 0xA7D17C06u;
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS, int BKT = BK>
 int launch_t(const Plan& pl, cudaStream_t s) {
-  auto kfn = gemm_kernel<BN, STAGES, A_MN, B_MN, CTAS>;
-  using L = SmemLayout<BN, STAGES, CTAS>;
+  auto kfn = gemm_kernel<BN, STAGES, A_MN, B_MN, CTAS, BKT>;
+  using L = SmemLayout<BN, STAGES, CTAS, BKT>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
@@ -728,7 +751,12 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   AVDN_REQUIRE(d && plan_host, "avdn_gemm_plan: null pointer");
   AVDN_REQUIRE(plan_bytes >= sizeof(Plan), "avdn_gemm_plan: plan buffer too small (%zu < %zu)", plan_bytes, sizeof(Plan));
   AVDN_REQUIRE(d->core.mode >= AVDN_GEMM_PLAIN && d->core.mode <= AVDN_GEMM_WGRAD, "avdn_gemm_plan: bad mode");
-  AVDN_REQUIRE(d->bn == 64 || d->bn == 128 || d->bn == 256, "avdn_gemm_plan: bn must be 64/128/256");
+  AVDN_REQUIRE(d->bn == 32 || d->bn == 64 || d->bn == 128 || d->bn == 256, "avdn_gemm_plan: bn must be 32/64/128/256");
+  AVDN_REQUIRE(d->bk == 64 || d->bk == 32, "avdn_gemm_plan: bk must be 64 or 32");
+  AVDN_REQUIRE(d->bk == 64 || (!d->a_mn && !d->b_mn && d->bn == 64 && d->ctas == 1),
+               "avdn_gemm_plan: 32-element k-blocks need K-major operands, bn = 64, single CTAs");
+  AVDN_REQUIRE(d->bn != 32 || (!d->a_mn && !d->b_mn && d->bk == 64 && d->core.out_dtype == AVDN_DT_BF16),
+               "avdn_gemm_plan: bn = 32 is the K-major bf16-output variant only");
   AVDN_REQUIRE(d->n_a >= 1 && d->n_a <= 4 && d->n_b >= 1 && d->n_b <= 4, "avdn_gemm_plan: 1..4 operand maps");
   AVDN_REQUIRE(d->core.out, "avdn_gemm_plan: null output");
   AVDN_REQUIRE(d->core.split_k >= 1 && d->core.num_kb >= 1, "avdn_gemm_plan: bad k split");
@@ -744,6 +772,7 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   pl->a_mn = d->a_mn;
   pl->b_mn = d->b_mn;
   pl->ctas = d->ctas;
+  pl->bk = d->bk;
   pl->kp.c = d->core;
   const avdn_gemm_core& c = d->core;
   for (int i = 0; i < d->n_a; ++i) {
@@ -767,7 +796,7 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   };
   const long long a_bytes = box_bytes(d->a[0]) * (d->a_mn ? 2 : 1);
   const long long b_bytes = box_bytes(d->b[0]) * (d->b_mn ? d->bn / 64 : 1);
-  AVDN_REQUIRE(a_bytes <= BM * BK * 2 && b_bytes <= (long long)d->bn * BK * 2, "avdn_gemm_plan: boxes exceed the stage");
+  AVDN_REQUIRE(a_bytes <= BM * d->bk * 2 && b_bytes <= (long long)d->bn * d->bk * 2, "avdn_gemm_plan: boxes exceed the stage");
   pl->kp.c.tx_bytes = (uint32_t)(a_bytes * d->ctas + b_bytes);
   pl->kp.grid_m = d->grid_m;
   pl->kp.grid_n = d->grid_n;
@@ -783,7 +812,7 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   pl->kp.out_tma = 0;
   if (!c.relu_mask) {
     const int eb = (c.out_dtype == AVDN_DT_BF16) ? 2 : 4;
-    const int slab_cols = 128 / eb;
+    const int slab_cols = (d->bn == 32) ? 32 : 128 / eb;
     int64_t dim[4], str[4];
     int32_t box[4];
     const uint8_t* base = reinterpret_cast<const uint8_t*>(c.out);
@@ -840,7 +869,9 @@ extern "C" int avdn_gemm_run(const void* plan_host, avdn_stream_t stream) {
       case 256: return launch_bn<256, 5, 2>(*pl, s);
     }
   } else {
+    if (pl->bk == 32) return launch_t<64, 8, false, false, 1, 32>(*pl, s);
     switch (pl->bn) {
+      case 32: return launch_t<32, 8, false, false, 1, 64>(*pl, s);
       case 64: return launch_bn<64, 6, 1>(*pl, s);
       case 128: return launch_bn<128, 5, 1>(*pl, s);
       case 256: return launch_bn<256, 3, 1>(*pl, s);

@@ -282,6 +282,39 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwf, int Cout
   }
 }
 
+// Weight gradient computed on PIXEL-PAIR views (32-channel activations: two adjacent pixels form one
+// 128-byte row, so the MN-major wgrad operands keep 64-element rows).
+//   stride 1: both operands paired.  D'[(a,co)][blk(kh,s)][(b,ci)] = sum_P dZ[2P+a][co] X[2(P+s)+b (+kh row)][ci]
+//             tap dw of pixel parity a lands in (s,b) = f(a+dw): -1->(-1,1) 0->(0,0) 1->(0,1) 2->(1,0)
+//   stride 2: only X paired (pair index = output pixel).  D'[co][blk(kh,s)][(b,ci)], dw -> (s,b): -1->(-1,1) 0->(0,0) 1->(0,1)
+// grad [Cout,Cin,k,k] += the blocks that make up each filter tap.
+__global__ void unpack_conv_wgrad_pairs_kernel(const float* __restrict__ dwp, int Cout, int Cin, int k, int stride,
+                                               int Cout_p, int Cin_p, float* __restrict__ grad) {
+  const int kk = k * k, pad = (k - 1) / 2;
+  const int Np = 2 * Cin_p;
+  const int nshift = (stride == 2) ? 2 : (k == 3 ? 3 : 1);
+  const long long ld = (long long)k * nshift * Np;
+  const long long n = (long long)Cout * Cin * kk;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % kk), ci = (int)((i / kk) % Cin), co = (int)(i / ((long long)kk * Cin));
+    const int kh = t / k, dw = t % k - pad;
+    float v = 0.f;
+    if (stride == 2) {
+      const int s = (dw < 0) ? -1 : 0, b = (dw == 0) ? 0 : 1;
+      v = dwp[(long long)co * ld + (long long)(kh * 2 + (s + 1)) * Np + b * Cin_p + ci];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int u = a + dw;                         // -1 .. 2
+        const int s = (u < 0) ? -1 : (u > 1 ? 1 : 0), b = u & 1;
+        const int blk = kh * nshift + (k == 3 ? s + 1 : 0);
+        v += dwp[(long long)(a * Cout_p + co) * ld + (long long)blk * Np + b * Cin_p + ci];
+      }
+    }
+    grad[i] += v;
+  }
+}
+
 // fp32 -> bf16 cast (linear-layer weights, features)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -423,6 +456,16 @@ extern "C" int avdn_unpack_conv_wgrad(const float* dwf, int Cout, int Cin, int k
   const long long n = (long long)Cout * Cin * k * k;
   unpack_conv_wgrad_kernel<<<grid_for(n), 256, 0, avdn::to_cuda(stream)>>>(dwf, Cout, Cin, k, Cin_p, grad);
   return avdn::check_launch("avdn_unpack_conv_wgrad");
+}
+
+extern "C" int avdn_unpack_conv_wgrad_pairs(const float* dwp, int Cout, int Cin, int k, int stride, int Cout_p,
+                                            int Cin_p, float* grad, avdn_stream_t stream) {
+  AVDN_REQUIRE(dwp && grad && (k == 1 || k == 3) && (stride == 1 || (stride == 2 && k == 3)),
+               "avdn_unpack_conv_wgrad_pairs: bad argument");
+  const long long n = (long long)Cout * Cin * k * k;
+  unpack_conv_wgrad_pairs_kernel<<<grid_for(n), 256, 0, avdn::to_cuda(stream)>>>(dwp, Cout, Cin, k, stride, Cout_p,
+                                                                                  Cin_p, grad);
+  return avdn::check_launch("avdn_unpack_conv_wgrad_pairs");
 }
 
 extern "C" int avdn_cast_f32_bf16(const float* in, void* out, long long n, avdn_stream_t stream) {

@@ -44,7 +44,7 @@ class GemmCore(C.Structure):
 
 class GemmDesc(C.Structure):
     _fields_ = [("core", GemmCore), ("bn", i32), ("a_mn", i32), ("b_mn", i32), ("n_a", i32), ("n_b", i32),
-                ("grid_m", i32), ("grid_n", i32), ("grid_z", i32), ("ctas", i32),
+                ("grid_m", i32), ("grid_n", i32), ("grid_z", i32), ("ctas", i32), ("bk", i32),
                 ("a", Operand * 4), ("b", Operand * 4)]
 
 
@@ -101,6 +101,8 @@ class GemmPlan:
 
 
 def pick_bn(N):
+    if N <= 32:
+        return 32
     if N <= 64:
         return 64
     if N <= 128 or N % 256 != 0:
@@ -118,8 +120,9 @@ def plan_plain(*, M, N, K, a_ptr, lda, a_mn, b_ptr, ldb, b_mn, out, ldc, bias=No
     the M/N index).  ``a_bs``/``b_bs``/``out_bs`` are the element strides of the two
     batch dims; ``b_bs=None`` shares B across the batch.
     """
-    bn = bn or pick_bn(N)
+    bn = bn or max(64, pick_bn(N))
     d = GemmDesc()
+    d.bk = 64
     c = d.core
     c.mode, c.M, c.N = PLAIN, M, N
     c.num_kb = _cdiv(K, 64)
@@ -250,16 +253,19 @@ def _x_views(x, Cin, W, H, N, stride, box):
 def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=None, stats=None, ctas=None):
     """z[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) ; ``w_f`` is ``[Cout, k*k*Cin]`` bf16
     (tap-major, channel-minor).  Channels are multiples of 64."""
-    assert Cin % 64 == 0 and Cout % 64 == 0
+    assert (Cin % 64 == 0 or Cin == 32) and (Cout % 64 == 0 or Cout == 32)
     Ho, Wo = H // stride, W // stride
     bn = bn or pick_bn(Cout)
+    bk = 64 if Cin % 64 == 0 else 32           # 32-channel input: 64-byte rows, 64-byte swizzle
+    assert not (bk == 32 and bn != 64), "32-channel input with a 32-channel output is not planned"
     bw, bh, bnn = conv_box(Wo, Ho, N, 128)
     d = GemmDesc()
+    d.bk = bk
     c = d.core
     c.mode, c.M, c.N = CONV, 0, Cout
     taps = conv_taps_fwd(k, stride, Cin)
     _fill_taps(c, taps)
-    c.cblocks = Cin // 64
+    c.cblocks = Cin // bk
     c.num_kb = len(taps) * c.cblocks
     c.split_k, c.batch0, c.batch1 = 1, 1, 1
     c.tiles_w, c.tiles_h, c.tiles_n = _cdiv(Wo, bw), _cdiv(Ho, bh), _cdiv(N, bnn)
@@ -270,12 +276,12 @@ def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=No
     c.ldc = Cout
     c.out = z.data_ptr()
     d.bn, d.a_mn, d.b_mn = bn, 0, 0
-    views = _x_views(x, Cin, W, H, N, stride, (64, bw, bh, bnn))
+    views = _x_views(x, Cin, W, H, N, stride, (bk, bw, bh, bnn))
     d.n_a, d.n_b = len(views), 1
     for i, v in enumerate(views):
         d.a[i] = v
     Kt = k * k * Cin
-    d.b[0] = operand(w_f.data_ptr(), (Kt, Cout, 1, 1), (1, Kt, Kt * Cout, Kt * Cout), (64, bn, 1, 1))
+    d.b[0] = operand(w_f.data_ptr(), (Kt, Cout, 1, 1), (1, Kt, Kt * Cout, Kt * Cout), (bk, bn, 1, 1))
     d.grid_m, d.grid_n, d.grid_z = c.tiles_w * c.tiles_h * c.tiles_n, _cdiv(Cout, bn), 1
     d.ctas = pick_ctas(bn, d.grid_m, ctas)
     if stats is not None:        # fused BatchNorm statistics: f64 [2, Cout]
@@ -289,9 +295,11 @@ def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0,
     """dx[N,H,W,Cin] (+)= conv_transpose(dz[N,Ho,Wo,Cout], w); ``w_d`` is
     ``[Cin, k*k*Cout]`` bf16 (tap-major, out-channel-minor).  Returns a list of plans
     (4 output-parity plans for stride 2)."""
-    assert Cin % 64 == 0 and Cout % 64 == 0
+    assert (Cin % 64 == 0 or Cin == 32) and (Cout % 64 == 0 or Cout == 32)
     Ho, Wo = H // stride, W // stride
     bn = bn or pick_bn(Cin)
+    bk = 64 if Cout % 64 == 0 else 32
+    assert not (bk == 32 and bn != 64)
     pad = (k - 1) // 2
     Kt = k * k * Cout
     plans = []
@@ -307,10 +315,11 @@ def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0,
             gw, gh = Wo, Ho
         bw, bh, bnn = conv_box(gw, gh, N, 128)
         d = GemmDesc()
+        d.bk = bk
         c = d.core
         c.mode, c.M, c.N = CONV, 0, Cin
         _fill_taps(c, taps)
-        c.cblocks = Cout // 64
+        c.cblocks = Cout // bk
         c.num_kb = len(taps) * c.cblocks
         c.split_k, c.batch0, c.batch1 = 1, 1, 1
         c.tiles_w, c.tiles_h, c.tiles_n = _cdiv(gw, bw), _cdiv(gh, bh), _cdiv(N, bnn)
@@ -323,8 +332,8 @@ def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0,
         c.ldc = Cin
         c.out = dx.data_ptr()
         d.bn, d.a_mn, d.b_mn, d.n_a, d.n_b = bn, 0, 0, 1, 1
-        d.a[0] = _act_operand(dz.data_ptr(), Cout, Wo, Ho, N, (64, bw, bh, bnn))
-        d.b[0] = operand(w_d.data_ptr(), (Kt, Cin, 1, 1), (1, Kt, Kt * Cin, Kt * Cin), (64, bn, 1, 1))
+        d.a[0] = _act_operand(dz.data_ptr(), Cout, Wo, Ho, N, (bk, bw, bh, bnn))
+        d.b[0] = operand(w_d.data_ptr(), (Kt, Cin, 1, 1), (1, Kt, Kt * Cin, Kt * Cin), (bk, bn, 1, 1))
         d.grid_m, d.grid_n, d.grid_z = c.tiles_w * c.tiles_h * c.tiles_n, _cdiv(Cin, bn), 1
         d.ctas = pick_ctas(bn, d.grid_m, ctas)
         fl = flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin
@@ -341,6 +350,7 @@ def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, b
     bn = bn or pick_bn(Cin)
     bw, bh, bnn = wgrad_box(Wo, Ho, N)
     d = GemmDesc()
+    d.bk = 64
     c = d.core
     c.mode, c.M, c.N = WGRAD, Cout, Cin
     taps = conv_taps_fwd(k, stride, Cin)
@@ -364,4 +374,67 @@ def plan_conv_wgrad(dz, x, dw, *, N, H, W, Cin, Cout, k, stride, split_k=None, b
     d.grid_m, d.grid_n, d.grid_z = gm, gn, len(taps) * split_k
     d.ctas = pick_ctas(bn, gm, ctas)
     return GemmPlan(d, keep=(dz, x, dw), flops=flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin,
+                    tag="gemm_conv_wgrad")
+
+
+def plan_conv_wgrad_pairs(dz, x, dwp, *, N, H, W, Cin, Cout, k, stride, split_k=None, sms=148, flops=None, ctas=None):
+    """Weight gradient of a conv whose input and/or output has 32 channels, on PIXEL-PAIR views: two
+    adjacent pixels (2 x 32 channels = 128 bytes) are one operand row, so both MN-major operands keep
+    64-element rows.  ``dwp`` (fp32, zero it first) receives blocks that
+    ``avdn_unpack_conv_wgrad_pairs`` folds into the [Cout,Cin,k,k] gradient:
+
+    * stride 1: both operands paired along W -> D'[(a,co)][blk(kh,s)][(b,ci)], s = pair shift in {-1,0,1}
+    * stride 2: X paired (pair index = output pixel), dZ as is -> D'[co][blk(kh,s)][(b,ci)], s in {-1,0}
+    """
+    assert W % 2 == 0 and dwp.dtype == torch.float32
+    pad = (k - 1) // 2
+    Np = 2 * Cin
+    d = GemmDesc()
+    d.bk = 64
+    c = d.core
+    if stride == 1:
+        Wp = W // 2
+        Mp = 2 * Cout
+        shifts = (-1, 0, 1) if k == 3 else (0,)
+        taps = [(0, s, kh - pad, (kh * len(shifts) + i) * Np) for kh in range(k) for i, s in enumerate(shifts)]
+        bw, bh, bnn = wgrad_box(Wp, H, N)
+        a_op = operand(dz.data_ptr(), (Mp, Wp, H, N), (1, Mp, W * Cout, H * W * Cout), (64, bw, bh, bnn))
+        b_ops = [operand(x.data_ptr(), (Np, Wp, H, N), (1, Np, W * Cin, H * W * Cin), (64, bw, bh, bnn))]
+        gw, gh = Wp, H
+    else:
+        assert k == 3 and H % 2 == 0
+        Wp, Hp = W // 2, H // 2
+        Mp = Cout
+        taps = []
+        for kh in range(3):
+            ph, dh = ((1, -1), (0, 0), (1, 0))[kh]
+            for i, s in enumerate((-1, 0)):
+                taps.append((ph, s, dh, (kh * 2 + i) * Np))
+        bw, bh, bnn = wgrad_box(Wp, Hp, N)
+        a_op = operand(dz.data_ptr(), (Cout, Wp, Hp, N), (1, Cout, Wp * Cout, Hp * Wp * Cout), (64, bw, bh, bnn))
+        b_ops = [operand(x.data_ptr() + ph * W * Cin * 2, (Np, Wp, Hp, N), (1, Np, 2 * W * Cin, H * W * Cin),
+                         (64, bw, bh, bnn)) for ph in range(2)]
+        gw, gh = Wp, Hp
+    bn = 64 if Np <= 64 else 128
+    c.mode, c.M, c.N = WGRAD, Mp, Np
+    _fill_taps(c, taps)
+    c.tiles_w, c.tiles_h, c.tiles_n = _cdiv(gw, bw), _cdiv(gh, bh), _cdiv(N, bnn)
+    c.box_w, c.box_h, c.box_n = bw, bh, bnn
+    c.num_kb = c.tiles_w * c.tiles_h * c.tiles_n
+    gm, gn = _cdiv(Mp, 128), _cdiv(Np, bn)
+    if split_k is None:
+        split_k = max(1, min(c.num_kb, (4 * sms) // max(1, gm * gn * len(taps))))
+    c.split_k, c.batch0, c.batch1 = split_k, 1, 1
+    c.out_dtype, c.accumulate, c.relu, c.alpha = DT_F32, 2, 0, 1.0
+    c.ldc = len(taps) * Np
+    assert dwp.numel() >= Mp * c.ldc
+    c.out = dwp.data_ptr()
+    d.bn, d.a_mn, d.b_mn = bn, 1, 1
+    d.a[0] = a_op
+    d.n_a, d.n_b = 1, len(b_ops)
+    for i, v in enumerate(b_ops):
+        d.b[i] = v
+    d.grid_m, d.grid_n, d.grid_z = gm, gn, len(taps) * split_k
+    d.ctas = pick_ctas(bn, gm, ctas)
+    return GemmPlan(d, keep=(dz, x, dwp), flops=flops if flops is not None else 2 * N * (H // stride) * (W // stride) * Cout * k * k * Cin,
                     tag="gemm_conv_wgrad")

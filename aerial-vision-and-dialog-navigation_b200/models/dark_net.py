@@ -51,7 +51,9 @@ def parse_model_config(path):
 
 
 def _pad64(c):
-    return (c + 63) // 64 * 64
+    """Stored channel count: multiples of 64 (one 128-byte k-block), except that 32-channel tensors
+    (trunk blocks 0 and 2) are stored as they are -- half the HBM traffic of a padded copy."""
+    return 32 if c == 32 else (c + 63) // 64 * 64
 
 
 class EmptyLayer(nn.Module):
@@ -206,9 +208,17 @@ class _Engine:
                 L.dw = torch.zeros((L.Cout, L.Cin, L.k, L.k), dtype=f32, device=dev)
             if L.first:
                 continue
-            L.dwf = torch.zeros((L.Cout_p, L.k * L.k * L.Cin_p), dtype=f32, device=dev)
-            L.p_wgrad = G.plan_conv_wgrad(dz, L.src.a, L.dwf, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
-                                          Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
+            L.pairs = (L.Cin_p == 32 or L.Cout_p == 32)      # 32-channel operand: pixel-pair wgrad
+            if L.pairs:
+                nblk = 6 if L.s == 2 else L.k * (3 if L.k == 3 else 1)
+                mp = L.Cout_p if L.s == 2 else 2 * L.Cout_p
+                L.dwf = torch.zeros((mp, nblk * 2 * L.Cin_p), dtype=f32, device=dev)
+                L.p_wgrad = G.plan_conv_wgrad_pairs(dz, L.src.a, L.dwf, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
+                                                    Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
+            else:
+                L.dwf = torch.zeros((L.Cout_p, L.k * L.k * L.Cin_p), dtype=f32, device=dev)
+                L.p_wgrad = G.plan_conv_wgrad(dz, L.src.a, L.dwf, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
+                                              Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
             # the input's gradient buffer already holds the skip gradient iff the input is a
             # residual source whose consumer (a later fused shortcut) was processed before
             acc = 1 if id(L.src) in seen_as_input else 0
@@ -267,6 +277,27 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
     return out
 
 
+def _layer_backward(eng, L):
+    """Backward of one conv block: BN/LeakyReLU backward (dz, dgamma, dbeta), weight gradient,
+    input gradient.  Returns the number of kernel launches."""
+    call, ptr = _lib.call, _lib.ptr
+    call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
+         L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
+    n = 4
+    if L.first:
+        call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
+        return n + 1
+    L.dwf.zero_()
+    L.p_wgrad.run()
+    if L.pairs:
+        call("avdn_unpack_conv_wgrad_pairs", ptr(L.dwf), L.Cout, L.Cin, L.k, L.s, L.Cout_p, L.Cin_p, ptr(L.dw))
+    else:
+        call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
+    for p in L.p_dgrad:
+        p.run()
+    return n + 3 + len(L.p_dgrad)
+
+
 def _trunk_backward(net, eng, dout, after_layer=None):
     """Backward of every block; parameter gradients are ACCUMULATED into the
     engine's gradient tensors (``L.dw / L.dgamma / L.dbeta``: views of the optimiser
@@ -279,20 +310,7 @@ def _trunk_backward(net, eng, dout, after_layer=None):
     n = 1
     call("avdn_nchw_f32_to_nhwc", ptr(dout), ptr(last.g), eng.N, last.Hout * last.Wout, last.Cout_p)
     for li in reversed(range(len(eng.layers))):
-        L = eng.layers[li]
-        call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
-             L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
-        n += 4
-        if L.first:
-            call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
-            n += 1
-        else:
-            L.dwf.zero_()
-            L.p_wgrad.run()
-            call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
-            for p in L.p_dgrad:
-                p.run()
-            n += 3 + len(L.p_dgrad)
+        n += _layer_backward(eng, eng.layers[li])
         if after_layer is not None:
             after_layer(li)
     eng.launches += n

@@ -127,7 +127,7 @@ enum { AVDN_DT_BF16 = 0, AVDN_DT_F32 = 1 };
 typedef struct avdn_tap { int32_t map, d1, d2, bk; } avdn_tap;
 
 /* A bf16 operand as a rank-4 strided tensor; dim[0] is contiguous.  Strides in
- * elements.  box = TMA box (box[0] must be 64). */
+ * elements.  box = TMA box (box[0] = 64, or 32 with bk = 32). */
 typedef struct avdn_operand {
   const void* ptr;
   int64_t dim[4];
@@ -166,12 +166,14 @@ typedef struct avdn_gemm_core {
 
 typedef struct avdn_gemm_desc {
   avdn_gemm_core core;
-  int32_t bn;                 /* N tile: 64, 128 or 256 */
+  int32_t bn;                 /* N tile: 32 (K-major, bf16 out), 64, 128 or 256 */
   int32_t a_mn, b_mn;         /* 0 = K-major operand, 1 = MN-major operand */
   int32_t n_a, n_b;           /* number of A / B views (parity views of stride-2 convs) */
   int32_t grid_m, grid_n, grid_z;  /* tile space: 128-row tiles x bn-column tiles x (batch | taps*split_k) */
   int32_t ctas;               /* 1, or 2 = CTA pairs (tcgen05 cta_group::2): a pair computes 256 x bn and
                                  each CTA loads half of B; needs bn >= 128 */
+  int32_t bk;                 /* k-block in elements: 64 (128-byte swizzle) or 32 (64-byte swizzle; K-major
+                                 operands, bn = 64: the 32-channel activations of trunk blocks 0 and 2) */
   avdn_operand a[4];
   avdn_operand b[4];
 } avdn_gemm_desc;
@@ -188,8 +190,8 @@ int avdn_gemm_run(const void* plan_host, avdn_stream_t stream);
 /* First convolution 3->32, 3x3, pad 1 (module_list.0.conv_0; K = 27 is too thin
  * for a tcgen05 tile: warp-level mma.sync).  x [N,H,W,4] bf16 (R,G,B,0:
  * avdn_render_views' norm_nhwc), w [32,3,3,3] fp32 (nn.Conv2d layout, rounded to
- * bf16 for the tensor cores), z [N,H,W,64] bf16 (ch 32..63 = 0).  stats: NULL or
- * [2,64] f64 receiving the BatchNorm batch statistics of z (sum, sum of squares;
+ * bf16 for the tensor cores), z [N,H,W,32] bf16.  stats: NULL or
+ * [2,32] f64 receiving the BatchNorm batch statistics of z (sum, sum of squares;
  * zeroed by the call), to be finished by avdn_bn_finalize.  W % 16 == H % 4 == 0. */
 int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W, double* stats,
                    avdn_stream_t stream);
@@ -232,6 +234,12 @@ int avdn_pack_conv_weight(const float* w, int Cout, int Cin, int k, int Cout_p, 
 /* grad [Cout,Cin,k,k] fp32 += dwf [Cout_p][k*k][Cin_p] fp32 (WGRAD output layout). */
 int avdn_unpack_conv_wgrad(const float* dwf, int Cout, int Cin, int k, int Cin_p, float* grad,
                            avdn_stream_t stream);
+/* The same for a gradient computed on pixel-pair views (32-channel activations keep 128-byte
+ * operand rows when two adjacent pixels are read as one row; planners in gemm.py):
+ * dwp is [2*Cout_p][k*3][2*Cin_p] (stride 1, k = 3), [2*Cout_p][1][2*Cin_p] (k = 1) or
+ * [Cout_p][3*2][2*Cin_p] (stride 2); grad [Cout,Cin,k,k] fp32 += the blocks of each tap.   */
+int avdn_unpack_conv_wgrad_pairs(const float* dwp, int Cout, int Cin, int k, int stride, int Cout_p, int Cin_p,
+                                 float* grad, avdn_stream_t stream);
 int avdn_cast_f32_bf16(const float* in, void* out, long long n, avdn_stream_t stream);
 /* Trunk output [N,HW,C] bf16 NHWC -> `frames` [N,C,HW] fp32 (the .view at
  * src/xview_et/agent.py:594) and its adjoint for the backward pass.           */

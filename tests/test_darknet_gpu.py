@@ -177,16 +177,7 @@ def test_full_trunk_224_backward_layerwise(built_lib):
         g_in = L.g[..., :L.Cout].float().permute(0, 3, 1, 2).clone()
         acc = (not L.first) and any(p.desc.core.accumulate for p in L.p_dgrad)
         before = L.src.g.float().clone() if acc else None
-        call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
-             L.Cout_p, L.Cout, DN.LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
-        if L.first:
-            call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
-        else:
-            L.dwf.zero_()
-            L.p_wgrad.run()
-            call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
-            for p in L.p_dgrad:
-                p.run()
+        DN._layer_backward(eng, L)
         xin = (eng.x_in[..., :3] if L.first else L.src.a[..., :L.Cin]).float().permute(0, 3, 1, 2)
         xin = xin.clone().requires_grad_(True)
         w = conv.weight.detach().clone().requires_grad_(True)

@@ -63,16 +63,7 @@ for li in reversed(range(len(eng.layers))):
     if not L.first:
         src_g_before = L.src.g.float().clone()
     dgam0, dbet0 = L.dgamma.clone(), L.dbeta.clone()
-    call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
-         L.Cout_p, L.Cout, DN.LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
-    if L.first:
-        call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
-    else:
-        L.dwf.zero_()
-        L.p_wgrad.run()
-        call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
-        for p in L.p_dgrad:
-            p.run()
+    DN._layer_backward(eng, L)
     # ---- teacher-forced reference of this block
     if L.first:
         xin = eng.x_in[..., :3].float().permute(0, 3, 1, 2)
