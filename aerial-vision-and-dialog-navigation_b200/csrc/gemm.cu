@@ -15,14 +15,17 @@
 //          -> nn.Conv2d / nn.Linear weight gradients
 //
 // Structure (one CTA -- or one CTA pair, cta_group::2 -- per SM, looping over tiles):
-//   warp 0      TMA producer: fills a ring of STAGES x (A 16 KB + B) smem stages, 128-byte swizzle,
-//               running ahead across tile boundaries
+//   warp 0      TMA producer: fills a ring of smem stages (128-byte swizzle), running ahead across tile
+//               boundaries.  A stage holds up to KPS k-blocks (A 16 KB + B each): one mbarrier round trip and
+//               one tcgen05.commit cost ~300 cycles of the issuing thread, so thin k-blocks are batched.
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma kind::f16 (bf16 x bf16 -> fp32)
 //               into one of TWO TMEM accumulators; tcgen05.commit frees smem stages and hands
 //               the finished accumulator to the epilogue
 //   warps 2..5  epilogue: tcgen05.ld (one TMEM lane quarter each) -> alpha/bias/ReLU -> bf16|fp32
 //               -> 128-byte-swizzled smem slab -> TMA store (or TMA reduce-add for the
 //               accumulating modes); the epilogue of tile i overlaps the main loop of tile i+1.
+//               Slabs rotate through up to 4 buffers: a bulk store needs ~2500 cycles until its
+//               shared-memory source has been read.
 //               Optional fused BatchNorm statistics: per-channel sum / sum of squares of the
 //               rounded outputs, accumulated per CTA and committed with fp64 atomics
 //               (nn.BatchNorm2d batch statistics, dark_net.py:31).
@@ -32,6 +35,7 @@
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -117,6 +121,12 @@ template <int N>
 __device__ __forceinline__ void tma_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// at most `n` (1..3) bulk groups may still be reading their shared-memory source
+__device__ __forceinline__ void tma_wait_group_read_n(int n) {
+  if (n >= 3) tma_wait_group_read<3>();
+  else if (n == 2) tma_wait_group_read<2>();
+  else tma_wait_group_read<1>();
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -169,6 +179,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
   }
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+        "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -199,6 +222,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+constexpr int MAX_STAGES = 12;
+constexpr int MAX_SLABS = 4;
+
 struct alignas(64) KernelParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB[4];
@@ -207,38 +233,46 @@ struct alignas(64) KernelParams {
   int32_t grid_m, grid_n, grid_z;   // tile space (grid_m counts 128-row tiles)
   int32_t out_tma;      // 1: epilogue goes through smem slabs + TMA store / reduce-add
   int32_t rows_in_box;  // rows of a tile that exist (CONV: bw*bh*bn <= 128; otherwise 128)
-  int32_t pad_;
+  int32_t stages;       // smem ring depth (<= MAX_STAGES)
+  int32_t kps;          // k-blocks per stage (1..4)
+  int32_t slabs;        // epilogue slab buffers (2..MAX_SLABS)
+  int32_t dbg;          // timing experiments (AVDN_GEMM_DBG): 1 no bulk store, 2 no TMEM load, 4 no staging stores
+  long long* dbg_out;   // NULL, or a device buffer receiving a clock64 trace of CTA 0 (AVDN_GEMM_DBG_BUF;
+                        // tools/gemm_epilogue_probe.py)
 };
 
-template <int BN, int STAGES, int CTAS, int BKT = BK>
-struct SmemLayout {
+// smem: [stages x kps x (A|B)] [slabs x 16 KB] [float 2 x BN] [barriers] [tmem slot]
+template <int BN, int CTAS, int BKT>
+struct Tiles {
   static constexpr int A_BYTES = BM * BKT * 2;                 // 16 KB (8 KB for 32-element k-blocks)
   static constexpr int B_BYTES = (BN / CTAS) * BKT * 2;        // this CTA's part of B
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLAB_OFF = STAGES * STAGE_BYTES;
-  static constexpr int STAT_OFF = SLAB_OFF + 2 * SLAB_BYTES;   // float [2][BN]
-  static constexpr int BAR_OFF = STAT_OFF + 2 * BN * 4;
-  static constexpr int NUM_BARS = 2 * STAGES + 4;
-  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int SUB_BYTES = A_BYTES + B_BYTES;          // one k-block
+  static constexpr int NUM_BARS = 2 * MAX_STAGES + 4;
+  static constexpr int TAIL_BYTES = 2 * BN * 4 + NUM_BARS * 8 + 16 + 1024;   // stats + barriers + slot + align slack
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS, int BKT>
+template <int BN, bool A_MN, bool B_MN, int CTAS, int BKT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ KernelParams p) {
   static_assert(BKT == 64 || (BKT == 32 && !A_MN && !B_MN), "32-element k-blocks: K-major operands only");
-  using L = SmemLayout<BN, STAGES, CTAS, BKT>;
+  using L = Tiles<BN, CTAS, BKT>;
+  constexpr int BNH = BN / CTAS;                                // B columns this CTA loads
   constexpr uint32_t KLAYOUT = (BKT == 64) ? 2u : 4u;          // swizzle mode of the K-major operands
   constexpr uint32_t KSBO = 8u * BKT * 2u;                     // 8 rows of BKT bf16
-  constexpr int BNH = BN / CTAS;                                // B columns this CTA loads
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + L::BAR_OFF;
+  const int STAGES = p.stages, KPS = p.kps, NSLAB = p.slabs;
+  const uint32_t stage_bytes = (uint32_t)KPS * L::SUB_BYTES;
+  const uint32_t slab_off = (uint32_t)STAGES * stage_bytes;
+  const uint32_t stat_off = slab_off + (uint32_t)NSLAB * SLAB_BYTES;
+  const uint32_t bar_off = stat_off + 2 * BN * 4;
+  const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFF + 8 * L::NUM_BARS);
-  float* s_stat = reinterpret_cast<float*>(smem_gen + L::STAT_OFF);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 8 * L::NUM_BARS);
+  float* s_stat = reinterpret_cast<float*>(smem_gen + stat_off);
 
   const avdn_gemm_core& c = p.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -246,33 +280,69 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
   const bool leader = (rank == 0);
 
   // ---- tile space: pair-tiles when CTAS == 2 (two adjacent 128-row tiles share one B) -----
-  const int pm = (p.grid_m + CTAS - 1) / CTAS;
-  const long long total = (long long)pm * p.grid_n * p.grid_z;
-  const long long t_begin = blockIdx.x / CTAS, t_step = gridDim.x / CTAS;
+  // Tile index t = nt + grid_n * (mtp + pm * z), visited as t = t_begin, t_begin + t_step, ...
+  // The three roles walk it with carry arithmetic (no divisions on the per-tile path: the roles are
+  // single threads / single warps and a 64-bit division costs more than a whole k-step).
+  const uint32_t pm = (uint32_t)(p.grid_m + CTAS - 1) / CTAS;
+  const uint32_t gn = (uint32_t)p.grid_n;
+  const uint32_t total = pm * gn * (uint32_t)p.grid_z;
+  const uint32_t t_begin = blockIdx.x / CTAS, t_step = gridDim.x / CTAS;
   const int kb_per = (c.num_kb + c.split_k - 1) / c.split_k;
 
   struct Tile { int mt, nt, z0, z1, tap, kb_begin, my_kb; };
-  auto decode = [&](long long t) {
-    Tile T;
-    T.nt = (int)(t % p.grid_n);
-    const long long r = t / p.grid_n;
-    T.mt = (int)(r % pm) * CTAS + (int)rank;
-    int z = (int)(r / pm);
-    int split;
-    T.z0 = T.z1 = T.tap = 0;
-    if (c.mode == AVDN_GEMM_WGRAD) {
-      // taps fastest: the CTAs running side by side sweep the SAME pixel range for all filter
-      // taps, so dZ and X are fetched from HBM once and re-read from L2 by the other taps
-      T.tap = z % c.n_taps;
-      split = z / c.n_taps;
-    } else {
-      split = z % c.split_k;  z /= c.split_k;
-      T.z0 = z % c.batch0; T.z1 = z / c.batch0;
+  struct Walk {
+    uint32_t t, nt, mtp, z;          // current tile
+    uint32_t dn, dm, dz;             // t_step decomposed
+    uint32_t zc; int z0, z1, tap, kb_begin, my_kb;   // cached decomposition of z
+  };
+  auto walk_init = [&]() {
+    Walk w;
+    w.t = t_begin;
+    w.nt = t_begin % gn;
+    uint32_t r = t_begin / gn;
+    w.mtp = r % pm;
+    w.z = r / pm;
+    w.dn = t_step % gn;
+    r = t_step / gn;
+    w.dm = r % pm;
+    w.dz = r / pm;
+    w.zc = 0xFFFFFFFFu;
+    w.z0 = w.z1 = w.tap = w.kb_begin = w.my_kb = 0;
+    return w;
+  };
+  auto walk_tile = [&](Walk& w) {
+    if (w.z != w.zc) {               // z changes once per (pm * grid_n) tiles
+      w.zc = w.z;
+      int z = (int)w.z, split;
+      w.z0 = w.z1 = w.tap = 0;
+      if (c.mode == AVDN_GEMM_WGRAD) {
+        // taps fastest: the CTAs running side by side sweep the SAME pixel range for all filter
+        // taps, so dZ and X are fetched from HBM once and re-read from L2 by the other taps
+        w.tap = z % c.n_taps;
+        split = z / c.n_taps;
+      } else {
+        split = z % c.split_k;  z /= c.split_k;
+        w.z0 = z % c.batch0; w.z1 = z / c.batch0;
+      }
+      w.kb_begin = split * kb_per;
+      const int kb_end = min(c.num_kb, w.kb_begin + kb_per);
+      w.my_kb = max(0, kb_end - w.kb_begin);
     }
-    T.kb_begin = split * kb_per;
-    const int kb_end = min(c.num_kb, T.kb_begin + kb_per);
-    T.my_kb = max(0, kb_end - T.kb_begin);
+    Tile T;
+    T.nt = (int)w.nt;
+    T.mt = (int)w.mtp * CTAS + (int)rank;
+    T.z0 = w.z0; T.z1 = w.z1; T.tap = w.tap; T.kb_begin = w.kb_begin; T.my_kb = w.my_kb;
     return T;
+  };
+  auto walk_next = [&](Walk& w) {
+    w.t += t_step;
+    w.nt += w.dn;
+    uint32_t carry = (w.nt >= gn) ? 1u : 0u;
+    w.nt -= carry * gn;
+    w.mtp += w.dm + carry;
+    carry = (w.mtp >= pm) ? 1u : 0u;
+    w.mtp -= carry * pm;
+    w.z += w.dz + carry;
   };
 
   // ---- one-time setup -----------------------------------------------------
@@ -308,53 +378,76 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     // =========================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_total = c.tx_bytes;                 // bytes both CTAs deposit per k-step
-      for (long long t = t_begin; t < total; t += t_step) {
-        const Tile T = decode(t);
+      const uint32_t tx_kb = c.tx_bytes;                    // bytes both CTAs deposit per k-block
+      const uint32_t twh = (uint32_t)(c.tiles_w * c.tiles_h);
+      for (Walk wk = walk_init(); wk.t < total; walk_next(wk)) {
+        const Tile T = walk_tile(wk);
+        if (T.my_kb == 0) continue;
         const int n0 = T.nt * BN + (int)rank * BNH;         // this CTA's slice of B
         const int m0 = T.mt * BM;
         int w0 = 0, h0 = 0, i0 = 0;
+        // k-block cursors (advanced incrementally: no division inside the k loop)
+        int cb = 0, tp_i = 0, k0 = 0, pw = 0, ph = 0, pn = 0;
+        avdn_tap tp = c.taps[0];
         if (c.mode == AVDN_GEMM_CONV) {
-          w0 = (T.mt % c.tiles_w) * c.box_w;
-          h0 = ((T.mt / c.tiles_w) % c.tiles_h) * c.box_h;
-          i0 = (T.mt / (c.tiles_w * c.tiles_h)) * c.box_n;  // phantom tile of an odd pair: out of bounds -> zeros
+          const uint32_t mt = (uint32_t)T.mt;
+          const uint32_t q = mt / (uint32_t)c.tiles_w, in = mt / twh;
+          w0 = (int)(mt - q * c.tiles_w) * c.box_w;
+          h0 = (int)(q - in * c.tiles_h) * c.box_h;
+          i0 = (int)in * c.box_n;                           // phantom tile of an odd pair: out of bounds -> zeros
+          tp_i = T.kb_begin / c.cblocks;
+          cb = T.kb_begin - tp_i * c.cblocks;
+          tp = c.taps[tp_i];
+        } else if (c.mode == AVDN_GEMM_WGRAD) {
+          tp = c.taps[T.tap];
+          const uint32_t kb = (uint32_t)T.kb_begin;
+          const uint32_t q = kb / (uint32_t)c.tiles_w, in = kb / twh;
+          pw = (int)(kb - q * c.tiles_w) * c.box_w;
+          ph = (int)(q - in * c.tiles_h) * c.box_h;
+          pn = (int)in * c.box_n;
+        } else {
+          k0 = T.kb_begin * BKT;
         }
-        for (int kb = T.kb_begin; kb < T.kb_begin + T.my_kb; ++kb) {
+        const int zb0 = T.z0 * c.b_batched, zb1 = T.z1 * c.b_batched;
+        for (int rem = T.my_kb; rem > 0;) {
+          const int nkb = rem < KPS ? rem : KPS;
+          rem -= nkb;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-          const uint32_t sb = sa + L::A_BYTES;
           uint32_t fb = full_bar(stage);
           if (CTAS == 2) fb = mapa_rank(fb, 0);
-          if (leader) mbar_expect_tx(full_bar(stage), tx_total);
-          if (c.mode == AVDN_GEMM_PLAIN) {
-            const int k0 = kb * BKT;
-            if (!A_MN) tma_load_4d<CTAS>(sa, &p.tmA[0], fb, k0, m0, T.z0, T.z1);
-            else {
-              tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, k0, T.z0, T.z1);
-              tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, k0, T.z0, T.z1);
-            }
-            if (!B_MN) tma_load_4d<CTAS>(sb, &p.tmB[0], fb, k0, n0, T.z0 * c.b_batched, T.z1 * c.b_batched);
-            else {
+          if (leader) mbar_expect_tx(full_bar(stage), tx_kb * (uint32_t)nkb);
+          uint32_t sa = smem_base + stage * stage_bytes;
+          for (int j = 0; j < nkb; ++j, sa += L::SUB_BYTES) {
+            const uint32_t sb = sa + L::A_BYTES;
+            if (c.mode == AVDN_GEMM_PLAIN) {
+              if (!A_MN) tma_load_4d<CTAS>(sa, &p.tmA[0], fb, k0, m0, T.z0, T.z1);
+              else {
+                tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, k0, T.z0, T.z1);
+                tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, k0, T.z0, T.z1);
+              }
+              if (!B_MN) tma_load_4d<CTAS>(sb, &p.tmB[0], fb, k0, n0, zb0, zb1);
+              else {
 #pragma unroll
-              for (int j = 0; j < BNH / 64; ++j)
-                tma_load_4d<CTAS>(sb + j * 8192, &p.tmB[0], fb, n0 + 64 * j, k0, T.z0 * c.b_batched,
-                                  T.z1 * c.b_batched);
-            }
-          } else if (c.mode == AVDN_GEMM_CONV) {
-            const int tp_i = kb / c.cblocks, cb = kb - tp_i * c.cblocks;
-            const avdn_tap tp = c.taps[tp_i];
-            tma_load_4d<CTAS>(sa, &p.tmA[tp.map], fb, cb * BKT, w0 + tp.d1, h0 + tp.d2, i0);
-            tma_load_4d<CTAS>(sb, &p.tmB[0], fb, tp.bk + cb * BKT, n0, 0, 0);
-          } else {  // WGRAD: k-step = one pixel tile (box_w*box_h*box_n == 64 pixels)
-            const avdn_tap tp = c.taps[T.tap];
-            const int pw = (kb % c.tiles_w) * c.box_w;
-            const int ph = ((kb / c.tiles_w) % c.tiles_h) * c.box_h;
-            const int pn = (kb / (c.tiles_w * c.tiles_h)) * c.box_n;
-            tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, pw, ph, pn);
-            tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, pw, ph, pn);
+                for (int jj = 0; jj < BNH / 64; ++jj)
+                  tma_load_4d<CTAS>(sb + jj * 8192, &p.tmB[0], fb, n0 + 64 * jj, k0, zb0, zb1);
+              }
+              k0 += BKT;
+            } else if (c.mode == AVDN_GEMM_CONV) {
+              tma_load_4d<CTAS>(sa, &p.tmA[tp.map], fb, cb * BKT, w0 + tp.d1, h0 + tp.d2, i0);
+              tma_load_4d<CTAS>(sb, &p.tmB[0], fb, tp.bk + cb * BKT, n0, 0, 0);
+              if (++cb == c.cblocks) { cb = 0; ++tp_i; tp = c.taps[tp_i < c.n_taps ? tp_i : 0]; }
+            } else {  // WGRAD: k-block = one pixel tile (box_w*box_h*box_n == 64 pixels)
+              tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, pw, ph, pn);
+              tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, pw, ph, pn);
 #pragma unroll
-            for (int j = 0; j < BNH / 64; ++j)
-              tma_load_4d<CTAS>(sb + j * 8192, &p.tmB[tp.map], fb, n0 + 64 * j, pw + tp.d1, ph + tp.d2, pn);
+              for (int jj = 0; jj < BNH / 64; ++jj)
+                tma_load_4d<CTAS>(sb + jj * 8192, &p.tmB[tp.map], fb, n0 + 64 * jj, pw + tp.d1, ph + tp.d2, pn);
+              pw += c.box_w;
+              if (pw >= c.tiles_w * c.box_w) {
+                pw = 0; ph += c.box_h;
+                if (ph >= c.tiles_h * c.box_h) { ph = 0; pn += c.box_n; }
+              }
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -369,29 +462,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
                              ((uint32_t)((BM * CTAS) >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       uint32_t it = 0;
-      for (long long t = t_begin; t < total; t += t_step) {
-        const Tile T = decode(t);
+      int trace_n = 0;
+      // descriptors of stage 0, k = 0; the start-address field (bits 0..13, 16-byte units) is advanced by
+      // plain additions: + stage * stage_bytes / 16, + j * SUB_BYTES / 16, + k * (bytes per UMMA_K) / 16
+      const uint64_t ad0 = A_MN ? make_smem_desc(smem_base, 8192, 1024)
+                                : make_smem_desc(smem_base, 16, KSBO, KLAYOUT);
+      const uint64_t bd0 = B_MN ? make_smem_desc(smem_base + L::A_BYTES, 8192, 1024)
+                                : make_smem_desc(smem_base + L::A_BYTES, 16, KSBO, KLAYOUT);
+      constexpr uint32_t AK = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      constexpr uint32_t BKS = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint32_t stage_units = stage_bytes >> 4;
+      for (Walk wk = walk_init(); wk.t < total; walk_next(wk)) {
+        const Tile T = walk_tile(wk);
         if (T.my_kb == 0) continue;
         const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
         ++it;
         mbar_wait(tempty_bar(as), aphase ^ 1);              // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < T.my_kb; ++kb) {
+        uint32_t first = 0u;                                 // 0 for the very first MMA of the tile
+        for (int rem = T.my_kb; rem > 0;) {
+          const int nkb = rem < KPS ? rem : KPS;
+          rem -= nkb;
+          const bool trace = p.dbg_out && blockIdx.x == 0 && trace_n < 256;
+          long long tc0 = 0, tc1 = 0;
+          if (trace) tc0 = clock64();
           mbar_wait(full_bar(stage), phase);
+          if (trace) tc1 = clock64();
           tcgen05_fence_after();
-          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
-          const uint32_t sb = sa + L::A_BYTES;
+          uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * stage_units), bd = bd0 + (uint64_t)((uint32_t)stage * stage_units);
+          for (int j = 0; j < nkb; ++j) {
 #pragma unroll
-          for (int k = 0; k < BKT / UMMA_K; ++k) {
-            const uint64_t ad = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), 8192, 1024)
-                                     : make_smem_desc(sa + k * (UMMA_K * 2), 16, KSBO, KLAYOUT);
-            const uint64_t bd = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), 8192, 1024)
-                                     : make_smem_desc(sb + k * (UMMA_K * 2), 16, KSBO, KLAYOUT);
-            umma_bf16<CTAS>(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BKT / UMMA_K; ++k) {
+              umma_bf16<CTAS>(tmem_d, ad + (uint64_t)(k * AK), bd + (uint64_t)(k * BKS), idesc, first);
+              first = 1u;
+            }
+            ad += (uint64_t)(L::SUB_BYTES >> 4);
+            bd += (uint64_t)(L::SUB_BYTES >> 4);
           }
           tcgen05_commit<CTAS>(empty_bar(stage));           // frees the smem stage when the MMAs retire
-          if (kb == T.my_kb - 1) tcgen05_commit<CTAS>(tfull_bar(as));
+          if (rem == 0) tcgen05_commit<CTAS>(tfull_bar(as));
+          if (trace) {
+            p.dbg_out[trace_n * 4 + 0] = tc0; p.dbg_out[trace_n * 4 + 1] = tc1;
+            p.dbg_out[trace_n * 4 + 2] = clock64(); p.dbg_out[trace_n * 4 + 3] = nkb;
+            ++trace_n;
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -403,8 +518,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     const int et = threadIdx.x - 64;             // 0..127
     const bool is_bf16 = (c.out_dtype == AVDN_DT_BF16);
     const float alpha = c.alpha;
+    const bool has_alpha = (alpha != 1.0f);
+    const float* __restrict__ bias = c.bias;
     uint32_t it = 0, slab_ctr = 0;
     int stat_nt = -1;
+    int etrace_n = 0;
+    const bool etrace = p.dbg_out && blockIdx.x == 0 && et == 0;
+    long long* eout = p.dbg_out ? p.dbg_out + 2048 : nullptr;
+#define ETR(slot) do { if (etrace && etrace_n < 200) eout[etrace_n * 8 + (slot)] = clock64(); } while (0)
     auto flush_stats = [&]() {
       // all epilogue threads: commit the CTA's running column sums of tile column `stat_nt`
       epi_bar_sync();
@@ -416,121 +537,176 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       }
       epi_bar_sync();
     };
-    for (long long t = t_begin; t < total; t += t_step) {
-      const Tile T = decode(t);
+    // The epilogue warps run one per scheduler: their speed is the single-warp issue rate (~4 cycles per
+    // dependent instruction), so the common case (alpha = 1, no bias, no ReLU: every convolution) must not
+    // pay per-element predicates.  Rows of a tile beyond rows_in_box hold garbage: they are neither stored
+    // (the TMA box ends before them) nor counted by the statistics pass.
+    const bool need_fin = has_alpha || (bias != nullptr) || (c.relu != 0);
+    auto finish32 = [&](uint32_t (&v)[32], int col0) {
+      const bool full = (col0 + 32) <= c.N;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]) * alpha;
+        if (bias && (full || (col0 + j) < c.N)) x += __ldg(bias + col0 + j);
+        if (c.relu) x = fmaxf(x, 0.f);
+        v[j] = __float_as_uint(x);
+      }
+    };
+    const uint32_t twh = (uint32_t)(c.tiles_w * c.tiles_h);
+    for (Walk wk = walk_init(); wk.t < total; walk_next(wk)) {
+      const Tile T = walk_tile(wk);
       if (T.my_kb == 0) continue;
       const uint32_t as = it & 1u, aphase = (it >> 1) & 1u;
       ++it;
       const int n0 = T.nt * BN, m0 = T.mt * BM;
       int w0 = 0, h0 = 0, i0 = 0;
       if (c.mode == AVDN_GEMM_CONV) {
-        w0 = (T.mt % c.tiles_w) * c.box_w;
-        h0 = ((T.mt / c.tiles_w) % c.tiles_h) * c.box_h;
-        i0 = (T.mt / (c.tiles_w * c.tiles_h)) * c.box_n;
+        const uint32_t mt = (uint32_t)T.mt;
+        const uint32_t qq = mt / (uint32_t)c.tiles_w, in = mt / twh;
+        w0 = (int)(mt - qq * c.tiles_w) * c.box_w;
+        h0 = (int)(qq - in * c.tiles_h) * c.box_h;
+        i0 = (int)in * c.box_n;
       }
       if (c.stats && stat_nt != T.nt) {
         if (stat_nt >= 0) flush_stats();
         stat_nt = T.nt;
       }
+      ETR(0);
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
+      ETR(1);
       const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
 
       if (p.out_tma) {
         // ---- TMEM -> registers -> swizzled smem slab -> TMA store / reduce-add ----
-        const bool row_live = row < p.rows_in_box;
-        const bool slab64 = (BN == 32);           // bf16 tile of 32 columns: 64-byte slab rows, 64-byte swizzle
+        constexpr bool SLAB64 = (BN == 32);       // bf16 tile of 32 columns: 64-byte slab rows, 64-byte swizzle
+        // one slab = 128 bytes per row: 64 bf16 columns (two 32-column TMEM chunks) or 32 fp32 columns
+        auto issue_store = [&](uint8_t* slab, int scol) {
+          if (et == 0) {
+            const uint32_t srca = smem_u32(slab);
+            int c0 = scol, c1, c2, c3;
+            if (c.mode == AVDN_GEMM_CONV) { c1 = w0; c2 = h0; c3 = i0; }
+            else if (c.mode == AVDN_GEMM_WGRAD) { c0 = scol + c.taps[T.tap].bk; c1 = m0; c2 = 0; c3 = 0; }
+            else { c1 = m0; c2 = T.z0; c3 = T.z1; }
+            if (!(p.dbg & 1)) {
+              if (c.accumulate) tma_reduce_add_4d(&p.tmC, srca, c0, c1, c2, c3);
+              else tma_store_4d(&p.tmC, srca, c0, c1, c2, c3);
+            }
+            tma_commit_group();
+          }
+        };
+        auto acquire_slab = [&]() {
+          // the bulk store that read this buffer NSLAB slabs ago must have finished reading it
+          uint8_t* slab = smem_gen + slab_off + slab_ctr * SLAB_BYTES;
+          if (et == 0 && !(p.dbg & 32)) tma_wait_group_read_n(NSLAB - 1);
+          if (!(p.dbg & 16)) epi_bar_sync();
+          return slab;
+        };
+        if (is_bf16) {
 #pragma unroll 1
-        for (int cc = 0; cc < BN; cc += 32) {
-          const int col0 = n0 + cc;
-          if (col0 >= c.N) break;                                   // uniform: whole slab out of range
-          uint32_t v[32];
-          tmem_ld32(tmem_acc + (uint32_t)cc, v);
-          float f[32];
+          for (int cc = 0; cc < BN; cc += 64) {
+            const int col0 = n0 + cc;
+            if (col0 >= c.N) break;                                 // uniform: whole slab out of range
+            const bool two = (!SLAB64) && (col0 + 32 < c.N);
+            uint32_t va[32], vb[32];
+            if (!(p.dbg & 2)) {
+              tmem_ld32_async(tmem_acc + (uint32_t)cc, va);           // both chunks in flight while we wait for
+              if (two) tmem_ld32_async(tmem_acc + (uint32_t)cc + 32u, vb);   // the slab buffer
+            } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) * alpha;
-            if (c.bias && (col0 + j) < c.N) x += __ldg(c.bias + col0 + j);
-            if (c.relu) x = fmaxf(x, 0.f);
-            f[j] = row_live ? x : 0.f;
-          }
-          const bool slab_first = (is_bf16 && !slab64) ? ((cc & 32) == 0) : true;
-          const bool slab_last = (is_bf16 && !slab64) ? ((cc & 32) != 0 || col0 + 32 >= c.N) : true;
-          uint8_t* slab = smem_gen + L::SLAB_OFF + (slab_ctr & 1u) * SLAB_BYTES;
-          if (slab_first) {
-            // the TMA store that read this buffer two slabs ago must have finished reading it
-            if (et == 0) tma_wait_group_read<1>();
-            epi_bar_sync();
-          }
-          uint8_t* rowp = slab + row * 128;
-          const int sw = row & 7;
-          if (slab64) {
-            uint8_t* rp = slab + row * 64;
-            const int s4 = (row >> 1) & 3;
+              for (int j = 0; j < 32; ++j) { va[j] = 0x3f800000u + j + cc; vb[j] = 0x3f900000u + j; }
+            }
+            if (cc == 0) ETR(2);
+            uint8_t* slab = acquire_slab();
+            if (cc == 0) ETR(3);
+            tmem_wait_ld();
+            if (cc == 0) ETR(4);
+            if (need_fin) {
+              finish32(va, col0);
+              if (two) finish32(vb, col0 + 32);
+            }
+            if (p.dbg & 4) {
+              if (va[0] == 12345u && vb[5] == 77u) slab[row] = 1;
+            } else if (SLAB64) {
+              uint8_t* rp = slab + row * 64;
+              const int s4 = (row >> 1) & 3;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t w[4];
+              for (int g = 0; g < 4; ++g) {
+                uint32_t w[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
-                w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                for (int j = 0; j < 4; ++j) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(va[g * 8 + 2 * j]),
+                                                                  __uint_as_float(va[g * 8 + 2 * j + 1]));
+                  w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                *reinterpret_cast<uint4*>(rp + ((g ^ s4) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
               }
-              *reinterpret_cast<uint4*>(rp + ((g ^ s4) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          } else if (is_bf16) {
-            const int cbase = (cc & 32) ? 4 : 0;
+            } else {
+              uint8_t* rowp = slab + row * 128;
+              const int sw = row & 7;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t w[4];
+              for (int g = 0; g < 8; ++g) {
+                uint32_t w[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 2 * j], f[g * 8 + 2 * j + 1]);
-                w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                for (int j = 0; j < 4; ++j) {
+                  const int e = (g & 3) * 8 + 2 * j;
+                  const float x0 = __uint_as_float(g < 4 ? va[e] : vb[e]);
+                  const float x1 = __uint_as_float(g < 4 ? va[e + 1] : vb[e + 1]);
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(x0, x1);
+                  w[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                const uint4 val = (g < 4 || two) ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(rowp + ((g ^ sw) << 4)) = val;
               }
-              *reinterpret_cast<uint4*>(rowp + (((cbase + g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            if (slab_first && slab_last) {                          // N tail: zero the unused half
-#pragma unroll
-              for (int g = 4; g < 8; ++g) *reinterpret_cast<uint4*>(rowp + ((g ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+            if (cc == 0) ETR(5);
+            if (!(p.dbg & 8)) fence_proxy_async_smem();
+            if (!(p.dbg & 16)) epi_bar_sync();
+            if (cc == 0) ETR(6);
+            issue_store(slab, col0);
+            if (c.stats) {
+              // fused BatchNorm statistics of the ROUNDED outputs: thread -> (column pair, row group); one
+              // 32-bit shared-memory read per row brings two columns
+              const int npair = SLAB64 ? 16 : 32;                 // column pairs per slab row
+              const int jp = et & (npair - 1), grp = et / npair;  // 4 (8) row groups
+              const int rows_per = 128 / (EPI_THREADS / npair);
+              const int r0 = grp * rows_per, r1 = min(p.rows_in_box, r0 + rows_per);
+              float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll 4
+              for (int r = r0; r < r1; ++r) {
+                const uint8_t* qp = SLAB64 ? slab + r * 64 + (((jp >> 2) ^ ((r >> 1) & 3)) << 4) + (jp & 3) * 4
+                                           : slab + r * 128 + (((jp >> 2) ^ (r & 7)) << 4) + (jp & 3) * 4;
+                const uint32_t wv = *reinterpret_cast<const uint32_t*>(qp);
+                const float x0 = __uint_as_float(wv << 16), x1 = __uint_as_float(wv & 0xFFFF0000u);
+                s1a += x0; s2a = fmaf(x0, x0, s2a);
+                s1b += x1; s2b = fmaf(x1, x1, s2b);
+              }
+              atomicAdd(&s_stat[cc + 2 * jp], s1a);
+              atomicAdd(&s_stat[cc + 2 * jp + 1], s1b);
+              atomicAdd(&s_stat[BN + cc + 2 * jp], s2a);
+              atomicAdd(&s_stat[BN + cc + 2 * jp + 1], s2b);
             }
-          } else {
+            if (++slab_ctr == (uint32_t)NSLAB) slab_ctr = 0;
+          }
+        } else {
+#pragma unroll 1
+          for (int cc = 0; cc < BN; cc += 32) {
+            const int col0 = n0 + cc;
+            if (col0 >= c.N) break;
+            uint32_t va[32];
+            tmem_ld32_async(tmem_acc + (uint32_t)cc, va);
+            uint8_t* slab = acquire_slab();
+            tmem_wait_ld();
+            if (need_fin) finish32(va, col0);
+            uint8_t* rowp = slab + row * 128;
+            const int sw = row & 7;
 #pragma unroll
             for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<float4*>(rowp + ((g ^ sw) << 4)) =
-                  make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
-          }
-          if (slab_last) {
+              *reinterpret_cast<uint4*>(rowp + ((g ^ sw) << 4)) = make_uint4(va[4 * g], va[4 * g + 1], va[4 * g + 2], va[4 * g + 3]);
             fence_proxy_async_smem();
             epi_bar_sync();
-            const int scol = n0 + ((is_bf16 && !slab64) ? (cc & ~32) : cc);      // first column of this slab
-            if (et == 0) {
-              const uint32_t src = smem_u32(slab);
-              int c0 = scol, c1, c2, c3;
-              if (c.mode == AVDN_GEMM_CONV) { c1 = w0; c2 = h0; c3 = i0; }
-              else if (c.mode == AVDN_GEMM_WGRAD) { c0 = scol + c.taps[T.tap].bk; c1 = m0; c2 = 0; c3 = 0; }
-              else { c1 = m0; c2 = T.z0; c3 = T.z1; }
-              if (c.accumulate) tma_reduce_add_4d(&p.tmC, src, c0, c1, c2, c3);
-              else tma_store_4d(&p.tmC, src, c0, c1, c2, c3);
-              tma_commit_group();
-            }
-            if (c.stats) {
-              // fused BatchNorm statistics of the ROUNDED outputs: thread -> (column, row group)
-              const int ncol = slab64 ? 32 : 64, rows_per = slab64 ? 32 : 64;
-              const int j = et & (ncol - 1), grp = et / ncol;
-              const int r0 = grp * rows_per, r1 = min(p.rows_in_box, r0 + rows_per);
-              float s1 = 0.f, s2 = 0.f;
-              for (int r = r0; r < r1; ++r) {
-                const uint8_t* q = slab64 ? slab + r * 64 + (((j >> 3) ^ ((r >> 1) & 3)) << 4) + (j & 7) * 2
-                                          : slab + r * 128 + (((j >> 3) ^ (r & 7)) << 4) + (j & 7) * 2;
-                const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(q));
-                s1 += x;
-                s2 = fmaf(x, x, s2);
-              }
-              const int jj = (scol - n0) + j;
-              atomicAdd(&s_stat[jj], s1);
-              atomicAdd(&s_stat[BN + jj], s2);
-            }
-            ++slab_ctr;
+            issue_store(slab, col0);
+            if (++slab_ctr == (uint32_t)NSLAB) slab_ctr = 0;
           }
         }
         tcgen05_fence_before();
@@ -538,6 +714,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           if (CTAS == 1) mbar_arrive(tempty_bar(as));
           else mbar_arrive_cluster(tempty_bar(as), 0);
         }
+        ETR(7);
+        if (etrace) ++etrace_n;
       } else {
         // ---- direct path: each thread stores its own row (relu_mask, unaligned or tiny outputs) ----
         const bool row_ok = (m0 + row) < c.M;
@@ -554,7 +732,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = __uint_as_float(v[j]) * alpha;
-            if (c.bias && (col0 + j) < c.N) x += __ldg(c.bias + col0 + j);
+            if (bias && (col0 + j) < c.N) x += __ldg(bias + col0 + j);
             if (c.relu) x = fmaxf(x, 0.f);
             f[j] = x;
           }
@@ -626,6 +804,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
     if (c.stats && stat_nt >= 0) flush_stats();
     if (et == 0) tma_wait_group_read<0>();       // smem slabs must outlive the bulk stores reading them
+#undef ETR
   }
 
   // ---- teardown -------------------------------------------------------------
@@ -702,27 +881,28 @@ int encode_operand(const avdn_operand& o, CUtensorMap* out) {
 
 struct Plan {
   uint32_t magic;
-  int32_t bn, stages, a_mn, b_mn, ctas, bk;
+  int32_t bn, a_mn, b_mn, ctas, bk;
   int32_t grid;
-  int smem;
+  int32_t smem;
   KernelParams kp;
 };
 constexpr uint32_t PLAN_MAGIC = 0xA7D17C06u;
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int CTAS, int BKT = BK>
+constexpr int SMEM_MAX = 232448;       // 227 KB: the dynamic shared memory a CTA can opt in to on sm_100
+
+template <int BN, bool A_MN, bool B_MN, int CTAS, int BKT = BK>
 int launch_t(const Plan& pl, cudaStream_t s) {
-  auto kfn = gemm_kernel<BN, STAGES, A_MN, B_MN, CTAS, BKT>;
-  using L = SmemLayout<BN, STAGES, CTAS, BKT>;
+  auto kfn = gemm_kernel<BN, A_MN, B_MN, CTAS, BKT>;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX) != cudaSuccess)
       return avdn::check_launch("cudaFuncSetAttribute(gemm_kernel)");
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)pl.grid, 1, 1);
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.dynamicSmemBytes = (size_t)pl.smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -735,12 +915,12 @@ int launch_t(const Plan& pl, cudaStream_t s) {
   return avdn::check_launch("gemm_kernel");
 }
 
-template <int BN, int STAGES, int CTAS>
+template <int BN, int CTAS>
 int launch_bn(const Plan& pl, cudaStream_t s) {
-  if (!pl.a_mn && !pl.b_mn) return launch_t<BN, STAGES, false, false, CTAS>(pl, s);
-  if (!pl.a_mn && pl.b_mn) return launch_t<BN, STAGES, false, true, CTAS>(pl, s);
-  if (pl.a_mn && !pl.b_mn) return launch_t<BN, STAGES, true, false, CTAS>(pl, s);
-  return launch_t<BN, STAGES, true, true, CTAS>(pl, s);
+  if (!pl.a_mn && !pl.b_mn) return launch_t<BN, false, false, CTAS>(pl, s);
+  if (!pl.a_mn && pl.b_mn) return launch_t<BN, false, true, CTAS>(pl, s);
+  if (pl.a_mn && !pl.b_mn) return launch_t<BN, true, false, CTAS>(pl, s);
+  return launch_t<BN, true, true, CTAS>(pl, s);
 }
 
 }  // namespace
@@ -804,6 +984,12 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   AVDN_REQUIRE(d->grid_m >= 1 && d->grid_n >= 1 && d->grid_z >= 1, "avdn_gemm_plan: bad tile space %d x %d x %d",
                d->grid_m, d->grid_n, d->grid_z);
   pl->kp.rows_in_box = BM;
+  {
+    const char* e = getenv("AVDN_GEMM_DBG");
+    pl->kp.dbg = e ? atoi(e) : 0;
+    const char* b = getenv("AVDN_GEMM_DBG_BUF");      // device address of a >= 64 KB trace buffer
+    pl->kp.dbg_out = b ? reinterpret_cast<long long*>(strtoull(b, nullptr, 0)) : nullptr;
+  }
   if (c.mode == AVDN_GEMM_CONV) {
     pl->kp.rows_in_box = c.box_w * c.box_h * c.box_n;
     AVDN_REQUIRE(pl->kp.rows_in_box >= 1 && pl->kp.rows_in_box <= BM, "avdn_gemm_plan: conv box of %d rows", pl->kp.rows_in_box);
@@ -845,10 +1031,39 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   }
   AVDN_REQUIRE(!c.stats || pl->kp.out_tma, "avdn_gemm_plan: fused statistics need the TMA epilogue");
   AVDN_REQUIRE(pl->kp.out_tma || c.mode != AVDN_GEMM_CONV, "avdn_gemm_plan: conv output cannot be described to TMA");
+  // ---- shared-memory plan: slabs, k-blocks per stage, ring depth ----
+  {
+    const int sub = BM * d->bk * 2 + (d->bn / d->ctas) * d->bk * 2;         // one k-block (this CTA)
+    const int tail = 2 * d->bn * 4 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
+    // k-blocks per stage: one barrier round trip + commit costs the issuing thread ~300 cycles, a k-block of
+    // MMAs (bn/256 * 512 cycles at bk = 64) should not be much shorter than that
+    int kps = 1;
+    const int mma_cycles = d->bn * 2 * d->bk / 64;                           // tensor time of one k-block
+    const int budget = SMEM_MAX - tail - MAX_SLABS * SLAB_BYTES;
+    while (kps < 4 && kps * mma_cycles < 1024 && (budget / ((kps + 1) * sub)) * (kps + 1) >= 4 &&
+           budget / ((kps + 1) * sub) >= 2)
+      ++kps;
+    if (c.mode == AVDN_GEMM_CONV && c.n_taps == 9 && kps == 4) kps = 3;     // whole filter rows
+    if (kps > c.num_kb) kps = c.num_kb;
+    const char* ek = getenv("AVDN_GEMM_KPS");
+    if (ek && atoi(ek) >= 1 && atoi(ek) <= 4) kps = atoi(ek);
+    int slabs = MAX_SLABS;
+    const char* es = getenv("AVDN_GEMM_SLABS");
+    if (es && atoi(es) >= 2 && atoi(es) <= MAX_SLABS) slabs = atoi(es);
+    int stages = (SMEM_MAX - tail - slabs * SLAB_BYTES) / (kps * sub);
+    while (stages < 2 && slabs > 2) { --slabs; stages = (SMEM_MAX - tail - slabs * SLAB_BYTES) / (kps * sub); }
+    while (stages < 2 && kps > 1) { --kps; stages = (SMEM_MAX - tail - slabs * SLAB_BYTES) / (kps * sub); }
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    AVDN_REQUIRE(stages >= 2, "avdn_gemm_plan: shared memory plan failed (bn %d bk %d)", d->bn, d->bk);
+    pl->kp.stages = stages;
+    pl->kp.kps = kps;
+    pl->kp.slabs = slabs;
+    pl->smem = stages * kps * sub + slabs * SLAB_BYTES + tail;
+  }
   // ---- launch geometry: persistent, one CTA (pair) per SM ----
-  pl->stages = 0;
   const long long pm = (d->grid_m + d->ctas - 1) / d->ctas;
   const long long tiles = pm * d->grid_n * d->grid_z;
+  AVDN_REQUIRE(tiles < (1ll << 31), "avdn_gemm_plan: too many tiles");
   const long long slots = avdn::sm_count() / d->ctas;
   pl->grid = (int)((tiles < slots ? tiles : slots) * d->ctas);
   pl->magic = PLAN_MAGIC;
@@ -865,16 +1080,16 @@ extern "C" int avdn_gemm_run(const void* plan_host, avdn_stream_t stream) {
   }
   if (pl->ctas == 2) {
     switch (pl->bn) {
-      case 128: return launch_bn<128, 6, 2>(*pl, s);
-      case 256: return launch_bn<256, 5, 2>(*pl, s);
+      case 128: return launch_bn<128, 2>(*pl, s);
+      case 256: return launch_bn<256, 2>(*pl, s);
     }
   } else {
-    if (pl->bk == 32) return launch_t<64, 8, false, false, 1, 32>(*pl, s);
+    if (pl->bk == 32) return launch_t<64, false, false, 1, 32>(*pl, s);
     switch (pl->bn) {
-      case 32: return launch_t<32, 8, false, false, 1, 64>(*pl, s);
-      case 64: return launch_bn<64, 6, 1>(*pl, s);
-      case 128: return launch_bn<128, 5, 1>(*pl, s);
-      case 256: return launch_bn<256, 3, 1>(*pl, s);
+      case 32: return launch_t<32, false, false, 1, 64>(*pl, s);
+      case 64: return launch_bn<64, 1>(*pl, s);
+      case 128: return launch_bn<128, 1>(*pl, s);
+      case 256: return launch_bn<256, 1>(*pl, s);
     }
   }
   return avdn::set_err(AVDN_ERR_UNSUPPORTED, "avdn_gemm_run: bn %d ctas %d", pl->bn, pl->ctas);
