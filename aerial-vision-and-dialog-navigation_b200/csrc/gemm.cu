@@ -134,6 +134,18 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// true in exactly one (elected) lane of a converged warp; the loops around it stay warp-uniform, so the
+// compiler keeps addresses / descriptors in uniform registers (no per-instruction R2UR chains)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -376,7 +388,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
 
   if (warp == 0) {
     // =========================== TMA producer ===============================
-    if (lane == 0) {
+    // the whole warp walks the loops (uniform control flow); one elected lane issues
+    {
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx_kb = c.tx_bytes;                    // bytes both CTAs deposit per k-block
       const uint32_t twh = (uint32_t)(c.tiles_w * c.tiles_h);
@@ -415,33 +428,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
           mbar_wait(empty_bar(stage), phase ^ 1);
           uint32_t fb = full_bar(stage);
           if (CTAS == 2) fb = mapa_rank(fb, 0);
-          if (leader) mbar_expect_tx(full_bar(stage), tx_kb * (uint32_t)nkb);
+          const bool issuer = elect_one();
+          if (leader && issuer) mbar_expect_tx(full_bar(stage), tx_kb * (uint32_t)nkb);
           uint32_t sa = smem_base + stage * stage_bytes;
           for (int j = 0; j < nkb; ++j, sa += L::SUB_BYTES) {
             const uint32_t sb = sa + L::A_BYTES;
             if (c.mode == AVDN_GEMM_PLAIN) {
-              if (!A_MN) tma_load_4d<CTAS>(sa, &p.tmA[0], fb, k0, m0, T.z0, T.z1);
-              else {
-                tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, k0, T.z0, T.z1);
-                tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, k0, T.z0, T.z1);
+              if (!A_MN) {
+                if (issuer) tma_load_4d<CTAS>(sa, &p.tmA[0], fb, k0, m0, T.z0, T.z1);
+              } else {
+                if (issuer) tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, k0, T.z0, T.z1);
+                if (issuer) tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, k0, T.z0, T.z1);
               }
-              if (!B_MN) tma_load_4d<CTAS>(sb, &p.tmB[0], fb, k0, n0, zb0, zb1);
-              else {
+              if (!B_MN) {
+                if (issuer) tma_load_4d<CTAS>(sb, &p.tmB[0], fb, k0, n0, zb0, zb1);
+              } else {
 #pragma unroll
                 for (int jj = 0; jj < BNH / 64; ++jj)
-                  tma_load_4d<CTAS>(sb + jj * 8192, &p.tmB[0], fb, n0 + 64 * jj, k0, zb0, zb1);
+                  if (issuer) tma_load_4d<CTAS>(sb + jj * 8192, &p.tmB[0], fb, n0 + 64 * jj, k0, zb0, zb1);
               }
               k0 += BKT;
             } else if (c.mode == AVDN_GEMM_CONV) {
-              tma_load_4d<CTAS>(sa, &p.tmA[tp.map], fb, cb * BKT, w0 + tp.d1, h0 + tp.d2, i0);
-              tma_load_4d<CTAS>(sb, &p.tmB[0], fb, tp.bk + cb * BKT, n0, 0, 0);
+              if (issuer) tma_load_4d<CTAS>(sa, &p.tmA[tp.map], fb, cb * BKT, w0 + tp.d1, h0 + tp.d2, i0);
+              if (issuer) tma_load_4d<CTAS>(sb, &p.tmB[0], fb, tp.bk + cb * BKT, n0, 0, 0);
               if (++cb == c.cblocks) { cb = 0; ++tp_i; tp = c.taps[tp_i < c.n_taps ? tp_i : 0]; }
             } else {  // WGRAD: k-block = one pixel tile (box_w*box_h*box_n == 64 pixels)
-              tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, pw, ph, pn);
-              tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, pw, ph, pn);
+              if (issuer) tma_load_4d<CTAS>(sa, &p.tmA[0], fb, m0, pw, ph, pn);
+              if (issuer) tma_load_4d<CTAS>(sa + 8192, &p.tmA[0], fb, m0 + 64, pw, ph, pn);
 #pragma unroll
               for (int jj = 0; jj < BNH / 64; ++jj)
-                tma_load_4d<CTAS>(sb + jj * 8192, &p.tmB[tp.map], fb, n0 + 64 * jj, pw + tp.d1, ph + tp.d2, pn);
+                if (issuer) tma_load_4d<CTAS>(sb + jj * 8192, &p.tmB[tp.map], fb, n0 + 64 * jj, pw + tp.d1, ph + tp.d2, pn);
               pw += c.box_w;
               if (pw >= c.tiles_w * c.box_w) {
                 pw = 0; ph += c.box_h;
@@ -455,7 +471,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ================================
-    if (lane == 0 && leader) {
+    // the whole warp of the leader CTA walks the loops; one elected lane issues the MMAs and commits
+    if (leader) {
       // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                              ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
@@ -484,29 +501,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
         for (int rem = T.my_kb; rem > 0;) {
           const int nkb = rem < KPS ? rem : KPS;
           rem -= nkb;
-          const bool trace = p.dbg_out && blockIdx.x == 0 && trace_n < 256;
+          const bool trace = p.dbg_out && blockIdx.x == 0 && trace_n < 256;   // (all lanes count, lane 0 writes)
           long long tc0 = 0, tc1 = 0;
           if (trace) tc0 = clock64();
           mbar_wait(full_bar(stage), phase);
           if (trace) tc1 = clock64();
           tcgen05_fence_after();
-          uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * stage_units), bd = bd0 + (uint64_t)((uint32_t)stage * stage_units);
-          for (int j = 0; j < nkb; ++j) {
+          if (elect_one()) {
+            uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * stage_units), bd = bd0 + (uint64_t)((uint32_t)stage * stage_units);
+            uint32_t acc = first;
+            for (int j = 0; j < nkb; ++j) {
 #pragma unroll
-            for (int k = 0; k < BKT / UMMA_K; ++k) {
-              umma_bf16<CTAS>(tmem_d, ad + (uint64_t)(k * AK), bd + (uint64_t)(k * BKS), idesc, first);
-              first = 1u;
+              for (int k = 0; k < BKT / UMMA_K; ++k) {
+                umma_bf16<CTAS>(tmem_d, ad + (uint64_t)(k * AK), bd + (uint64_t)(k * BKS), idesc, acc);
+                acc = 1u;
+              }
+              ad += (uint64_t)(L::SUB_BYTES >> 4);
+              bd += (uint64_t)(L::SUB_BYTES >> 4);
             }
-            ad += (uint64_t)(L::SUB_BYTES >> 4);
-            bd += (uint64_t)(L::SUB_BYTES >> 4);
+            tcgen05_commit<CTAS>(empty_bar(stage));         // frees the smem stage when the MMAs retire
+            if (rem == 0) tcgen05_commit<CTAS>(tfull_bar(as));
           }
-          tcgen05_commit<CTAS>(empty_bar(stage));           // frees the smem stage when the MMAs retire
-          if (rem == 0) tcgen05_commit<CTAS>(tfull_bar(as));
-          if (trace) {
+          __syncwarp();
+          first = 1u;
+          if (trace && lane == 0) {
             p.dbg_out[trace_n * 4 + 0] = tc0; p.dbg_out[trace_n * 4 + 1] = tc1;
             p.dbg_out[trace_n * 4 + 2] = clock64(); p.dbg_out[trace_n * 4 + 3] = nkb;
-            ++trace_n;
           }
+          if (trace) ++trace_n;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
