@@ -295,6 +295,12 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = wl.units_per_step() * world * e_steps / float(te.item())
 
+    # collective parts of the roofline measurement (the instrumented training step all-reduces) run on
+    # every rank; only rank 0 formats the result
+    prep = getattr(wl, "prepare_roofline", None)
+    if prep is not None:
+        prep()
+    barrier()
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:

@@ -101,7 +101,7 @@ class RolloutWorkload:
         torch.cuda.current_stream().synchronize()
         return h2d, int(self.res_host.numel() * 8)
 
-    def roofline(self, peaks):
+    def prepare_roofline(self):
         from avdn_b200 import _lib
         _lib.PROFILE = []
         self.agent.rollout_greedy(self.batch, T_STEPS)
@@ -111,6 +111,12 @@ class RolloutWorkload:
             a = agg.setdefault(name, [0, 0.0, 0])
             a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl
         _lib.PROFILE = None
+        self.profile = agg
+
+    def roofline(self, peaks):
+        if self.profile is None:
+            self.prepare_roofline()
+        agg = self.profile
         g = {k: v for k, v in agg.items() if k.startswith("gemm")}
         g_ms, g_fl = sum(v[1] for v in g.values()), sum(v[2] for v in g.values())
         tot = sum(v[1] for v in agg.values())

@@ -139,6 +139,11 @@ class TrainWorkload:
         self.profile = agg
         return agg
 
+    def prepare_roofline(self):
+        """Called on EVERY rank: the instrumented step is a full data-parallel step (all-reduce inside)."""
+        if self.profile is None:
+            self.profile_step()
+
     def flops_per_step(self):
         return (DARKNET_GFLOP_IMG * 1e9 * self.B * T_STEPS + et_flops_fwd() * self.B) * 3
 
