@@ -20,7 +20,7 @@ c_void_p, c_int, c_i64, c_f32, c_f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 class TileDesc(C.Structure):
     """``avdn_tile_desc`` of include/avdn.h."""
-    _fields_ = [("tile4", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32)]
+    _fields_ = [("tile8", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32)]
 
 
 # name -> argtypes ; every function returns int (avdn_status) unless noted

@@ -4,8 +4,9 @@
 // calls (map and attention map) + the agent's image normalisation
 // (src/xview_et/agent.py:586-592) with three kernels:
 //
-//   pack_tile_kernel     one-off per map: BGR u8 HWC (+ attention) -> u32/pixel
-//                        B|G<<8|R<<16|ATT<<24 with a 1-px zero border
+//   pack_tile_kernel     one-off per map: BGR u8 HWC (+ attention) -> one 8-byte
+//                        record per pixel holding the pixel AND the one below it
+//                        (each B|G<<8|R<<16|ATT<<24), with a 1-px zero border
 //   homography_kernel    one thread per pose: OpenCV's 8x8 LU + 3x3 adjugate
 //                        inverse in float64, same operation order, no FMA
 //   render_kernel        one CTA per (pose, 32-row band): fixed-point bilinear
@@ -13,12 +14,16 @@
 //
 // The warp is a gather: every output pixel reads a 2x2 footprint of the source
 // at a data-dependent position.  It is bound by L2->SM sector traffic, not by
-// tensor cores; the design rules that matter are (i) one aligned 32-bit load
-// per tap (all four channels at once), (ii) lanes of a warp arranged as an 8x4
-// output patch so that a warp's footprint stays compact under any rotation,
-// (iii) the band is staged in shared memory and leaves the SM as full 16-byte
-// coalesced stores (a 32-row band of a 224x224x3 view is one contiguous
-// 21 504-byte range of HBM).
+// tensor cores; the design rules that matter are (i) one aligned 64-bit load
+// per tap COLUMN (both rows, all four channels at once): the 2x2 footprint is
+// two adjacent records = 16 contiguous bytes, inside one 32-byte sector three
+// times out of four (a row-major 4-byte tile needs 2.25 sectors per footprint),
+// (ii) lanes of a warp arranged as an 8x4 output patch so that a warp's
+// footprint stays compact under any rotation, (iii) the blend runs on packed
+// 16-bit lanes (vertical) and dp2a (horizontal), (iv) the band is staged in
+// shared memory as BGRA words and leaves the SM as full 16-byte coalesced
+// stores (a 32-row band of a 224x224x3 view is one contiguous 21 504-byte
+// range of HBM).
 //
 // Exactness: OpenCV evaluates, in float64 and per 64-pixel-wide block,
 //   X0 = (M0*xb + M1*y) + M2 ... W = W0 + M6*x1 ; W = W ? 32/W : 0
@@ -43,22 +48,30 @@ constexpr int INTER_BITS = 5;
 constexpr int INTER_TAB = 1 << INTER_BITS;
 
 // ---------------------------------------------------------------- pack tile
+__device__ __forceinline__ uint32_t packed_pixel(const uint8_t* __restrict__ map_bgr,
+                                                 const uint8_t* __restrict__ att, int att_ch,
+                                                 int H, int W, int yy, int xx) {
+  // (xx, yy) in padded coordinates: source pixel (xx-1, yy-1), zero outside
+  if (yy < 1 || yy > H || xx < 1 || xx > W) return 0u;
+  const long long s = (long long)(yy - 1) * W + (xx - 1);
+  const uint8_t* p = map_bgr + s * 3;
+  uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+  if (att) v |= (uint32_t)att[s * att_ch] << 24;
+  return v;
+}
+
 __global__ void pack_tile_kernel(const uint8_t* __restrict__ map_bgr,
                                  const uint8_t* __restrict__ att, int att_ch,
-                                 int H, int W, uint32_t* __restrict__ tile4) {
+                                 int H, int W, uint2* __restrict__ tile8) {
   const int pitch = W + 2;
-  const long long n = (long long)(H + 2) * pitch;
+  const long long n = (long long)(H + 1) * pitch;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const int yy = (int)(i / pitch), xx = (int)(i - (long long)yy * pitch);
-    uint32_t v = 0;
-    if (yy >= 1 && yy <= H && xx >= 1 && xx <= W) {
-      const long long s = (long long)(yy - 1) * W + (xx - 1);
-      const uint8_t* p = map_bgr + s * 3;
-      v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-      if (att) v |= (uint32_t)att[s * att_ch] << 24;
-    }
-    tile4[i] = v;
+    uint2 v;
+    v.x = packed_pixel(map_bgr, att, att_ch, H, W, yy, xx);        // row yy
+    v.y = packed_pixel(map_bgr, att, att_ch, H, W, yy + 1, xx);    // row yy + 1
+    tile8[i] = v;
   }
 }
 
@@ -163,8 +176,7 @@ __global__ void homography_kernel(const int32_t* __restrict__ corners_px, int P,
 // ------------------------------------------------------------------- render
 // Exactly OpenCV's per-pixel sequence (WarpPerspectiveInvoker), used by the
 // rare lanes whose fast-path result sits next to a rounding tie.
-__device__ __noinline__ void exact_coords(const double* __restrict__ m, int xb, int x1,
-                                          int y, int* X, int* Y) {
+__device__ __noinline__ int2 exact_coords(const double* __restrict__ m, int xb, int x1, int y) {
   const double dxb = (double)xb, dx1 = (double)x1, dy = (double)y;
   const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m[0], dxb), __dmul_rn(m[1], dy)), m[2]);
   const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m[3], dxb), __dmul_rn(m[4], dy)), m[5]);
@@ -175,8 +187,7 @@ __device__ __noinline__ void exact_coords(const double* __restrict__ m, int xb, 
   double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(m[3], dx1)), W);
   fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
   fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
-  *X = __double2int_rn(fX);
-  *Y = __double2int_rn(fY);
+  return make_int2(__double2int_rn(fX), __double2int_rn(fY));
 }
 
 __device__ __forceinline__ double rcp_seed(double x) {
@@ -197,7 +208,29 @@ __device__ __forceinline__ bool fast_round(double f, int* out) {
   return ((hi >> 20) == 0x41Fu) && (d > 8 || d < -8);
 }
 
-__global__ void __launch_bounds__(THREADS, 3)
+// Blend of one output pixel from the two records of its footprint.
+//   r0 = (p00 | p10 << 32) at column sx, r1 = (p01 | p11 << 32) at column sx + 1
+// out_c = (sum_taps p_c * wy * wx + 512) >> 10  (SURVEY App. A), evaluated as a vertical
+// blend on packed 16-bit lanes (two channels per IMAD; <= 255 * 32 fits 13 bits) followed by
+// one dp2a per channel for the horizontal blend.  Pure integer refactoring: bit-exact.
+template <bool ATT>
+__device__ __forceinline__ uint32_t blend(uint2 r0, uint2 r1, uint32_t ax, uint32_t ay) {
+  const uint32_t wy0 = INTER_TAB - ay, wy1 = ay;
+  const uint32_t wx = (INTER_TAB - ax) | (ax << 8);
+  const uint32_t vBR0 = __byte_perm(r0.x, 0, 0x4240) * wy0 + __byte_perm(r0.y, 0, 0x4240) * wy1;
+  const uint32_t vGA0 = __byte_perm(r0.x, 0, 0x4341) * wy0 + __byte_perm(r0.y, 0, 0x4341) * wy1;
+  const uint32_t vBR1 = __byte_perm(r1.x, 0, 0x4240) * wy0 + __byte_perm(r1.y, 0, 0x4240) * wy1;
+  const uint32_t vGA1 = __byte_perm(r1.x, 0, 0x4341) * wy0 + __byte_perm(r1.y, 0, 0x4341) * wy1;
+  const uint32_t oB = __dp2a_lo(__byte_perm(vBR0, vBR1, 0x5410), wx, 512u) >> 10;
+  const uint32_t oR = __dp2a_lo(__byte_perm(vBR0, vBR1, 0x7632), wx, 512u) >> 10;
+  const uint32_t oG = __dp2a_lo(__byte_perm(vGA0, vGA1, 0x5410), wx, 512u) >> 10;
+  uint32_t o = oB | (oG << 8) | (oR << 16);
+  if (ATT) o |= (__dp2a_lo(__byte_perm(vGA0, vGA1, 0x7632), wx, 512u) >> 10) << 24;
+  return o;
+}
+
+template <bool ATT>
+__global__ void __launch_bounds__(THREADS, 4)
 render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restrict__ tile_idx,
               const double* __restrict__ minv, int P,
               uint8_t* __restrict__ views, uint8_t* __restrict__ att,
@@ -205,8 +238,7 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
               const float* __restrict__ norm_lut) {
   __shared__ double s_m[9];
   __shared__ double s_tab[4][BAND][3];                       // 32*X0, 32*Y0, W0
-  __shared__ __align__(16) uint8_t s_view[BAND * VIEW * 3];  // 21504 B
-  __shared__ __align__(16) uint8_t s_att[BAND * VIEW];       // 7168 B
+  __shared__ __align__(16) uint32_t s_px[BAND * VIEW];       // BGRA per pixel, 28672 B
   __shared__ float s_lut[3 * 256];
 
   const int p = blockIdx.x / NBAND, band = blockIdx.x - p * NBAND;
@@ -237,7 +269,7 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
   const double c3s = __dmul_rn(s_m[3], dx1) * 32.0;
   const double c6 = __dmul_rn(s_m[6], dx1);
   const int pitch = td.W + 2;
-  const uint32_t* __restrict__ tile = td.tile4;
+  const uint2* __restrict__ tile = reinterpret_cast<const uint2*>(td.tile8);
 
   const int n_xb = (x1 < 32) ? 4 : 3;             // 224 = 3*64 + 32 (warp-uniform)
   for (int xbi = 0; xbi < n_xb; ++xbi) {
@@ -255,50 +287,63 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
       int X, Y;
       const bool okx = fast_round(fX, &X);
       const bool oky = fast_round(fY, &Y);
-      if (!(okx && oky)) exact_coords(s_m, xbi * 64, x1, band * BAND + r, &X, &Y);
+      if (!(okx && oky)) {   // rare: re-evaluate exactly as OpenCV does (matrix re-read from global)
+        const int2 e = exact_coords(minv + (size_t)p * 9, xbi * 64, x1, band * BAND + r);
+        X = e.x;
+        Y = e.y;
+      }
       const int sx = X >> INTER_BITS, sy = Y >> INTER_BITS;
-      const int ax = X & (INTER_TAB - 1), ay = Y & (INTER_TAB - 1);
-      uint32_t p00 = 0, p01 = 0, p10 = 0, p11 = 0;
+      uint2 r0 = make_uint2(0u, 0u), r1 = make_uint2(0u, 0u);
       if ((unsigned)(sx + 1) <= (unsigned)td.W && (unsigned)(sy + 1) <= (unsigned)td.H) {
-        const uint32_t* q = tile + (size_t)(sy + 1) * pitch + (sx + 1);
-        p00 = __ldg(q);
-        p01 = __ldg(q + 1);
-        p10 = __ldg(q + pitch);
-        p11 = __ldg(q + pitch + 1);
+        const uint2* q = tile + (size_t)(sy + 1) * pitch + (sx + 1);
+        r0 = __ldg(q);
+        r1 = __ldg(q + 1);
       }
-      const int w00 = (INTER_TAB - ay) * (INTER_TAB - ax), w01 = (INTER_TAB - ay) * ax;
-      const int w10 = ay * (INTER_TAB - ax), w11 = ay * ax;
-      const int o = r * VIEW + x;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int sh = 8 * c;
-        const int v = (int)((p00 >> sh) & 255u) * w00 + (int)((p01 >> sh) & 255u) * w01 +
-                      (int)((p10 >> sh) & 255u) * w10 + (int)((p11 >> sh) & 255u) * w11;
-        const uint8_t b = (uint8_t)((v + 512) >> 10);
-        if (c < 3) s_view[o * 3 + c] = b; else s_att[o] = b;
-      }
+      s_px[r * VIEW + x] = blend<ATT>(r0, r1, (uint32_t)(X & (INTER_TAB - 1)),
+                                      (uint32_t)(Y & (INTER_TAB - 1)));
     }
   }
   __syncthreads();
 
   const size_t band_px = (size_t)p * VIEW * VIEW + (size_t)band * BAND * VIEW;
-  if (views) {
-    uint4* dst = reinterpret_cast<uint4*>(views + band_px * 3);
-    const uint4* src = reinterpret_cast<const uint4*>(s_view);
-    for (int i = t; i < BAND * VIEW * 3 / 16; i += THREADS) dst[i] = src[i];
-  }
-  if (att) {
-    uint4* dst = reinterpret_cast<uint4*>(att + band_px);
-    const uint4* src = reinterpret_cast<const uint4*>(s_att);
-    for (int i = t; i < BAND * VIEW / 16; i += THREADS) dst[i] = src[i];
+  if (views || (ATT && att)) {
+    // 16 pixels per work item: 4 x 16 B of BGRA words -> 3 x 16 B of BGR bytes (+ 16 B of attention)
+    uint4* vdst = reinterpret_cast<uint4*>(views + band_px * 3);
+    uint4* adst = reinterpret_cast<uint4*>(att + band_px);
+    const uint4* src = reinterpret_cast<const uint4*>(s_px);
+    for (int g = t; g < BAND * VIEW / 16; g += THREADS) {
+      uint4 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] = src[g * 4 + k];
+      if (views) {
+        uint32_t w[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w[3 * k + 0] = __byte_perm(q[k].x, q[k].y, 0x4210);
+          w[3 * k + 1] = __byte_perm(q[k].y, q[k].z, 0x5421);
+          w[3 * k + 2] = __byte_perm(q[k].z, q[k].w, 0x6542);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          vdst[g * 3 + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+      }
+      if (ATT && att) {
+        uint32_t a4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          a4[k] = __byte_perm(__byte_perm(q[k].x, q[k].y, 0x0073), __byte_perm(q[k].z, q[k].w, 0x0073), 0x5410);
+        adst[g] = make_uint4(a4[0], a4[1], a4[2], a4[3]);
+      }
+    }
   }
   if (norm_nhwc) {
     // [P,224,224,4] bf16: R,G,B,0 -> one 8-byte store per pixel, coalesced
     uint2* dst = reinterpret_cast<uint2*>(norm_nhwc) + band_px;
     for (int i = t; i < BAND * VIEW; i += THREADS) {
-      const float r_ = s_lut[s_view[i * 3 + 2]];
-      const float g_ = s_lut[256 + s_view[i * 3 + 1]];
-      const float b_ = s_lut[512 + s_view[i * 3 + 0]];
+      const uint32_t v = s_px[i];
+      const float r_ = s_lut[(v >> 16) & 255u];
+      const float g_ = s_lut[256 + ((v >> 8) & 255u)];
+      const float b_ = s_lut[512 + (v & 255u)];
       const __nv_bfloat162 rg = __floats2bfloat162_rn(r_, g_);
       const __nv_bfloat162 b0 = __floats2bfloat162_rn(b_, 0.f);
       uint2 o;
@@ -309,15 +354,18 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
   }
   if (norm_nchw) {
     // [P,3,224,224] f32, channel c = RGB -> BGR byte 2-c; 4 pixels per store
+    const uint4* src = reinterpret_cast<const uint4*>(s_px);
     for (int i = t; i < 3 * BAND * VIEW / 4; i += THREADS) {
       const int c = i / (BAND * VIEW / 4);
-      const int j = (i - c * (BAND * VIEW / 4)) * 4;     // pixel index inside the band
+      const int j4 = i - c * (BAND * VIEW / 4);          // group of 4 pixels inside the band
+      const uint4 q = src[j4];
+      const int sh = 8 * (2 - c);
       float4 o;
-      o.x = s_lut[c * 256 + s_view[(j + 0) * 3 + 2 - c]];
-      o.y = s_lut[c * 256 + s_view[(j + 1) * 3 + 2 - c]];
-      o.z = s_lut[c * 256 + s_view[(j + 2) * 3 + 2 - c]];
-      o.w = s_lut[c * 256 + s_view[(j + 3) * 3 + 2 - c]];
-      float* base = norm_nchw + ((size_t)p * 3 + c) * VIEW * VIEW + (size_t)band * BAND * VIEW + j;
+      o.x = s_lut[c * 256 + ((q.x >> sh) & 255u)];
+      o.y = s_lut[c * 256 + ((q.y >> sh) & 255u)];
+      o.z = s_lut[c * 256 + ((q.z >> sh) & 255u)];
+      o.w = s_lut[c * 256 + ((q.w >> sh) & 255u)];
+      float* base = norm_nchw + ((size_t)p * 3 + c) * VIEW * VIEW + (size_t)band * BAND * VIEW + j4 * 4;
       *reinterpret_cast<float4*>(base) = o;
     }
   }
@@ -327,13 +375,15 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
 
 // ===================================================================== C ABI
 extern "C" int avdn_pack_tile(const uint8_t* map_bgr, const uint8_t* att, int att_ch, int H,
-                              int W, uint32_t* tile4, avdn_stream_t stream) {
-  AVDN_REQUIRE(map_bgr && tile4, "avdn_pack_tile: null pointer");
+                              int W, void* tile8, avdn_stream_t stream) {
+  AVDN_REQUIRE(map_bgr && tile8, "avdn_pack_tile: null pointer");
+  AVDN_REQUIRE(((uintptr_t)tile8 & 7) == 0, "avdn_pack_tile: tile8 must be 8-byte aligned");
   AVDN_REQUIRE(H > 0 && W > 0 && H <= 32766 && W <= 32766, "avdn_pack_tile: bad size %dx%d", H, W);
   AVDN_REQUIRE(!att || att_ch >= 1, "avdn_pack_tile: att_ch must be >= 1");
-  const long long n = (long long)(H + 2) * (W + 2);
+  const long long n = (long long)(H + 1) * (W + 2);
   const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  pack_tile_kernel<<<blocks, 256, 0, avdn::to_cuda(stream)>>>(map_bgr, att, att_ch, H, W, tile4);
+  pack_tile_kernel<<<blocks, 256, 0, avdn::to_cuda(stream)>>>(map_bgr, att, att_ch, H, W,
+                                                              reinterpret_cast<uint2*>(tile8));
   return avdn::check_launch("avdn_pack_tile");
 }
 
@@ -369,8 +419,13 @@ extern "C" int avdn_render_views(const avdn_tile_desc* tiles, int n_tiles, const
                    ((uintptr_t)norm_nchw & 15) == 0 && ((uintptr_t)norm_nhwc & 15) == 0,
                "avdn_render_views: outputs must be 16-byte aligned");
   AVDN_REQUIRE((long long)P * NBAND < 2147483647LL, "avdn_render_views: too many poses");
-  render_kernel<<<P * NBAND, THREADS, 0, avdn::to_cuda(stream)>>>(
-      tiles, tile_idx, minv, P, views, att, norm_nchw,
-      reinterpret_cast<__nv_bfloat16*>(norm_nhwc), norm_lut);
+  if (att)
+    render_kernel<true><<<P * NBAND, THREADS, 0, avdn::to_cuda(stream)>>>(
+        tiles, tile_idx, minv, P, views, att, norm_nchw,
+        reinterpret_cast<__nv_bfloat16*>(norm_nhwc), norm_lut);
+  else
+    render_kernel<false><<<P * NBAND, THREADS, 0, avdn::to_cuda(stream)>>>(
+        tiles, tile_idx, minv, P, views, att, norm_nchw,
+        reinterpret_cast<__nv_bfloat16*>(norm_nhwc), norm_lut);
   return avdn::check_launch("avdn_render_views");
 }

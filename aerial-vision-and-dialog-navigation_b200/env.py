@@ -47,7 +47,7 @@ class ViewRenderer:
             raise RuntimeError("ViewRenderer needs a CUDA device (sm_100); there is no CPU fallback")
         _lib.lib()
         self.device = torch.device(device)
-        self._maps = {}            # name -> dict(tile4=tensor, H, W, index)
+        self._maps = {}            # name -> dict(tile8=tensor, H, W, index)
         self._order = []           # index -> name
         self._table = None         # device array of avdn_tile_desc
         self._lut = torch.from_numpy(normalisation_lut()).to(self.device)
@@ -77,14 +77,14 @@ class ViewRenderer:
             if a.shape[2] == 3 and not (torch.equal(a[..., 0], a[..., 1]) and torch.equal(a[..., 0], a[..., 2])):
                 raise ValueError("attention map must be gray (R=G=B), as built by src/env.py:224-231")
             a_ch = int(a.shape[2])
-        tile4 = torch.empty((H + 2) * (W + 2), dtype=torch.int32, device=self.device)
-        _lib.call("avdn_pack_tile", _lib.ptr(m), _lib.ptr(a), a_ch, H, W, _lib.ptr(tile4))
+        tile8 = torch.empty((H + 1) * (W + 2), dtype=torch.int64, device=self.device)
+        _lib.call("avdn_pack_tile", _lib.ptr(m), _lib.ptr(a), a_ch, H, W, _lib.ptr(tile8))
         if name in self._maps:
             idx = self._maps[name]["index"]
         else:
             idx = len(self._order)
             self._order.append(name)
-        self._maps[name] = dict(tile4=tile4, H=H, W=W, index=idx, has_att=a is not None)
+        self._maps[name] = dict(tile8=tile8, H=H, W=W, index=idx, has_att=a is not None)
         self._rebuild_table()
         return idx
 
@@ -115,7 +115,7 @@ class ViewRenderer:
         arr = (_lib.TileDesc * n)()
         for i, name in enumerate(self._order):
             e = self._maps[name]
-            arr[i].tile4 = e["tile4"].data_ptr()
+            arr[i].tile8 = e["tile8"].data_ptr()
             arr[i].H, arr[i].W = e["H"], e["W"]
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         self._table = torch.from_numpy(raw).to(self.device)

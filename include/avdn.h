@@ -50,16 +50,18 @@ int avdn_device_supported(void);
  * ---------------------------------------------------------------------- */
 
 /* Map preparation: packs a BGR u8 HWC satellite tile and (optionally) its
- * human-attention map into the renderer's HBM layout: one u32 per pixel
- * (B | G<<8 | R<<16 | ATT<<24) with a 1-pixel zero border, row pitch W+2.
- * The zero border implements BORDER_CONSTANT(0) of cv2.warpPerspective
- * (src/env.py:290,292) without per-tap predicates.
+ * human-attention map into the renderer's HBM layout: one 8-byte record per
+ * pixel of the zero-bordered tile, record(X,Y) = pix(X,Y) | pix(X,Y+1) << 32
+ * with pix = B | G<<8 | R<<16 | ATT<<24; X in [0,W+1], Y in [0,H], row pitch
+ * W+2 records.  A bilinear 2x2 footprint is then two adjacent records (16
+ * contiguous bytes).  The zero border implements BORDER_CONSTANT(0) of
+ * cv2.warpPerspective (src/env.py:290,292) without per-tap predicates.
  *   map_bgr  [H,W,3] u8      (self.map_batch[name],           src/env.py:217-221)
  *   att      [H,W,att_ch] u8 or NULL; channel 0 is taken
  *                            (self.attention_map_batch[name], src/env.py:224-231)
- *   tile4    [(H+2)*(W+2)] u32 (out)                                            */
+ *   tile8    [(H+1)*(W+2)] 8-byte records (out), 8-byte aligned                 */
 int avdn_pack_tile(const uint8_t* map_bgr, const uint8_t* att, int att_ch,
-                   int H, int W, uint32_t* tile4, avdn_stream_t stream);
+                   int H, int W, void* tile8, avdn_stream_t stream);
 
 /* gps_to_img_coords (src/env.py:189-196), batched and bit-exact:
  *   x = rint((lng - bl_lng) / lat_ratio), y = rint((tr_lat - lat) / lat_ratio)
@@ -79,7 +81,7 @@ int avdn_homography_from_corners(const int32_t* corners_px, int P, double* minv,
 
 /* One packed tile as the renderer sees it. */
 typedef struct avdn_tile_desc {
-  const uint32_t* tile4; /* avdn_pack_tile output */
+  const void* tile8;     /* avdn_pack_tile output */
   int32_t H, W;          /* un-padded size */
 } avdn_tile_desc;
 
