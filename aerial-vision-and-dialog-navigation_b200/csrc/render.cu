@@ -44,6 +44,7 @@ constexpr int VIEW = AVDN_VIEW;       // 224
 constexpr int BAND = 32;              // rows per CTA
 constexpr int NBAND = VIEW / BAND;    // 7
 constexpr int THREADS = 256;
+constexpr int SPITCH = 232;            // shared-memory row pitch of a band, in pixels (words)
 constexpr int INTER_BITS = 5;
 constexpr int INTER_TAB = 1 << INTER_BITS;
 
@@ -238,7 +239,8 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
               const float* __restrict__ norm_lut) {
   __shared__ double s_m[9];
   __shared__ double s_tab[4][BAND][3];                       // 32*X0, 32*Y0, W0
-  __shared__ __align__(16) uint32_t s_px[BAND * VIEW];       // BGRA per pixel, 28672 B
+  // BGRA per pixel; row pitch 232 words: the 4 rows of a warp's 8x4 patch fall in distinct banks
+  __shared__ __align__(16) uint32_t s_px[BAND * SPITCH];
   __shared__ float s_lut[3 * 256];
 
   const int p = blockIdx.x / NBAND, band = blockIdx.x - p * NBAND;
@@ -299,7 +301,7 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
         r0 = __ldg(q);
         r1 = __ldg(q + 1);
       }
-      s_px[r * VIEW + x] = blend<ATT>(r0, r1, (uint32_t)(X & (INTER_TAB - 1)),
+      s_px[r * SPITCH + x] = blend<ATT>(r0, r1, (uint32_t)(X & (INTER_TAB - 1)),
                                       (uint32_t)(Y & (INTER_TAB - 1)));
     }
   }
@@ -312,9 +314,10 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
     uint4* adst = reinterpret_cast<uint4*>(att + band_px);
     const uint4* src = reinterpret_cast<const uint4*>(s_px);
     for (int g = t; g < BAND * VIEW / 16; g += THREADS) {
+      const int row = g / (VIEW / 16), c16 = g - row * (VIEW / 16);
       uint4 q[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) q[k] = src[g * 4 + k];
+      for (int k = 0; k < 4; ++k) q[k] = src[row * (SPITCH / 4) + c16 * 4 + k];
       if (views) {
         uint32_t w[12];
 #pragma unroll
@@ -340,7 +343,8 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
     // [P,224,224,4] bf16: R,G,B,0 -> one 8-byte store per pixel, coalesced
     uint2* dst = reinterpret_cast<uint2*>(norm_nhwc) + band_px;
     for (int i = t; i < BAND * VIEW; i += THREADS) {
-      const uint32_t v = s_px[i];
+      const int row = i / VIEW;
+      const uint32_t v = s_px[i + row * (SPITCH - VIEW)];
       const float r_ = s_lut[(v >> 16) & 255u];
       const float g_ = s_lut[256 + ((v >> 8) & 255u)];
       const float b_ = s_lut[512 + (v & 255u)];
@@ -358,7 +362,7 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
     for (int i = t; i < 3 * BAND * VIEW / 4; i += THREADS) {
       const int c = i / (BAND * VIEW / 4);
       const int j4 = i - c * (BAND * VIEW / 4);          // group of 4 pixels inside the band
-      const uint4 q = src[j4];
+      const uint4 q = src[j4 + (j4 / (VIEW / 4)) * ((SPITCH - VIEW) / 4)];
       const int sh = 8 * (2 - c);
       float4 o;
       o.x = s_lut[c * 256 + ((q.x >> sh) & 255u)];

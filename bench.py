@@ -110,7 +110,7 @@ class RenderWorkload:
         return {"workload": "env.py view rendering: 4096 poses/GPU, 3000x3000x3 u8 tile -> 224x224x3 u8 views "
                             "(BASELINE configs[2])",
                 "poses_per_gpu": self.P, "tile": [self.SIZE, self.SIZE, 3],
-                "cache": "outputs (616 MB/step) exceed L2; the packed tile (36 MB) is L2-resident by design",
+                "cache": "outputs (616 MB/step) exceed L2; the packed tile (72 MB of row-pair records) is L2-resident by design",
                 "parallelism": f"pose-sharded x{self.world}, no collective"}
 
     def setup_gpu(self, dev):
