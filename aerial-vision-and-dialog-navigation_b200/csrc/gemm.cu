@@ -564,6 +564,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     // pay per-element predicates.  Rows of a tile beyond rows_in_box hold garbage: they are neither stored
     // (the TMA box ends before them) nor counted by the statistics pass.
     const bool need_fin = has_alpha || (bias != nullptr) || (c.relu != 0);
+    // Fused eval-mode BatchNorm + LeakyReLU (+ shortcut): per-column scale/shift of the current tile column
+    // live in s_stat (the statistics scratch; the two uses exclude each other).
+    const bool has_aff = (c.col_scale != nullptr);
+    const float slope = c.leaky_slope;
+    const __nv_bfloat16* res_row = nullptr;
+    int aff_nt = -1;
+    auto finish_aff = [&](uint32_t (&v)[32], int col0, int cc) {
+      const float4* sc4 = reinterpret_cast<const float4*>(s_stat + cc);
+      const float4* sh4 = reinterpret_cast<const float4*>(s_stat + BN + cc);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 sc = sc4[g], sh = sh4[g];
+        float x0 = fmaf(__uint_as_float(v[4 * g + 0]), sc.x, sh.x);
+        float x1 = fmaf(__uint_as_float(v[4 * g + 1]), sc.y, sh.y);
+        float x2 = fmaf(__uint_as_float(v[4 * g + 2]), sc.z, sh.z);
+        float x3 = fmaf(__uint_as_float(v[4 * g + 3]), sc.w, sh.w);
+        v[4 * g + 0] = __float_as_uint(fmaxf(x0, x0 * slope));
+        v[4 * g + 1] = __float_as_uint(fmaxf(x1, x1 * slope));
+        v[4 * g + 2] = __float_as_uint(fmaxf(x2, x2 * slope));
+        v[4 * g + 3] = __float_as_uint(fmaxf(x3, x3 * slope));
+      }
+      if (res_row) {
+        const uint4* rp = reinterpret_cast<const uint4*>(res_row + col0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 q = __ldg(rp + g);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[8 * g + 2 * j] = __float_as_uint(__uint_as_float(v[8 * g + 2 * j]) + __uint_as_float(w[j] << 16));
+            v[8 * g + 2 * j + 1] =
+                __float_as_uint(__uint_as_float(v[8 * g + 2 * j + 1]) + __uint_as_float(w[j] & 0xFFFF0000u));
+          }
+        }
+      }
+    };
     auto finish32 = [&](uint32_t (&v)[32], int col0) {
       const bool full = (col0 + 32) <= c.N;
 #pragma unroll
@@ -592,6 +628,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
       if (c.stats && stat_nt != T.nt) {
         if (stat_nt >= 0) flush_stats();
         stat_nt = T.nt;
+      }
+      if (has_aff) {
+        if (aff_nt != T.nt) {
+          epi_bar_sync();                                  // readers of the previous tile column are done
+          for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+            const int j = (i < BN) ? i : i - BN, col = n0 + j;
+            s_stat[i] = (col < c.N) ? __ldg((i < BN ? c.col_scale : c.col_shift) + col) : 0.f;
+          }
+          epi_bar_sync();
+          aff_nt = T.nt;
+        }
+        res_row = nullptr;
+        if (c.residual) {
+          const int wi = row % c.box_w, t2 = row / c.box_w;
+          const int hi = t2 % c.box_h, ni = t2 / c.box_h;
+          const int w = w0 + wi, h = h0 + hi, n = i0 + ni;
+          if (row < p.rows_in_box && w < c.valid_w && h < c.valid_h && n < c.valid_n)
+            res_row = reinterpret_cast<const __nv_bfloat16*>(c.residual) +
+                      ((size_t)((size_t)n * c.out_H + h) * c.out_W + w) * (size_t)c.ldc;
+        }
       }
       ETR(0);
       mbar_wait(tfull_bar(as), aphase);
@@ -643,7 +699,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             if (cc == 0) ETR(3);
             tmem_wait_ld();
             if (cc == 0) ETR(4);
-            if (need_fin) {
+            if (has_aff) {
+              finish_aff(va, col0, cc);
+              if (two) finish_aff(vb, col0 + 32, cc + 32);
+            } else if (need_fin) {
               finish32(va, col0);
               if (two) finish32(vb, col0 + 32);
             }
@@ -1052,6 +1111,13 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
     }
   }
   AVDN_REQUIRE(!c.stats || pl->kp.out_tma, "avdn_gemm_plan: fused statistics need the TMA epilogue");
+  AVDN_REQUIRE((c.col_scale == nullptr) == (c.col_shift == nullptr), "avdn_gemm_plan: col_scale and col_shift go together");
+  AVDN_REQUIRE(!c.col_scale || (pl->kp.out_tma && c.out_dtype == AVDN_DT_BF16 && !c.stats && c.accumulate == 0 &&
+                                !c.bias && !c.relu && c.alpha == 1.0f),
+               "avdn_gemm_plan: the affine epilogue needs a plain bf16 TMA store (no stats/accumulate/bias/relu)");
+  AVDN_REQUIRE(!c.residual || (c.col_scale && c.mode == AVDN_GEMM_CONV && c.out_sh == 1 && c.out_sw == 1 &&
+                               c.out_oh == 0 && c.out_ow == 0 && (c.ldc % 8) == 0 && ((uintptr_t)c.residual & 15) == 0),
+               "avdn_gemm_plan: residual needs the affine epilogue of a unit-stride CONV output");
   AVDN_REQUIRE(pl->kp.out_tma || c.mode != AVDN_GEMM_CONV, "avdn_gemm_plan: conv output cannot be described to TMA");
   // ---- shared-memory plan: slabs, k-blocks per stage, ring depth ----
   {

@@ -39,7 +39,9 @@ class GemmCore(C.Structure):
                 ("out_dtype", i32), ("accumulate", i32), ("relu", i32), ("alpha", f32),
                 ("tx_bytes", u32), ("pad_", i32),
                 ("ldc", i64), ("out_bs0", i64), ("out_bs1", i64),
-                ("out", C.c_void_p), ("bias", C.c_void_p), ("relu_mask", C.c_void_p), ("stats", C.c_void_p)]
+                ("out", C.c_void_p), ("bias", C.c_void_p), ("relu_mask", C.c_void_p), ("stats", C.c_void_p),
+                ("col_scale", C.c_void_p), ("col_shift", C.c_void_p), ("residual", C.c_void_p),
+                ("leaky_slope", f32), ("pad2_", i32)]
 
 
 class GemmDesc(C.Structure):
@@ -250,9 +252,13 @@ def _x_views(x, Cin, W, H, N, stride, box):
     return views
 
 
-def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=None, stats=None, ctas=None):
+def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=None, stats=None, ctas=None,
+                  affine=None, residual=None):
     """z[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) ; ``w_f`` is ``[Cout, k*k*Cin]`` bf16
-    (tap-major, channel-minor).  Channels are multiples of 64."""
+    (tap-major, channel-minor).  Channels are multiples of 64.
+    ``affine=(scale, shift, slope)`` (fp32 ``[Cout]`` tensors): the epilogue writes
+    ``leaky_slope(conv*scale + shift) (+ residual)`` instead -- eval-mode BatchNorm + LeakyReLU +
+    shortcut folded into the convolution."""
     assert (Cin % 64 == 0 or Cin == 32) and (Cout % 64 == 0 or Cout == 32)
     Ho, Wo = H // stride, W // stride
     bn = bn or pick_bn(Cout)
@@ -287,7 +293,17 @@ def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=No
     if stats is not None:        # fused BatchNorm statistics: f64 [2, Cout]
         assert stats.dtype == torch.float64 and stats.numel() >= 2 * Cout
         c.stats = stats.data_ptr()
-    return GemmPlan(d, keep=(x, w_f, z, stats), flops=flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin,
+    if affine is not None:
+        sc, sh, slope = affine
+        assert stats is None and sc.dtype == torch.float32 and sh.dtype == torch.float32
+        assert sc.numel() >= Cout and sh.numel() >= Cout
+        c.col_scale, c.col_shift, c.leaky_slope = sc.data_ptr(), sh.data_ptr(), float(slope)
+        if residual is not None:
+            assert residual.dtype == torch.bfloat16 and residual.shape == z.shape and residual.is_contiguous()
+            c.residual = residual.data_ptr()
+    else:
+        assert residual is None
+    return GemmPlan(d, keep=(x, w_f, z, stats, affine, residual), flops=flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin,
                     tag="gemm_conv_fwd")
 
 

@@ -161,6 +161,7 @@ class _Engine:
         self.dz = None
         self._max_elems = max_elems
         self._fwd_plans = False
+        self._eval_plans = False
         self._bwd_plans = False
         self.launches = 0
 
@@ -179,6 +180,20 @@ class _Engine:
                 L.p_fwd_stats = G.plan_conv_fwd(L.src.a, L.wf, L.z, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
                                                 Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops, stats=L.sums)
             self._fwd_plans = True
+
+    def build_fwd_eval(self):
+        """Eval mode: the BN affine is known before the convolution runs, so BatchNorm + LeakyReLU +
+        the shortcut add are the convolution's epilogue (no z round trip, no elementwise pass)."""
+        if self._eval_plans:
+            return
+        for L in self.layers:
+            if L.first:
+                continue
+            L.p_fwd_eval = G.plan_conv_fwd(L.src.a, L.wf, L.a, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
+                                           Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops,
+                                           affine=(L.scale, L.shift, LEAKY_SLOPE),
+                                           residual=L.res.a if L.res is not None else None)
+        self._eval_plans = True
 
     def build_bwd(self, net=None):
         if self._bwd_plans:
@@ -241,29 +256,40 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
     n = 0
     reuse = frozen and not train and getattr(eng, "_frozen_ready", False)
     eng._frozen_ready = (not train)
+    if not train:
+        eng.build_fwd_eval()
     for li, L in enumerate(eng.layers):
         conv = net.module_list[L.idx][0]
         bn = net.module_list[L.idx][1]
-        if L.first:
-            call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win,
-                 ptr(L.sums) if train else None)
-            n += 2 if train else 1
-        else:
+        if not L.first and not reuse:
+            call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
+                 ptr(L.wd))
+            n += 1
+        if not train:
+            # eval: affine from the running statistics first, then conv with the fused epilogue
             if not reuse:
-                call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
-                     ptr(L.wd))
+                call("avdn_bn_eval_coeffs", L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+                     ptr(bn.running_var), BN_EPS, ptr(L.scale), ptr(L.shift))
                 n += 1
-            (L.p_fwd_stats if train else L.p_fwd).run()
+            if L.first:
+                call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win, None)
+                call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), None, ptr(L.a), L.R, L.Cout_p,
+                     LEAKY_SLOPE)
+                n += 2
+            else:
+                L.p_fwd_eval.run()
+                n += 1
+            continue
+        if L.first:
+            call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win, ptr(L.sums))
+            n += 2
+        else:
+            L.p_fwd_stats.run()
             n += 1
-        if train:
-            call("avdn_bn_finalize", ptr(L.sums), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
-                 ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.scale),
-                 ptr(L.shift), ptr(L.mean), ptr(L.rstd))
-            n += 1 if L.first else 2    # finalize (+ the stats memset inside avdn_gemm_run)
-        elif not reuse:
-            call("avdn_bn_eval_coeffs", L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
-                 ptr(bn.running_var), BN_EPS, ptr(L.scale), ptr(L.shift))
-            n += 1
+        call("avdn_bn_finalize", ptr(L.sums), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
+             ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.scale),
+             ptr(L.shift), ptr(L.mean), ptr(L.rstd))
+        n += 1 if L.first else 2    # finalize (+ the stats memset inside avdn_gemm_run)
         call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.res.a) if L.res is not None else None,
              ptr(L.a), L.R, L.Cout_p, LEAKY_SLOPE)
         n += 1

@@ -164,6 +164,15 @@ typedef struct avdn_gemm_core {
   double* stats;              /* NULL, or [2][N] f64: fused BatchNorm statistics -- per output column the
                                  sum and the sum of squares of the (bf16-rounded) outputs; zeroed by
                                  avdn_gemm_run before the launch (bf16 store epilogue only) */
+  /* Fused eval-mode BatchNorm + LeakyReLU (+ shortcut) epilogue (dark_net.py:22-33,224-226 in eval mode,
+   * where the BN affine is known before the convolution runs): out = leaky(acc*col_scale + col_shift)
+   * (+ residual).  col_scale/col_shift [N] fp32 or both NULL; residual: bf16 tensor addressed like `out`
+   * (CONV mode, unit output stride) or NULL.  bf16 TMA-store epilogue only; excludes stats/accumulate.   */
+  const float* col_scale;
+  const float* col_shift;
+  const void* residual;
+  float leaky_slope;
+  int32_t pad2_;
 } avdn_gemm_core;
 
 typedef struct avdn_gemm_desc {

@@ -148,6 +148,55 @@ def test_full_trunk_224_layerwise(built_lib):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
 
 
+def test_full_trunk_224_eval_layerwise(built_lib):
+    """Eval mode: BatchNorm (running statistics) + LeakyReLU + shortcut are the convolution's epilogue
+    (avdn_gemm_core.col_scale/col_shift/residual).  Every block is checked teacher-forced against
+    torch fp32 on OUR input activation; non-trivial running statistics and affine parameters."""
+    import torch.nn.functional as F
+    from avdn_b200.models.dark_net import Darknet
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(mo.yolov3_trunk_cfg())
+    torch.manual_seed(1)
+    net = Darknet(f.name, 224).cuda()
+    os.unlink(f.name)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, device="cuda", generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, device="cuda", generator=g) * 0.5 + 0.05)
+            m.weight.data.copy_(torch.rand(m.num_features, device="cuda", generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, device="cuda", generator=g) * 0.3)
+    net.eval()
+    N = 3
+    x = torch.randn(N, 3, 224, 224, device="cuda", generator=g)
+    with torch.no_grad():
+        y = net(x)
+    assert y.shape == (N, 512, 7, 7)
+    eng = list(net._engines.values())[0]
+    n_res = 0
+    for L in eng.layers:
+        conv, bn = net.module_list[L.idx][0], net.module_list[L.idx][1]
+        if L.first:
+            xin = eng.x_in[..., :3].float().permute(0, 3, 1, 2)
+        else:
+            xin = L.src.a[..., :L.Cin].float().permute(0, 3, 1, 2)
+        z = F.conv2d(xin, conv.weight.float(), None, stride=L.s, padding=(L.k - 1) // 2)
+        a = F.leaky_relu(F.batch_norm(z, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.1, 1e-5), 0.01)
+        if L.res is not None:
+            a = a + L.res.a[..., :L.Cout].float().permute(0, 3, 1, 2)
+            n_res += 1
+        ours = L.a[..., :L.Cout].float().permute(0, 3, 1, 2)
+        r = _rel2(ours, a)
+        assert r < 1e-2, (L.idx, L.Cin, L.Cout, L.k, L.s, r)
+        if L.Cout_p > L.Cout:
+            assert (L.a[..., L.Cout:] == 0).all()
+    assert n_res == 23
+    # the frozen second pass (weights / coefficients reused) gives the same result
+    from avdn_b200.models.dark_net import _trunk_forward
+    y2 = _trunk_forward(net, eng, eng.x_in, False, frozen=True)
+    assert torch.equal(y, y2)
+
+
 def test_full_trunk_224_backward_layerwise(built_lib):
     """Backward of every block in isolation (teacher forcing): torch fp32 autograd of the block
     is fed OUR input activation and OUR upstream gradient.  Expected error: storing the
