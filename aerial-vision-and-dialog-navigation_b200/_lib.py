@@ -34,6 +34,7 @@ _SIGNATURES = {
     "avdn_gemm_plan": [c_void_p, c_void_p, C.c_size_t],
     "avdn_gemm_run": [c_void_p, c_void_p],
     "avdn_conv0_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "avdn_conv0_fwd_eval": [c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_void_p, c_int, c_int, c_int, c_void_p],
     "avdn_conv0_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "avdn_bn_stats": [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_f32,
                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -59,6 +60,18 @@ _SIGNATURES = {
     "avdn_ln_bwd": [c_void_p] * 6 + [c_i64, c_int] + [c_void_p] * 4 + [c_void_p],
     "avdn_softmax_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "avdn_softmax_bwd": [c_void_p, c_void_p, c_i64, c_int, c_int, c_f32, c_void_p, c_void_p],
+    # train-mode variants: nn.Dropout sites evaluated from a stateless hash of (seed, site, element)
+    "avdn_ln_fwd_drop": [c_void_p] * 4 + [c_i64, c_int, c_f32] + [c_void_p] * 5 + [c_f32, C.c_uint64, C.c_uint32, c_void_p],
+    "avdn_ln_bwd_drop": [c_void_p] * 6 + [c_i64, c_int] + [c_void_p] * 4 + [c_f32, C.c_uint64, C.c_uint32, c_void_p],
+    "avdn_softmax_fwd_drop": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_f32,
+                              C.c_uint64, C.c_uint32, c_void_p],
+    "avdn_softmax_bwd_drop": [c_void_p, c_void_p, c_i64, c_int, c_int, c_f32, c_void_p, c_f32, C.c_uint64, C.c_uint32,
+                              c_void_p],
+    "avdn_dropout_bf16": [c_void_p, c_i64, c_f32, C.c_uint64, C.c_uint32, c_void_p],
+    "avdn_dropout_keep_scale": [c_void_p, c_i64, c_f32, C.c_uint64, C.c_uint32, c_void_p],
+    "avdn_heads_fwd_drop": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 + [c_f32, C.c_uint64, C.c_uint32,
+                                                                                     c_void_p],
+    "avdn_heads_bwd_drop": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 18 + [c_f32, c_void_p],
     "avdn_build_masks": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "avdn_colsum": [c_void_p, c_int, c_i64, c_int, c_i64, c_void_p, c_void_p],
     "avdn_heads_fwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 + [c_void_p],

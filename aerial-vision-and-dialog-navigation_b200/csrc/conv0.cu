@@ -56,7 +56,9 @@ constexpr int OUT_PITCH = 80;          // bytes per pixel row of the per-warp ou
 
 __global__ void __launch_bounds__(THREADS) conv0_fwd_kernel(const uint2* __restrict__ x, const float* __restrict__ w,
                                                             uint4* __restrict__ z, int N, int H, int W,
-                                                            double* __restrict__ stats) {
+                                                            double* __restrict__ stats,
+                                                            const float* __restrict__ aff_scale,
+                                                            const float* __restrict__ aff_shift, float slope) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint2* xs = reinterpret_cast<uint2*>(smem);                                  // [(F_ROWS+2)][W+2]
   uint8_t* outs = smem + ((size_t)(F_ROWS + 2) * (W + 2) + 2) * 8;              // [WARPS][16][OUT_PITCH]
@@ -85,6 +87,15 @@ __global__ void __launch_bounds__(THREADS) conv0_fwd_kernel(const uint2* __restr
   float st1[4][2], st2[4][2];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) { st1[nt][0] = st1[nt][1] = st2[nt][0] = st2[nt][1] = 0.f; }
+  // eval mode: BatchNorm affine + LeakyReLU folded into the store (this lane's channels nt*8 + 2t, +1)
+  float asc[4][2], ash[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      asc[nt][e] = aff_scale ? aff_scale[nt * 8 + 2 * t + e] : 1.f;
+      ash[nt][e] = aff_scale ? aff_shift[nt * 8 + 2 * t + e] : 0.f;
+    }
 
   const int strips_per_img = H / F_ROWS, tiles_per_row = W / 16;
   const int pitch = W + 2;
@@ -113,6 +124,15 @@ __global__ void __launch_bounds__(THREADS) conv0_fwd_kernel(const uint2* __restr
         for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a, wf[kh][nt][0], wf[kh][nt][1]);
       }
       // C fragment: (pixel g, co nt*8+2t..+1), (pixel g+8, ...) -> bf16 -> per-warp staging
+      if (aff_scale) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float y = fmaf(acc[nt][e], asc[nt][e & 1], ash[nt][e & 1]);
+            acc[nt][e] = fmaxf(y, y * slope);
+          }
+      }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const uint32_t lo = pack_bf16(acc[nt][0], acc[nt][1]), hi = pack_bf16(acc[nt][2], acc[nt][3]);
@@ -246,11 +266,12 @@ __global__ void __launch_bounds__(THREADS) conv0_wgrad_kernel(const uint8_t* __r
 }  // namespace
 
 // ===================================================================== C ABI
-extern "C" int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W, double* stats,
-                              avdn_stream_t stream) {
-  AVDN_REQUIRE(x_nhwc4 && w && z && N > 0 && H > 0 && W > 0, "avdn_conv0_fwd: bad argument");
+static int conv0_fwd_launch(const char* who, const void* x_nhwc4, const float* w, void* out, int N, int H, int W,
+                            double* stats, const float* scale, const float* shift, float slope,
+                            avdn_stream_t stream) {
+  AVDN_REQUIRE(x_nhwc4 && w && out && N > 0 && H > 0 && W > 0, "%s: bad argument", who);
   if (W % 16 != 0 || H % F_ROWS != 0 || W > 2048)
-    return avdn::set_err(AVDN_ERR_UNSUPPORTED, "avdn_conv0_fwd: W %% 16 == 0, H %% 4 == 0, W <= 2048 required (%dx%d)", H, W);
+    return avdn::set_err(AVDN_ERR_UNSUPPORTED, "%s: W %% 16 == 0, H %% 4 == 0, W <= 2048 required (%dx%d)", who, H, W);
   cudaStream_t s = avdn::to_cuda(stream);
   if (stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C0_PAD, s) != cudaSuccess)
     return avdn::check_launch("avdn_conv0_fwd memset");
@@ -264,8 +285,19 @@ extern "C" int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int 
   const long long strips = (long long)N * (H / F_ROWS);
   const long long cap = (long long)avdn::sm_count() * 6;
   conv0_fwd_kernel<<<(unsigned)(strips < cap ? strips : cap), THREADS, smem, s>>>(
-      reinterpret_cast<const uint2*>(x_nhwc4), w, reinterpret_cast<uint4*>(z), N, H, W, stats);
-  return avdn::check_launch("avdn_conv0_fwd");
+      reinterpret_cast<const uint2*>(x_nhwc4), w, reinterpret_cast<uint4*>(out), N, H, W, stats, scale, shift, slope);
+  return avdn::check_launch(who);
+}
+
+extern "C" int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W, double* stats,
+                              avdn_stream_t stream) {
+  return conv0_fwd_launch("avdn_conv0_fwd", x_nhwc4, w, z, N, H, W, stats, nullptr, nullptr, 0.f, stream);
+}
+
+extern "C" int avdn_conv0_fwd_eval(const void* x_nhwc4, const float* w, const float* scale, const float* shift,
+                                   float slope, void* a, int N, int H, int W, avdn_stream_t stream) {
+  AVDN_REQUIRE(scale && shift, "avdn_conv0_fwd_eval: scale/shift are required");
+  return conv0_fwd_launch("avdn_conv0_fwd_eval", x_nhwc4, w, a, N, H, W, nullptr, scale, shift, slope, stream);
 }
 
 extern "C" int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int H, int W,

@@ -283,7 +283,9 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ a
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      long long M, float eps, float* __restrict__ v_out,
                                                      float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
-                                                     float* __restrict__ mean, float* __restrict__ rstd) {
+                                                     float* __restrict__ mean, float* __restrict__ rstd,
+                                                     unsigned int dthr, float dscale, unsigned long long seed,
+                                                     unsigned int site) {
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -293,7 +295,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ a
   for (int i = 0; i < EPL; ++i) {
     const int j = lane + 32 * i;
     float t = a[row * E + j];
-    if (b) t += b[row * E + j];
+    if (b) {
+      float bv = b[row * E + j];
+      if (dthr) bv = avdn_drop_keep(seed, site, (unsigned long long)(row * E + j), dthr) ? bv * dscale : 0.f;
+      t += bv;
+    }
     x[i] = t;
     s += t;
   }
@@ -321,7 +327,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      long long M, float* __restrict__ dv,
                                                      __nv_bfloat16* __restrict__ dv16, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta) {
+                                                     float* __restrict__ dbeta, unsigned int dthr, float dscale,
+                                                     unsigned long long seed, unsigned int site) {
   const int lane = threadIdx.x & 31;
   const long long w0 = blockIdx.x * 8LL + (threadIdx.x >> 5), nw = gridDim.x * 8LL;
   float dg[EPL], db[EPL], gm[EPL];
@@ -350,7 +357,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       const int j = lane + 32 * i;
       const float o = rs * (g[i] - s1 - xh[i] * s2);
       if (dv) dv[row * E + j] = o;
-      if (dv16) dv16[row * E + j] = __float2bfloat16_rn(o);
+      if (dv16) {
+        // gradient of the dropped branch b of v = a + dropout(b)
+        float ob = o;
+        if (dthr) ob = avdn_drop_keep(seed, site, (unsigned long long)(row * E + j), dthr) ? o * dscale : 0.f;
+        dv16[row * E + j] = __float2bfloat16_rn(ob);
+      }
     }
   }
 #pragma unroll
@@ -373,7 +385,9 @@ __device__ __forceinline__ bool may_attend(int q, int k, int L, int T, int len) 
 // scores [B,H,S,Sp] fp32 -> P [B,H,S,Sp] bf16 (0 where masked / padded).  One warp per row.
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ scores,
                                                           const int* __restrict__ lens, int B, int H, int L, int T,
-                                                          int Sp, __nv_bfloat16* __restrict__ P) {
+                                                          int Sp, __nv_bfloat16* __restrict__ P,
+                                                          __nv_bfloat16* __restrict__ P_full, unsigned int dthr,
+                                                          float dscale, unsigned long long seed, unsigned int site) {
   const int S = L + 2 * T;
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= (long long)B * H * S) return;
@@ -393,6 +407,12 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
   for (int k = lane; k < Sp; k += 32) {
     float p = 0.f;
     if (k < S && may_attend(q, k, L, T, len)) p = __expf(sr[k] - m) * s;
+    if (dthr) {
+      // attention dropout (nn.MultiheadAttention(dropout=p)): the PV GEMM consumes the dropped
+      // probabilities, the softmax backward needs the full ones
+      P_full[row * Sp + k] = __float2bfloat16_rn(p);
+      p = avdn_drop_keep(seed, site, (unsigned long long)(row * Sp + k), dthr) ? p * dscale : 0.f;
+    }
     pr[k] = __float2bfloat16_rn(p);
   }
 }
@@ -400,18 +420,26 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
 // dS = alpha * P * (dP - sum_k P*dP)  (bf16 out, 0 in the padding)
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P,
                                                           const float* __restrict__ dP, long long rows, int S, int Sp,
-                                                          float alpha, __nv_bfloat16* __restrict__ dS) {
+                                                          float alpha, __nv_bfloat16* __restrict__ dS,
+                                                          unsigned int dthr, float dscale, unsigned long long seed,
+                                                          unsigned int site) {
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const __nv_bfloat16* pr = P + row * Sp;
   const float* dr = dP + row * Sp;
+  // with attention dropout, dP arrives w.r.t. the dropped probabilities: d(full) = keep ? d * scale : 0
+  auto dp_at = [&](int k) {
+    float d = dr[k];
+    if (dthr) d = avdn_drop_keep(seed, site, (unsigned long long)(row * Sp + k), dthr) ? d * dscale : 0.f;
+    return d;
+  };
   float dot = 0.f;
-  for (int k = lane; k < S; k += 32) dot = fmaf(__bfloat162float(pr[k]), dr[k], dot);
+  for (int k = lane; k < S; k += 32) dot = fmaf(__bfloat162float(pr[k]), dp_at(k), dot);
   dot = warp_sum(dot);
   for (int k = lane; k < Sp; k += 32) {
     float o = 0.f;
-    if (k < S) o = alpha * __bfloat162float(pr[k]) * (dr[k] - dot);
+    if (k < S) o = alpha * __bfloat162float(pr[k]) * (dp_at(k) - dot);
     dS[row * Sp + k] = __float2bfloat16_rn(o);
   }
 }
@@ -461,7 +489,11 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(const float* __restrict_
                                                         const float* __restrict__ w2, const float* __restrict__ b2,
                                                         const float* __restrict__ wf, const float* __restrict__ bf,
                                                         float* __restrict__ h0_out, float* __restrict__ h1_out,
-                                                        float* __restrict__ output, float* __restrict__ h_sali) {
+                                                        float* __restrict__ output, float* __restrict__ h_sali,
+                                                        unsigned int dthr, float dscale, unsigned long long seed,
+                                                        unsigned int site) {
+  // train mode: Dropout(0.2) after both hidden ReLUs of decoder_2_action_full (sites site, site+1) and
+  // between fc's Linear and ReLU (site+2) -- ET_haa.py:98-119.  relu(dropout(z)) == dropout(relu(z)).
   __shared__ float s_dir[E], s_vis[E], s_h0[256], s_h1[32];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int j = tid; j < E; j += 256) {
@@ -473,20 +505,32 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(const float* __restrict_
     float a = 0.f;
     for (int j = lane; j < E; j += 32) a = fmaf(w0[(size_t)o * E + j], s_dir[j], a);
     a = warp_sum(a);
-    if (lane == 0) { a = fmaxf(a + b0[o], 0.f); s_h0[o] = a; h0_out[b * 256 + o] = a; }
+    if (lane == 0) {
+      a = fmaxf(a + b0[o], 0.f);
+      if (dthr) a = avdn_drop_keep(seed, site, (unsigned long long)(b * 256 + o), dthr) ? a * dscale : 0.f;
+      s_h0[o] = a; h0_out[b * 256 + o] = a;
+    }
   }
   for (int o = warp; o < 64; o += 8) {
     float a = 0.f;
     for (int j = lane; j < E; j += 32) a = fmaf(wf[(size_t)o * E + j], s_vis[j], a);
     a = warp_sum(a);
-    if (lane == 0) h_sali[b * 64 + o] = fmaxf(a + bf[o], 0.f);
+    if (lane == 0) {
+      a = fmaxf(a + bf[o], 0.f);
+      if (dthr) a = avdn_drop_keep(seed, site + 2, (unsigned long long)(b * 64 + o), dthr) ? a * dscale : 0.f;
+      h_sali[b * 64 + o] = a;
+    }
   }
   __syncthreads();
   for (int o = warp; o < 32; o += 8) {
     float a = 0.f;
     for (int j = lane; j < 256; j += 32) a = fmaf(w1[o * 256 + j], s_h0[j], a);
     a = warp_sum(a);
-    if (lane == 0) { a = fmaxf(a + b1[o], 0.f); s_h1[o] = a; h1_out[b * 32 + o] = a; }
+    if (lane == 0) {
+      a = fmaxf(a + b1[o], 0.f);
+      if (dthr) a = avdn_drop_keep(seed, site + 1, (unsigned long long)(b * 32 + o), dthr) ? a * dscale : 0.f;
+      s_h1[o] = a; h1_out[b * 32 + o] = a;
+    }
   }
   __syncthreads();
   if (warp < 4) {
@@ -503,7 +547,10 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(
     const float* __restrict__ h0, const float* __restrict__ h1, const float* __restrict__ h_sali,
     const float* __restrict__ d_output, const float* __restrict__ d_h_sali, float* __restrict__ dx,
     float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1, float* __restrict__ db1,
-    float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dwf, float* __restrict__ dbf) {
+    float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dwf, float* __restrict__ dbf,
+    float dscale) {
+  // dscale = 1/(1-p) of the heads' dropout (1 in eval mode): a dropped activation was stored as 0, so the
+  // ReLU mask already removes it; kept ones carry the factor.
   __shared__ float s_dir[E], s_vis[E], s_h0[256], s_h1[32], s_d2[4], s_d1[32], s_d0[256], s_ds[64];
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int j = tid; j < E; j += 256) {
@@ -513,14 +560,14 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(
   s_h0[tid] = h0[b * 256 + tid];
   if (tid < 32) s_h1[tid] = h1[b * 32 + tid];
   if (tid < 4) s_d2[tid] = d_output[b * 4 + tid];
-  if (tid < 64) s_ds[tid] = h_sali[b * 64 + tid] > 0.f ? d_h_sali[b * 64 + tid] : 0.f;
+  if (tid < 64) s_ds[tid] = h_sali[b * 64 + tid] > 0.f ? d_h_sali[b * 64 + tid] * dscale : 0.f;
   __syncthreads();
   if (tid < 4) atomicAdd(&db2[tid], s_d2[tid]);
   if (tid < 128) atomicAdd(&dw2[tid], s_d2[tid >> 5] * s_h1[tid & 31]);
   if (tid < 32) {
     float a = 0.f;
     for (int o = 0; o < 4; ++o) a = fmaf(w2[o * 32 + tid], s_d2[o], a);
-    a = s_h1[tid] > 0.f ? a : 0.f;
+    a = s_h1[tid] > 0.f ? a * dscale : 0.f;
     s_d1[tid] = a;
     atomicAdd(&db1[tid], a);
   }
@@ -530,7 +577,7 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(
   {
     float a = 0.f;
     for (int o = 0; o < 32; ++o) a = fmaf(w1[o * 256 + tid], s_d1[o], a);
-    a = s_h0[tid] > 0.f ? a : 0.f;
+    a = s_h0[tid] > 0.f ? a * dscale : 0.f;
     s_d0[tid] = a;
     atomicAdd(&db0[tid], a);
   }
@@ -554,7 +601,26 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(
   }
 }
 
+// in-place dropout of a bf16 tensor (the FFN hidden activation after ReLU)
+__global__ void __launch_bounds__(256) dropout_bf16_kernel(__nv_bfloat16* __restrict__ x, long long n, unsigned int dthr,
+                                                           float dscale, unsigned long long seed, unsigned int site) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = __bfloat162float(x[i]);
+    x[i] = __float2bfloat16_rn(avdn_drop_keep(seed, site, (unsigned long long)i, dthr) ? v * dscale : 0.f);
+  }
+}
+
+// the keep-scale factor (0 or 1/(1-p)) of every element of a site, for tests and debugging
+__global__ void __launch_bounds__(256) dropout_keep_scale_kernel(float* __restrict__ out, long long n, unsigned int dthr,
+                                                                 float dscale, unsigned long long seed,
+                                                                 unsigned int site) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    out[i] = avdn_drop_keep(seed, site, (unsigned long long)i, dthr) ? dscale : 0.f;
+}
+
 inline int rows_grid(long long rows) { return (int)((rows + 7) / 8); }
+inline bool drop_ok(float p) { return p >= 0.f && p < 1.f; }
+inline float drop_scale(float p) { return 1.0f / (1.0f - p); }
 
 }  // namespace
 
@@ -601,19 +667,35 @@ extern "C" int avdn_embed_dir_bwd(const float* dv, const float* dirs, int B, int
   return avdn::check_launch("avdn_embed_dir_bwd");
 }
 
+extern "C" int avdn_ln_fwd_drop(const float* a, const float* b, const float* gamma, const float* beta, long long M,
+                                int D, float eps, float* v_out, float* y, void* y16, float* mean, float* rstd,
+                                float p, unsigned long long seed, unsigned int site, avdn_stream_t stream) {
+  AVDN_REQUIRE(D == E, "avdn_ln_fwd: d_model must be 768 (got %d)", D);
+  AVDN_REQUIRE(a && gamma && beta && mean && rstd && M > 0, "avdn_ln_fwd: bad argument");
+  AVDN_REQUIRE(drop_ok(p) && (p == 0.f || b), "avdn_ln_fwd: dropout p in [0,1) and needs the branch operand b");
+  ln_fwd_kernel<<<rows_grid(M), 256, 0, avdn::to_cuda(stream)>>>(a, b, gamma, beta, M, eps, v_out, y,
+                                                               reinterpret_cast<__nv_bfloat16*>(y16), mean, rstd,
+                                                               avdn_drop_thresh(p), drop_scale(p), seed, site);
+  return avdn::check_launch("avdn_ln_fwd");
+}
+
 extern "C" int avdn_ln_fwd(const float* a, const float* b, const float* gamma, const float* beta, long long M, int D,
                            float eps, float* v_out, float* y, void* y16, float* mean, float* rstd,
                            avdn_stream_t stream) {
-  AVDN_REQUIRE(D == E, "avdn_ln_fwd: d_model must be 768 (got %d)", D);
-  AVDN_REQUIRE(a && gamma && beta && mean && rstd && M > 0, "avdn_ln_fwd: bad argument");
-  ln_fwd_kernel<<<rows_grid(M), 256, 0, avdn::to_cuda(stream)>>>(a, b, gamma, beta, M, eps, v_out, y,
-                                                               reinterpret_cast<__nv_bfloat16*>(y16), mean, rstd);
-  return avdn::check_launch("avdn_ln_fwd");
+  return avdn_ln_fwd_drop(a, b, gamma, beta, M, D, eps, v_out, y, y16, mean, rstd, 0.f, 0ull, 0u, stream);
 }
 
 extern "C" int avdn_ln_bwd(const float* dy1, const float* dy2, const float* v, const float* mean, const float* rstd,
                            const float* gamma, long long M, int D, float* dv, void* dv16, float* dgamma, float* dbeta,
                            avdn_stream_t stream) {
+  return avdn_ln_bwd_drop(dy1, dy2, v, mean, rstd, gamma, M, D, dv, dv16, dgamma, dbeta, 0.f, 0ull, 0u, stream);
+}
+
+extern "C" int avdn_ln_bwd_drop(const float* dy1, const float* dy2, const float* v, const float* mean,
+                                const float* rstd, const float* gamma, long long M, int D, float* dv, void* dv16,
+                                float* dgamma, float* dbeta, float p, unsigned long long seed, unsigned int site,
+                                avdn_stream_t stream) {
+  AVDN_REQUIRE(drop_ok(p), "avdn_ln_bwd: dropout p must be in [0,1)");
   AVDN_REQUIRE(D == E, "avdn_ln_bwd: d_model must be 768 (got %d)", D);
   AVDN_REQUIRE(dy1 && v && mean && rstd && gamma && dgamma && dbeta && M > 0, "avdn_ln_bwd: bad argument");
   long long blocks = rows_grid(M);
@@ -621,24 +703,63 @@ extern "C" int avdn_ln_bwd(const float* dy1, const float* dy2, const float* v, c
   if (blocks > cap) blocks = cap;
   ln_bwd_kernel<<<(unsigned)blocks, 256, 0, avdn::to_cuda(stream)>>>(dy1, dy2, v, mean, rstd, gamma, M, dv,
                                                                    reinterpret_cast<__nv_bfloat16*>(dv16), dgamma,
-                                                                   dbeta);
+                                                                   dbeta, avdn_drop_thresh(p), drop_scale(p), seed,
+                                                                   site);
   return avdn::check_launch("avdn_ln_bwd");
+}
+
+extern "C" int avdn_softmax_fwd_drop(const float* scores, const int* lens, int B, int H, int L, int T, int Sp, void* P,
+                                     void* P_full, float p, unsigned long long seed, unsigned int site,
+                                     avdn_stream_t stream) {
+  AVDN_REQUIRE(scores && lens && P && T >= 1 && Sp >= L + 2 * T, "avdn_softmax_fwd: bad argument");
+  AVDN_REQUIRE(drop_ok(p) && (p == 0.f || P_full), "avdn_softmax_fwd: dropout p in [0,1) and needs P_full");
+  softmax_fwd_kernel<<<rows_grid((long long)B * H * (L + 2 * T)), 256, 0, avdn::to_cuda(stream)>>>(
+      scores, lens, B, H, L, T, Sp, reinterpret_cast<__nv_bfloat16*>(P), reinterpret_cast<__nv_bfloat16*>(P_full),
+      avdn_drop_thresh(p), drop_scale(p), seed, site);
+  return avdn::check_launch("avdn_softmax_fwd");
 }
 
 extern "C" int avdn_softmax_fwd(const float* scores, const int* lens, int B, int H, int L, int T, int Sp, void* P,
                                 avdn_stream_t stream) {
-  AVDN_REQUIRE(scores && lens && P && T >= 1 && Sp >= L + 2 * T, "avdn_softmax_fwd: bad argument");
-  softmax_fwd_kernel<<<rows_grid((long long)B * H * (L + 2 * T)), 256, 0, avdn::to_cuda(stream)>>>(
-      scores, lens, B, H, L, T, Sp, reinterpret_cast<__nv_bfloat16*>(P));
-  return avdn::check_launch("avdn_softmax_fwd");
+  return avdn_softmax_fwd_drop(scores, lens, B, H, L, T, Sp, P, nullptr, 0.f, 0ull, 0u, stream);
+}
+
+extern "C" int avdn_softmax_bwd_drop(const void* P, const float* dP, long long rows, int S, int Sp, float alpha,
+                                     void* dS, float p, unsigned long long seed, unsigned int site,
+                                     avdn_stream_t stream) {
+  AVDN_REQUIRE(P && dP && dS && rows > 0, "avdn_softmax_bwd: bad argument");
+  AVDN_REQUIRE(drop_ok(p), "avdn_softmax_bwd: dropout p must be in [0,1)");
+  softmax_bwd_kernel<<<rows_grid(rows), 256, 0, avdn::to_cuda(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(P), dP, rows, S, Sp, alpha, reinterpret_cast<__nv_bfloat16*>(dS),
+      avdn_drop_thresh(p), drop_scale(p), seed, site);
+  return avdn::check_launch("avdn_softmax_bwd");
 }
 
 extern "C" int avdn_softmax_bwd(const void* P, const float* dP, long long rows, int S, int Sp, float alpha, void* dS,
                                 avdn_stream_t stream) {
-  AVDN_REQUIRE(P && dP && dS && rows > 0, "avdn_softmax_bwd: bad argument");
-  softmax_bwd_kernel<<<rows_grid(rows), 256, 0, avdn::to_cuda(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(P), dP, rows, S, Sp, alpha, reinterpret_cast<__nv_bfloat16*>(dS));
-  return avdn::check_launch("avdn_softmax_bwd");
+  return avdn_softmax_bwd_drop(P, dP, rows, S, Sp, alpha, dS, 0.f, 0ull, 0u, stream);
+}
+
+extern "C" int avdn_dropout_bf16(void* x, long long n, float p, unsigned long long seed, unsigned int site,
+                                 avdn_stream_t stream) {
+  AVDN_REQUIRE(x && n >= 0 && drop_ok(p), "avdn_dropout_bf16: bad argument");
+  if (n == 0 || p == 0.f) return AVDN_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dropout_bf16_kernel<<<(unsigned)blocks, 256, 0, avdn::to_cuda(stream)>>>(reinterpret_cast<__nv_bfloat16*>(x), n,
+                                                                         avdn_drop_thresh(p), drop_scale(p), seed, site);
+  return avdn::check_launch("avdn_dropout_bf16");
+}
+
+extern "C" int avdn_dropout_keep_scale(float* out, long long n, float p, unsigned long long seed, unsigned int site,
+                                       avdn_stream_t stream) {
+  AVDN_REQUIRE(out && n >= 0 && drop_ok(p), "avdn_dropout_keep_scale: bad argument");
+  if (n == 0) return AVDN_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dropout_keep_scale_kernel<<<(unsigned)blocks, 256, 0, avdn::to_cuda(stream)>>>(out, n, avdn_drop_thresh(p),
+                                                                               drop_scale(p), seed, site);
+  return avdn::check_launch("avdn_dropout_keep_scale");
 }
 
 extern "C" int avdn_build_masks(const int* lens, int B, int L, int T, uint8_t* mask_pad, float* mask_attn,
@@ -671,12 +792,23 @@ extern "C" int avdn_heads_fwd(const float* x, int B, int S, int row_vis, int row
                               const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
                               const float* wf, const float* bf, float* h0, float* h1, float* output, float* h_sali,
                               avdn_stream_t stream) {
+  return avdn_heads_fwd_drop(x, B, S, row_vis, row_dir, w0, b0, w1, b1, w2, b2, wf, bf, h0, h1, output, h_sali, 0.f,
+                             0ull, 0u, stream);
+}
+
+extern "C" int avdn_heads_fwd_drop(const float* x, int B, int S, int row_vis, int row_dir, const float* w0,
+                                   const float* b0, const float* w1, const float* b1, const float* w2,
+                                   const float* b2, const float* wf, const float* bf, float* h0, float* h1,
+                                   float* output, float* h_sali, float p, unsigned long long seed,
+                                   unsigned int site, avdn_stream_t stream) {
+  AVDN_REQUIRE(drop_ok(p), "avdn_heads_fwd: dropout p must be in [0,1)");
   AVDN_REQUIRE(x && w0 && b0 && w1 && b1 && w2 && b2 && wf && bf && h0 && h1 && output && h_sali,
                "avdn_heads_fwd: null pointer");
   AVDN_REQUIRE(row_vis >= 0 && row_vis < S && row_dir >= 0 && row_dir < S, "avdn_heads_fwd: row out of range");
   if (B == 0) return AVDN_OK;
   heads_fwd_kernel<<<B, 256, 0, avdn::to_cuda(stream)>>>(x, S, row_vis, row_dir, w0, b0, w1, b1, w2, b2, wf, bf, h0,
-                                                       h1, output, h_sali);
+                                                       h1, output, h_sali, avdn_drop_thresh(p), drop_scale(p), seed,
+                                                       site);
   return avdn::check_launch("avdn_heads_fwd");
 }
 
@@ -685,12 +817,22 @@ extern "C" int avdn_heads_bwd(const float* x, int B, int S, int row_vis, int row
                               const float* h_sali, const float* d_output, const float* d_h_sali, float* dx,
                               float* dw0, float* db0, float* dw1, float* db1, float* dw2, float* db2, float* dwf,
                               float* dbf, avdn_stream_t stream) {
+  return avdn_heads_bwd_drop(x, B, S, row_vis, row_dir, w0, w1, w2, wf, h0, h1, h_sali, d_output, d_h_sali, dx, dw0,
+                             db0, dw1, db1, dw2, db2, dwf, dbf, 0.f, stream);
+}
+
+extern "C" int avdn_heads_bwd_drop(const float* x, int B, int S, int row_vis, int row_dir, const float* w0,
+                                   const float* w1, const float* w2, const float* wf, const float* h0,
+                                   const float* h1, const float* h_sali, const float* d_output,
+                                   const float* d_h_sali, float* dx, float* dw0, float* db0, float* dw1, float* db1,
+                                   float* dw2, float* db2, float* dwf, float* dbf, float p, avdn_stream_t stream) {
+  AVDN_REQUIRE(drop_ok(p), "avdn_heads_bwd: dropout p must be in [0,1)");
   AVDN_REQUIRE(x && w0 && w1 && w2 && wf && h0 && h1 && h_sali && d_output && d_h_sali && dx && dw0 && db0 && dw1 &&
                    db1 && dw2 && db2 && dwf && dbf,
                "avdn_heads_bwd: null pointer");
   if (B == 0) return AVDN_OK;
   heads_bwd_kernel<<<B, 256, 0, avdn::to_cuda(stream)>>>(x, S, row_vis, row_dir, w0, w1, w2, wf, h0, h1, h_sali,
                                                        d_output, d_h_sali, dx, dw0, db0, dw1, db1, dw2, db2, dwf,
-                                                       dbf);
+                                                       dbf, drop_scale(p));
   return avdn::check_launch("avdn_heads_bwd");
 }

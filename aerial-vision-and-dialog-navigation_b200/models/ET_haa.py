@@ -69,17 +69,23 @@ class ET(nn.Module):
             self._engines[key] = eng
         return eng
 
-    def _check_dropout(self):
-        if self.training:
-            raise NotImplementedError(
-                "ET.forward in train mode applies Dropout(0.1/0.2) in the reference; the CUDA path implements the "
-                "deterministic arithmetic only -- call .eval() (gradients are still computed; parity mode of "
-                "SURVEY.md §8d)")
+    HEAD_DROPOUT = 0.2                   # nn.Dropout(0.2) of decoder_2_action_full / fc (ET_haa.py:98-119)
+
+    def dropout_config(self):
+        """(p_encoder, p_heads, seed) of the next forward: the reference's train-mode dropout
+        (nn.TransformerEncoderLayer(dropout=dropout_transformer_encoder), Dropout(0.2) in the heads), zeros
+        in eval mode.  The seed advances every train-mode forward and derives from torch's global seed."""
+        if not self.training:
+            return 0.0, 0.0, 0
+        if float(getattr(self.args, "dropout_emb", 0.0)) != 0.0:
+            raise NotImplementedError("dropout_emb > 0 (EncoderVL's embedding dropout) is not implemented")
+        self._drop_step = getattr(self, "_drop_step", 0) + 1
+        seed = (torch.initial_seed() * 1000003 + self._drop_step) & 0xFFFFFFFFFFFFFFFF
+        return float(self.args.dropout_transformer_encoder), self.HEAD_DROPOUT, seed
 
     def forward_features(self, **inputs):
         """Like ``forward`` but returns ``(output [B,4], h_sali [B,64])`` -- the 8x8
         saliency map before the 224x224 upsample, which ``avdn_loss`` fuses."""
-        self._check_dropout()
         frames, lang, lang_cls, dirs = inputs["frames"], inputs["lang"], inputs["lang_cls"], inputs["directions"]
         _lib.require_cuda(frames, lang, lang_cls, dirs)
         B, T = frames.shape[:2]
@@ -88,6 +94,7 @@ class ET(nn.Module):
             raise ValueError("frames must be [B,T,512,49] (src/xview_et/agent.py:594,615)")
         lenths = [int(x) for x in inputs["lenths"]]
         eng = self.engine(B, L, T, frames.device)
+        eng.set_dropout(*self.dropout_config())
         return _ETFn.apply(self, eng, lenths, frames, lang, lang_cls, dirs, *self.used_parameters().values())
 
     def forward(self, **inputs):

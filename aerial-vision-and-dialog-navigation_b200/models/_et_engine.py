@@ -100,6 +100,21 @@ class ETEngine:
             self.output = buf((B, 4)); self.h_sali = buf((B, 64))
         self._sig = None
         self._bwd_ready = False
+        # train-mode dropout (nn.TransformerEncoderLayer p, heads p): off until set_dropout()
+        self.p_enc, self.p_head, self.seed = 0.0, 0.0, 0
+        self._drop_plans_p = None
+
+    HEAD_SITE = 1000
+
+    def set_dropout(self, p_enc=0.0, p_head=0.0, seed=0):
+        """Dropout of the NEXT forward/backward pair: ``p_enc`` at the four sites of every encoder layer
+        (attention probabilities, dropout1, FFN hidden, dropout2: sites 4l..4l+3), ``p_head`` in the heads
+        (sites 1000..1002).  Masks are a stateless hash of (seed, site, element): nothing is stored."""
+        self.p_enc, self.p_head, self.seed = float(p_enc), float(p_head), int(seed) & 0xFFFFFFFFFFFFFFFF
+        if self.p_enc > 0.0:
+            for Lb in self.layers:
+                if getattr(Lb, "Pu", None) is None:
+                    Lb.Pu = torch.empty_like(Lb.Pm)          # full softmax (the backward needs it)
 
     # ------------------------------------------------------------------ names
     @staticmethod
@@ -212,11 +227,23 @@ class ETEngine:
                                       split_k=sk(_cdiv(3 * E, 128), _cdiv(E, 256)), keep=(self.dqkv, Lb.xin))
         self._bwd_ready = True
 
+    def _ensure_drop_plans(self):
+        """FFN-hidden dropout: d(relu+dropout) = relu_mask epilogue with alpha = 1/(1-p)."""
+        if self._drop_plans_p == self.p_enc:
+            return
+        M, FF = self.M, self.FF
+        for Lb in self.layers:
+            Lb.b_ff2_d_drop = G.plan_plain(M=M, N=FF, K=E, a_ptr=self.dvh.data_ptr(), lda=E, a_mn=0,
+                                           b_ptr=Lb.w_2.data_ptr(), ldb=FF, b_mn=1, out=self.dh, ldc=FF,
+                                           relu_mask=Lb.h, alpha=1.0 / (1.0 - self.p_enc), keep=(self.dvh, Lb.w_2))
+        self._drop_plans_p = self.p_enc
+
     def _ensure_plans(self):
         sig = self._signature()
         if sig != self._sig:
             self._build_fwd_plans()
             self._bwd_ready = False
+            self._drop_plans_p = None
             self._sig = sig
 
     # ---------------------------------------------------------------- forward
@@ -275,16 +302,21 @@ class ETEngine:
             pre = self.lp(l)
             self._run(Lb.p_qkv)
             self._run(Lb.p_scores)
-            self._call("avdn_softmax_fwd", ptr(self.scores), ptr(self.lens), B, H, L, T, self.Sp, ptr(Lb.Pm))
+            pd, sd, st = self.p_enc, self.seed, 4 * l
+            self._call("avdn_softmax_fwd_drop", ptr(self.scores), ptr(self.lens), B, H, L, T, self.Sp, ptr(Lb.Pm),
+                       ptr(Lb.Pu) if pd > 0 else None, pd, sd, st)
             self._run(Lb.p_pv)
             self._run(Lb.p_o)
-            self._call("avdn_ln_fwd", ptr(x), ptr(self.tmp_f32), ptr(P[pre + "norm1.weight"]), ptr(P[pre + "norm1.bias"]),
-                       M, E, LN_EPS, ptr(Lb.v1), ptr(Lb.x1), ptr(Lb.x1h), ptr(Lb.mean1), ptr(Lb.rstd1))
+            self._call("avdn_ln_fwd_drop", ptr(x), ptr(self.tmp_f32), ptr(P[pre + "norm1.weight"]),
+                       ptr(P[pre + "norm1.bias"]), M, E, LN_EPS, ptr(Lb.v1), ptr(Lb.x1), ptr(Lb.x1h), ptr(Lb.mean1),
+                       ptr(Lb.rstd1), pd, sd, st + 1)
             self._run(Lb.p_ff1)
+            if pd > 0:
+                self._call("avdn_dropout_bf16", ptr(Lb.h), Lb.h.numel(), pd, sd, st + 2)
             self._run(Lb.p_ff2)
-            self._call("avdn_ln_fwd", ptr(Lb.x1), ptr(self.tmp_f32), ptr(P[pre + "norm2.weight"]),
+            self._call("avdn_ln_fwd_drop", ptr(Lb.x1), ptr(self.tmp_f32), ptr(P[pre + "norm2.weight"]),
                        ptr(P[pre + "norm2.bias"]), M, E, LN_EPS, ptr(Lb.v2), ptr(Lb.x2), ptr(Lb.x2h), ptr(Lb.mean2),
-                       ptr(Lb.rstd2))
+                       ptr(Lb.rstd2), pd, sd, st + 3)
             x = Lb.x2
         return x
 
@@ -293,10 +325,10 @@ class ETEngine:
         P, ptr = self.P, _lib.ptr
         d = "decoder_2_action_full."
         rv, rd = self.L + self.T - 1, self.L + 2 * self.T - 1
-        self._call("avdn_heads_fwd", ptr(x), self.B, self.S, rv, rd, ptr(P[d + "0.weight"]), ptr(P[d + "0.bias"]),
+        self._call("avdn_heads_fwd_drop", ptr(x), self.B, self.S, rv, rd, ptr(P[d + "0.weight"]), ptr(P[d + "0.bias"]),
                    ptr(P[d + "3.weight"]), ptr(P[d + "3.bias"]), ptr(P[d + "6.weight"]), ptr(P[d + "6.bias"]),
                    ptr(P["fc.0.weight"]), ptr(P["fc.0.bias"]), ptr(self.h0), ptr(self.h1), ptr(self.output),
-                   ptr(self.h_sali))
+                   ptr(self.h_sali), self.p_head, self.seed, self.HEAD_SITE)
         return self.output, self.h_sali
 
     def forward(self, frames, lang, lang_cls, dirs, lenths, pe):
@@ -319,11 +351,11 @@ class ETEngine:
         rv, rd = self.L + self.T - 1, self.L + 2 * self.T - 1
         self.dx.zero_()
         self.launches += 1
-        self._call("avdn_heads_bwd", ptr(x), self.B, self.S, rv, rd, ptr(P[d + "0.weight"]), ptr(P[d + "3.weight"]),
-                   ptr(P[d + "6.weight"]), ptr(P["fc.0.weight"]), ptr(self.h0), ptr(self.h1), ptr(self.h_sali),
-                   ptr(d_output), ptr(d_h_sali), ptr(self.dx), ptr(Gd[d + "0.weight"]), ptr(Gd[d + "0.bias"]),
-                   ptr(Gd[d + "3.weight"]), ptr(Gd[d + "3.bias"]), ptr(Gd[d + "6.weight"]), ptr(Gd[d + "6.bias"]),
-                   ptr(Gd["fc.0.weight"]), ptr(Gd["fc.0.bias"]))
+        self._call("avdn_heads_bwd_drop", ptr(x), self.B, self.S, rv, rd, ptr(P[d + "0.weight"]),
+                   ptr(P[d + "3.weight"]), ptr(P[d + "6.weight"]), ptr(P["fc.0.weight"]), ptr(self.h0), ptr(self.h1),
+                   ptr(self.h_sali), ptr(d_output), ptr(d_h_sali), ptr(self.dx), ptr(Gd[d + "0.weight"]),
+                   ptr(Gd[d + "0.bias"]), ptr(Gd[d + "3.weight"]), ptr(Gd[d + "3.bias"]), ptr(Gd[d + "6.weight"]),
+                   ptr(Gd[d + "6.bias"]), ptr(Gd["fc.0.weight"]), ptr(Gd["fc.0.bias"]), self.p_head)
 
     def backward_encoder(self, d_out=None):
         """Backward through the transformer stack.  The gradient w.r.t. the encoder
@@ -337,33 +369,37 @@ class ETEngine:
         if d_out is not None:
             self.dx.copy_(d_out.reshape(M, E))
             self.launches += 1
+        pd, sd = self.p_enc, self.seed
+        if pd > 0:
+            self._ensure_drop_plans()
         dy1, dy2 = self.dx, None
         for l in reversed(range(self.NL)):
             Lb = self.layers[l]
             pre = self.lp(l)
-            # norm2
-            self._call("avdn_ln_bwd", ptr(dy1), ptr(dy2), ptr(Lb.v2), ptr(Lb.mean2), ptr(Lb.rstd2),
+            st = 4 * l
+            # norm2 (dvh = gradient of the dropout2 branch)
+            self._call("avdn_ln_bwd_drop", ptr(dy1), ptr(dy2), ptr(Lb.v2), ptr(Lb.mean2), ptr(Lb.rstd2),
                        ptr(P[pre + "norm2.weight"]), M, E, ptr(self.dva), ptr(self.dvh), ptr(Gd[pre + "norm2.weight"]),
-                       ptr(Gd[pre + "norm2.bias"]))
+                       ptr(Gd[pre + "norm2.bias"]), pd, sd, st + 3)
             # FFN
             self._call("avdn_colsum", ptr(self.dvh), BF, M, E, E, ptr(Gd[pre + "linear2.bias"]))
             self._run(Lb.b_ff2_w)
-            self._run(Lb.b_ff2_d)
+            self._run(Lb.b_ff2_d_drop if pd > 0 else Lb.b_ff2_d)
             self._call("avdn_colsum", ptr(self.dh), BF, M, FF, FF, ptr(Gd[pre + "linear1.bias"]))
             self._run(Lb.b_ff1_w)
             self._run(Lb.b_ff1_d)
             # norm1: dy = dva (residual) + dbranch (through the FFN)
-            self._call("avdn_ln_bwd", ptr(self.dva), ptr(self.dbranch), ptr(Lb.v1), ptr(Lb.mean1), ptr(Lb.rstd1),
+            self._call("avdn_ln_bwd_drop", ptr(self.dva), ptr(self.dbranch), ptr(Lb.v1), ptr(Lb.mean1), ptr(Lb.rstd1),
                        ptr(P[pre + "norm1.weight"]), M, E, ptr(self.dvb), ptr(self.dvh), ptr(Gd[pre + "norm1.weight"]),
-                       ptr(Gd[pre + "norm1.bias"]))
+                       ptr(Gd[pre + "norm1.bias"]), pd, sd, st + 1)
             # attention
             self._call("avdn_colsum", ptr(self.dvh), BF, M, E, E, ptr(Gd[pre + "self_attn.out_proj.bias"]))
             self._run(Lb.b_o_w)
             self._run(Lb.b_o_d)
             self._run(Lb.b_dp)
             self._run(Lb.b_dv)
-            self._call("avdn_softmax_bwd", ptr(Lb.Pm), ptr(self.scores), B * H * S, S, Sp, 1.0 / math.sqrt(64.0),
-                       ptr(self.dS))
+            self._call("avdn_softmax_bwd_drop", ptr(Lb.Pu if pd > 0 else Lb.Pm), ptr(self.scores), B * H * S, S, Sp,
+                       1.0 / math.sqrt(64.0), ptr(self.dS), pd, sd, st)
             self._run(Lb.b_dq)
             self._run(Lb.b_dk)
             self._call("avdn_colsum", ptr(self.dqkv), BF, M, 3 * E, 3 * E, ptr(Gd[pre + "self_attn.in_proj_bias"]))

@@ -272,10 +272,9 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
                      ptr(bn.running_var), BN_EPS, ptr(L.scale), ptr(L.shift))
                 n += 1
             if L.first:
-                call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win, None)
-                call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), None, ptr(L.a), L.R, L.Cout_p,
-                     LEAKY_SLOPE)
-                n += 2
+                call("avdn_conv0_fwd_eval", ptr(x_nhwc4), ptr(conv.weight), ptr(L.scale), ptr(L.shift), LEAKY_SLOPE,
+                     ptr(L.a), eng.N, L.Hin, L.Win)
+                n += 1
             else:
                 L.p_fwd_eval.run()
                 n += 1

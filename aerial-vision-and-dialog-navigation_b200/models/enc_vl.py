@@ -28,16 +28,21 @@ class EncoderVL(nn.Module):
         self.n_heads, self.n_layers, self.d_ff = args.encoder_heads, args.encoder_layers, args.demb
         self._engines = {}
 
-    def _check_dropout(self):
-        if self.training and (self.enc_dropout.p > 0 or self.enc_transformer.layers[0].dropout.p > 0):
-            raise NotImplementedError(
-                "dropout > 0 in train mode is not implemented by the CUDA path; construct the model with "
-                "dropout_transformer_encoder=0 / dropout_emb=0 or call .eval() (parity mode, SURVEY.md §8d)")
+    def _dropout_config(self):
+        """Train mode: nn.TransformerEncoderLayer's dropout p at its four sites (stateless hash masks,
+        ``ETEngine.set_dropout``); the embedding dropout (dropout_emb, 0 in the reference's configs) is not
+        implemented."""
+        if not self.training:
+            return 0.0, 0.0, 0
+        if self.enc_dropout.p > 0:
+            raise NotImplementedError("dropout_emb > 0 (EncoderVL's embedding dropout) is not implemented")
+        self._drop_step = getattr(self, "_drop_step", 0) + 1
+        seed = (torch.initial_seed() * 1000003 + self._drop_step) & 0xFFFFFFFFFFFFFFFF
+        return float(self.enc_transformer.layers[0].dropout.p), 0.0, seed
 
     def forward(self, emb_lang, emb_frames, emb_directions, lengths):
         """enc_vl.py:34-69 -> (output [B,S,768], mask_pad [B,S] bool)."""
         _lib.require_cuda(emb_lang, emb_frames, emb_directions)
-        self._check_dropout()
         B, L, _ = emb_lang.shape
         T = emb_frames.shape[1]
         key = (B, L, T, str(emb_lang.device))
@@ -47,6 +52,7 @@ class EncoderVL(nn.Module):
             eng = ETEngine(params, self.n_heads, self.n_layers, self.d_ff, B, L, T, emb_lang.device,
                            with_frame_attn=False, with_heads=False)
             self._engines[key] = eng
+        eng.set_dropout(*self._dropout_config())
         out = _EncoderFn.apply(self, eng, list(lengths), emb_lang, emb_frames, emb_directions,
                                *[p for _, p in self.named_parameters()])
         return out, model_util.generate_pad_mask(lengths, L, emb_lang.device)

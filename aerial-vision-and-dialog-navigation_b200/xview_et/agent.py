@@ -164,6 +164,8 @@ class NavCMTAgent:
         et = self.vln_model
         eng = et.engine(B, L, T, self.device)
         e0 = eng.launches
+        et.train(bool(train) and not getattr(self.args, "no_dropout", False))
+        eng.set_dropout(*et.dropout_config())
         output, h_sali = eng.forward(bufs["frames"].view(B * T, 512, 49), lang, lang_cls, dirs, batch["lenths"],
                                      et.encoder_vl.enc_pos.pe[0])
         self.loss_total.zero_()

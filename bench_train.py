@@ -75,7 +75,7 @@ class TrainWorkload:
                             "+ ET(2x768, 12 heads) + waypoint & human-attention heads, loss, backward, clip, AdamW "
                             "(BASELINE configs[1]; configs[3] under torchrun)",
                 "global_batch": self.B * self.world, "per_gpu_batch": self.B, "views_per_step_per_gpu": self.B * T_STEPS,
-                "seq_len": L_LANG + 2 * T_STEPS, "dropout": "0 (parity mode; the reference's 0.1/0.2 dropout is not applied)",
+                "seq_len": L_LANG + 2 * T_STEPS, "dropout": "train mode: 0.1 at the 4 sites of each encoder layer, 0.2 in the heads (stateless hash masks)",
                 "cache": "per-step working set (~40 GB of activations) far exceeds L2; L2 is also flushed between steps",
                 "parallelism": f"dp{self.world} by episode, NCCL all-reduce of gradients" if self.world > 1 else "dp1"}
 

@@ -206,6 +206,10 @@ int avdn_gemm_run(const void* plan_host, avdn_stream_t stream);
  * zeroed by the call), to be finished by avdn_bn_finalize.  W % 16 == H % 4 == 0. */
 int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int N, int H, int W, double* stats,
                    avdn_stream_t stream);
+/* Eval mode: the same convolution with BatchNorm (running statistics) + LeakyReLU folded into the store:
+ * a [N,H,W,32] bf16 = leaky_slope(conv(x) * scale + shift); scale/shift [32] fp32 from avdn_bn_eval_coeffs. */
+int avdn_conv0_fwd_eval(const void* x_nhwc4, const float* w, const float* scale, const float* shift, float slope,
+                        void* a, int N, int H, int W, avdn_stream_t stream);
 /* dw [32,3,3,3] fp32 += sum_pixels dz * x (weight gradient of the same layer). */
 int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int H, int W, avdn_stream_t stream);
 
@@ -317,6 +321,43 @@ int avdn_softmax_fwd(const float* scores, const int* lens, int B, int H, int L, 
 /* dS = alpha * P * (dP - sum_k P*dP), bf16, zero in the padding. */
 int avdn_softmax_bwd(const void* P, const float* dP, long long rows, int S, int Sp, float alpha, void* dS,
                      avdn_stream_t stream);
+/* Train mode: the nn.Dropout sites of nn.TransformerEncoderLayer (enc_vl.py:16-22, p =
+ * dropout_transformer_encoder) and of the heads (ET_haa.py:98-119, p = 0.2).  A mask is never stored:
+ * element `idx` of site `site` is kept iff hash24(seed, site, idx) >= p * 2^24, and the forward and the
+ * backward kernel evaluate the same hash.  Kept values are scaled by 1/(1-p); p = 0 disables.
+ *   avdn_ln_fwd_drop      v = a + dropout(b)            (dropout1 / dropout2; idx = row*768 + col)
+ *   avdn_ln_bwd_drop      dv16 = dropout'(dv) (gradient of the branch b); dv fp32 stays the residual gradient
+ *   avdn_softmax_fwd_drop P = dropout(softmax) (operand of the PV GEMM), P_full = softmax (for the backward);
+ *                         idx = row*Sp + k over [B,H,S,Sp]
+ *   avdn_softmax_bwd_drop P = P_full, dP = gradient w.r.t. the dropped probabilities
+ *   avdn_dropout_bf16     in-place dropout of a bf16 tensor (FFN hidden activation; its backward is the
+ *                         relu_mask epilogue with alpha = 1/(1-p))
+ *   avdn_dropout_keep_scale  out[idx] = 0 or 1/(1-p): the mask of a site, for tests
+ *   avdn_heads_fwd_drop   sites site (h0, idx = b*256+o), site+1 (h1, b*32+o), site+2 (fc, b*64+o)
+ *   avdn_heads_bwd_drop   p of the forward (dropped activations are stored as zeros)                    */
+int avdn_ln_fwd_drop(const float* a, const float* b, const float* gamma, const float* beta, long long M, int D,
+                     float eps, float* v_out, float* y, void* y16, float* mean, float* rstd, float p,
+                     unsigned long long seed, unsigned int site, avdn_stream_t stream);
+int avdn_ln_bwd_drop(const float* dy1, const float* dy2, const float* v, const float* mean, const float* rstd,
+                     const float* gamma, long long M, int D, float* dv, void* dv16, float* dgamma, float* dbeta,
+                     float p, unsigned long long seed, unsigned int site, avdn_stream_t stream);
+int avdn_softmax_fwd_drop(const float* scores, const int* lens, int B, int H, int L, int T, int Sp, void* P,
+                          void* P_full, float p, unsigned long long seed, unsigned int site, avdn_stream_t stream);
+int avdn_softmax_bwd_drop(const void* P, const float* dP, long long rows, int S, int Sp, float alpha, void* dS,
+                          float p, unsigned long long seed, unsigned int site, avdn_stream_t stream);
+int avdn_dropout_bf16(void* x, long long n, float p, unsigned long long seed, unsigned int site,
+                      avdn_stream_t stream);
+int avdn_dropout_keep_scale(float* out, long long n, float p, unsigned long long seed, unsigned int site,
+                            avdn_stream_t stream);
+int avdn_heads_fwd_drop(const float* x, int B, int S, int row_vis, int row_dir, const float* w0, const float* b0,
+                        const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
+                        const float* bf, float* h0, float* h1, float* output, float* h_sali, float p,
+                        unsigned long long seed, unsigned int site, avdn_stream_t stream);
+int avdn_heads_bwd_drop(const float* x, int B, int S, int row_vis, int row_dir, const float* w0, const float* w1,
+                        const float* w2, const float* wf, const float* h0, const float* h1, const float* h_sali,
+                        const float* d_output, const float* d_h_sali, float* dx, float* dw0, float* db0, float* dw1,
+                        float* db1, float* dw2, float* db2, float* dwf, float* dbf, float p, avdn_stream_t stream);
+
 /* The two masks materialised exactly as the reference builds them (bit-exact
  * parity tests): mask_pad [B,S] u8 (1 = padded key), mask_attn [S,S] f32 (0 / -inf). */
 int avdn_build_masks(const int* lens, int B, int L, int T, uint8_t* mask_pad, float* mask_attn,

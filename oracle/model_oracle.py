@@ -260,9 +260,13 @@ def _layer_norm(x, w, b, eps=1e-5):
     return F.layer_norm(x, (x.shape[-1],), w, b, eps)
 
 
-def transformer_layer(x, sd, prefix, n_heads, mask_attn, mask_padding):
-    """One post-norm nn.TransformerEncoderLayer(d, h, ff, dropout, relu) in eval
-    arithmetic (dropout inactive), batch-first here."""
+def transformer_layer(x, sd, prefix, n_heads, mask_attn, mask_padding, drop=None):
+    """One post-norm nn.TransformerEncoderLayer(d, h, ff, dropout, relu), batch-first here.
+    ``drop`` = None: eval arithmetic (dropout inactive).  Otherwise a dict of explicit keep-scale
+    masks (0 or 1/(1-p)) for the layer's four nn.Dropout sites, in torch's order:
+    ``attn`` [B,H,S,S] on the softmax output (nn.MultiheadAttention(dropout=p)), ``drop1`` [B,S,E]
+    on the attention block's output, ``ffn`` [B,S,FF] after the ReLU, ``drop2`` [B,S,E] on linear2's
+    output."""
     B, S, E = x.shape
     dh = E // n_heads
     qkv = x @ sd[prefix + "self_attn.in_proj_weight"].t() + sd[prefix + "self_attn.in_proj_bias"]
@@ -274,17 +278,25 @@ def transformer_layer(x, sd, prefix, n_heads, mask_attn, mask_padding):
     scores = scores + mask_attn[None, None]
     scores = scores.masked_fill(mask_padding[:, None, None, :], float("-inf"))
     p = torch.softmax(scores, dim=-1)
+    if drop is not None:
+        p = p * drop["attn"]
     o = (p @ v).transpose(1, 2).reshape(B, S, E)
     o = o @ sd[prefix + "self_attn.out_proj.weight"].t() + sd[prefix + "self_attn.out_proj.bias"]
+    if drop is not None:
+        o = o * drop["drop1"]
     x = _layer_norm(x + o, sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"])
     ff = torch.relu(x @ sd[prefix + "linear1.weight"].t() + sd[prefix + "linear1.bias"])
+    if drop is not None:
+        ff = ff * drop["ffn"]
     ff = ff @ sd[prefix + "linear2.weight"].t() + sd[prefix + "linear2.bias"]
+    if drop is not None:
+        ff = ff * drop["drop2"]
     return _layer_norm(x + ff, sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"])
 
 
 def encoder_vl_forward(emb_lang, emb_frames, emb_dirs, lengths, sd, n_heads=12, n_layers=2,
-                       prefix="encoder_vl."):
-    """enc_vl.py:34-83."""
+                       prefix="encoder_vl.", drop=None):
+    """enc_vl.py:34-83.  ``drop``: None or a list (one dict per layer) of explicit dropout masks."""
     B, L, E = emb_lang.shape
     T = emb_frames.shape[1]
     assert T == int(np.max(lengths))
@@ -297,12 +309,16 @@ def encoder_vl_forward(emb_lang, emb_frames, emb_dirs, lengths, sd, n_heads=12, 
     mp = mask_pad(lengths, L)
     ma = attention_mask(L, T)
     for l in range(n_layers):
-        x = transformer_layer(x, sd, f"{prefix}enc_transformer.layers.{l}.", n_heads, ma, mp)
+        x = transformer_layer(x, sd, f"{prefix}enc_transformer.layers.{l}.", n_heads, ma, mp,
+                              None if drop is None else drop[l])
     return x, mp
 
 
-def et_forward(sd, directions, frames, lenths, lang, lang_cls, n_heads=12, n_layers=2):
-    """ET_haa.py:121-184 (eval arithmetic: dropout inactive).
+def et_forward(sd, directions, frames, lenths, lang, lang_cls, n_heads=12, n_layers=2, drop=None):
+    """ET_haa.py:121-184.  ``drop`` = None: eval arithmetic (dropout inactive); otherwise
+    ``{"layers": [per-layer mask dicts], "h0": [B,256], "h1": [B,32], "fc": [B,64]}`` -- explicit
+    keep-scale masks of the train-mode nn.Dropout sites (ET_haa.py:98-119: Dropout(0.2) after the two
+    hidden ReLUs of decoder_2_action_full and between fc's Linear and its ReLU).
     Returns (output [B,4], pred_saliency [B,1,224,224], h_sali [B,64])."""
     B, T = frames.shape[:2]
     L = lang.shape[1]
@@ -316,14 +332,22 @@ def et_forward(sd, directions, frames, lenths, lang, lang_cls, n_heads=12, n_lay
     emb_frames = emb_frames.view(B, T, -1)
     emb_dirs = directions.reshape(-1, 2) @ sd["direction_embedding.weight"].t() + sd["direction_embedding.bias"]
     emb_dirs = emb_dirs.view(B, T, -1)
-    enc, _ = encoder_vl_forward(lang, emb_frames, emb_dirs, lenths, sd, n_heads, n_layers)
+    enc, _ = encoder_vl_forward(lang, emb_frames, emb_dirs, lenths, sd, n_heads, n_layers,
+                                drop=None if drop is None else drop["layers"])
     tmax = int(np.max(lenths))
     vis = enc[:, L + tmax - 1]
     dire = enc[:, L + 2 * tmax - 1]
     h = torch.relu(dire @ sd["decoder_2_action_full.0.weight"].t() + sd["decoder_2_action_full.0.bias"])
+    if drop is not None:
+        h = h * drop["h0"]
     h = torch.relu(h @ sd["decoder_2_action_full.3.weight"].t() + sd["decoder_2_action_full.3.bias"])
+    if drop is not None:
+        h = h * drop["h1"]
     output = h @ sd["decoder_2_action_full.6.weight"].t() + sd["decoder_2_action_full.6.bias"]
-    h_sali = torch.relu(vis @ sd["fc.0.weight"].t() + sd["fc.0.bias"])       # Linear -> Dropout -> ReLU
+    hs = vis @ sd["fc.0.weight"].t() + sd["fc.0.bias"]                       # Linear -> Dropout -> ReLU
+    if drop is not None:
+        hs = hs * drop["fc"]
+    h_sali = torch.relu(hs)
     pred = F.interpolate(h_sali.view(-1, 1, 8, 8), size=(224, 224), mode="bilinear", align_corners=False)
     return output, pred, h_sali
 

@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 def _args(cfg_path):
     return types.SimpleNamespace(demb=768, encoder_heads=12, encoder_layers=2, dropout_transformer_encoder=0.1,
                                  num_input_actions=1, dropout_emb=0.0, darknet_model_file=cfg_path,
-                                 darknet_weight_file=None, lr=1e-5, nss_w=0.1, nss_r=0, ml_weight=0.2)
+                                 darknet_weight_file=None, lr=1e-5, nss_w=0.1, nss_r=0, ml_weight=0.2,
+                                 no_dropout=True)     # parity mode: the oracle arithmetic has no dropout
 
 
 def _loss_case(B, seed, nss_r=0):

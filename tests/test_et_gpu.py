@@ -155,11 +155,70 @@ def test_encoder_vl_standalone(et):
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
 
 
-def test_train_mode_dropout_is_refused(et):
+def _site_mask(n, p, seed, site):
+    from avdn_b200 import _lib
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    _lib.call("avdn_dropout_keep_scale", _lib.ptr(out), n, float(p), int(seed), int(site))
+    return out.cpu()
+
+
+def test_train_mode_dropout_vs_oracle_with_same_masks(et):
+    """Train mode applies the reference's nn.Dropout sites (0.1 x 4 per encoder layer, 0.2 x 3 in the
+    heads) with stateless hash masks.  The masks of the step are read back (avdn_dropout_keep_scale) and
+    fed to the fp32 oracle as explicit masks: outputs and every gradient must then agree."""
+    torch.manual_seed(9)
+    B, L, T, H, S = 3, 40, 5, 12, 50
+    Sp = 64
+    lens = [5, 3, 4]
+    lang = torch.randn(B, L, 768)
+    lang_cls = torch.relu(torch.randn(B, 49))
+    frames = torch.randn(B, T, 512, 49) * 0.5
+    deg = torch.randint(0, 360, (B, T)).float()
+    dirs = torch.stack([torch.sin(deg / 180 * 3.14159), torch.cos(deg / 180 * 3.14159)], -1)
+    w_out, w_hs = torch.randn(B, 4), torch.randn(B, 64)
+    f2 = frames.cuda().requires_grad_(True)
+    l2 = lang.cuda().requires_grad_(True)
     et.train()
     try:
-        with pytest.raises(NotImplementedError):
-            et(directions=torch.zeros(1, 1, 2).cuda(), frames=torch.zeros(1, 1, 512, 49).cuda(), lenths=[1],
-               lang=torch.zeros(1, 4, 768).cuda(), lang_cls=torch.zeros(1, 49).cuda())
+        et.zero_grad()
+        out, hs = et.forward_features(directions=dirs.cuda(), frames=f2, lenths=lens, lang=l2,
+                                      lang_cls=lang_cls.cuda())
+        eng = et.engine(B, L, T, f2.device)
+        p, ph, seed = eng.p_enc, eng.p_head, eng.seed
+        assert p == pytest.approx(0.1) and ph == pytest.approx(0.2) and eng.Sp == Sp
+        ((out * w_out.cuda()).sum() + (hs * w_hs.cuda()).sum()).backward()
+        # a second train-mode forward draws different masks
+        out_b, _ = et.forward_features(directions=dirs.cuda(), frames=f2.detach(), lenths=lens, lang=l2.detach(),
+                                       lang_cls=lang_cls.cuda())
+        assert eng.seed != seed and not torch.equal(out_b, out)
     finally:
         et.eval()
+    layers = []
+    for l in range(2):
+        attn = _site_mask(B * H * S * Sp, p, seed, 4 * l).view(B, H, S, Sp)[..., :S].contiguous()
+        layers.append(dict(attn=attn,
+                           drop1=_site_mask(B * S * 768, p, seed, 4 * l + 1).view(B, S, 768),
+                           ffn=_site_mask(B * S * 768, p, seed, 4 * l + 2).view(B, S, 768),
+                           drop2=_site_mask(B * S * 768, p, seed, 4 * l + 3).view(B, S, 768)))
+    drop = dict(layers=layers, h0=_site_mask(B * 256, ph, seed, 1000).view(B, 256),
+                h1=_site_mask(B * 32, ph, seed, 1001).view(B, 32), fc=_site_mask(B * 64, ph, seed, 1002).view(B, 64))
+    # the masks are Bernoulli(1-p) scaled by 1/(1-p)
+    m = layers[0]["drop1"]
+    u = torch.unique(m)
+    assert len(u) == 2 and u[0].item() == 0.0 and abs(u[1].item() - 1 / 0.9) < 1e-6
+    keep = (m > 0).float().mean().item()
+    assert abs(keep - 0.9) < 4 * (0.9 * 0.1 / m.numel()) ** 0.5 + 1e-3, keep
+    keep_a = (layers[1]["attn"] > 0).float().mean().item()
+    assert abs(keep_a - 0.9) < 5e-3, keep_a
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in et.state_dict().items()}
+    fr = frames.clone().requires_grad_(True)
+    lg = lang.clone().requires_grad_(True)
+    oo, _, hs_o = mo.et_forward(sd, dirs, fr, lens, lg, lang_cls, drop=drop)
+    ((oo * w_out).sum() + (hs_o * w_hs).sum()).backward()
+    assert _rel(out, oo) < 1e-2, _rel(out, oo)
+    assert _rel(hs, hs_o) < 1e-2, _rel(hs, hs_o)
+    for n, pp in et.used_parameters().items():
+        r = _rel2(pp.grad, sd[n].grad)
+        assert r < 5e-2, (n, r)
+    assert _rel2(f2.grad, fr.grad) < 5e-2
+    assert _rel2(l2.grad, lg.grad) < 5e-2
