@@ -38,6 +38,15 @@ __device__ __forceinline__ float ang_ref(float v0, float v1) {
 //   agent.py:663-669  4 x MSELoss(reduction='sum') + angular term
 //   agent.py:673-681  nss_w * NSS(pred_saliency[i], gt_saliency[i]) when sum(gt) > 0
 //   agent.py:883-885  loss += ml_loss * train_ml / batch_size   (== `scale`)
+//
+// NSS without ever forming the 224x224 prediction: the upsample is linear and separable,
+//   p[y,x] = sum_ab Wy[y,a] Wx[x,b] h[a,b]        (Wy = Wx = W, the 224x8 bilinear tap matrix)
+// so with c[a] = sum_y W[y,a], G[a,a'] = sum_y W[y,a] W[y,a'] (constants) and ONE pass over the
+// fixation map f for F[a,b] = sum_yx W[y,a] W[x,b] f[y,x] and SF = sum f:
+//   sum p   = sum_ab h[a,b] c[a] c[b]          sum p^2 = sum_ab h[a,b] (G h G^T)[a,b]
+//   sum p f = sum_ab h[a,b] F[a,b]
+//   dL/dh[a,b] = k1 (F[a,b] - fm c[a] c[b]) - k2 ((G h G^T)[a,b] - m c[a] c[b])
+// (the adjoint of the upsample applied to the per-pixel gradient k1 (f - fm) - k2 (p - m)).
 __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ output, const float* __restrict__ h_sali,
                                                    const float* __restrict__ gt_xy, const float* __restrict__ gt_alt,
                                                    const float* __restrict__ gt_prog, const uint8_t* __restrict__ att,
@@ -47,36 +56,81 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ out
                                                    float* __restrict__ d_h_sali) {
   __shared__ float s_h[64];
   __shared__ float s_dh[64];
-  __shared__ double s_red[4][8];
+  __shared__ double s_c[8], s_G[8][8], s_F[8][8], s_GhG[8][8], s_T[8][8];
+  __shared__ double s_col[8][VIEW];          // per-column partial sums A[a][x] = sum_y W[y,a] f[y,x]
+  __shared__ double s_red[8];
   __shared__ double s_stat[6];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < 64) { s_h[tid] = h_sali[b * 64 + tid]; s_dh[tid] = 0.f; }
+  if (tid < 64) {
+    s_h[tid] = h_sali[b * 64 + tid]; s_dh[tid] = 0.f;
+    (&s_G[0][0])[tid] = 0.0; (&s_F[0][0])[tid] = 0.0;
+  }
+  if (tid < 8) s_c[tid] = 0.0;
   __syncthreads();
   double nss_term = 0.0;
   bool use_nss = false;
   if (att != nullptr && nss_w != 0.f) {
     const uint8_t* f = att + (size_t)b * NPX;
-    double sp = 0, spp = 0, sf = 0, spf = 0;
-    for (int i = tid; i < NPX; i += 256) {
-      const int y = i / VIEW, x = i - y * VIEW;
-      int y0, y1, x0, x1; float ly, lx;
-      bilin_tap(y, &y0, &y1, &ly);
-      bilin_tap(x, &x0, &x1, &lx);
-      const float p = (1.f - ly) * ((1.f - lx) * s_h[y0 * 8 + x0] + lx * s_h[y0 * 8 + x1]) +
-                      ly * ((1.f - lx) * s_h[y1 * 8 + x0] + lx * s_h[y1 * 8 + x1]);
-      const double fv = (double)f[i] / 255.0;
-      sp += p; spp += (double)p * p; sf += fv; spf += (double)p * fv;
+    int t0 = 0, t1 = 0; float tl = 0.f;
+    double sf = 0.0;
+    if (tid < VIEW) {
+      bilin_tap(tid, &t0, &t1, &tl);           // this thread's taps, as a row (for c, G) and as a column
+      const double w0 = (double)(1.f - tl), w1 = (double)tl;
+      atomicAdd(&s_c[t0], w0); atomicAdd(&s_c[t1], w1);
+      atomicAdd(&s_G[t0][t0], w0 * w0); atomicAdd(&s_G[t0][t1], w0 * w1);
+      atomicAdd(&s_G[t1][t0], w1 * w0); atomicAdd(&s_G[t1][t1], w1 * w1);
+#pragma unroll
+      for (int a = 0; a < 8; ++a) s_col[a][tid] = 0.0;
+      // column pass: coalesced byte loads (thread = x), weights of row y into its two tap cells
+      for (int y = 0; y < VIEW; ++y) {
+        int y0, y1; float ly;
+        bilin_tap(y, &y0, &y1, &ly);           // warp-uniform
+        const double fv = (double)f[y * VIEW + tid] / 255.0;
+        sf += fv;
+        s_col[y0][tid] += (double)(1.f - ly) * fv;
+        s_col[y1][tid] += (double)ly * fv;
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const double v = s_col[a][tid];
+        atomicAdd(&s_F[a][t0], v * w0);
+        atomicAdd(&s_F[a][t1], v * w1);
+      }
     }
-    sp = warp_sum_d(sp); spp = warp_sum_d(spp); sf = warp_sum_d(sf); spf = warp_sum_d(spf);
-    if (lane == 0) { s_red[0][warp] = sp; s_red[1][warp] = spp; s_red[2][warp] = sf; s_red[3][warp] = spf; }
+    sf = warp_sum_d(sf);
+    if (lane == 0) s_red[warp] = sf;
+    __syncthreads();
+    if (tid < 64) {                            // T = G h  (rows), then GhG = T G^T (columns)
+      const int a = tid >> 3, c2 = tid & 7;
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += s_G[a][k] * (double)s_h[k * 8 + c2];
+      s_T[a][c2] = t;
+    }
+    __syncthreads();
+    if (tid < 64) {
+      const int a = tid >> 3, c2 = tid & 7;
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += s_T[a][k] * s_G[c2][k];
+      s_GhG[a][c2] = t;
+    }
     __syncthreads();
     if (tid == 0) {
-      double t[4] = {0, 0, 0, 0};
-      for (int k = 0; k < 4; ++k) for (int w = 0; w < 8; ++w) t[k] += s_red[k][w];
-      const double m = t[0] / NPX;
-      double var = (t[1] - NPX * m * m) / (NPX - 1);
+      double SF = 0.0;
+      for (int w = 0; w < 8; ++w) SF += s_red[w];
+      double sp = 0.0, spp = 0.0, spf = 0.0;
+      for (int a = 0; a < 8; ++a)
+        for (int c2 = 0; c2 < 8; ++c2) {
+          const double h = (double)s_h[a * 8 + c2];
+          sp += h * s_c[a] * s_c[c2];
+          spp += h * s_GhG[a][c2];
+          spf += h * s_F[a][c2];
+        }
+      const double m = sp / NPX;
+      double var = (spp - NPX * m * m) / (NPX - 1);
       if (var < 0) var = 0;
-      s_stat[0] = m; s_stat[1] = sqrt(var); s_stat[2] = t[2]; s_stat[3] = t[3];
+      s_stat[0] = m; s_stat[1] = sqrt(var); s_stat[2] = SF; s_stat[3] = spf;
     }
     __syncthreads();
     const double m = s_stat[0], sd = s_stat[1], SF = s_stat[2], SPF = s_stat[3];
@@ -89,23 +143,13 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ out
       if (nss_r == 1) sum_nf += SF;
       else if (nss_r == -1) sum_nf -= SF;
       nss_term = -(double)nss_w * sum_nf / Fe;
-      // d/dp_ij = c * [ (f_ij - SF/N)/sd - A (p_ij - m) / ((N-1) sd^3) ]
+      // per pixel: d/dp = c * [ (f - SF/N)/sd - A (p - m) / ((N-1) sd^3) ]; its upsample adjoint:
       const double c = -(double)nss_w * half / Fe * scale;
       const double k1 = c / sd, k2 = c * A / ((NPX - 1.0) * sd * sd * sd), fm = SF / NPX;
-      for (int i = tid; i < NPX; i += 256) {
-        const int y = i / VIEW, x = i - y * VIEW;
-        int y0, y1, x0, x1; float ly, lx;
-        bilin_tap(y, &y0, &y1, &ly);
-        bilin_tap(x, &x0, &x1, &lx);
-        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-        const float p = w00 * s_h[y0 * 8 + x0] + w01 * s_h[y0 * 8 + x1] + w10 * s_h[y1 * 8 + x0] +
-                        w11 * s_h[y1 * 8 + x1];
-        const double fv = (double)f[i] / 255.0;
-        const float g = (float)(k1 * (fv - fm) - k2 * ((double)p - m));
-        atomicAdd(&s_dh[y0 * 8 + x0], g * w00);
-        atomicAdd(&s_dh[y0 * 8 + x1], g * w01);
-        atomicAdd(&s_dh[y1 * 8 + x0], g * w10);
-        atomicAdd(&s_dh[y1 * 8 + x1], g * w11);
+      if (tid < 64) {
+        const int a = tid >> 3, c2 = tid & 7;
+        const double cc = s_c[a] * s_c[c2];
+        s_dh[tid] = (float)(k1 * (s_F[a][c2] - fm * cc) - k2 * (s_GhG[a][c2] - m * cc));
       }
     }
   }

@@ -96,7 +96,7 @@ class RenderWorkload:
     SIZE = 3000
 
     def __init__(self, rank, world):
-        from oracle import warp_oracle as wo          # synthetic inputs only (generators)
+        from avdn_b200.utils import synthetic as wo   # synthetic inputs (product-side generators)
         self.rank, self.world = rank, world
         self.tile = wo.synthetic_tile(seed=0, size=self.SIZE)
         allc = wo.synthetic_pose_corners(self.P_TOTAL * world, seed=0, size=self.SIZE)
@@ -185,6 +185,16 @@ except ImportError:
     RolloutWorkload = None
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """Write the one JSON result line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,7 +225,7 @@ def run_reference(args, W):
                              "sample": f"{n} units per step of the workload, {info['what']}"},
             "e2e": {"value": val, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -227,6 +237,12 @@ def main():
     ap.add_argument("--workload", default="train" if "train" in WORKLOADS else "render", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON result): anything libraries print on file descriptor 1
+    # (e.g. NCCL's version banner) is sent to stderr instead
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     W = WORKLOADS[args.workload]
 
@@ -321,7 +337,7 @@ def main():
         extra = getattr(wl, "extra", None)
         if extra:
             line.update(extra(ms / args.steps))
-        print(json.dumps(line))
+        emit(line)
     if use_dist:
         dist.destroy_process_group()
 

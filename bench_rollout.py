@@ -64,8 +64,8 @@ class RolloutWorkload:
                 "parallelism": f"episode-sharded x{self.world}, no collective"}
 
     def setup_gpu(self, dev):
-        from oracle import model_oracle as mo
-        from oracle import warp_oracle as wo
+        from avdn_b200.utils import synthetic as mo
+        from avdn_b200.utils import synthetic as wo
         from avdn_b200.xview_lstm.agent import NavCMTAgent
         self.dev = dev
         with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:

@@ -34,7 +34,7 @@ def make_args(cfg_path):
 
 def synthetic_batch(B, T, L, seed, tile_size=SIZE):
     """Host (numpy / torch CPU) episode tensors of the ANDH shape."""
-    from oracle import warp_oracle as wo          # generators of the synthetic inputs only
+    from avdn_b200.utils import synthetic as wo   # synthetic inputs (product-side generators)
     g = torch.Generator().manual_seed(seed)
     rng = np.random.default_rng(seed)
     corners = wo.synthetic_pose_corners(B * T, seed=seed, size=tile_size, edge_frac=0.05).reshape(B, T, 4, 2)
@@ -82,8 +82,8 @@ class TrainWorkload:
     # --------------------------------------------------------------------- GPU
     def setup_gpu(self, dev):
         import tempfile
-        from oracle import model_oracle as mo
-        from oracle import warp_oracle as wo
+        from avdn_b200.utils import synthetic as mo
+        from avdn_b200.utils import synthetic as wo
         from avdn_b200.xview_et.agent import NavCMTAgent
         self.dev = dev
         with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
