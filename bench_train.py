@@ -10,6 +10,7 @@ backward, Darknet backward, (gradient all-reduce), clip + AdamW on both models.
 from __future__ import annotations
 
 import math
+import json
 import os
 import time
 import types
@@ -159,9 +160,22 @@ class TrainWorkload:
         peak = peaks["bf16_sustained"]
         self._peak = peak
         top = sorted(self.profile.items(), key=lambda kv: -kv[1][1])[:14]
+        # DRAM bytes of the step's gemm_kernel launches from the committed ncu capture of this same command
+        # (profiles/r01_train_step_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum, single GPU)
+        traffic, traffic_src = None, None
+        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_train_step_traffic.json")
+        if self.world == 1 and os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    tj = json.load(f)["gemm_kernel"]
+                if tj["n"] == g_n:
+                    traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+                    traffic_src = "profiles/r01_train_step_traffic.json (ncu, sum over the step's gemm_kernel launches)"
+            except (KeyError, ValueError):
+                pass
         return {"kernel": "gemm_kernel (tcgen05 implicit-GEMM conv fwd/dgrad/wgrad + transformer GEMMs)",
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": (ach / peak) if ach else None, "traffic": None,
+                "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peaks["source"] + " (sustained bf16 cuBLAS; kernel timed inside a long step)",
                 "algorithmic_flops_per_step": g_fl, "gemm_launches_per_step": g_n, "gemm_ms_per_step": g_ms,
                 "gemm_share_of_kernel_time": g_ms / tot if tot else None,
