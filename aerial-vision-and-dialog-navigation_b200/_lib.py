@@ -18,6 +18,13 @@ _lib = None
 c_void_p, c_int, c_i64, c_f32, c_f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 
+class ConvItem(C.Structure):
+    """``avdn_conv_item`` of include/avdn.h."""
+    _fields_ = [("w", C.c_void_p), ("wf", C.c_void_p), ("wd", C.c_void_p), ("dwf", C.c_void_p), ("grad", C.c_void_p),
+                ("Cout", C.c_int32), ("Cin", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32),
+                ("Cout_p", C.c_int32), ("Cin_p", C.c_int32), ("pairs", C.c_int32), ("pad_", C.c_int32)]
+
+
 class TileDesc(C.Structure):
     """``avdn_tile_desc`` of include/avdn.h."""
     _fields_ = [("tile8", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32)]
@@ -48,6 +55,8 @@ _SIGNATURES = {
     "avdn_pack_conv_weight": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "avdn_unpack_conv_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "avdn_unpack_conv_wgrad_pairs": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "avdn_pack_conv_weights": [c_void_p, c_int, c_void_p],
+    "avdn_unpack_conv_wgrads": [c_void_p, c_int, c_int, c_void_p],
     "avdn_cast_f32_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "avdn_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "avdn_nchw_f32_to_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -257,8 +257,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* _
 
 // ------------------------------------------------------- weight (un)packing
 // w [Cout,Cin,k,k] fp32 -> wf [Cout_p][k*k][Cin_p] bf16 and wd [Cin_p][k*k][Cout_p] bf16 (zero padded)
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cout_p, int Cin_p,
-                                        __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+__device__ __forceinline__ void pack_conv_weight_body(const float* __restrict__ w, int Cout, int Cin, int k, int Cout_p,
+                                                      int Cin_p, __nv_bfloat16* __restrict__ wf,
+                                                      __nv_bfloat16* __restrict__ wd) {
   const int kk = k * k;
   const long long n = (long long)Cout_p * kk * Cin_p;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -270,10 +271,57 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
     wd[((long long)ci * kk + t) * Cout_p + co] = b;
   }
 }
-
-// grad [Cout,Cin,k,k] += dwf [Cout_p][k*k][Cin_p]
-__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwf, int Cout, int Cin, int k, int Cin_p,
-                                         float* __restrict__ grad) {
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cout_p, int Cin_p,
+                                        __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  pack_conv_weight_body(w, Cout, Cin, k, Cout_p, Cin_p, wf, wd);
+}
+// every layer of the trunk in one launch: blockIdx.y = table entry.  Both outputs are transposes of the
+// [Cout x Cin] matrix per tap, so a CTA moves 32(co) x 32(ci) x k*k tiles through shared memory: the fp32
+// read is contiguous along (ci, tap), the wf write along ci, the wd write along co.
+template <int KK>
+__device__ __forceinline__ void pack_tiles(const avdn_conv_item& it, __nv_bfloat16 (*tile)[32][34]) {
+  constexpr int kk = KK;
+  const int tco = it.Cout_p / 32, tci = (it.Cin_p + 31) / 32;
+  __nv_bfloat16* __restrict__ wf = reinterpret_cast<__nv_bfloat16*>(it.wf);
+  __nv_bfloat16* __restrict__ wd = reinterpret_cast<__nv_bfloat16*>(it.wd);
+  const int tid = threadIdx.x;
+  for (int tl = blockIdx.x; tl < tco * tci; tl += gridDim.x) {
+    const int co0 = (tl / tci) * 32, ci0 = (tl % tci) * 32;
+    __syncthreads();
+    // load: row r = co, contiguous run of 32*kk floats (ci, tap)
+    constexpr int run = 32 * kk;
+    for (int e = tid; e < 32 * run; e += 256) {
+      const int r = e / run, q = e - r * run, ci = q / kk, t = q - ci * kk;
+      const int co = co0 + r, cg = ci0 + ci;
+      float v = 0.f;
+      if (co < it.Cout && cg < it.Cin) v = __ldg(it.w + ((long long)co * it.Cin + cg) * kk + t);
+      tile[t][r][ci] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    // wf[co][t][ci]: 32 contiguous ci per (co, t)
+    for (int e = tid; e < 32 * kk * 32; e += 256) {
+      const int ci = e & 31, rt = e >> 5, t = rt % kk, r = rt / kk;
+      if (ci0 + ci < it.Cin_p)
+        wf[((long long)(co0 + r) * kk + t) * it.Cin_p + ci0 + ci] = tile[t][r][ci];
+    }
+    // wd[ci][t][co]: 32 contiguous co per (ci, t)
+    for (int e = tid; e < 32 * kk * 32; e += 256) {
+      const int r = e & 31, ct = e >> 5, t = ct % kk, ci = ct / kk;
+      if (ci0 + ci < it.Cin_p)
+        wd[((long long)(ci0 + ci) * kk + t) * it.Cout_p + co0 + r] = tile[t][r][ci];
+    }
+  }
+}
+__global__ void __launch_bounds__(256) pack_conv_weights_kernel(const avdn_conv_item* __restrict__ items) {
+  __shared__ __nv_bfloat16 tile[9][32][34];
+  const avdn_conv_item it = items[blockIdx.y];
+  if (it.k == 3) pack_tiles<9>(it, tile);
+  else pack_tiles<1>(it, tile);
+}
+// a range of layers in one launch: blockIdx.y = table entry (relative to `items`).  Plain layout: tiles of
+// 32(co) x 32(ci) x k*k through shared memory (dwf is contiguous along ci, grad along (ci, tap)).
+__device__ __forceinline__ void unpack_conv_wgrad_body(const float* __restrict__ dwf, int Cout, int Cin, int k,
+                                                       int Cin_p, float* __restrict__ grad) {
   const int kk = k * k;
   const long long n = (long long)Cout * Cin * kk;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -288,8 +336,13 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwf, int Cout
 //             tap dw of pixel parity a lands in (s,b) = f(a+dw): -1->(-1,1) 0->(0,0) 1->(0,1) 2->(1,0)
 //   stride 2: only X paired (pair index = output pixel).  D'[co][blk(kh,s)][(b,ci)], dw -> (s,b): -1->(-1,1) 0->(0,0) 1->(0,1)
 // grad [Cout,Cin,k,k] += the blocks that make up each filter tap.
-__global__ void unpack_conv_wgrad_pairs_kernel(const float* __restrict__ dwp, int Cout, int Cin, int k, int stride,
-                                               int Cout_p, int Cin_p, float* __restrict__ grad) {
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwf, int Cout, int Cin, int k, int Cin_p,
+                                         float* __restrict__ grad) {
+  unpack_conv_wgrad_body(dwf, Cout, Cin, k, Cin_p, grad);
+}
+__device__ __forceinline__ void unpack_conv_wgrad_pairs_body(const float* __restrict__ dwp, int Cout, int Cin, int k,
+                                                             int stride, int Cout_p, int Cin_p,
+                                                             float* __restrict__ grad) {
   const int kk = k * k, pad = (k - 1) / 2;
   const int Np = 2 * Cin_p;
   const int nshift = (stride == 2) ? 2 : (k == 3 ? 3 : 1);
@@ -313,6 +366,44 @@ __global__ void unpack_conv_wgrad_pairs_kernel(const float* __restrict__ dwp, in
     }
     grad[i] += v;
   }
+}
+__global__ void unpack_conv_wgrad_pairs_kernel(const float* __restrict__ dwp, int Cout, int Cin, int k, int stride,
+                                               int Cout_p, int Cin_p, float* __restrict__ grad) {
+  unpack_conv_wgrad_pairs_body(dwp, Cout, Cin, k, stride, Cout_p, Cin_p, grad);
+}
+template <int KK>
+__device__ __forceinline__ void unpack_tiles(const avdn_conv_item& it, float (*tile)[32][33]) {
+  constexpr int kk = KK;
+  const int tco = (it.Cout + 31) / 32, tci = (it.Cin + 31) / 32;
+  const int tid = threadIdx.x;
+  for (int tl = blockIdx.x; tl < tco * tci; tl += gridDim.x) {
+    const int co0 = (tl / tci) * 32, ci0 = (tl % tci) * 32;
+    __syncthreads();
+    for (int e = tid; e < 32 * kk * 32; e += 256) {
+      const int ci = e & 31, rt = e >> 5, t = rt % kk, r = rt / kk;
+      float v = 0.f;
+      if (co0 + r < it.Cout && ci0 + ci < it.Cin)
+        v = it.dwf[((long long)(co0 + r) * kk + t) * it.Cin_p + ci0 + ci];
+      tile[t][r][ci] = v;
+    }
+    __syncthreads();
+    constexpr int run = 32 * kk;
+    for (int e = tid; e < 32 * run; e += 256) {
+      const int r = e / run, q = e - r * run, ci = q / kk, t = q - ci * kk;
+      const int co = co0 + r, cg = ci0 + ci;
+      if (co < it.Cout && cg < it.Cin) it.grad[((long long)co * it.Cin + cg) * kk + t] += tile[t][r][ci];
+    }
+  }
+}
+__global__ void __launch_bounds__(256) unpack_conv_wgrads_kernel(const avdn_conv_item* __restrict__ items) {
+  __shared__ float tile[9][32][33];
+  const avdn_conv_item it = items[blockIdx.y];
+  if (it.pairs) {
+    unpack_conv_wgrad_pairs_body(it.dwf, it.Cout, it.Cin, it.k, it.stride, it.Cout_p, it.Cin_p, it.grad);
+    return;
+  }
+  if (it.k == 3) unpack_tiles<9>(it, tile);
+  else unpack_tiles<1>(it, tile);
 }
 
 // fp32 -> bf16 cast (linear-layer weights, features)
@@ -448,6 +539,22 @@ extern "C" int avdn_pack_conv_weight(const float* w, int Cout, int Cin, int k, i
   pack_conv_weight_kernel<<<grid_for(n), 256, 0, avdn::to_cuda(stream)>>>(
       w, Cout, Cin, k, Cout_p, Cin_p, reinterpret_cast<__nv_bfloat16*>(wf), reinterpret_cast<__nv_bfloat16*>(wd));
   return avdn::check_launch("avdn_pack_conv_weight");
+}
+
+extern "C" int avdn_pack_conv_weights(const avdn_conv_item* items_dev, int n_items, avdn_stream_t stream) {
+  AVDN_REQUIRE(n_items >= 0 && n_items <= 65535, "avdn_pack_conv_weights: bad item count");
+  if (n_items == 0) return AVDN_OK;
+  AVDN_REQUIRE(items_dev, "avdn_pack_conv_weights: null table");
+  pack_conv_weights_kernel<<<dim3(2 * avdn::sm_count(), n_items), 256, 0, avdn::to_cuda(stream)>>>(items_dev);
+  return avdn::check_launch("avdn_pack_conv_weights");
+}
+
+extern "C" int avdn_unpack_conv_wgrads(const avdn_conv_item* items_dev, int first, int count, avdn_stream_t stream) {
+  AVDN_REQUIRE(first >= 0 && count >= 0 && count <= 65535, "avdn_unpack_conv_wgrads: bad range");
+  if (count == 0) return AVDN_OK;
+  AVDN_REQUIRE(items_dev, "avdn_unpack_conv_wgrads: null table");
+  unpack_conv_wgrads_kernel<<<dim3(2 * avdn::sm_count(), count), 256, 0, avdn::to_cuda(stream)>>>(items_dev + first);
+  return avdn::check_launch("avdn_unpack_conv_wgrads");
 }
 
 extern "C" int avdn_unpack_conv_wgrad(const float* dwf, int Cout, int Cin, int k, int Cin_p, float* grad,

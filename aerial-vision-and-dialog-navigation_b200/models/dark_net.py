@@ -181,6 +181,31 @@ class _Engine:
                                                 Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops, stats=L.sums)
             self._fwd_plans = True
 
+    def conv_table(self, net):
+        """Device array of ``avdn_conv_item`` (one per tcgen05 conv block, layer order) for the one-launch
+        weight packing / gradient unpacking; rebuilt when a pointer changes (e.g. ``net.to()``)."""
+        import ctypes as C
+        import numpy as np
+        tc = [L for L in self.layers if not L.first]
+        sig = tuple((net.module_list[L.idx][0].weight.data_ptr(),
+                     0 if getattr(L, "dwf", None) is None else L.dwf.data_ptr(),
+                     0 if getattr(L, "dw", None) is None else L.dw.data_ptr()) for L in tc)
+        if getattr(self, "_table_sig", None) != sig:
+            arr = (_lib.ConvItem * len(tc))()
+            for i, L in enumerate(tc):
+                it = arr[i]
+                it.w = net.module_list[L.idx][0].weight.data_ptr()
+                it.wf, it.wd = L.wf.data_ptr(), L.wd.data_ptr()
+                it.dwf, it.grad = sig[i][1] or None, sig[i][2] or None
+                it.Cout, it.Cin, it.k, it.stride = L.Cout, L.Cin, L.k, L.s
+                it.Cout_p, it.Cin_p = L.Cout_p, L.Cin_p
+                it.pairs = 1 if getattr(L, "pairs", False) else 0
+            raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+            self._table = torch.from_numpy(raw).to(self.device)
+            self._table_sig = sig
+            self._table_n = len(tc)
+        return self._table
+
     def build_fwd_eval(self):
         """Eval mode: the BN affine is known before the convolution runs, so BatchNorm + LeakyReLU +
         the shortcut add are the convolution's epilogue (no z round trip, no elementwise pass)."""
@@ -208,6 +233,15 @@ class _Engine:
             if L.res is not None:
                 assert L.res.g is None
                 L.res.g = L.g
+        # WGRAD outputs (fp32, split-K reduce-add targets) live in one arena: zeroed with one memset per step
+        def dwf_shape(L):
+            if L.Cin_p == 32 or L.Cout_p == 32:
+                nblk = 6 if L.s == 2 else L.k * (3 if L.k == 3 else 1)
+                return (L.Cout_p if L.s == 2 else 2 * L.Cout_p, nblk * 2 * L.Cin_p)
+            return (L.Cout_p, L.k * L.k * L.Cin_p)
+        tot = sum((dwf_shape(L)[0] * dwf_shape(L)[1] + 63) // 64 * 64 for L in self.layers if not L.first)
+        self.dwf_arena = torch.zeros(tot, dtype=f32, device=dev)
+        dwf_off = 0
         seen_as_input = set()
         for L in reversed(self.layers):
             dz = self.dz[: L.R * L.Cout_p].view(self.N, L.Hout, L.Wout, L.Cout_p)
@@ -224,14 +258,13 @@ class _Engine:
             if L.first:
                 continue
             L.pairs = (L.Cin_p == 32 or L.Cout_p == 32)      # 32-channel operand: pixel-pair wgrad
+            shp = dwf_shape(L)
+            L.dwf = self.dwf_arena[dwf_off: dwf_off + shp[0] * shp[1]].view(shp)
+            dwf_off += (shp[0] * shp[1] + 63) // 64 * 64
             if L.pairs:
-                nblk = 6 if L.s == 2 else L.k * (3 if L.k == 3 else 1)
-                mp = L.Cout_p if L.s == 2 else 2 * L.Cout_p
-                L.dwf = torch.zeros((mp, nblk * 2 * L.Cin_p), dtype=f32, device=dev)
                 L.p_wgrad = G.plan_conv_wgrad_pairs(dz, L.src.a, L.dwf, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
                                                     Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
             else:
-                L.dwf = torch.zeros((L.Cout_p, L.k * L.k * L.Cin_p), dtype=f32, device=dev)
                 L.p_wgrad = G.plan_conv_wgrad(dz, L.src.a, L.dwf, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
                                               Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
             # the input's gradient buffer already holds the skip gradient iff the input is a
@@ -258,13 +291,14 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
     eng._frozen_ready = (not train)
     if not train:
         eng.build_fwd_eval()
+    if not reuse:
+        # fp32 master weights -> bf16 GEMM operands (wf, wd) of every block, one launch
+        tbl = eng.conv_table(net)
+        call("avdn_pack_conv_weights", ptr(tbl), eng._table_n)
+        n += 1
     for li, L in enumerate(eng.layers):
         conv = net.module_list[L.idx][0]
         bn = net.module_list[L.idx][1]
-        if not L.first and not reuse:
-            call("avdn_pack_conv_weight", ptr(conv.weight), L.Cout, L.Cin, L.k, L.Cout_p, L.Cin_p, ptr(L.wf),
-                 ptr(L.wd))
-            n += 1
         if not train:
             # eval: affine from the running statistics first, then conv with the fused epilogue
             if not reuse:
@@ -302,9 +336,10 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
     return out
 
 
-def _layer_backward(eng, L):
+def _layer_backward(eng, L, unpack=True, zero=True):
     """Backward of one conv block: BN/LeakyReLU backward (dz, dgamma, dbeta), weight gradient,
-    input gradient.  Returns the number of kernel launches."""
+    input gradient.  Returns the number of kernel launches.  ``unpack=False`` / ``zero=False``: the caller
+    zeroes the WGRAD arena once and unpacks ranges of layers in one launch (``_trunk_backward``)."""
     call, ptr = _lib.call, _lib.ptr
     call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
          L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
@@ -312,30 +347,47 @@ def _layer_backward(eng, L):
     if L.first:
         call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
         return n + 1
-    L.dwf.zero_()
+    if zero:
+        L.dwf.zero_()
+        n += 1
     L.p_wgrad.run()
-    if L.pairs:
-        call("avdn_unpack_conv_wgrad_pairs", ptr(L.dwf), L.Cout, L.Cin, L.k, L.s, L.Cout_p, L.Cin_p, ptr(L.dw))
-    else:
-        call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
+    n += 1
+    if unpack:
+        if L.pairs:
+            call("avdn_unpack_conv_wgrad_pairs", ptr(L.dwf), L.Cout, L.Cin, L.k, L.s, L.Cout_p, L.Cin_p, ptr(L.dw))
+        else:
+            call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
+        n += 1
     for p in L.p_dgrad:
         p.run()
-    return n + 3 + len(L.p_dgrad)
+    return n + len(L.p_dgrad)
 
 
-def _trunk_backward(net, eng, dout, after_layer=None):
+def _trunk_backward(net, eng, dout, after_layer=None, flush_layers=None):
     """Backward of every block; parameter gradients are ACCUMULATED into the
     engine's gradient tensors (``L.dw / L.dgamma / L.dbeta``: views of the optimiser
     arena when one is attached, engine-owned buffers otherwise).
+    The WGRAD outputs are folded into the weight gradients in one launch per range of layers: at
+    every layer index in ``flush_layers`` (the blocks that close a data-parallel bucket) and at the end.
     ``after_layer(i)`` is called once the gradients of conv block ``i`` (counted from
     the input) are complete -- the hook the data-parallel bucketing uses."""
     call, ptr = _lib.call, _lib.ptr
     eng.build_bwd(net)
+    tbl = eng.conv_table(net)                      # now carries the dwf / grad pointers
     last = eng.last
-    n = 1
+    eng.dwf_arena.zero_()
+    n = 2
     call("avdn_nchw_f32_to_nhwc", ptr(dout), ptr(last.g), eng.N, last.Hout * last.Wout, last.Cout_p)
+    flush = set(flush_layers or ())
+    hi = len(eng.layers) - 1                       # highest layer whose WGRAD output is still pending
     for li in reversed(range(len(eng.layers))):
-        n += _layer_backward(eng, eng.layers[li])
+        n += _layer_backward(eng, eng.layers[li], unpack=False, zero=False)
+        if li in flush or li == 0:
+            lo = max(li, 1)                        # layer 0 (conv0) writes its gradient directly
+            if hi >= lo:
+                call("avdn_unpack_conv_wgrads", ptr(tbl), lo - 1, hi - lo + 1)
+                n += 1
+            hi = li - 1
         if after_layer is not None:
             after_layer(li)
     eng.launches += n

@@ -211,7 +211,8 @@ class NavCMTAgent:
                                if li in buckets else None)
         else:
             hook = None
-        DN._trunk_backward(self.vision_model, teng, bufs["d_frames"].view(-1, 512, 7, 7), after_layer=hook)
+        DN._trunk_backward(self.vision_model, teng, bufs["d_frames"].view(-1, 512, 7, 7), after_layer=hook,
+                           flush_layers=set(buckets) if dp else None)
         if dp:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         gs = 1.0 / self.world

@@ -255,6 +255,22 @@ int avdn_unpack_conv_wgrad(const float* dwf, int Cout, int Cin, int k, int Cin_p
  * [Cout_p][3*2][2*Cin_p] (stride 2); grad [Cout,Cin,k,k] fp32 += the blocks of each tap.   */
 int avdn_unpack_conv_wgrad_pairs(const float* dwp, int Cout, int Cin, int k, int stride, int Cout_p, int Cin_p,
                                  float* grad, avdn_stream_t stream);
+/* The three calls above for a whole trunk in ONE launch each.  `items_dev` is a DEVICE array describing the
+ * tcgen05 convolution blocks in layer order; avdn_pack_conv_weights packs all of them (w -> wf, wd),
+ * avdn_unpack_conv_wgrads adds the WGRAD outputs of entries [first, first+count) into their gradients
+ * (grad += dwf, plain or pixel-pair layout).                                                            */
+typedef struct avdn_conv_item {
+  const float* w;   /* [Cout,Cin,k,k] fp32 master weight (pack) */
+  void* wf;         /* bf16 [Cout_p][k*k][Cin_p] (pack) */
+  void* wd;         /* bf16 [Cin_p][k*k][Cout_p] (pack) */
+  const float* dwf; /* WGRAD output (unpack) */
+  float* grad;      /* [Cout,Cin,k,k] fp32 gradient, accumulated (unpack) */
+  int32_t Cout, Cin, k, stride, Cout_p, Cin_p;
+  int32_t pairs;    /* 1: dwf is in the pixel-pair layout of avdn_unpack_conv_wgrad_pairs */
+  int32_t pad_;
+} avdn_conv_item;
+int avdn_pack_conv_weights(const avdn_conv_item* items_dev, int n_items, avdn_stream_t stream);
+int avdn_unpack_conv_wgrads(const avdn_conv_item* items_dev, int first, int count, avdn_stream_t stream);
 int avdn_cast_f32_bf16(const float* in, void* out, long long n, avdn_stream_t stream);
 /* Trunk output [N,HW,C] bf16 NHWC -> `frames` [N,C,HW] fp32 (the .view at
  * src/xview_et/agent.py:594) and its adjoint for the backward pass.           */
