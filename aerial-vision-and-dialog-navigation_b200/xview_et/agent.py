@@ -14,8 +14,15 @@ What is here
   restated because the reference evaluates them on the host per sample),
   ``save`` / ``load`` (agent.py:899-940; ``lang_model`` is outside the path).
 
+* ``rollout_greedy``: the student-feedback (inference / validation) loop of ``rollout``
+  (agent.py:580-760) with the growing episode history: every step renders the B current views,
+  runs the trunk in eval mode, appends the features and the heading to the history, runs the ET
+  over the t+1 steps seen so far, discretises the waypoint and moves the view -- all on the device;
+  the host reads the B stop flags once per step (the reference's ``lenths`` bookkeeping).
+
 What is not here: the dataset-driven ``rollout`` with the shapely teacher
-(``teacher_action``, agent.py:386-507) -- SURVEY.md §8f N3 ("next").
+(``teacher_action``, agent.py:386-507) -- SURVEY.md §8f N3 ("next"); the language side (BERT ->
+``lang`` / ``lang_cls``, agent.py:527-543) is an input of the path (N1).
 """
 from __future__ import annotations
 
@@ -223,6 +230,129 @@ class NavCMTAgent:
         if sync_loss:
             return float(self.loss_total.item())
         return self.loss_total
+
+    # ----------------------------------------------------------------- inference
+    STOP_THRESHOLD = 0.5               # agent.py:738-745 (the LSTM agent uses 0.25)
+
+    @torch.no_grad()
+    def rollout_greedy(self, batch, max_action_len=None, stop_threshold=None):
+        """Greedy (student-feedback) rollout of ``B`` episodes, the inference path of the HAA-Transformer
+        (agent.py:580-760 with ``feedback == 'student'``, no teacher / loss).
+
+        ``batch`` (device tensors): ``corners_gps`` f64 [B,4,2] (lat,lng; FL,FR,BR,BL = gt_path_corners[0]),
+        ``directions`` [B] (starting_angle, degrees), ``geo`` f64 [B,5] = (bl_lat, bl_lng, tr_lat, tr_lng,
+        lat_ratio), ``tile_idx`` i32 [B] or None, ``lang`` f32 [B,L,768], ``lang_cls`` f32 [B,49].
+
+        Step t: observation at the current corners (env._get_obs, agent.py:769) -> Darknet, eval mode ->
+        ``frames`` / ``directions`` grow by one step for EVERY sample, ``lenths`` only for the samples that
+        have not ended (agent.py:603-620) -> ``ET`` over the t+1 steps -> post-processing, stop test
+        (progress > 0.5 or last step) and ``move_view_corners`` (agent.py:637-653,736-760).  The loop ends
+        early once every sample has ended (agent.py:773-774).
+
+        Returns device tensors: ``corners`` [T+1,B,4,2], ``directions`` [T+1,B], ``ended`` [T,B],
+        ``output`` [T,B,4], ``angle`` / ``altitude`` [T,B], ``dist`` [T,B], and ``steps`` (the number of
+        steps actually run).  Rows after ``steps`` repeat the final state."""
+        ptr, call = _lib.ptr, _lib.call
+        T = int(max_action_len if max_action_len is not None else getattr(self.args, "max_action_len", 20))
+        thr = float(self.STOP_THRESHOLD if stop_threshold is None else stop_threshold)
+        lang, lang_cls = batch["lang"].contiguous().float(), batch["lang_cls"].contiguous().float()
+        B, L = lang.shape[0], lang.shape[1]
+        dev = self.device
+        key = ("rollout", B, T)
+        bf = self._bufs.get(key)
+        if bf is None:
+            f64, i32 = torch.float64, torch.int32
+            bf = dict(x=torch.empty((B, 224, 224, 4), dtype=torch.bfloat16, device=dev),
+                      frames=torch.empty((B, 512, 7, 7), dtype=torch.float32, device=dev),
+                      frames_hist=torch.zeros((T, B, 512, 49), dtype=torch.float32, device=dev),
+                      dirs_hist=torch.zeros((T, B, 2), dtype=torch.float32, device=dev),
+                      corners=torch.empty((B, 4, 2), dtype=f64, device=dev),
+                      cur_dir=torch.empty(B, dtype=f64, device=dev),
+                      ended=torch.empty(B, dtype=torch.uint8, device=dev),
+                      px=torch.empty((B, 4, 2), dtype=i32, device=dev),
+                      minv=torch.empty((B, 3, 3), dtype=f64, device=dev),
+                      corners_hist=torch.empty((T + 1, B, 4, 2), dtype=f64, device=dev),
+                      dir_hist=torch.empty((T + 1, B), dtype=f64, device=dev),
+                      ended_hist=torch.empty((T, B), dtype=torch.uint8, device=dev),
+                      output_hist=torch.zeros((T, B, 4), dtype=torch.float32, device=dev),
+                      angle=torch.zeros((T, B), dtype=i32, device=dev),
+                      altitude=torch.zeros((T, B), dtype=i32, device=dev),
+                      dist=torch.zeros((T, B), dtype=f64, device=dev))
+            self._bufs[key] = bf
+        geo = batch["geo"].contiguous()
+        bounds = geo[:, :4].contiguous()
+        ti = batch.get("tile_idx")
+        bf["corners"].copy_(batch["corners_gps"])
+        bf["cur_dir"].copy_(batch["directions"])
+        bf["ended"].zero_()
+        vm, et, r = self.vision_model, self.vln_model, self.renderer
+        vm.eval()
+        et.eval()
+        teng = vm.engine(B, 224, 224, dev)
+        l0 = teng.launches
+        lens = [0] * B
+        ended_host = [False] * B
+        n, steps = 0, 0
+        for t in range(T):
+            steps = t + 1
+            bf["corners_hist"][t].copy_(bf["corners"])
+            bf["dir_hist"][t].copy_(bf["cur_dir"])
+            # ---- observation -> trunk features of the step ----
+            call("avdn_gps_to_pixels", ptr(bf["corners"]), ptr(geo), B, ptr(bf["px"]))
+            call("avdn_homography_from_corners", ptr(bf["px"]), B, ptr(bf["minv"]))
+            r.render(None, ti, views=False, norm_nhwc=True, minv=bf["minv"], out={"norm_nhwc": bf["x"]})
+            DN._trunk_forward(vm, teng, bf["x"], False, out=bf["frames"], frozen=(t > 0))
+            bf["frames_hist"][t].copy_(bf["frames"].view(B, 512, 49))
+            rad = bf["cur_dir"].float() / 180 * PI_REF                  # agent.py:605-606 (float32, pi = 3.14159)
+            bf["dirs_hist"][t, :, 0] = torch.sin(rad)
+            bf["dirs_hist"][t, :, 1] = torch.cos(rad)
+            for i in range(B):
+                if not ended_host[i]:
+                    lens[i] += 1
+            # ---- ET over the history [B, t+1, ...] ----
+            Tc = t + 1
+            frames = bf["frames_hist"][:Tc].permute(1, 0, 2, 3).contiguous().view(B * Tc, 512, 49)
+            dirs = bf["dirs_hist"][:Tc].permute(1, 0, 2).contiguous()
+            eng = et.engine(B, L, Tc, dev)
+            e0 = eng.launches
+            eng.set_dropout(0.0, 0.0, 0)
+            output, _ = eng.forward(frames, lang, lang_cls, dirs, lens, et.encoder_vl.enc_pos.pe[0])
+            bf["output_hist"][t].copy_(output)
+            # ---- simulator: post-processing, stop test, move_view_corners ----
+            call("avdn_waypoint_step", ptr(output), ptr(bf["corners"]), ptr(bounds), ptr(bf["cur_dir"]),
+                 ptr(bf["ended"]), B, thr, int(t == T - 1), ptr(bf["angle"][t]), ptr(bf["dist"][t]),
+                 ptr(bf["altitude"][t]))
+            bf["ended_hist"][t].copy_(bf["ended"])
+            n += 12 + (eng.launches - e0)
+            ended_host = [bool(v) for v in bf["ended"].cpu().tolist()]  # the step's only host read
+            if all(ended_host):
+                break
+        for t2 in range(steps, T + 1):
+            bf["corners_hist"][t2].copy_(bf["corners"])
+            bf["dir_hist"][t2].copy_(bf["cur_dir"])
+        for t2 in range(steps, T):
+            bf["ended_hist"][t2].copy_(bf["ended"])
+        self.launches += n + (teng.launches - l0)
+        return dict(corners=bf["corners_hist"], directions=bf["dir_hist"], ended=bf["ended_hist"],
+                    output=bf["output_hist"], angle=bf["angle"], altitude=bf["altitude"], dist=bf["dist"],
+                    steps=steps)
+
+    @staticmethod
+    def trajectories(res):
+        """Host view of a rollout result: per sample the list of (corners [4,2], direction) the reference
+        appends to ``traj['path_corners']`` (agent.py:563,762-767)."""
+        corners = res["corners"].cpu().numpy()
+        dirs = res["directions"].cpu().numpy()
+        ended = res["ended"].cpu().numpy().astype(bool)
+        T, B = ended.shape
+        out = []
+        for i in range(B):
+            path = [(corners[0, i], dirs[0, i])]
+            for t in range(min(T, int(res.get("steps", T)))):
+                if not ended[t, i]:
+                    path.append((corners[t + 1, i], dirs[t + 1, i]))
+            out.append(path)
+        return out
 
     # ------------------------------------------------------------ API helpers
     def NSS(self, sal, fix):

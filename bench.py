@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the AVDN hot path on B200 (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout|et_rollout]
     python bench.py --impl reference ...        # the reference's CPU path, same metric
 
 One JSON line on stdout (rank 0).  Under torchrun (N>1) every rank runs its shard
@@ -179,8 +179,9 @@ except ImportError:
 
 
 try:
-    from bench_rollout import RolloutWorkload      # noqa: E402
+    from bench_rollout import RolloutWorkload, ETRolloutWorkload      # noqa: E402
     WORKLOADS["rollout"] = RolloutWorkload
+    WORKLOADS["et_rollout"] = ETRolloutWorkload
 except ImportError:
     RolloutWorkload = None
 

@@ -175,3 +175,102 @@ class RolloutWorkload:
         return {"kind": "port", "cores": int(torch.get_num_threads()),
                 "what": "oracle/model_oracle.py (torch CPU fp32: Darknet eval forward + ViT_LSTM step + simulator update), "
                         "4 episodes x 2 of 20 steps per unit batch, scaled to whole rollouts (view rendering not included)"}
+
+
+class ETRolloutWorkload(RolloutWorkload):
+    """HAA-Transformer inference: greedy rollout of the ET agent (growing episode history), batch 64 per GPU,
+    20 steps, never stopping early (stop threshold above 1) so that every rollout does the same work."""
+    name = "et_rollout"
+    metric = "et_haa greedy-rollout episodes/s"
+    B = 64
+
+    def config(self):
+        return {"workload": "et_haa greedy waypoint-rollout inference (student feedback, src/xview_et/agent.py:580-760), "
+                            "batch 64/GPU, 20 steps, 250-token dialog, views rendered from a 3000x3000 tile, Darknet "
+                            "(eval BN) per step + ET over the growing history (1..20 steps) + simulator update; no early stop",
+                "per_gpu_batch": self.B, "steps_per_rollout": T_STEPS, "views_per_rollout_per_gpu": self.B * T_STEPS,
+                "cache": "L2 is flushed between rollouts",
+                "parallelism": f"episode-sharded x{self.world}, no collective"}
+
+    def setup_gpu(self, dev):
+        from avdn_b200.utils import synthetic as syn
+        from avdn_b200.xview_et.agent import NavCMTAgent
+        from bench_train import make_args
+        self.dev = dev
+        with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+            f.write(syn.yolov3_trunk_cfg())
+        torch.manual_seed(0)
+        args = make_args(f.name)
+        args.max_action_len = T_STEPS
+        self.agent = NavCMTAgent(args, rank=self.rank, world_size=1, device=dev)
+        os.unlink(f.name)
+        self.agent.renderer.add_map("tile", syn.synthetic_tile(seed=0, size=SIZE), None)
+        hb = synthetic_rollout_batch(self.B, L_LANG, seed=self.rank)
+        self.host = dict(corners_gps=hb["corners_gps"], directions=hb["directions"], geo=hb["geo"],
+                         lang=hb["lang_feature"], lang_cls=hb["cls_hidden"])
+        self.pinned = {k: v.pin_memory() for k, v in self.host.items()}
+        self.batch = {k: v.to(dev) for k, v in self.host.items()}
+        self.batch["tile_idx"] = None
+        self.res_host = torch.empty((T_STEPS + 1, self.B, 4, 2), dtype=torch.float64).pin_memory()
+        self.profile = None
+
+    def step(self):
+        l0 = self.agent.launches
+        self.agent.rollout_greedy(self.batch, T_STEPS, stop_threshold=2.0)
+        return self.agent.launches - l0
+
+    def step_e2e(self):
+        h2d = 0
+        b = {"tile_idx": None}
+        for k, v in self.pinned.items():
+            b[k] = v.to(self.dev, non_blocking=True)
+            h2d += v.numel() * v.element_size()
+        res = self.agent.rollout_greedy(b, T_STEPS, stop_threshold=2.0)
+        self.res_host.copy_(res["corners"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h2d, int(self.res_host.numel() * 8)
+
+    def prepare_roofline(self):
+        from avdn_b200 import _lib
+        _lib.PROFILE = []
+        self.agent.rollout_greedy(self.batch, T_STEPS, stop_threshold=2.0)
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, fl, nb in _lib.PROFILE:
+            a = agg.setdefault(name, [0, 0.0, 0])
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl
+        _lib.PROFILE = None
+        self.profile = agg
+
+    def cpu_step(self, n):
+        """Oracle port of the reference loop body (torch CPU fp32): trunk in eval mode + ET over the history +
+        simulator update; CPU_SAMPLE episodes x the first 2 steps, scaled to a 20-step rollout by step count."""
+        from oracle import model_oracle as mo
+        if getattr(self, "_cpu", None) is None:
+            cfg = mo.yolov3_trunk_cfg()
+            hb = synthetic_rollout_batch(self.CPU_SAMPLE, L_LANG, seed=0)
+            self._cpu = (cfg, mo.random_trunk_state(cfg, seed=0), mo.random_et_state(seed=0), hb,
+                         torch.randn(self.CPU_SAMPLE, 3, 224, 224))
+        cfg, sd, esd, hb, images = self._cpu
+        B, steps, done = self.CPU_SAMPLE, 2, 0.0
+        with torch.no_grad():
+            while done < n:
+                corners, dirs = hb["corners_gps"].numpy().copy(), hb["directions"].numpy().copy()
+                ended = np.zeros(B, dtype=bool)
+                fh, dh = [], []
+                for t in range(steps):
+                    fh.append(mo.darknet_forward(images, sd, cfg, train=False).view(B, 1, 512, 49))
+                    rad = torch.from_numpy(dirs).float() / 180 * 3.14159
+                    dh.append(torch.stack([torch.sin(rad), torch.cos(rad)], -1).view(B, 1, 2))
+                    out, _, _ = mo.et_forward(esd, torch.cat(dh, 1), torch.cat(fh, 1), [t + 1] * B, hb["lang_feature"],
+                                              hb["cls_hidden"])
+                    corners, dirs, ended, *_ = mo.waypoint_step(out.numpy(), corners, hb["geo"][:, :4].numpy(), dirs,
+                                                                ended, 2.0, False)
+                done += B * steps / T_STEPS
+        return done
+
+    def cpu_info(self):
+        return {"kind": "port", "cores": int(torch.get_num_threads()),
+                "what": "oracle/model_oracle.py (torch CPU fp32: Darknet eval forward + ET over the history + simulator "
+                        "update), 4 episodes x the first 2 of 20 steps per unit batch, scaled by step count (view "
+                        "rendering not included; later steps attend over longer histories)"}

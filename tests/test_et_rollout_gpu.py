@@ -1,0 +1,124 @@
+"""GPU: the HAA-Transformer's inference path -- ``NavCMTAgent.rollout_greedy`` of the ET agent (student
+feedback loop of src/xview_et/agent.py:580-760) against the oracle pipeline.
+
+Step 0 end to end (cv2-exact views -> fp32 trunk in eval mode -> ET); every later step teacher-forced:
+the oracle ET is fed OUR feature / heading history and the reference's ``lenths`` bookkeeping, the oracle
+simulator OUR network outputs (the discretisation may legitimately flip between an fp32 and a bf16 trunk,
+the history handling and the update rule may not)."""
+import os
+import tempfile
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle as mo
+from oracle import warp_oracle as wo
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return (a.float().cpu() - b.float().cpu()).abs().max().item() / max(b.abs().max().item(), 1e-6)
+
+
+def _poses(B, seed):
+    rng = np.random.default_rng(seed)
+    bl, tr = np.array([40.0, -75.0]), np.array([40.02, -74.98])
+    corners = np.zeros((B, 4, 2))
+    dirs = np.zeros(B)
+    for i in range(B):
+        ctr = np.array([40.01, -74.99]) + rng.uniform(-0.0085, 0.0085, size=2)
+        half = rng.uniform(0.0004, 0.0018)
+        th = rng.uniform(0, 2 * np.pi)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        corners[i] = ctr + (np.array([[1, -1], [1, 1], [-1, 1], [-1, -1]]) * half) @ R.T
+        dirs[i] = round(mo.get_direction(np.mean(corners[i], axis=0), (corners[i][0] + corners[i][1]) / 2)) % 360
+    return corners, dirs, np.tile(np.concatenate([bl, tr]), (B, 1))
+
+
+@pytest.fixture(scope="module")
+def agent(built_lib):
+    from avdn_b200.xview_et.agent import NavCMTAgent
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(mo.yolov3_trunk_cfg())
+    args = types.SimpleNamespace(demb=768, encoder_heads=12, encoder_layers=2, dropout_transformer_encoder=0.1,
+                                 num_input_actions=1, dropout_emb=0.0, darknet_model_file=f.name,
+                                 darknet_weight_file=None, lr=1e-5, nss_w=0.1, nss_r=0, ml_weight=0.2, max_action_len=5)
+    torch.manual_seed(0)
+    a = NavCMTAgent(args, device="cuda")
+    os.unlink(f.name)
+    tile = wo.synthetic_tile(seed=2, size=1024)
+    a.renderer.add_map("m", tile, None)
+    a._tile = tile
+    return a
+
+
+@pytest.mark.parametrize("thr_mode", ["reference", "median"])
+def test_et_greedy_rollout_vs_oracle_pipeline(agent, thr_mode):
+    B, T, L = 4, 5, 12
+    size = 1024
+    lat_ratio = 0.02 / size
+    geo = np.tile(np.array([40.0, -75.0, 40.02, -74.98, lat_ratio]), (B, 1))
+    corners, dirs, bounds = _poses(B, 3)
+    g = torch.Generator().manual_seed(2)
+    lang = torch.randn(B, L, 768, generator=g)
+    cls = torch.relu(torch.randn(B, 49, generator=g))
+    batch = dict(corners_gps=torch.from_numpy(corners).cuda(), directions=torch.from_numpy(dirs).cuda(),
+                 geo=torch.from_numpy(geo).cuda(), tile_idx=None, lang=lang.cuda(), lang_cls=cls.cuda())
+    thr = 0.5
+    if thr_mode == "median":                       # make some (not all) episodes stop after the first step
+        probe = agent.rollout_greedy(batch, max_action_len=T, stop_threshold=1e9)
+        thr = float(probe["output"][0, :, 3].clamp(0, 1).median().item())
+    res = agent.rollout_greedy(batch, max_action_len=T, stop_threshold=thr)
+    torch.cuda.synchronize()
+    steps = res["steps"]
+    out = res["output"].cpu()
+    ch = res["corners"].cpu().numpy()
+    dh = res["directions"].cpu().numpy()
+    eh = res["ended"].cpu().numpy().astype(bool)
+    assert np.array_equal(ch[0], corners) and np.array_equal(dh[0], dirs)
+    sd_t = {k: v.detach().cpu() for k, v in agent.vision_model.state_dict().items()}
+    sd_e = {k: v.detach().cpu() for k, v in agent.vln_model.state_dict().items()}
+    # ---- step 0 through the oracle pipeline ----
+    px = np.zeros((B, 4, 2), dtype=np.int32)
+    for i in range(B):
+        for k in range(4):
+            lat, lng = corners[i, k]
+            px[i, k] = (int(round((lng - geo[i, 1]) / lat_ratio)), int(round((geo[i, 2] - lat) / lat_ratio)))
+    views = np.stack([wo.warp_fixed_point(agent._tile, wo.inverse_homography(px[i])) for i in range(B)])
+    x = torch.from_numpy(wo.normalise_views(views))
+    d0 = torch.from_numpy(dirs).float()
+    dirs0 = torch.stack([torch.sin(d0 / 180 * 3.14159), torch.cos(d0 / 180 * 3.14159)], -1).view(B, 1, 2)
+    with torch.no_grad():
+        feats = mo.darknet_forward(x, sd_t, mo.yolov3_trunk_cfg(), train=False).view(B, 1, 512, 49)
+        o0, _, _ = mo.et_forward(sd_e, dirs0, feats, [1] * B, lang, cls)
+    assert _rel(out[0], o0) < 2e-2, _rel(out[0], o0)
+    # ---- later steps, teacher-forced on OUR history ----
+    bf = agent._bufs[("rollout", B, T)]
+    fh = bf["frames_hist"].cpu()                   # [T,B,512,49]
+    dhist = bf["dirs_hist"].cpu()                  # [T,B,2]
+    ended = np.zeros(B, dtype=bool)
+    lens = [0] * B
+    for t in range(steps):
+        for i in range(B):
+            if not ended[i]:
+                lens[i] += 1                        # agent.py:617-619
+        rad = torch.from_numpy(dh[t]).float() / 180 * 3.14159
+        assert torch.allclose(dhist[t], torch.stack([torch.sin(rad), torch.cos(rad)], -1), atol=2e-6)
+        with torch.no_grad():
+            ot, _, _ = mo.et_forward(sd_e, dhist[:t + 1].permute(1, 0, 2), fh[:t + 1].permute(1, 0, 2, 3), list(lens),
+                                     lang, cls)
+        assert _rel(out[t], ot) < 1e-2, (t, _rel(out[t], ot))
+        nc, nd, ended, ang, alt, dist = mo.waypoint_step(out[t].numpy(), ch[t], bounds, dh[t], ended, thr, t == T - 1)
+        assert np.array_equal(res["angle"][t].cpu().numpy().astype(np.int64), ang), t
+        assert np.array_equal(res["altitude"][t].cpu().numpy().astype(np.int64), alt), t
+        assert np.array_equal(eh[t], ended), t
+        assert np.array_equal(dh[t + 1], nd), t
+        np.testing.assert_allclose(ch[t + 1], nc, rtol=1e-12, atol=0)
+    assert ended.all() and eh[T - 1].all()
+    if thr_mode == "median":
+        assert 0 < eh[0].sum() < B                  # ragged lengths were exercised
+    traj = agent.trajectories(res)
+    assert len(traj) == B and all(len(p) >= 1 for p in traj)
