@@ -81,6 +81,7 @@ _SIGNATURES = {
     "avdn_heads_fwd_drop": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 + [c_f32, C.c_uint64, C.c_uint32,
                                                                                      c_void_p],
     "avdn_heads_bwd_drop": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 18 + [c_f32, c_void_p],
+    "avdn_attn_decode": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_f32, c_void_p, c_void_p],
     "avdn_build_masks": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "avdn_colsum": [c_void_p, c_int, c_i64, c_int, c_i64, c_void_p, c_void_p],
     "avdn_heads_fwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 + [c_void_p],

@@ -444,6 +444,39 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// Incremental ("decode") attention of the ET inference path.  Rows of earlier steps never change (the mask is
+// causal over steps and LayerNorm / FFN are row-wise), so a rollout step only computes its R = 2 new rows per
+// sample (frame t, direction t); they attend to the first n rows of the layer's K|V cache (language rows, then
+// frame/direction rows of steps 0..t interleaved).  One warp per (sample, head, new row); fp32 online softmax.
+//   qkv_new [B*R, 2304] bf16 (q | k | v of the new rows; q is read), cache [B, Lc, 1536] bf16 (k | v),
+//   ctx [B*R, 768] bf16.
+__global__ void __launch_bounds__(256) attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv_new,
+                                                          const __nv_bfloat16* __restrict__ cache, int B, int R, int H,
+                                                          int Lc, int n, float scale, __nv_bfloat16* __restrict__ ctx) {
+  const long long w = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (w >= (long long)B * H * R) return;
+  const int lane = threadIdx.x & 31;
+  const int r = (int)(w % R), h = (int)((w / R) % H), b = (int)(w / ((long long)R * H));
+  const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(qkv_new + ((size_t)b * R + r) * (3 * E) + h * 64 + 2 * lane);
+  const float q0 = __low2float(q2) * scale, q1 = __high2float(q2) * scale;
+  const __nv_bfloat16* kv = cache + (size_t)b * Lc * (2 * E) + h * 64 + 2 * lane;
+  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(kv + (size_t)j * (2 * E));
+    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(kv + (size_t)j * (2 * E) + E);
+    const float sc = warp_sum(fmaf(q0, __low2float(k2), q1 * __high2float(k2)));
+    const float mn = fmaxf(m, sc);
+    const float corr = __expf(m - mn), pj = __expf(sc - mn);
+    l = fmaf(l, corr, pj);
+    a0 = fmaf(a0, corr, pj * __low2float(v2));
+    a1 = fmaf(a1, corr, pj * __high2float(v2));
+    m = mn;
+  }
+  const float inv = 1.f / l;
+  *reinterpret_cast<__nv_bfloat162*>(ctx + ((size_t)b * R + r) * E + h * 64 + 2 * lane) =
+      __floats2bfloat162_rn(a0 * inv, a1 * inv);
+}
+
 // materialised masks for the bit-exact parity tests (E3 / E5)
 __global__ void build_masks_kernel(const int* __restrict__ lens, int B, int L, int T, uint8_t* __restrict__ mask_pad,
                                    float* __restrict__ mask_attn) {
@@ -654,7 +687,9 @@ extern "C" int avdn_frame_attn_bwd(const float* frames, const float* lang_cls, c
 extern "C" int avdn_embed_fwd(const float* lang, const float* emb_frames, const float* dirs, const float* wd,
                               const float* bd, const float* pe, int B, int L, int T, float* v,
                               avdn_stream_t stream) {
-  AVDN_REQUIRE(lang && emb_frames && dirs && pe && v && (wd == nullptr || bd != nullptr), "avdn_embed_fwd: null pointer");
+  AVDN_REQUIRE((lang || L == 0) && emb_frames && dirs && pe && v && (wd == nullptr || bd != nullptr),
+               "avdn_embed_fwd: null pointer");
+  AVDN_REQUIRE(B > 0 && L >= 0 && T >= 1, "avdn_embed_fwd: bad shape");
   embed_fwd_kernel<<<rows_grid((long long)B * (L + 2 * T)), 256, 0, avdn::to_cuda(stream)>>>(
       lang, emb_frames, dirs, wd, bd, pe, B, L, T, v);
   return avdn::check_launch("avdn_embed_fwd");
@@ -760,6 +795,16 @@ extern "C" int avdn_dropout_keep_scale(float* out, long long n, float p, unsigne
   dropout_keep_scale_kernel<<<(unsigned)blocks, 256, 0, avdn::to_cuda(stream)>>>(out, n, avdn_drop_thresh(p),
                                                                                drop_scale(p), seed, site);
   return avdn::check_launch("avdn_dropout_keep_scale");
+}
+
+extern "C" int avdn_attn_decode(const void* qkv_new, const void* cache, int B, int R, int H, int Lc, int n, float scale,
+                                void* ctx, avdn_stream_t stream) {
+  AVDN_REQUIRE(qkv_new && cache && ctx && B > 0 && R > 0 && H * 64 == E && n >= 1 && n <= Lc,
+               "avdn_attn_decode: bad argument (d_model 768 = H x 64, 1 <= n <= Lc)");
+  attn_decode_kernel<<<rows_grid((long long)B * H * R), 256, 0, avdn::to_cuda(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_new), reinterpret_cast<const __nv_bfloat16*>(cache), B, R, H, Lc, n,
+      scale, reinterpret_cast<__nv_bfloat16*>(ctx));
+  return avdn::check_launch("avdn_attn_decode");
 }
 
 extern "C" int avdn_build_masks(const int* lens, int B, int L, int T, uint8_t* mask_pad, float* mask_attn,

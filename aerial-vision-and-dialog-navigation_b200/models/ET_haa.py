@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from ._et_engine import ETEngine, E, NCH, NSP
+from ._et_engine import ETEngine, ETDecodeState, E, NCH, NSP
 from .enc_vl import EncoderVL
 
 
@@ -68,6 +68,15 @@ class ET(nn.Module):
                            grads=self._grad_arena)
             self._engines[key] = eng
         return eng
+
+    def decoder(self, B, L, Tmax, device):
+        """Incremental inference state of a greedy rollout (``_et_engine.ETDecodeState``)."""
+        key = ("dec", B, L, Tmax, str(device))
+        d = self._engines.get(key)
+        if d is None:
+            d = ETDecodeState(self.engine(B, L, 1, device), Tmax)
+            self._engines[key] = d
+        return d
 
     HEAD_DROPOUT = 0.2                   # nn.Dropout(0.2) of decoder_2_action_full / fc (ET_haa.py:98-119)
 

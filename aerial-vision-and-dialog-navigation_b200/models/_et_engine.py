@@ -438,3 +438,116 @@ class ETEngine:
                    ptr(Gd["attention_layer_vision.linear_out.weight"]), ptr(Gd["fc2.weight"]), ptr(Gd["fc2.bias"]))
         d_lang = dv0[:, :L].contiguous() if need_lang_grad else None
         return d_frames, d_lang
+
+
+class ETDecodeState:
+    """Incremental ET inference for a greedy rollout (one per (B, L, Tmax)).
+
+    The reference re-runs the whole encoder over the growing history at every step
+    (src/xview_et/agent.py:620-627).  Rows of earlier steps cannot change: the attention mask is causal
+    over steps (model_util.py:213-241: language rows see language only; frame/direction row t sees
+    language and the frame/direction rows <= t) and LayerNorm / FFN act row by row.  So step 0 runs the
+    full engine once (T = 1) and keeps every layer's K|V rows; step t >= 1 computes only its two new rows
+    per sample (frame t, direction t) against the cache (``avdn_attn_decode``) -- the language rows, 93 %
+    of the sequence, are encoded once per rollout instead of once per step.
+
+    Cache layout per layer: bf16 ``[B, L + 2*Tmax, 1536]`` (k | v); row j < L = language token j, row
+    L + 2s = frame s, row L + 2s + 1 = direction s (the T = 1 engine's row order for s = 0).
+    Samples that have ended keep receiving rows (their outputs are ignored, as in the reference)."""
+
+    R = 2
+
+    def __init__(self, eng1: ETEngine, Tmax: int):
+        assert eng1.T == 1 and eng1.with_frame_attn and eng1.with_heads
+        self.e = eng1
+        self.B, self.L, self.Tmax = eng1.B, eng1.L, Tmax
+        self.Lc = self.L + 2 * Tmax
+        B, dev, FF = self.B, eng1.dev, eng1.FF
+        f32, bf = torch.float32, torch.bfloat16
+        M = self.R * B
+        self.M = M
+        buf = lambda shape, dt=f32: torch.empty(shape, dtype=dt, device=dev)
+        self.cache = [torch.zeros((B, self.Lc, 2 * E), dtype=bf, device=dev) for _ in eng1.layers]
+        self.v0, self.x0, self.x0h = buf((M, E)), buf((M, E)), buf((M, E), bf)
+        self.mean, self.rstd = buf(M), buf(M)
+        self.qkv = buf((M, 3 * E), bf)
+        self.ctx = buf((M, E), bf)
+        self.tmp = buf((M, E))
+        self.h = buf((M, FF), bf)
+        self.xa = [(buf((M, E)), buf((M, E), bf)) for _ in eng1.layers]      # after norm1
+        self.xb = [(buf((M, E)), buf((M, E), bf)) for _ in eng1.layers]      # after norm2
+        self.launches = 0
+        self._plans = None
+
+    def _build_plans(self):
+        e, M, FF, P = self.e, self.M, self.e.FF, self.e.P
+        self._plans = []
+        for l, Lb in enumerate(e.layers):
+            pre = e.lp(l)
+            xin = self.x0h if l == 0 else self.xb[l - 1][1]
+            x1h, _ = self.xa[l][1], None
+            pl = dict(
+                qkv=G.plan_plain(M=M, N=3 * E, K=E, a_ptr=xin.data_ptr(), lda=E, a_mn=0, b_ptr=Lb.w_in.data_ptr(), ldb=E,
+                                 b_mn=0, out=self.qkv, ldc=3 * E, bias=P[pre + "self_attn.in_proj_bias"],
+                                 keep=(xin, Lb.w_in)),
+                o=G.plan_plain(M=M, N=E, K=E, a_ptr=self.ctx.data_ptr(), lda=E, a_mn=0, b_ptr=Lb.w_o.data_ptr(), ldb=E,
+                               b_mn=0, out=self.tmp, ldc=E, bias=P[pre + "self_attn.out_proj.bias"],
+                               keep=(self.ctx, Lb.w_o)),
+                ff1=G.plan_plain(M=M, N=FF, K=E, a_ptr=x1h.data_ptr(), lda=E, a_mn=0, b_ptr=Lb.w_1.data_ptr(), ldb=E,
+                                 b_mn=0, out=self.h, ldc=FF, bias=P[pre + "linear1.bias"], relu=True,
+                                 keep=(x1h, Lb.w_1)),
+                ff2=G.plan_plain(M=M, N=E, K=FF, a_ptr=self.h.data_ptr(), lda=FF, a_mn=0, b_ptr=Lb.w_2.data_ptr(),
+                                 ldb=FF, b_mn=0, out=self.tmp, ldc=E, bias=P[pre + "linear2.bias"],
+                                 keep=(self.h, Lb.w_2)))
+            self._plans.append(pl)
+        self._sig = e._signature()
+
+    def start(self):
+        """After the T = 1 engine's forward of step 0: keep the K|V rows of every layer."""
+        e = self.e
+        S1 = self.L + 2
+        for l, Lb in enumerate(e.layers):
+            self.cache[l][:, :S1].copy_(Lb.qkv.view(self.B, S1, 3 * E)[:, :, E:])
+            self.launches += 1
+
+    def step(self, t, frames_t, dirs_t, lang_cls, pe):
+        """Step t >= 1: ``frames_t`` [B,512,49] fp32, ``dirs_t`` [B,2] fp32 -> (output [B,4], h_sali [B,64])."""
+        e, P, ptr, call = self.e, self.e.P, _lib.ptr, _lib.call
+        B, L, M, H = self.B, self.L, self.M, e.H
+        assert 1 <= t < self.Tmax
+        if self._plans is None or self._sig != e._signature():
+            self._build_plans()
+        n0 = e.launches
+        emb = e.frame_attention(frames_t, lang_cls)                      # [B,768] (T = 1 buffers)
+        # the two new rows: frame t and direction t, both at position L + t (encodings.py:22-49)
+        call("avdn_embed_fwd", None, ptr(emb), ptr(dirs_t), ptr(P["direction_embedding.weight"]),
+             ptr(P["direction_embedding.bias"]), pe.data_ptr() + (L + t) * E * 4, B, 0, 1, ptr(self.v0))
+        call("avdn_ln_fwd", ptr(self.v0), None, ptr(P["encoder_vl.enc_layernorm.weight"]),
+             ptr(P["encoder_vl.enc_layernorm.bias"]), M, E, LN_EPS, None, ptr(self.x0), ptr(self.x0h), ptr(self.mean),
+             ptr(self.rstd))
+        x = self.x0
+        row = L + 2 * t
+        n = 2
+        for l, pl in enumerate(self._plans):
+            pre = e.lp(l)
+            pl["qkv"].run()
+            self.cache[l][:, row:row + 2].copy_(self.qkv.view(B, 2, 3 * E)[:, :, E:])
+            call("avdn_attn_decode", ptr(self.qkv), ptr(self.cache[l]), B, self.R, H, self.Lc, row + 2,
+                 1.0 / math.sqrt(64.0), ptr(self.ctx))
+            pl["o"].run()
+            x1, x1h = self.xa[l]
+            call("avdn_ln_fwd", ptr(x), ptr(self.tmp), ptr(P[pre + "norm1.weight"]), ptr(P[pre + "norm1.bias"]), M, E,
+                 LN_EPS, None, ptr(x1), ptr(x1h), ptr(self.mean), ptr(self.rstd))
+            pl["ff1"].run()
+            pl["ff2"].run()
+            x2, x2h = self.xb[l]
+            call("avdn_ln_fwd", ptr(x1), ptr(self.tmp), ptr(P[pre + "norm2.weight"]), ptr(P[pre + "norm2.bias"]), M, E,
+                 LN_EPS, None, ptr(x2), ptr(x2h), ptr(self.mean), ptr(self.rstd))
+            x = x2
+            n += 9
+        d = "decoder_2_action_full."
+        call("avdn_heads_fwd", ptr(x), B, 2, 0, 1, ptr(P[d + "0.weight"]), ptr(P[d + "0.bias"]), ptr(P[d + "3.weight"]),
+             ptr(P[d + "3.bias"]), ptr(P[d + "6.weight"]), ptr(P[d + "6.bias"]), ptr(P["fc.0.weight"]),
+             ptr(P["fc.0.bias"]), ptr(e.h0), ptr(e.h1), ptr(e.output), ptr(e.h_sali))
+        self.launches += n + 1 + (e.launches - n0)
+        return e.output, e.h_sali

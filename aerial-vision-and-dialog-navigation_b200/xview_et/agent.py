@@ -235,7 +235,7 @@ class NavCMTAgent:
     STOP_THRESHOLD = 0.5               # agent.py:738-745 (the LSTM agent uses 0.25)
 
     @torch.no_grad()
-    def rollout_greedy(self, batch, max_action_len=None, stop_threshold=None):
+    def rollout_greedy(self, batch, max_action_len=None, stop_threshold=None, incremental=True):
         """Greedy (student-feedback) rollout of ``B`` episodes, the inference path of the HAA-Transformer
         (agent.py:580-760 with ``feedback == 'student'``, no teacher / loss).
 
@@ -248,6 +248,11 @@ class NavCMTAgent:
         have not ended (agent.py:603-620) -> ``ET`` over the t+1 steps -> post-processing, stop test
         (progress > 0.5 or last step) and ``move_view_corners`` (agent.py:637-653,736-760).  The loop ends
         early once every sample has ended (agent.py:773-774).
+
+        ``incremental=True`` (default): step 0 runs the full encoder once, later steps compute only their
+        two new rows per sample against cached keys / values (``ETDecodeState``: earlier rows cannot change
+        under the causal mask); ``False`` re-runs the encoder over the whole history every step, exactly as
+        the reference does.  The two agree to bf16 rounding for every sample that has not ended.
 
         Returns device tensors: ``corners`` [T+1,B,4,2], ``directions`` [T+1,B], ``ended`` [T,B],
         ``output`` [T,B,4], ``angle`` / ``altitude`` [T,B], ``dist`` [T,B], and ``steps`` (the number of
@@ -311,19 +316,29 @@ class NavCMTAgent:
                     lens[i] += 1
             # ---- ET over the history [B, t+1, ...] ----
             Tc = t + 1
-            frames = bf["frames_hist"][:Tc].permute(1, 0, 2, 3).contiguous().view(B * Tc, 512, 49)
-            dirs = bf["dirs_hist"][:Tc].permute(1, 0, 2).contiguous()
-            eng = et.engine(B, L, Tc, dev)
-            e0 = eng.launches
-            eng.set_dropout(0.0, 0.0, 0)
-            output, _ = eng.forward(frames, lang, lang_cls, dirs, lens, et.encoder_vl.enc_pos.pe[0])
+            pe = et.encoder_vl.enc_pos.pe[0]
+            if incremental and t > 0:
+                dec = et.decoder(B, L, T, dev)
+                e0 = dec.launches
+                output, _ = dec.step(t, bf["frames_hist"][t], bf["dirs_hist"][t], lang_cls, pe)
+                n += dec.launches - e0
+            else:
+                frames = bf["frames_hist"][:Tc].permute(1, 0, 2, 3).contiguous().view(B * Tc, 512, 49)
+                dirs = bf["dirs_hist"][:Tc].permute(1, 0, 2).contiguous()
+                eng = et.engine(B, L, Tc, dev)
+                e0 = eng.launches
+                eng.set_dropout(0.0, 0.0, 0)
+                output, _ = eng.forward(frames, lang, lang_cls, dirs, lens if not incremental else [1] * B, pe)
+                n += eng.launches - e0
+                if incremental:
+                    et.decoder(B, L, T, dev).start()
             bf["output_hist"][t].copy_(output)
             # ---- simulator: post-processing, stop test, move_view_corners ----
             call("avdn_waypoint_step", ptr(output), ptr(bf["corners"]), ptr(bounds), ptr(bf["cur_dir"]),
                  ptr(bf["ended"]), B, thr, int(t == T - 1), ptr(bf["angle"][t]), ptr(bf["dist"][t]),
                  ptr(bf["altitude"][t]))
             bf["ended_hist"][t].copy_(bf["ended"])
-            n += 12 + (eng.launches - e0)
+            n += 12
             ended_host = [bool(v) for v in bf["ended"].cpu().tolist()]  # the step's only host read
             if all(ended_host):
                 break

@@ -374,6 +374,14 @@ int avdn_heads_bwd_drop(const float* x, int B, int S, int row_vis, int row_dir, 
                         const float* d_output, const float* d_h_sali, float* dx, float* dw0, float* db0, float* dw1,
                         float* db1, float* dw2, float* db2, float* dwf, float* dbf, float p, avdn_stream_t stream);
 
+/* Incremental attention of the ET inference path (NavCMTAgent.rollout, src/xview_et/agent.py:580-760 re-runs the
+ * whole encoder every step; the rows of earlier steps cannot change because the attention mask is causal over
+ * steps, model_util.py:213-241).  The R new rows of a step (frame t, direction t) attend to the first n rows of
+ * the layer's cache: qkv_new [B*R,2304] bf16 (q|k|v; q is read), cache [B,Lc,1536] bf16 (k|v per row: language
+ * rows, then frame/direction rows of steps 0..t interleaved), ctx [B*R,768] bf16 = softmax(q k^T * scale) v.  */
+int avdn_attn_decode(const void* qkv_new, const void* cache, int B, int R, int H, int Lc, int n, float scale,
+                     void* ctx, avdn_stream_t stream);
+
 /* The two masks materialised exactly as the reference builds them (bit-exact
  * parity tests): mask_pad [B,S] u8 (1 = padded key), mask_attn [S,S] f32 (0 / -inf). */
 int avdn_build_masks(const int* lens, int B, int L, int T, uint8_t* mask_pad, float* mask_attn,
