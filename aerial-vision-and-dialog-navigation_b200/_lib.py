@@ -82,6 +82,12 @@ _SIGNATURES = {
                                                                                      c_void_p],
     "avdn_heads_bwd_drop": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 18 + [c_f32, c_void_p],
     "avdn_attn_decode": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_f32, c_void_p, c_void_p],
+    "avdn_bert_embed_ln": [c_void_p] * 6 + [c_int, c_int, c_int, c_f32] + [c_void_p] * 5 + [c_void_p],
+    "avdn_bert_embed_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "avdn_gelu_fwd": [c_void_p, c_void_p, c_i64, c_void_p],
+    "avdn_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
+    "avdn_linear_f32_bwd": [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_i64,
+                            c_int, c_void_p, c_void_p, c_void_p],
     "avdn_build_masks": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "avdn_colsum": [c_void_p, c_int, c_i64, c_int, c_i64, c_void_p, c_void_p],
     "avdn_heads_fwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 + [c_void_p],

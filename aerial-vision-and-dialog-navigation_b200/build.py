@@ -33,6 +33,7 @@ SOURCES = {
     "lstm.cu": ["-fmad=false"],
     "encoder.cu": [],
     "agent.cu": [],
+    "bert.cu": [],
 }
 
 

@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 // may query row q attend key k in sample with `len` valid steps?  (model_util.py:213-241
 // + enc_vl.py:48-55; L language tokens, T = max length)
 __device__ __forceinline__ bool may_attend(int q, int k, int L, int T, int len) {
+  if (T == 0) return k < len;        // key-padding mask only (BERT: len = number of real tokens of the sample)
   if (k < L) return true;            // everyone sees language
   if (q < L) return false;           // language sees only language
   const int tk = (k - L) % T, tq = (q - L) % T;
@@ -746,7 +747,7 @@ extern "C" int avdn_ln_bwd_drop(const float* dy1, const float* dy2, const float*
 extern "C" int avdn_softmax_fwd_drop(const float* scores, const int* lens, int B, int H, int L, int T, int Sp, void* P,
                                      void* P_full, float p, unsigned long long seed, unsigned int site,
                                      avdn_stream_t stream) {
-  AVDN_REQUIRE(scores && lens && P && T >= 1 && Sp >= L + 2 * T, "avdn_softmax_fwd: bad argument");
+  AVDN_REQUIRE(scores && lens && P && T >= 0 && Sp >= L + 2 * T, "avdn_softmax_fwd: bad argument");
   AVDN_REQUIRE(drop_ok(p) && (p == 0.f || P_full), "avdn_softmax_fwd: dropout p in [0,1) and needs P_full");
   softmax_fwd_kernel<<<rows_grid((long long)B * H * (L + 2 * T)), 256, 0, avdn::to_cuda(stream)>>>(
       scores, lens, B, H, L, T, Sp, reinterpret_cast<__nv_bfloat16*>(P), reinterpret_cast<__nv_bfloat16*>(P_full),

@@ -331,7 +331,7 @@ int avdn_ln_bwd(const float* dy1, const float* dy2, const float* v, const float*
  * (model_util.py:213-241) and the key-padding mask (enc_vl.py:44-55) are
  * evaluated as a predicate of (q, k, L, T, lens[b]) — never materialised.
  *   scores [B,H,S,Sp] fp32 (S = L+2T, Sp >= S row pitch) -> P [B,H,S,Sp] bf16,
- *   zero where masked and in the pitch padding.                              */
+ *   zero where masked and in the pitch padding.  T = 0: plain key-padding mask, keys k < lens[b] (BERT).  */
 int avdn_softmax_fwd(const float* scores, const int* lens, int B, int H, int L, int T, int Sp, void* P,
                      avdn_stream_t stream);
 /* dS = alpha * P * (dP - sum_k P*dP), bf16, zero in the padding. */
@@ -381,6 +381,30 @@ int avdn_heads_bwd_drop(const float* x, int B, int S, int row_vis, int row_dir, 
  * rows, then frame/direction rows of steps 0..t interleaved), ctx [B*R,768] bf16 = softmax(q k^T * scale) v.  */
 int avdn_attn_decode(const void* qkv_new, const void* cache, int B, int R, int H, int Lc, int n, float scale,
                      void* ctx, avdn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Language encoder: CustomBERTModel, src/models/vln_model.py:128-159 = HuggingFace BertModel
+ * ('bert-base-uncased' architecture) + Linear(768,64)-ReLU-Dropout-Linear(64,49)-ReLU on the pooler output; call
+ * sites src/xview_et/agent.py:527-538.  GEMMs: avdn_gemm_*; LayerNorm (eps 1e-12): avdn_ln_*; masked softmax:
+ * avdn_softmax_* with T = 0 (key-padding mode: sample b attends keys k < lens[b]); these are the rest.
+ * ---------------------------------------------------------------------- */
+/* BertEmbeddings: v = (word[ids] + token_type[0]) + position[s]; y = LayerNorm(v) (eps).  ids [B,S] int64 (clamped
+ * to the vocabulary).  Outputs as avdn_ln_fwd (v_out / y / y16 may be NULL).                                     */
+int avdn_bert_embed_ln(const long long* ids, const float* word, const float* pos, const float* type0,
+                       const float* gamma, const float* beta, int B, int S, int vocab, float eps, float* v_out,
+                       float* y, void* y16, float* mean, float* rstd, avdn_stream_t stream);
+/* d_word[ids] += dv, d_pos[s] += dv, d_type0 += dv  (dv [B*S,768] = gradient w.r.t. v).                          */
+int avdn_bert_embed_bwd(const long long* ids, const float* dv, int B, int S, int vocab, float* d_word, float* d_pos,
+                        float* d_type0, avdn_stream_t stream);
+/* erf-GELU (hidden_act = "gelu") of a bf16 tensor and its backward du = dh * gelu'(u).                          */
+int avdn_gelu_fwd(const void* u, void* h, long long n, avdn_stream_t stream);
+int avdn_gelu_bwd(const void* u, const void* dh, void* du, long long n, avdn_stream_t stream);
+/* Backward of y = act(x w^T + b) for the small fp32 heads (BertPooler, CustomBERTModel.linears): with
+ * g = dy * act'(y) (act 0 none / 1 ReLU / 2 tanh):  dx [M,K] (row pitch lddx; += if dx_accumulate; may be NULL),
+ * dw [N,K] +=, db [N] += (may be NULL).  x [M,K] row pitch ldx; y, dy [M,N] dense.                                */
+int avdn_linear_f32_bwd(const float* x, long long ldx, const float* w, const float* y, const float* dy, int M, int N,
+                        int K, int act, float* dx, long long lddx, int dx_accumulate, float* dw, float* db,
+                        avdn_stream_t stream);
 
 /* The two masks materialised exactly as the reference builds them (bit-exact
  * parity tests): mask_pad [B,S] u8 (1 = padded key), mask_attn [S,S] f32 (0 / -inf). */
