@@ -644,6 +644,27 @@ __global__ void __launch_bounds__(256) dropout_bf16_kernel(__nv_bfloat16* __rest
   }
 }
 
+// in-place dropout of an fp32 tensor, optionally refreshing its bf16 shadow (embedding dropout, head dropout)
+__global__ void __launch_bounds__(256) dropout_f32_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ x16,
+                                                          long long n, unsigned int dthr, float dscale,
+                                                          unsigned long long seed, unsigned int site) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = avdn_drop_keep(seed, site, (unsigned long long)i, dthr) ? x[i] * dscale : 0.f;
+    x[i] = v;
+    if (x16) x16[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// out = dropout'(a + b): the gradient entering a dropout site whose output fed two consumers
+__global__ void __launch_bounds__(256) add_dropout_f32_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                              float* __restrict__ out, long long n, unsigned int dthr,
+                                                              float dscale, unsigned long long seed, unsigned int site) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = a[i] + (b ? b[i] : 0.f);
+    out[i] = (!dthr || avdn_drop_keep(seed, site, (unsigned long long)i, dthr)) ? v * dscale : 0.f;
+  }
+}
+
 // the keep-scale factor (0 or 1/(1-p)) of every element of a site, for tests and debugging
 __global__ void __launch_bounds__(256) dropout_keep_scale_kernel(float* __restrict__ out, long long n, unsigned int dthr,
                                                                  float dscale, unsigned long long seed,
@@ -785,6 +806,28 @@ extern "C" int avdn_dropout_bf16(void* x, long long n, float p, unsigned long lo
   dropout_bf16_kernel<<<(unsigned)blocks, 256, 0, avdn::to_cuda(stream)>>>(reinterpret_cast<__nv_bfloat16*>(x), n,
                                                                          avdn_drop_thresh(p), drop_scale(p), seed, site);
   return avdn::check_launch("avdn_dropout_bf16");
+}
+
+extern "C" int avdn_dropout_f32(float* x, void* x16, long long n, float p, unsigned long long seed, unsigned int site,
+                                avdn_stream_t stream) {
+  AVDN_REQUIRE(x && n >= 0 && drop_ok(p), "avdn_dropout_f32: bad argument");
+  if (n == 0 || p == 0.f) return AVDN_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dropout_f32_kernel<<<(unsigned)blocks, 256, 0, avdn::to_cuda(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(x16), n,
+                                                                        avdn_drop_thresh(p), drop_scale(p), seed, site);
+  return avdn::check_launch("avdn_dropout_f32");
+}
+
+extern "C" int avdn_add_dropout_f32(const float* a, const float* b, float* out, long long n, float p,
+                                    unsigned long long seed, unsigned int site, avdn_stream_t stream) {
+  AVDN_REQUIRE(a && out && n >= 0 && drop_ok(p), "avdn_add_dropout_f32: bad argument");
+  if (n == 0) return AVDN_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_dropout_f32_kernel<<<(unsigned)blocks, 256, 0, avdn::to_cuda(stream)>>>(a, b, out, n, avdn_drop_thresh(p),
+                                                                            p == 0.f ? 1.f : drop_scale(p), seed, site);
+  return avdn::check_launch("avdn_add_dropout_f32");
 }
 
 extern "C" int avdn_dropout_keep_scale(float* out, long long n, float p, unsigned long long seed, unsigned int site,

@@ -11,9 +11,11 @@ and the FFN, with their backward; warp-level kernels for the embeddings + LayerN
 softmax, erf-GELU and the small fp32 heads.  ``mask`` must be right-padded (what ``tokenizer(padding=True)``
 produces, agent.py:527-529): sample b attends keys ``k < mask[b].sum()``.
 
-Dropout: HF's hidden/attention dropout (0.1) and the head's Dropout(0.2) are NOT applied -- the module computes the
-deterministic (eval) arithmetic in both modes and says so via ``self.deterministic``; gradients are exact for that
-arithmetic.  (The ET's dropout sites are implemented, ``_et_engine.set_dropout``; BERT's are next.)
+Dropout (train mode): HF's sites -- after the embedding LayerNorm, on the attention probabilities, on the attention
+output projection and on the FFN output (``hidden_dropout_prob`` / ``attention_probs_dropout_prob``) -- and the
+head's Dropout(0.2), as stateless hash masks of (seed, site, element) re-evaluated by the backward kernels
+(``BertEngine.set_dropout``; sites: 96 embeddings, 97 head, 100 + 3l + {0: probabilities, 1: attention output,
+2: FFN output}).  Eval mode is deterministic.
 """
 from __future__ import annotations
 
@@ -70,6 +72,18 @@ class BertEngine:
         self.pooled, self.h1, self.lin = buf((B, E)), buf((B, 64)), buf((B, 49))
         self.G = {n: torch.zeros_like(p) for n, p in params.items()}
         self._fwd_ready = self._bwd_ready = False
+        self.p_hid, self.p_att, self.p_head, self.seed = 0.0, 0.0, 0.0, 0
+
+    SITE_EMB, SITE_HEAD, SITE_LAYER0 = 96, 97, 100
+
+    def set_dropout(self, p_hidden=0.0, p_attn=0.0, p_head=0.0, seed=0):
+        """Dropout of the NEXT forward/backward pair (0 = off)."""
+        self.p_hid, self.p_att, self.p_head = float(p_hidden), float(p_attn), float(p_head)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        if self.p_att > 0:
+            for L in self.layers:
+                if getattr(L, "Pu", None) is None:
+                    L.Pu = torch.empty_like(L.Pm)
 
     @staticmethod
     def lp(l):
@@ -190,29 +204,36 @@ class BertEngine:
                    ptr(P[e + "position_embeddings.weight"]), ptr(P[e + "token_type_embeddings.weight"]),
                    ptr(P[e + "LayerNorm.weight"]), ptr(P[e + "LayerNorm.bias"]), B, S, self.V, LN_EPS, ptr(self.v0),
                    ptr(self.x0), ptr(self.x0h), ptr(self.mean0), ptr(self.rstd0))
+        ph, pa, sd = self.p_hid, self.p_att, self.seed
+        if ph > 0:
+            self._call("avdn_dropout_f32", ptr(self.x0), ptr(self.x0h), self.x0.numel(), ph, sd, self.SITE_EMB)
         x = self.x0
         for l, L in enumerate(self.layers):
             pre = self.lp(l)
+            st = self.SITE_LAYER0 + 3 * l
             self._run(L.p_qkv)
             self._run(L.p_scores)
-            self._call("avdn_softmax_fwd", ptr(self.scores), ptr(self.lens), B, H, S, 0, self.Sp, ptr(L.Pm))
+            self._call("avdn_softmax_fwd_drop", ptr(self.scores), ptr(self.lens), B, H, S, 0, self.Sp, ptr(L.Pm),
+                       ptr(L.Pu) if pa > 0 else None, pa, sd, st)
             self._run(L.p_pv)
             self._run(L.p_o)
-            self._call("avdn_ln_fwd", ptr(x), ptr(self.tmp), ptr(P[pre + "attention.output.LayerNorm.weight"]),
+            self._call("avdn_ln_fwd_drop", ptr(x), ptr(self.tmp), ptr(P[pre + "attention.output.LayerNorm.weight"]),
                        ptr(P[pre + "attention.output.LayerNorm.bias"]), M, E, LN_EPS, ptr(L.v1), ptr(L.x1), ptr(L.x1h),
-                       ptr(L.mean1), ptr(L.rstd1))
+                       ptr(L.mean1), ptr(L.rstd1), ph, sd, st + 1)
             self._run(L.p_ff1)
             self._call("avdn_gelu_fwd", ptr(L.u), ptr(L.h), L.u.numel())
             self._run(L.p_ff2)
-            self._call("avdn_ln_fwd", ptr(L.x1), ptr(self.tmp), ptr(P[pre + "output.LayerNorm.weight"]),
+            self._call("avdn_ln_fwd_drop", ptr(L.x1), ptr(self.tmp), ptr(P[pre + "output.LayerNorm.weight"]),
                        ptr(P[pre + "output.LayerNorm.bias"]), M, E, LN_EPS, ptr(L.v2), ptr(L.x2), ptr(L.x2h),
-                       ptr(L.mean2), ptr(L.rstd2))
+                       ptr(L.mean2), ptr(L.rstd2), ph, sd, st + 2)
             x = L.x2
         self.x_final = x
         lin = lambda xx, ldx, w, b, y, Mr, N, K, act: self._call("avdn_linear_f32", ptr(xx), ldx, ptr(w), K, ptr(b),
                                                                  ptr(y), N, Mr, N, K, act, 0)
         lin(x, S * E, P["bert.pooler.dense.weight"], P["bert.pooler.dense.bias"], self.pooled, B, E, E, 2)   # tanh(cls row)
         lin(self.pooled, E, P["linears.0.weight"], P["linears.0.bias"], self.h1, B, 64, E, 1)
+        if self.p_head > 0:
+            self._call("avdn_dropout_f32", ptr(self.h1), None, self.h1.numel(), self.p_head, sd, self.SITE_HEAD)
         lin(self.h1, 64, P["linears.3.weight"], P["linears.3.bias"], self.lin, B, 49, 64, 1)
         return x.view(B, S, E), self.lin, self.pooled
 
@@ -242,18 +263,23 @@ class BertEngine:
             dl = d_lin.contiguous().float()
             self._call("avdn_linear_f32_bwd", ptr(self.h1), 64, ptr(P["linears.3.weight"]), ptr(self.lin), ptr(dl), B, 49,
                        64, 1, ptr(self.d_h1), 64, 0, ptr(Gd["linears.3.weight"]), ptr(Gd["linears.3.bias"]))
+            if self.p_head > 0:          # through Dropout(0.2): the ReLU mask of the stored (dropped) h1 does the rest
+                self._call("avdn_dropout_f32", ptr(self.d_h1), None, self.d_h1.numel(), self.p_head, self.seed,
+                           self.SITE_HEAD)
             self._call("avdn_linear_f32_bwd", ptr(self.pooled), E, ptr(P["linears.0.weight"]), ptr(self.h1),
                        ptr(self.d_h1), B, 64, E, 1, ptr(self.d_pooled), E, 1, ptr(Gd["linears.0.weight"]),
                        ptr(Gd["linears.0.bias"]))
         self._call("avdn_linear_f32_bwd", ptr(self.x_final), S * E, ptr(P["bert.pooler.dense.weight"]), ptr(self.pooled),
                    ptr(self.d_pooled), B, E, E, 2, ptr(self.dx), S * E, 1, ptr(Gd["bert.pooler.dense.weight"]),
                    ptr(Gd["bert.pooler.dense.bias"]))
+        ph, pa, sd = self.p_hid, self.p_att, self.seed
         dy1, dy2 = self.dx, None
         for l in reversed(range(self.NL)):
             L, pre = self.layers[l], self.lp(l)
-            self._call("avdn_ln_bwd", ptr(dy1), ptr(dy2), ptr(L.v2), ptr(L.mean2), ptr(L.rstd2),
+            st = self.SITE_LAYER0 + 3 * l
+            self._call("avdn_ln_bwd_drop", ptr(dy1), ptr(dy2), ptr(L.v2), ptr(L.mean2), ptr(L.rstd2),
                        ptr(P[pre + "output.LayerNorm.weight"]), M, E, ptr(self.dva), ptr(self.dvh),
-                       ptr(Gd[pre + "output.LayerNorm.weight"]), ptr(Gd[pre + "output.LayerNorm.bias"]))
+                       ptr(Gd[pre + "output.LayerNorm.weight"]), ptr(Gd[pre + "output.LayerNorm.bias"]), ph, sd, st + 2)
             self._call("avdn_colsum", ptr(self.dvh), BF, M, E, E, ptr(Gd[pre + "output.dense.bias"]))
             self._run(L.b_ff2_w)
             self._run(L.b_ff2_d)
@@ -261,15 +287,17 @@ class BertEngine:
             self._call("avdn_colsum", ptr(self.du), BF, M, FF, FF, ptr(Gd[pre + "intermediate.dense.bias"]))
             self._run(L.b_ff1_w)
             self._run(L.b_ff1_d)
-            self._call("avdn_ln_bwd", ptr(self.dva), ptr(self.dbranch), ptr(L.v1), ptr(L.mean1), ptr(L.rstd1),
+            self._call("avdn_ln_bwd_drop", ptr(self.dva), ptr(self.dbranch), ptr(L.v1), ptr(L.mean1), ptr(L.rstd1),
                        ptr(P[pre + "attention.output.LayerNorm.weight"]), M, E, ptr(self.dvb), ptr(self.dvh),
-                       ptr(Gd[pre + "attention.output.LayerNorm.weight"]), ptr(Gd[pre + "attention.output.LayerNorm.bias"]))
+                       ptr(Gd[pre + "attention.output.LayerNorm.weight"]),
+                       ptr(Gd[pre + "attention.output.LayerNorm.bias"]), ph, sd, st + 1)
             self._call("avdn_colsum", ptr(self.dvh), BF, M, E, E, ptr(Gd[pre + "attention.output.dense.bias"]))
             self._run(L.b_o_w)
             self._run(L.b_o_d)
             self._run(L.b_dp)
             self._run(L.b_dv)
-            self._call("avdn_softmax_bwd", ptr(L.Pm), ptr(self.scores), B * H * S, S, Sp, 1.0 / 8.0, ptr(self.dS))
+            self._call("avdn_softmax_bwd_drop", ptr(L.Pu if pa > 0 else L.Pm), ptr(self.scores), B * H * S, S, Sp,
+                       1.0 / 8.0, ptr(self.dS), pa, sd, st)
             self._run(L.b_dq)
             self._run(L.b_dk)
             L.g_in.zero_(); L.gb_in.zero_()
@@ -282,6 +310,9 @@ class BertEngine:
             self.launches += 8
             dy1, dy2 = self.dvb, self.dbranch
         e = "bert.embeddings."
+        if ph > 0:                       # through the embedding dropout: d(LN output) = dropout'(dy1 + dy2)
+            self._call("avdn_add_dropout_f32", ptr(dy1), ptr(dy2), ptr(self.dva), self.dva.numel(), ph, sd, self.SITE_EMB)
+            dy1, dy2 = self.dva, None
         self._call("avdn_ln_bwd", ptr(dy1), ptr(dy2), ptr(self.v0), ptr(self.mean0), ptr(self.rstd0),
                    ptr(P[e + "LayerNorm.weight"]), M, E, ptr(self.dv0), None, ptr(Gd[e + "LayerNorm.weight"]),
                    ptr(Gd[e + "LayerNorm.bias"]))
@@ -303,8 +334,18 @@ class CustomBERTModel(nn.Module):
         if cfg.hidden_size != E or cfg.hidden_act != "gelu" or cfg.hidden_size // cfg.num_attention_heads != 64:
             raise NotImplementedError("only the bert-base geometry (768 wide, 64-wide heads, erf-GELU) is implemented")
         self.linears = nn.Sequential(nn.Linear(768, 64), nn.ReLU(), nn.Dropout(0.2), nn.Linear(64, 49), nn.ReLU())
-        self.deterministic = True        # dropout sites are not applied (see the module docstring)
         self._engines = {}
+        self._drop_step = 0
+
+    def dropout_config(self):
+        """(p_hidden, p_attention, p_head, seed) of the next forward: HF's and the head's dropout in train mode,
+        zeros in eval mode; the seed advances every train-mode forward and derives from torch's global seed."""
+        if not self.training:
+            return 0.0, 0.0, 0.0, 0
+        c = self.bert.config
+        self._drop_step += 1
+        seed = (torch.initial_seed() * 1000003 + 7919 * self._drop_step) & 0xFFFFFFFFFFFFFFFF
+        return float(c.hidden_dropout_prob), float(c.attention_probs_dropout_prob), float(self.linears[2].p), seed
 
     def used_parameters(self):
         return {n: p for n, p in self.named_parameters()}
@@ -325,7 +366,7 @@ class CustomBERTModel(nn.Module):
         if S > self.bert.config.max_position_embeddings:
             raise ValueError("sequence longer than the position table")
         eng = self.engine(B, S, ids.device)
-        names = list(self.used_parameters())
+        eng.set_dropout(*self.dropout_config())
         return _BertFn.apply(self, eng, ids, mask, *self.used_parameters().values())
 
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the AVDN hot path on B200 (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout|et_rollout]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout|et_rollout|bert]
     python bench.py --impl reference ...        # the reference's CPU path, same metric
 
 One JSON line on stdout (rank 0).  Under torchrun (N>1) every rank runs its shard
@@ -194,6 +194,13 @@ def emit(line):
     data = (json.dumps(line) + "\n").encode()
     sys.stdout.flush()
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+
+
+try:
+    from bench_bert import BertWorkload      # noqa: E402
+    WORKLOADS["bert"] = BertWorkload
+except ImportError:
+    BertWorkload = None
 
 
 def dist_env():

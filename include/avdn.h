@@ -365,6 +365,12 @@ int avdn_dropout_bf16(void* x, long long n, float p, unsigned long long seed, un
                       avdn_stream_t stream);
 int avdn_dropout_keep_scale(float* out, long long n, float p, unsigned long long seed, unsigned int site,
                             avdn_stream_t stream);
+/* In-place dropout of an fp32 tensor, x16 (bf16 shadow, may be NULL) refreshed; and out = dropout'(a + b)
+ * (b may be NULL): the gradient entering a dropout site (BertEmbeddings.dropout, CustomBERTModel.linears[2]). */
+int avdn_dropout_f32(float* x, void* x16, long long n, float p, unsigned long long seed, unsigned int site,
+                     avdn_stream_t stream);
+int avdn_add_dropout_f32(const float* a, const float* b, float* out, long long n, float p, unsigned long long seed,
+                         unsigned int site, avdn_stream_t stream);
 int avdn_heads_fwd_drop(const float* x, int B, int S, int row_vis, int row_dir, const float* w0, const float* b0,
                         const float* w1, const float* b1, const float* w2, const float* b2, const float* wf,
                         const float* bf, float* h0, float* h1, float* output, float* h_sali, float p,

@@ -29,7 +29,7 @@ def _model(layers, vocab, seed):
         for n, p in m.named_parameters():
             if n.endswith("bias") or "LayerNorm" in n:
                 p.add_(torch.randn(p.shape, device="cuda", generator=g) * 0.05)
-    return m
+    return m.eval()                               # deterministic arithmetic; the dropout test switches to train()
 
 
 def _case(B, S, seed, vocab):
@@ -73,6 +73,57 @@ def test_forward_and_all_gradients_vs_oracle(built_lib):
             continue
         worst[n] = _rel2(p.grad, ref)
         assert worst[n] < 5e-2, (n, worst[n])
+
+
+def _site_mask(n, p, seed, site):
+    from avdn_b200 import _lib
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    _lib.call("avdn_dropout_keep_scale", _lib.ptr(out), n, float(p), int(seed), int(site))
+    return out.cpu()
+
+
+def test_train_mode_dropout_vs_oracle_with_same_masks(built_lib):
+    """Train mode applies HF's dropout sites and the head's Dropout(0.2) with stateless hash masks; the step's
+    masks are read back and fed to the oracle: outputs and every gradient must agree."""
+    B, S, V, NL, H = 3, 40, 1000, 2, 12
+    Sp = 64
+    m = _model(NL, V, 4)
+    ids, mask = _case(B, S, 5, V)
+    m.train()
+    try:
+        seq, lin, cls = m(ids.cuda(), mask.cuda())
+        eng = m.engine(B, S, seq.device)
+        ph, pa, pd, seed = eng.p_hid, eng.p_att, eng.p_head, eng.seed
+        assert (ph, pa, pd) == (pytest.approx(0.1), pytest.approx(0.1), pytest.approx(0.2)) and eng.Sp == Sp
+        g = torch.Generator().manual_seed(6)
+        w_seq = torch.randn(B, S, 768, generator=g) * mask[..., None]
+        w_lin, w_cls = torch.randn(B, 49, generator=g), torch.randn(B, 768, generator=g)
+        m.zero_grad()
+        ((seq * w_seq.cuda()).sum() + (lin * w_lin.cuda()).sum() + (cls * w_cls.cuda()).sum()).backward()
+    finally:
+        m.eval()
+    layers = []
+    for l in range(NL):
+        st = eng.SITE_LAYER0 + 3 * l
+        layers.append(dict(attn=_site_mask(B * H * S * Sp, pa, seed, st).view(B, H, S, Sp)[..., :S].contiguous(),
+                           ao=_site_mask(B * S * 768, ph, seed, st + 1).view(B, S, 768),
+                           fo=_site_mask(B * S * 768, ph, seed, st + 2).view(B, S, 768)))
+    drop = dict(emb=_site_mask(B * S * 768, ph, seed, eng.SITE_EMB).view(B, S, 768), layers=layers,
+                head=_site_mask(B * 64, pd, seed, eng.SITE_HEAD).view(B, 64))
+    keep = (drop["emb"] > 0).float().mean().item()
+    assert abs(keep - 0.9) < 5e-3, keep
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()
+          if "position_ids" not in k}
+    seq_o, lin_o, cls_o = bo.custom_bert_forward(sd, ids, mask, drop=drop)
+    assert _rel(seq, seq_o) < 1e-2, _rel(seq, seq_o)
+    assert _rel(cls, cls_o) < 1e-2 and _rel(lin, lin_o) < 2e-2
+    ((seq_o * w_seq).sum() + (lin_o * w_lin).sum() + (cls_o * w_cls).sum()).backward()
+    for n, p in m.named_parameters():
+        ref = sd[n].grad
+        if ref.norm() < 1e-4:
+            assert p.grad.float().cpu().norm() < 5e-2, n
+            continue
+        assert _rel2(p.grad, ref) < 5e-2, (n, _rel2(p.grad, ref))
 
 
 def test_full_depth_forward(built_lib):
