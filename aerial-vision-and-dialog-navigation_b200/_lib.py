@@ -63,6 +63,7 @@ _SIGNATURES = {
     # ---- stage 3: ET
     "avdn_frame_attn_fwd": [c_void_p] * 6 + [c_int, c_int] + [c_void_p] * 4 + [c_void_p],
     "avdn_frame_attn_bwd": [c_void_p] * 5 + [c_int, c_int] + [c_void_p] * 9 + [c_void_p],
+    "avdn_frame_attn_bwd_cls": [c_void_p] * 5 + [c_int, c_int] + [c_void_p] * 10 + [c_void_p],
     "avdn_embed_fwd": [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_void_p],
     "avdn_embed_dir_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "avdn_ln_fwd": [c_void_p] * 4 + [c_i64, c_int, c_f32] + [c_void_p] * 5 + [c_void_p],

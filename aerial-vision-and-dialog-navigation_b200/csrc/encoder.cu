@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) frame_attn_bwd_kernel(
     const float* __restrict__ w_out, const float* __restrict__ fc2_w, int T, const float* __restrict__ attn,
     const float* __restrict__ wc, const float* __restrict__ e49, const float* __restrict__ d_emb,
     float* __restrict__ d_frames, float* __restrict__ d_w_in, float* __restrict__ d_w_out,
-    float* __restrict__ d_fc2_w, float* __restrict__ d_fc2_b) {
+    float* __restrict__ d_fc2_w, float* __restrict__ d_fc2_b, float* __restrict__ d_lang_cls) {
   __shared__ float s_h[NSP], s_t[NSP], s_wc[NSP], s_e[NSP], s_de[NSP], s_dpre[NSP], s_dwc[NSP], s_dt[NSP];
   __shared__ float s_demb[E], s_attn[NCH], s_dattn[NCH], s_red[8][NSP + 1];
   __shared__ float s_dot;
@@ -220,6 +220,13 @@ __global__ void __launch_bounds__(256) frame_attn_bwd_kernel(
   }
   __syncthreads();
   for (int idx = tid; idx < NSP * NSP; idx += 256) atomicAdd(&d_w_in[idx], s_dt[idx / NSP] * s_h[idx % NSP]);
+  // gradient of the query h = lang_cls (it feeds linear_in and the second half of linear_out's input);
+  // accumulated over the T frames of the sample
+  if (d_lang_cls != nullptr && tid < NSP) {
+    float a = 0.f;
+    for (int i = 0; i < NSP; ++i) a = fmaf(w_in[i * NSP + tid], s_dt[i], fmaf(w_out[i * 2 * NSP + NSP + tid], s_dpre[i], a));
+    atomicAdd(&d_lang_cls[b * NSP + tid], a);
+  }
 }
 
 // ------------------------------------------------------------------ embedding
@@ -696,13 +703,22 @@ extern "C" int avdn_frame_attn_bwd(const float* frames, const float* lang_cls, c
                                    const float* wc, const float* e49, const float* d_emb, float* d_frames,
                                    float* d_w_in, float* d_w_out, float* d_fc2_w, float* d_fc2_b,
                                    avdn_stream_t stream) {
+  return avdn_frame_attn_bwd_cls(frames, lang_cls, w_in, w_out, fc2_w, B, T, attn, wc, e49, d_emb, d_frames, d_w_in,
+                                 d_w_out, d_fc2_w, d_fc2_b, nullptr, stream);
+}
+
+extern "C" int avdn_frame_attn_bwd_cls(const float* frames, const float* lang_cls, const float* w_in,
+                                       const float* w_out, const float* fc2_w, int B, int T, const float* attn,
+                                       const float* wc, const float* e49, const float* d_emb, float* d_frames,
+                                       float* d_w_in, float* d_w_out, float* d_fc2_w, float* d_fc2_b,
+                                       float* d_lang_cls, avdn_stream_t stream) {
   AVDN_REQUIRE(frames && lang_cls && w_in && w_out && fc2_w && attn && wc && e49 && d_emb && d_frames && d_w_in &&
                    d_w_out && d_fc2_w && d_fc2_b,
                "avdn_frame_attn_bwd: null pointer");
   if (B * T == 0) return AVDN_OK;
   frame_attn_bwd_kernel<<<B * T, 256, 0, avdn::to_cuda(stream)>>>(frames, lang_cls, w_in, w_out, fc2_w, T, attn, wc,
                                                                 e49, d_emb, d_frames, d_w_in, d_w_out, d_fc2_w,
-                                                                d_fc2_b);
+                                                                d_fc2_b, d_lang_cls);
   return avdn::check_launch("avdn_frame_attn_bwd");
 }
 

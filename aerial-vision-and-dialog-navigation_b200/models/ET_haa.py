@@ -125,6 +125,7 @@ class _ETFn(torch.autograd.Function):
         ctx.mod, ctx.eng = mod, eng
         ctx.frames_shape = frames.shape
         ctx.need_lang = lang.requires_grad
+        ctx.need_cls = lang_cls.requires_grad
         ctx.need_frames = frames.requires_grad
         return output.clone(), h_sali.clone()
 
@@ -136,12 +137,13 @@ class _ETFn(torch.autograd.Function):
             eng.zero_grads()
         d_output = torch.zeros_like(eng.output) if d_output is None else d_output.contiguous().float()
         d_h_sali = torch.zeros_like(eng.h_sali) if d_h_sali is None else d_h_sali.contiguous().float()
-        d_frames, d_lang = eng.backward(d_output, d_h_sali, need_lang_grad=ctx.need_lang)
+        d_cls = torch.zeros((eng.B, NSP), dtype=torch.float32, device=eng.dev) if ctx.need_cls else None
+        d_frames, d_lang = eng.backward(d_output, d_h_sali, need_lang_grad=ctx.need_lang, d_lang_cls=d_cls)
         if own:
             grads = [eng.G[n].clone() for n in mod.used_parameters()]
         else:                            # gradients were accumulated straight into the optimiser arena
             grads = [None] * len(mod.used_parameters())
-        return (None, None, None, d_frames.view(ctx.frames_shape) if ctx.need_frames else None, d_lang, None, None,
+        return (None, None, None, d_frames.view(ctx.frames_shape) if ctx.need_frames else None, d_lang, d_cls, None,
                 *grads)
 
 

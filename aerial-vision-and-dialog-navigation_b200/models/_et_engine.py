@@ -415,9 +415,11 @@ class ETEngine:
         self._ensure_plans()
         self._build_bwd_plans()
 
-    def backward(self, d_output, d_h_sali, d_frames=None, need_lang_grad=False):
+    def backward(self, d_output, d_h_sali, d_frames=None, need_lang_grad=False, d_lang_cls=None):
         """Full ET backward: accumulates parameter gradients into ``self.G`` and
-        writes d_frames [B*T,512,49] (allocated if None).  Returns (d_frames, d_lang|None)."""
+        writes d_frames [B*T,512,49] (allocated if None).  Returns (d_frames, d_lang|None).
+        ``d_lang_cls`` [B,49] fp32 (zero-filled by the caller) receives the gradient of ``lang_cls``
+        (the BERT head's linear_cls, agent.py:527-543) when given."""
         P, Gd, ptr = self.P, self.G, _lib.ptr
         B, L, T, S = self.B, self.L, self.T, self.S
         frames, lang, lang_cls, dirs, pe = self._in
@@ -431,11 +433,13 @@ class ETEngine:
         self.launches += 1
         if d_frames is None:
             d_frames = torch.empty((B * T, NCH, NSP), dtype=torch.float32, device=self.dev)
-        self._call("avdn_frame_attn_bwd", ptr(frames), ptr(lang_cls), ptr(P["attention_layer_vision.linear_in.weight"]),
+        self._call("avdn_frame_attn_bwd_cls", ptr(frames), ptr(lang_cls),
+                   ptr(P["attention_layer_vision.linear_in.weight"]),
                    ptr(P["attention_layer_vision.linear_out.weight"]), ptr(P["fc2.weight"]), B, T, ptr(self.fa_attn),
                    ptr(self.fa_wc), ptr(self.fa_e49), ptr(self.d_emb), ptr(d_frames),
                    ptr(Gd["attention_layer_vision.linear_in.weight"]),
-                   ptr(Gd["attention_layer_vision.linear_out.weight"]), ptr(Gd["fc2.weight"]), ptr(Gd["fc2.bias"]))
+                   ptr(Gd["attention_layer_vision.linear_out.weight"]), ptr(Gd["fc2.weight"]), ptr(Gd["fc2.bias"]),
+                   ptr(d_lang_cls))
         d_lang = dv0[:, :L].contiguous() if need_lang_grad else None
         return d_frames, d_lang
 

@@ -42,7 +42,8 @@ class _LB:
 class BertEngine:
     """Buffers and GEMM plans of one (B, S) shape; forward and backward of BertModel + the head."""
 
-    def __init__(self, params: dict, n_layers: int, n_heads: int, d_ff: int, vocab: int, B: int, S: int, device):
+    def __init__(self, params: dict, n_layers: int, n_heads: int, d_ff: int, vocab: int, B: int, S: int, device,
+                 grads: dict | None = None):
         assert E // n_heads == 64
         self.P, self.NL, self.H, self.FF, self.V = params, n_layers, n_heads, d_ff, vocab
         self.B, self.S = B, S
@@ -70,7 +71,8 @@ class BertEngine:
             L.g_in, L.gb_in = torch.zeros((3 * E, E), dtype=f32, device=device), torch.zeros(3 * E, dtype=f32, device=device)
             self.layers.append(L)
         self.pooled, self.h1, self.lin = buf((B, E)), buf((B, 64)), buf((B, 49))
-        self.G = {n: torch.zeros_like(p) for n, p in params.items()}
+        # parameter gradients: the optimiser's flat arena when one is attached, engine-owned buffers otherwise
+        self.G = {n: (grads[n] if grads is not None and n in grads else torch.zeros_like(p)) for n, p in params.items()}
         self._fwd_ready = self._bwd_ready = False
         self.p_hid, self.p_att, self.p_head, self.seed = 0.0, 0.0, 0.0, 0
 
@@ -335,6 +337,7 @@ class CustomBERTModel(nn.Module):
             raise NotImplementedError("only the bert-base geometry (768 wide, 64-wide heads, erf-GELU) is implemented")
         self.linears = nn.Sequential(nn.Linear(768, 64), nn.ReLU(), nn.Dropout(0.2), nn.Linear(64, 49), nn.ReLU())
         self._engines = {}
+        self._grad_arena = None          # name -> tensor, set by the optimiser arena (xview_et.agent.attach_lang_model)
         self._drop_step = 0
 
     def dropout_config(self):
@@ -356,7 +359,7 @@ class CustomBERTModel(nn.Module):
         if e is None:
             c = self.bert.config
             e = BertEngine(self.used_parameters(), c.num_hidden_layers, c.num_attention_heads, c.intermediate_size,
-                           c.vocab_size, B, S, device)
+                           c.vocab_size, B, S, device, grads=self._grad_arena)
             self._engines[key] = e
         return e
 

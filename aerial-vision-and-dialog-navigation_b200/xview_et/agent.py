@@ -82,6 +82,8 @@ class NavCMTAgent:
         self.vln_model._grad_arena = self.et_optimizer.grads
         self.vision_model._grad_arena = self.vision_model_optimizer.grads
         self.optimizers = (self.et_optimizer, self.vision_model_optimizer)
+        # language encoder (agent.py:125-126,155: trained with its own AdamW): built on demand, see attach_lang_model
+        self.lang_model, self.lang_optimizer = None, None
         self.renderer = ViewRenderer(self.device)
         self.loss_total = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._bufs = {}
@@ -92,6 +94,20 @@ class NavCMTAgent:
             self.broadcast_parameters()
 
     # ------------------------------------------------------------ distributed
+    def attach_lang_model(self, lang_model=None, lr=None):
+        """Put ``CustomBERTModel`` into the training loop (src/xview_et/agent.py:125-126,155,249): ``train_step``
+        then takes ``input_ids`` / ``attention_mask`` instead of ``lang`` / ``lang_cls``, and the gradients of both
+        flow back into BERT and its head (one encoder pass per step = the reference's ``train_val_on_full`` mode,
+        agent.py:530-538)."""
+        from ..models.bert import CustomBERTModel
+        self.lang_model = (lang_model if lang_model is not None else CustomBERTModel()).to(self.device)
+        self.lang_optimizer = FusedAdamW(self.lang_model.used_parameters(),
+                                         lr=lr if lr is not None else getattr(self.args, "lr", 1e-5))
+        self.lang_model._grad_arena = self.lang_optimizer.grads
+        self.lang_model._engines.clear()
+        self.optimizers = (self.et_optimizer, self.vision_model_optimizer, self.lang_optimizer)
+        return self.lang_model
+
     def broadcast_parameters(self):
         """Replicas start identical (DDP semantics): rank 0's arenas and BN buffers."""
         parallel.broadcast_([opt.p for opt in self.optimizers], 0, self.pg)
@@ -140,6 +156,20 @@ class NavCMTAgent:
         ``lenths`` host list[int]; ``gt_xy`` [B,2], ``gt_alt`` [B], ``gt_prog`` [B] f32;
         optional ``att`` u8 [B,224,224], ``jitter`` f32 [B]."""
         ptr = _lib.ptr
+        self._lang_eng = None
+        if "input_ids" in batch:
+            if self.lang_model is None:
+                raise RuntimeError("batch carries input_ids but no language model is attached (attach_lang_model)")
+            lm = self.lang_model
+            lm.train(bool(train) and not getattr(self.args, "no_dropout", False))
+            ids, am = batch["input_ids"], batch["attention_mask"]
+            leng = lm.engine(ids.shape[0], ids.shape[1], self.device)
+            leng.set_dropout(*lm.dropout_config())
+            l0l = leng.launches
+            seq, lin, _ = leng.forward(ids.long(), am)
+            self.launches += leng.launches - l0l
+            batch = dict(batch, lang=seq, lang_cls=lin)
+            self._lang_eng = leng
         lang, lang_cls, dirs = batch["lang"], batch["lang_cls"], batch["directions"]
         B, T = dirs.shape[0], dirs.shape[1]
         L = lang.shape[1]
@@ -209,9 +239,20 @@ class NavCMTAgent:
         self.launches += 2
         self._forward(batch, True)
         teng, eng, bufs, l0, e0 = self._ctx
-        eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=bufs["d_frames"])
+        leng = self._lang_eng
+        if leng is None:
+            eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=bufs["d_frames"])
+        else:
+            d_cls = torch.zeros((eng.B, 49), dtype=torch.float32, device=self.device)
+            _, d_lang = eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=bufs["d_frames"], need_lang_grad=True,
+                                     d_lang_cls=d_cls)
+            l0l = leng.launches
+            leng.backward(d_lang, d_cls, None)
+            self.launches += leng.launches - l0l
         dp = self.world > 1
         if dp:
+            if leng is not None:
+                self._allreduce_async(self.lang_optimizer.g, 0, self.lang_optimizer.n)
             self._allreduce_async(self.et_optimizer.g, 0, self.et_optimizer.n)
             buckets = {c: (lo, hi) for c, lo, hi in self._trunk_buckets(teng)}
             hook = lambda li: (self._allreduce_async(self.vision_model_optimizer.g, *buckets[li])

@@ -172,8 +172,9 @@ class RenderWorkload:
 
 WORKLOADS = {"render": RenderWorkload}
 try:
-    from bench_train import TrainWorkload      # noqa: E402  (added once the training step exists)
+    from bench_train import TrainWorkload, TrainBertWorkload      # noqa: E402
     WORKLOADS["train"] = TrainWorkload
+    WORKLOADS["train_bert"] = TrainBertWorkload
 except ImportError:
     TrainWorkload = None
 

@@ -232,3 +232,43 @@ class TrainWorkload:
         return {"kind": "port", "cores": int(torch.get_num_threads()),
                 "what": "oracle/model_oracle.py (torch CPU fp32 restatement of Darknet + ET + loss, fwd+bwd), "
                         "BASELINE configs[0] shape (batch 4, 10 views, 250 tokens)"}
+
+
+class TrainBertWorkload(TrainWorkload):
+    """The training step with the language encoder in the loop (src/xview_et/agent.py:125-126,155,249,527-543):
+    token ids in, BERT-base forward + backward + AdamW inside the step."""
+    name = "train_bert"
+    metric = "HAA-Transformer + BERT train episodes/s"
+
+    def config(self):
+        c = super().config()
+        c["workload"] = c["workload"].replace("et_haa training step bf16", "et_haa training step with the language "
+                                              "encoder (CustomBERTModel, bert-base, 250 tokens) trained in the loop, bf16")
+        return c
+
+    def setup_gpu(self, dev):
+        super().setup_gpu(dev)
+        self.agent.attach_lang_model()
+        g = torch.Generator().manual_seed(100 + self.rank)
+        ids = torch.randint(0, 30522, (self.B, L_LANG), generator=g)
+        lens = torch.randint(L_LANG // 3, L_LANG + 1, (self.B,), generator=g)
+        lens[0] = L_LANG
+        mask = (torch.arange(L_LANG)[None] < lens[:, None]).long()
+        for d in (self.host, ):
+            d.pop("lang"); d.pop("lang_cls")
+            d["input_ids"], d["attention_mask"] = ids, mask
+        self.pinned = {k: v.pin_memory() for k, v in self.host.items() if torch.is_tensor(v)}
+        self.batch = {k: v.to(dev) for k, v in self.host.items() if torch.is_tensor(v)}
+        self.batch["lenths"] = self.host["lenths"]
+
+    def flops_per_step(self):
+        from bench_bert import bert_flops_fwd
+        return super().flops_per_step() + 3 * bert_flops_fwd(self.B, L_LANG)
+
+    def roofline(self, peaks, ms_per_step=None):
+        r = super().roofline(peaks, ms_per_step)
+        r["traffic"], r["traffic_source"] = None, None
+        return r
+
+    def cpu_step(self, n):
+        raise SystemExit("the train_bert workload has no CPU leg: use --no-cpu-baseline (train and bert have one each)")

@@ -303,6 +303,12 @@ int avdn_frame_attn_bwd(const float* frames, const float* lang_cls, const float*
                         const float* fc2_w, int B, int T, const float* attn, const float* wc, const float* e49,
                         const float* d_emb, float* d_frames, float* d_w_in, float* d_w_out, float* d_fc2_w,
                         float* d_fc2_b, avdn_stream_t stream);
+/* The same, also accumulating (+=) the gradient of the query into d_lang_cls [B,49] (NULL to skip): in the
+ * reference lang_cls = linear_cls comes from the trained BERT head (src/xview_et/agent.py:527-543).          */
+int avdn_frame_attn_bwd_cls(const float* frames, const float* lang_cls, const float* w_in, const float* w_out,
+                        const float* fc2_w, int B, int T, const float* attn, const float* wc, const float* e49,
+                        const float* d_emb, float* d_frames, float* d_w_in, float* d_w_out, float* d_fc2_w,
+                        float* d_fc2_b, float* d_lang_cls, avdn_stream_t stream);
 
 /* PosEncoding + concat + direction embedding (encodings.py:22-49,
  * enc_vl.py:71-83, ET_haa.py:147):

@@ -1,0 +1,81 @@
+"""GPU: the language encoder inside the training step (src/xview_et/agent.py:125-126,155,249,527-543):
+``NavCMTAgent.attach_lang_model`` + ``train_step`` on token ids.  The oracle pipeline (BERT restatement -> ET ->
+loss) is teacher-forced on OUR trunk features, so the comparison sees the language / transformer path only:
+step loss 1e-2, gradients that reach BERT and its head through ``lang`` and ``linear_cls``."""
+import os
+import tempfile
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bert_oracle as bo
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def test_train_step_with_language_encoder(built_lib):
+    from transformers import BertConfig
+    from avdn_b200.models.bert import CustomBERTModel
+    from avdn_b200.xview_et.agent import NavCMTAgent
+    B, T, S, V = 2, 2, 16, 500
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(mo.yolov3_trunk_cfg())
+    args = types.SimpleNamespace(demb=768, encoder_heads=12, encoder_layers=2, dropout_transformer_encoder=0.1,
+                                 num_input_actions=1, dropout_emb=0.0, darknet_model_file=f.name, darknet_weight_file=None,
+                                 lr=1e-5, nss_w=0.1, nss_r=0, ml_weight=0.2, no_dropout=True)
+    torch.manual_seed(0)
+    agent = NavCMTAgent(args, device="cuda")
+    os.unlink(f.name)
+    lm = agent.attach_lang_model(CustomBERTModel(BertConfig(num_hidden_layers=2, vocab_size=V)))
+    assert len(agent.optimizers) == 3
+    for opt in agent.optimizers:
+        opt.lr, opt.wd = 0.0, 0.0                  # keep the weights: we look at loss and gradients
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, V, (B, S), generator=g)
+    mask = torch.ones(B, S, dtype=torch.long)
+    mask[1, 11:] = 0
+    deg = torch.randint(0, 360, (B, T), generator=g).float()
+    dirs = torch.stack([torch.sin(deg / 180 * 3.14159), torch.cos(deg / 180 * 3.14159)], -1)
+    images = torch.zeros(B * T, 224, 224, 4)
+    images[..., :3] = torch.randn(B * T, 224, 224, 3, generator=g)
+    att = np.zeros((B, 224, 224), np.uint8)
+    att[0, 60:120, 80:160] = 255
+    att[1, 10:50, 150:200] = 255
+    hb = dict(input_ids=ids, attention_mask=mask, directions=dirs, images=images.bfloat16(), att=torch.from_numpy(att),
+              gt_xy=torch.rand(B, 2, generator=g) * 2 - 1, gt_alt=torch.rand(B, generator=g),
+              gt_prog=torch.rand(B, generator=g), lenths=[T, T - 1])
+    batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in hb.items()}
+    ours = agent.train_step(batch, sync_loss=True)
+    frames = agent._ctx[2]["frames"].detach().cpu().view(B, T, 512, 49)
+    # ---- oracle on the same weights, teacher-forced on our trunk features ----
+    sd_b = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in lm.state_dict().items()
+            if "position_ids" not in k}
+    sd_e = {k: v.detach().cpu().clone() for k, v in agent.vln_model.state_dict().items()}
+    seq, lin, _ = bo.custom_bert_forward(sd_b, ids, mask)
+    out, sal, _ = mo.et_forward(sd_e, dirs, frames, hb["lenths"], seq, lin)
+    gt_sal = torch.from_numpy(att.astype(np.float64) / 255)
+    loss = mo.step_loss(mo.et_loss(out, sal, hb["gt_xy"], hb["gt_alt"], hb["gt_prog"], gt_sal, 0.1), 0.2, B)
+    loss.backward()
+    ref = float(loss.detach())
+    assert abs(ours - ref) <= 1e-2 * abs(ref), (ours, ref)
+    report = {}
+    for n in ("bert.embeddings.word_embeddings.weight", "bert.encoder.layer.0.attention.self.query.weight",
+              "bert.encoder.layer.1.output.dense.weight", "bert.encoder.layer.1.output.LayerNorm.weight",
+              "bert.pooler.dense.weight", "linears.0.weight", "linears.3.weight", "linears.3.bias"):
+        report[n] = _rel2(agent.lang_optimizer.grads[n], sd_b[n].grad)
+        assert sd_b[n].grad.norm() > 0, n
+        assert report[n] < 0.1, (n, report[n])
+    print({k: round(v, 4) for k, v in report.items()})
+    # and the encoder learns with the rest of the step
+    for opt in agent.optimizers:
+        opt.lr = 1e-4
+    losses = [agent.train_step(batch, sync_loss=True) for _ in range(8)]
+    assert np.isfinite(losses).all() and losses[-1] < ours, (ours, losses)

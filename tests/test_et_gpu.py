@@ -125,12 +125,14 @@ def test_all_gradients_vs_oracle_ragged(et):
     sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in et.state_dict().items()}
     fr = frames.clone().requires_grad_(True)
     lg = lang.clone().requires_grad_(True)
-    oo, _, hs_o = mo.et_forward(sd, dirs, fr, lens, lg, lang_cls)
+    lc = lang_cls.clone().requires_grad_(True)
+    oo, _, hs_o = mo.et_forward(sd, dirs, fr, lens, lg, lc)
     ((oo * w_out).sum() + (hs_o * w_hs).sum()).backward()
     f2 = frames.cuda().requires_grad_(True)
     l2 = lang.cuda().requires_grad_(True)
+    c2 = lang_cls.cuda().requires_grad_(True)
     et.zero_grad()
-    out, hs = et.forward_features(directions=dirs.cuda(), frames=f2, lenths=lens, lang=l2, lang_cls=lang_cls.cuda())
+    out, hs = et.forward_features(directions=dirs.cuda(), frames=f2, lenths=lens, lang=l2, lang_cls=c2)
     assert _rel(out, oo) < 1e-2 and _rel(hs, hs_o) < 1e-2
     ((out * w_out.cuda()).sum() + (hs * w_hs.cuda()).sum()).backward()
     worst = {}
@@ -140,6 +142,7 @@ def test_all_gradients_vs_oracle_ragged(et):
         assert r < 5e-2, (n, r)
     assert _rel2(f2.grad, fr.grad) < 5e-2
     assert _rel2(l2.grad, lg.grad) < 5e-2
+    assert _rel2(c2.grad, lc.grad) < 5e-2          # linear_cls feeds the trained BERT head in the reference
 
 
 def test_encoder_vl_standalone(et):
