@@ -35,12 +35,9 @@ def take():
     n, e0, e1, fl, nb = next(it)
     return n, e0.elapsed_time(e1), fl
 fw = {}
+pack_all = take()            # one launch packs the weights of every block
 for L in eng.layers:
-    d = {}
-    if L.first:
-        d["conv"] = take()
-    else:
-        d["pack"] = take(); d["conv"] = take()
+    d = {"conv": take()}
     d["stats"] = take(); d["apply"] = take()
     fw[L.idx] = d
 take()  # nhwc->nchw
@@ -51,7 +48,7 @@ for L in reversed(eng.layers):
     if L.first:
         d["wgrad"] = take()
     else:
-        d["wgrad"] = take(); d["unpack"] = take()
+        d["wgrad"] = take()
         t, fl = 0.0, 0
         for _ in L.p_dgrad:
             n, ms, f2 = take(); t += ms; fl += f2
@@ -70,4 +67,6 @@ for L in eng.layers:
           f"{dg[1]:6.3f} {tf(dg):5.0f}")
     for k, v in list(f_.items()) + list(b_.items()):
         tot[k] = tot.get(k, 0.0) + v[1]
+unpack_all = take()          # one launch folds every WGRAD output into the weight gradients
+tot["pack"], tot["unpack"] = pack_all[1], unpack_all[1]
 print("totals ms:", {k: round(v, 2) for k, v in tot.items()}, "sum", round(sum(tot.values()), 2))
