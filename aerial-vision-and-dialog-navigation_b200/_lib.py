@@ -33,6 +33,8 @@ class TileDesc(C.Structure):
 # name -> argtypes ; every function returns int (avdn_status) unless noted
 _SIGNATURES = {
     "avdn_pack_tile": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "avdn_resize_area_width": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "avdn_raster_attention": [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "avdn_gps_to_pixels": [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "avdn_homography_from_corners": [c_void_p, c_int, c_void_p, c_void_p],
     "avdn_render_views": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

@@ -76,6 +76,75 @@ __global__ void pack_tile_kernel(const uint8_t* __restrict__ map_bgr,
   }
 }
 
+// ------------------------------------------------------- map preparation (N2)
+// cv2.resize(im, (new_w, H), INTER_AREA) for a horizontal shrink (src/env.py:221).  OpenCV's ResizeArea_
+// accumulates src * alpha in float, entry by entry of the decimation table (built on the host in float64 exactly
+// as computeResizeAreaTab does), then saturate_cast<uchar> (round half to even).  This file is compiled with
+// -fmad=false: the multiply and the add round separately, as in OpenCV's scalar code.
+__global__ void resize_area_width_kernel(const uint8_t* __restrict__ src, int H, int W, int new_w,
+                                         const int32_t* __restrict__ ofs, const int32_t* __restrict__ sidx,
+                                         const float* __restrict__ alpha, uint8_t* __restrict__ dst) {
+  const long long n = (long long)H * new_w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / new_w), dx = (int)(i - (long long)y * new_w);
+    const uint8_t* row = src + (size_t)y * W * 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int e = ofs[dx]; e < ofs[dx + 1]; ++e) {
+      const uint8_t* p = row + (size_t)sidx[e] * 3;
+      const float w = alpha[e];
+      a0 = __fadd_rn(a0, __fmul_rn((float)p[0], w));
+      a1 = __fadd_rn(a1, __fmul_rn((float)p[1], w));
+      a2 = __fadd_rn(a2, __fmul_rn((float)p[2], w));
+    }
+    uint8_t* o = dst + i * 3;
+    o[0] = (uint8_t)min(255, max(0, __float2int_rn(a0)));
+    o[1] = (uint8_t)min(255, max(0, __float2int_rn(a1)));
+    o[2] = (uint8_t)min(255, max(0, __float2int_rn(a2)));
+  }
+}
+
+// cv2.circle(att, center, radius, 255, thickness=-1) (src/env.py:226-230): OpenCV's Circle() walks the midpoint
+// algorithm and fills rows cy +- dy with half-width dx and rows cy +- dx with half-width dy.  One thread per spot
+// replays that walk into a half-width table hw[spot][0..r]; the raster kernel tests every pixel against the spots.
+__global__ void circle_spans_kernel(const int32_t* __restrict__ spots, int n, int rmax, int32_t* __restrict__ hw) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int radius = spots[3 * s + 2];
+  int32_t* t = hw + (size_t)s * (rmax + 1);
+  for (int d = 0; d <= rmax; ++d) t[d] = -1;
+  if (radius < 0 || radius > rmax) return;
+  int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+  while (dx >= dy) {
+    t[dy] = max(t[dy], dx);
+    t[dx] = max(t[dx], dy);
+    ++dy;
+    err += plus;
+    plus += 2;
+    const int mask = (err <= 0) - 1;
+    err -= minus & mask;
+    dx += mask;
+    minus -= mask & 2;
+  }
+}
+
+__global__ void raster_attention_kernel(const int32_t* __restrict__ spots, int n, int rmax,
+                                        const int32_t* __restrict__ hw, int H, int W, int ch, uint8_t* __restrict__ att) {
+  const long long np = (long long)H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    uint8_t v = 0;
+    for (int s = 0; s < n; ++s) {
+      const int cx = spots[3 * s], cy = spots[3 * s + 1], r = spots[3 * s + 2];
+      const int d = abs(y - cy);
+      if (d <= r && r <= rmax) {
+        const int h = hw[(size_t)s * (rmax + 1) + d];
+        if (h >= 0 && abs(x - cx) <= h) { v = 255; break; }
+      }
+    }
+    for (int c = 0; c < ch; ++c) att[i * ch + c] = v;
+  }
+}
+
 // ------------------------------------------------------------ gps -> pixels
 __global__ void gps_to_pixels_kernel(const double* __restrict__ corners_gps,
                                      const double* __restrict__ geo, int P,
@@ -389,6 +458,32 @@ extern "C" int avdn_pack_tile(const uint8_t* map_bgr, const uint8_t* att, int at
   pack_tile_kernel<<<blocks, 256, 0, avdn::to_cuda(stream)>>>(map_bgr, att, att_ch, H, W,
                                                               reinterpret_cast<uint2*>(tile8));
   return avdn::check_launch("avdn_pack_tile");
+}
+
+extern "C" int avdn_resize_area_width(const uint8_t* src, int H, int W, int new_w, const int32_t* ofs,
+                                      const int32_t* sidx, const float* alpha, uint8_t* dst, avdn_stream_t stream) {
+  AVDN_REQUIRE(src && dst && ofs && sidx && alpha && H > 0 && W > 0 && new_w > 0 && new_w <= W,
+               "avdn_resize_area_width: bad argument (horizontal shrink only)");
+  const long long n = (long long)H * new_w;
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  resize_area_width_kernel<<<blocks, 256, 0, avdn::to_cuda(stream)>>>(src, H, W, new_w, ofs, sidx, alpha, dst);
+  return avdn::check_launch("avdn_resize_area_width");
+}
+
+extern "C" int avdn_raster_attention(const int32_t* spots, int n_spots, int rmax, int32_t* hw_scratch, int H, int W,
+                                     int ch, uint8_t* att, avdn_stream_t stream) {
+  AVDN_REQUIRE(att && H > 0 && W > 0 && ch >= 1 && n_spots >= 0 && rmax >= 0, "avdn_raster_attention: bad argument");
+  AVDN_REQUIRE(n_spots == 0 || (spots && hw_scratch), "avdn_raster_attention: null spots / scratch");
+  cudaStream_t s = avdn::to_cuda(stream);
+  if (n_spots > 0) {
+    circle_spans_kernel<<<(n_spots + 63) / 64, 64, 0, s>>>(spots, n_spots, rmax, hw_scratch);
+    int r = avdn::check_launch("avdn_raster_attention (spans)");
+    if (r) return r;
+  }
+  const long long np = (long long)H * W;
+  const int blocks = (int)((np + 255) / 256 < 148 * 16 ? (np + 255) / 256 : 148 * 16);
+  raster_attention_kernel<<<blocks, 256, 0, s>>>(spots, n_spots, rmax, hw_scratch, H, W, ch, att);
+  return avdn::check_launch("avdn_raster_attention");
 }
 
 extern "C" int avdn_gps_to_pixels(const double* corners_gps, const double* geo, int P,

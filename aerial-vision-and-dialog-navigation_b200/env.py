@@ -88,6 +88,70 @@ class ViewRenderer:
         self._rebuild_table()
         return idx
 
+    @staticmethod
+    def area_table(ssize, dsize):
+        """OpenCV's ``computeResizeAreaTab`` for one axis (resize.cpp), float64 on the host: returns
+        (ofs int32 [dsize+1], sidx int32 [n], alpha float32 [n]); entries of destination column dx are
+        ``ofs[dx]:ofs[dx+1]`` in the order ``ResizeArea_`` accumulates them."""
+        import math
+        scale = ssize / dsize
+        ofs, sidx, alpha = [0], [], []
+        for dx in range(dsize):
+            fsx1 = dx * scale
+            fsx2 = fsx1 + scale
+            cell = min(scale, ssize - fsx1)
+            sx1, sx2 = math.ceil(fsx1), math.floor(fsx2)
+            sx2 = min(sx2, ssize - 1)
+            sx1 = min(sx1, sx2)
+            if sx1 - fsx1 > 1e-3:
+                sidx.append(sx1 - 1); alpha.append((sx1 - fsx1) / cell)
+            for sx in range(sx1, sx2):
+                sidx.append(sx); alpha.append(1.0 / cell)
+            if fsx2 - sx2 > 1e-3:
+                sidx.append(sx2); alpha.append(min(min(fsx2 - sx2, 1.0), cell) / cell)
+            ofs.append(len(sidx))
+        return (np.asarray(ofs, np.int32), np.asarray(sidx, np.int32), np.asarray(alpha, np.float64).astype(np.float32))
+
+    def prepare_map(self, name, im_bgr, lng_ratio, lat_ratio, attention_spots_px, keep_host_copies=False):
+        """Map preparation of ``next_batch`` (src/env.py:217-231) on the device, bit-exact with OpenCV:
+        ``cv2.resize(im, (int(W*lng_ratio/lat_ratio), H), INTER_AREA)``, the attention raster (zeros + one filled
+        white circle per ``(center (x, y) px, radius px)``) and the renderer's packed layout -- the decoded tile
+        is uploaded once and never comes back.  Returns ``(index, (H, new_w, 3))``; with ``keep_host_copies`` also
+        the two uint8 arrays the reference keeps in ``map_batch`` / ``attention_map_batch``."""
+        m = torch.as_tensor(np.ascontiguousarray(im_bgr)) if not torch.is_tensor(im_bgr) else im_bgr
+        if m.dtype != torch.uint8 or m.dim() != 3 or m.shape[2] != 3:
+            raise ValueError("map must be uint8 [H,W,3] (BGR)")
+        H, W = int(m.shape[0]), int(m.shape[1])
+        new_w = int(W * lng_ratio / lat_ratio)                         # src/env.py:221
+        if not 0 < new_w <= W:
+            raise NotImplementedError("only the horizontal shrink of src/env.py:221 (lng_ratio <= lat_ratio) is implemented")
+        dev = self.device
+        m = m.to(dev).contiguous()
+        if new_w == W:
+            resized = m
+        else:
+            key = (W, new_w)
+            tabs = getattr(self, "_area_tabs", None)
+            if tabs is None:
+                tabs = self._area_tabs = {}
+            if key not in tabs:                                         # the table depends on the two widths only
+                tabs[key] = tuple(torch.from_numpy(a).to(dev) for a in self.area_table(W, new_w))
+            t_ofs, t_sidx, t_alpha = tabs[key]
+            resized = torch.empty((H, new_w, 3), dtype=torch.uint8, device=dev)
+            _lib.call("avdn_resize_area_width", _lib.ptr(m), H, W, new_w, _lib.ptr(t_ofs), _lib.ptr(t_sidx),
+                      _lib.ptr(t_alpha), _lib.ptr(resized))
+        spots = np.asarray([[int(c[0]), int(c[1]), int(r)] for (c, r) in attention_spots_px], dtype=np.int32).reshape(-1, 3)
+        att = torch.empty((H, new_w, 1), dtype=torch.uint8, device=dev)
+        rmax = int(spots[:, 2].max()) if len(spots) else 0
+        t_spots = torch.from_numpy(spots).to(dev) if len(spots) else None
+        scratch = torch.empty((max(len(spots), 1), rmax + 1), dtype=torch.int32, device=dev)
+        _lib.call("avdn_raster_attention", _lib.ptr(t_spots), len(spots), rmax, _lib.ptr(scratch), H, new_w, 1,
+                  _lib.ptr(att))
+        idx = self.add_map(name, resized, att)
+        if keep_host_copies:
+            return idx, (H, new_w, 3), resized.cpu().numpy(), np.repeat(att.cpu().numpy(), 3, axis=2)
+        return idx, (H, new_w, 3)
+
     def remove_map(self, name):
         """Mirror of the reference's eviction of unused maps (src/env.py:234-240)."""
         if name in self._maps:
@@ -193,6 +257,23 @@ class ANDHNavBatch:
         self.attention_map_batch = {}
         self.renderer = ViewRenderer(device)
         self._uploaded = {}        # map name -> (id(map array), id(att array))
+        self._device_maps = {}     # map name -> shape of maps prepared on the device (load_map)
+
+    def load_map(self, name, im_bgr, item):
+        """The map-preparation branch of ``next_batch`` (src/env.py:217-231) for one decoded tile (``cv2.imread``
+        output, BGR u8) on the device: INTER_AREA width rescale by ``lng_ratio / lat_ratio``, the attention raster
+        from ``item['attention_list']`` = [((lat, lng), radius_px), ...] and the renderer's packed layout.  The
+        map then serves ``_get_obs`` like an entry of ``map_batch`` (whose host copy is not needed any more)."""
+        spots = [(self.gps_to_img_coords(a[0], item), a[1]) for a in item.get("attention_list", [])]
+        _, shape = self.renderer.prepare_map(name, im_bgr, item["lng_ratio"], item["lat_ratio"], spots)
+        self._device_maps[name] = shape
+        return shape
+
+    def drop_unused_maps(self, used_names):
+        """src/env.py:234-240: forget the maps the next batch does not use."""
+        for name in [n for n in self._device_maps if n not in used_names]:
+            self.renderer.remove_map(name)
+            del self._device_maps[name]
 
     def gps_to_img_coords(self, gps, ob):
         """src/env.py:189-196 (host scalar version, used by callers outside the path)."""
@@ -202,7 +283,7 @@ class ANDHNavBatch:
 
     def _sync_maps(self):
         for name in list(self._uploaded):
-            if name not in self.map_batch:
+            if name not in self.map_batch and name not in self._device_maps:
                 self.renderer.remove_map(name)
                 del self._uploaded[name]
         for name, m in self.map_batch.items():
@@ -253,7 +334,8 @@ class ANDHNavBatch:
             item = self.batch[i]
             obs.append({
                 "map_name": item["map_name"],
-                "map_size": self.map_batch[item["map_name"]].shape,
+                "map_size": (self._device_maps[item["map_name"]] if item["map_name"] in self._device_maps
+                             else self.map_batch[item["map_name"]].shape),
                 "route_index": item["route_index"],
                 "gps_botm_left": item["gps_botm_left"],
                 "gps_top_right": item["gps_top_right"],

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the AVDN hot path on B200 (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout|et_rollout|bert]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout|et_rollout|bert|train_bert|mapprep]
     python bench.py --impl reference ...        # the reference's CPU path, same metric
 
 One JSON line on stdout (rank 0).  Under torchrun (N>1) every rank runs its shard
@@ -170,7 +170,104 @@ class RenderWorkload:
     CPU_SAMPLE = 512
 
 
-WORKLOADS = {"render": RenderWorkload}
+# ================================================================= map preparation
+class MapPrepWorkload:
+    """SURVEY.md §8f N2 (src/env.py:217-231): per map, INTER_AREA width rescale of the decoded 3000x3000 tile,
+    the attention raster (8 filled circles) and the renderer's packed layout, 8 maps per step."""
+    name = "mapprep_n2"
+    metric = "prepared maps/s"
+    unit = "maps/s"
+    dtype = "u8"
+    MAPS = 8
+    SIZE = 3000
+    RATIO = (0.7593e-5, 1.0e-5)          # lng_ratio, lat_ratio at ~40 degrees latitude
+    CPU_SAMPLE = 8
+
+    def __init__(self, rank, world):
+        from avdn_b200.utils import synthetic as syn
+        self.rank, self.world = rank, world
+        self.tile = syn.synthetic_tile(seed=rank, size=self.SIZE)
+        rng = np.random.default_rng(rank)
+        self.new_w = int(self.SIZE * self.RATIO[0] / self.RATIO[1])
+        self.spots = [((int(rng.integers(0, self.new_w)), int(rng.integers(0, self.SIZE))), int(rng.integers(30, 150)))
+                      for _ in range(8)]
+
+    def units_per_step(self):
+        return self.MAPS
+
+    def config(self):
+        return {"workload": "map preparation (src/env.py:217-231): 3000x3000x3 u8 tile -> INTER_AREA width rescale to "
+                            f"{self.new_w} columns + 8 filled attention circles + packed renderer layout, 8 maps per step",
+                "maps_per_step": self.MAPS, "tile": [self.SIZE, self.SIZE, 3],
+                "cache": "each map moves 27 MB in and ~75 MB out; L2 is flushed between steps",
+                "parallelism": f"map-sharded x{self.world}, no collective"}
+
+    def setup_gpu(self, dev):
+        from avdn_b200.env import ViewRenderer
+        self.dev = dev
+        self.r = ViewRenderer(dev)
+        self.tile_dev = torch.from_numpy(self.tile).to(dev)
+        self.tile_pin = torch.from_numpy(self.tile).pin_memory()
+        self.ms = []
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        self.flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+    def _prep(self, tile):
+        for i in range(self.MAPS):
+            self.r.prepare_map(f"m{i}", tile, self.RATIO[0], self.RATIO[1], self.spots)
+        return 4 * self.MAPS
+
+    def step(self):
+        self.ev[0].record()
+        n = self._prep(self.tile_dev)
+        self.ev[1].record()
+        return n
+
+    def after_step(self, timed):
+        if timed:
+            self.ev[1].synchronize()
+            self.ms.append(self.ev[0].elapsed_time(self.ev[1]))
+
+    def step_e2e(self):
+        h2d = 0
+        for i in range(self.MAPS):
+            t = self.tile_pin.to(self.dev, non_blocking=True)
+            h2d += t.numel()
+            self.r.prepare_map(f"m{i}", t, self.RATIO[0], self.RATIO[1], self.spots)
+        self.flag.copy_(torch.ones(1, dtype=torch.int32, device=self.dev), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h2d, 4
+
+    def roofline(self, peaks):
+        # algorithmic bytes per map: read the tile once, write the resized tile, write the attention plane, read
+        # both and write the 8-byte packed records
+        H, W, nw = self.SIZE, self.SIZE, self.new_w
+        alg = self.MAPS * (H * W * 3 + H * nw * 3 + H * nw + H * nw * 4 + (H + 1) * (nw + 2) * 8)
+        ms = float(np.mean(self.ms)) if self.ms else None
+        ach = alg / (ms * 1e-3) / 1e9 if ms else None
+        return {"kernel": "resize_area_width_kernel + raster_attention_kernel + pack_tile_kernel", "bound": "hbm",
+                "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": (ach / peaks["hbm"]) if ach else None,
+                "traffic": None, "peak_source": peaks["source"] + " (burst copy)", "algorithmic_bytes_per_step": alg,
+                "step_ms": ms}
+
+    def cpu_step(self, n):
+        import cv2
+        done = 0
+        while done < n:
+            im = cv2.resize(self.tile, (self.new_w, self.SIZE), interpolation=cv2.INTER_AREA)
+            att = np.zeros((im.shape[0], im.shape[1], 3), np.uint8)
+            for c, r in self.spots:
+                cv2.circle(att, center=c, radius=r, color=(255, 255, 255), thickness=-1)
+            done += 1
+        return done
+
+    def cpu_info(self):
+        import cv2
+        return {"kind": "reference", "cores": int(cv2.getNumThreads()),
+                "what": "cv2.resize(INTER_AREA) + np.zeros + cv2.circle (the calls at src/env.py:221-230)"}
+
+
+WORKLOADS = {"render": RenderWorkload, "mapprep": MapPrepWorkload}
 try:
     from bench_train import TrainWorkload, TrainBertWorkload      # noqa: E402
     WORKLOADS["train"] = TrainWorkload

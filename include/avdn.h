@@ -63,6 +63,17 @@ int avdn_device_supported(void);
 int avdn_pack_tile(const uint8_t* map_bgr, const uint8_t* att, int att_ch,
                    int H, int W, void* tile8, avdn_stream_t stream);
 
+/* Map preparation (src/env.py:217-231), bit-exact with OpenCV:
+ *  - cv2.resize(im, (new_w, H), INTER_AREA), new_w = int(W * lng_ratio / lat_ratio) <= W: the decimation table
+ *    (ofs [new_w+1], sidx / alpha [ofs[new_w]]) is OpenCV's computeResizeAreaTab, built by the caller in float64;
+ *    the kernel accumulates src * alpha in float in table order and rounds half to even, as ResizeArea_ does.
+ *  - the human-attention raster: zeros + cv2.circle(center, radius, 255, thickness=-1) per spot; spots [n,3] i32 =
+ *    (cx, cy, radius) in pixels, hw_scratch [n, rmax+1] i32, att [H,W,ch] u8 fully overwritten.                  */
+int avdn_resize_area_width(const uint8_t* src, int H, int W, int new_w, const int32_t* ofs, const int32_t* sidx,
+                           const float* alpha, uint8_t* dst, avdn_stream_t stream);
+int avdn_raster_attention(const int32_t* spots, int n_spots, int rmax, int32_t* hw_scratch, int H, int W, int ch,
+                          uint8_t* att, avdn_stream_t stream);
+
 /* gps_to_img_coords (src/env.py:189-196), batched and bit-exact:
  *   x = rint((lng - bl_lng) / lat_ratio), y = rint((tr_lat - lat) / lat_ratio)
  * in float64 with round-half-even.
