@@ -85,6 +85,7 @@ class NavCMTAgent:
         # language encoder (agent.py:125-126,155: trained with its own AdamW): built on demand, see attach_lang_model
         self.lang_model, self.lang_optimizer = None, None
         self.renderer = ViewRenderer(self.device)
+        self.use_graphs = os.environ.get("AVDN_CUDA_GRAPHS", "1") != "0"     # rollouts replay the frozen trunk pass
         self.loss_total = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._bufs = {}
         self.launches = 0
@@ -347,7 +348,10 @@ class NavCMTAgent:
             call("avdn_gps_to_pixels", ptr(bf["corners"]), ptr(geo), B, ptr(bf["px"]))
             call("avdn_homography_from_corners", ptr(bf["px"]), B, ptr(bf["minv"]))
             r.render(None, ti, views=False, norm_nhwc=True, minv=bf["minv"], out={"norm_nhwc": bf["x"]})
-            DN._trunk_forward(vm, teng, bf["x"], False, out=bf["frames"], frozen=(t > 0))
+            if t == 0 or not self.use_graphs:
+                DN._trunk_forward(vm, teng, bf["x"], False, out=bf["frames"], frozen=(t > 0))
+            else:
+                DN._trunk_forward_graphed(vm, teng, bf["x"], bf["frames"])
             bf["frames_hist"][t].copy_(bf["frames"].view(B, 512, 49))
             rad = bf["cur_dir"].float() / 180 * PI_REF                  # agent.py:605-606 (float32, pi = 3.14159)
             bf["dirs_hist"][t, :, 0] = torch.sin(rad)

@@ -45,6 +45,7 @@ class NavCMTAgent:
             self.vision_model.load_state_dict(state)
         self.vln_model = ViT_LSTM(args, self.vision_model).to(self.device)      # trunk is a sub-module (agent.py:140-142)
         self.renderer = ViewRenderer(self.device)
+        self.use_graphs = os.environ.get("AVDN_CUDA_GRAPHS", "1") != "0"     # rollouts replay the frozen trunk pass
         self.launches = 0
         self._bufs = {}
 
@@ -107,7 +108,10 @@ class NavCMTAgent:
             call("avdn_homography_from_corners", ptr(bf["px"]), B, ptr(bf["minv"]))
             r.render(None, ti, views=False, norm_nhwc=True, minv=bf["minv"], out={"norm_nhwc": bf["x"]})
             # ---- policy (agent.py:592-602) ----
-            DN._trunk_forward(vm, eng, bf["x"], False, out=bf["frames"], frozen=(t > 0))
+            if t == 0 or not self.use_graphs:
+                DN._trunk_forward(vm, eng, bf["x"], False, out=bf["frames"], frozen=(t > 0))
+            else:
+                DN._trunk_forward_graphed(vm, eng, bf["x"], bf["frames"])
             output, _ = self.vln_model.step(bf["frames"].view(B, NCH, NSP), bf["cur_dir"], cls, lang,
                                             want_saliency=False)
             bf["output_hist"][t].copy_(output)
