@@ -308,10 +308,27 @@ def dist_env():
     return rank, world, local
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core they can."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
+    try:
+        import cv2
+        cv2.setNumThreads(n)
+    except Exception:
+        pass
+
+
 def run_reference(args, W):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    use_all_host_threads()
     wl = W(0, 1)
     n = wl.CPU_SAMPLE
     for _ in range(args.warmup):
@@ -426,6 +443,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
+            use_all_host_threads()
             n = wl.CPU_SAMPLE
             wl.cpu_step(max(1, n // 8))
             t0 = time.perf_counter()
