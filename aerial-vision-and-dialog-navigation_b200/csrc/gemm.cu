@@ -263,8 +263,12 @@ struct Tiles {
   static constexpr int TAIL_BYTES = 2 * BN * 4 + NUM_BARS * 8 + 16 + 1024;   // stats + barriers + slot + align slack
 };
 
+// Thin tiles (BN <= 64: the <= 64-channel blocks of the trunk) are bound by the latency of one CTA's
+// producer -> MMA -> epilogue chain, not by any throughput: two CTAs per SM (half the shared memory each, 2 x 2 x BN
+// TMEM columns) interleave two such chains.
 template <int BN, bool A_MN, bool B_MN, int CTAS, int BKT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, (BN <= 64 && CTAS == 1) ? 2 : 1)
+gemm_kernel(const __grid_constant__ KernelParams p) {
   static_assert(BKT == 64 || (BKT == 32 && !A_MN && !B_MN), "32-element k-blocks: K-major operands only");
   using L = Tiles<BN, CTAS, BKT>;
   constexpr int BNH = BN / CTAS;                                // B columns this CTA loads
@@ -965,6 +969,8 @@ struct Plan {
   int32_t bn, a_mn, b_mn, ctas, bk;
   int32_t grid;
   int32_t smem;
+  int32_t occ2;          // 1: thin tile planned for two CTAs per SM
+  int32_t pad_;
   KernelParams kp;
 };
 constexpr uint32_t PLAN_MAGIC = 0xA7D17C06u;
@@ -1138,9 +1144,19 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
     int slabs = MAX_SLABS;
     const char* es = getenv("AVDN_GEMM_SLABS");
     if (es && atoi(es) >= 2 && atoi(es) <= MAX_SLABS) slabs = atoi(es);
-    int stages = (SMEM_MAX - tail - slabs * SLAB_BYTES) / (kps * sub);
-    while (stages < 2 && slabs > 2) { --slabs; stages = (SMEM_MAX - tail - slabs * SLAB_BYTES) / (kps * sub); }
-    while (stages < 2 && kps > 1) { --kps; stages = (SMEM_MAX - tail - slabs * SLAB_BYTES) / (kps * sub); }
+    // two CTAs per SM for thin tiles: each gets half of the SM's shared memory (228 KB - 1 KB reserved per CTA)
+    int smem_cap = SMEM_MAX;
+    const char* eo = getenv("AVDN_GEMM_OCC2");
+    pl->occ2 = 0;
+    if (d->bn <= 64 && d->ctas == 1 && !(eo && atoi(eo) == 0)) {
+      const int cap2 = (228 * 1024) / 2 - 1024;
+      int k2 = kps;
+      while (k2 > 1 && (cap2 - tail - 2 * SLAB_BYTES) / (k2 * sub) < 2) --k2;      // fewer k-blocks per stage if needed
+      if ((cap2 - tail - 2 * SLAB_BYTES) / (k2 * sub) >= 2) { smem_cap = cap2; slabs = 2; kps = k2; pl->occ2 = 1; }
+    }
+    int stages = (smem_cap - tail - slabs * SLAB_BYTES) / (kps * sub);
+    while (stages < 2 && slabs > 2) { --slabs; stages = (smem_cap - tail - slabs * SLAB_BYTES) / (kps * sub); }
+    while (stages < 2 && kps > 1) { --kps; stages = (smem_cap - tail - slabs * SLAB_BYTES) / (kps * sub); }
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     AVDN_REQUIRE(stages >= 2, "avdn_gemm_plan: shared memory plan failed (bn %d bk %d)", d->bn, d->bk);
     pl->kp.stages = stages;
@@ -1152,7 +1168,7 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   const long long pm = (d->grid_m + d->ctas - 1) / d->ctas;
   const long long tiles = pm * d->grid_n * d->grid_z;
   AVDN_REQUIRE(tiles < (1ll << 31), "avdn_gemm_plan: too many tiles");
-  const long long slots = avdn::sm_count() / d->ctas;
+  const long long slots = (long long)avdn::sm_count() * (pl->occ2 ? 2 : 1) / d->ctas;
   pl->grid = (int)((tiles < slots ? tiles : slots) * d->ctas);
   pl->magic = PLAN_MAGIC;
   return AVDN_OK;
