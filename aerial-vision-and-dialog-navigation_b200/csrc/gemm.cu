@@ -267,7 +267,7 @@ struct Tiles {
 // producer -> MMA -> epilogue chain, not by any throughput: two CTAs per SM (half the shared memory each, 2 x 2 x BN
 // TMEM columns) interleave two such chains.
 template <int BN, bool A_MN, bool B_MN, int CTAS, int BKT>
-__global__ void __launch_bounds__(NUM_THREADS, (BN <= 64 && CTAS == 1) ? 2 : 1)
+__global__ void __launch_bounds__(NUM_THREADS, (BN <= 128) ? 2 : 1)
 gemm_kernel(const __grid_constant__ KernelParams p) {
   static_assert(BKT == 64 || (BKT == 32 && !A_MN && !B_MN), "32-element k-blocks: K-major operands only");
   using L = Tiles<BN, CTAS, BKT>;
@@ -1148,7 +1148,8 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
     int smem_cap = SMEM_MAX;
     const char* eo = getenv("AVDN_GEMM_OCC2");
     pl->occ2 = 0;
-    if (d->bn <= 64 && d->ctas == 1 && !(eo && atoi(eo) == 0)) {
+    const int occ_bn = eo ? atoi(eo) : 128;       // AVDN_GEMM_OCC2 = widest tile that runs two CTAs per SM (0 = off)
+    if (d->bn <= occ_bn && d->bn <= 128) {
       const int cap2 = (228 * 1024) / 2 - 1024;
       int k2 = kps;
       while (k2 > 1 && (cap2 - tail - 2 * SLAB_BYTES) / (k2 * sub) < 2) --k2;      // fewer k-blocks per stage if needed
