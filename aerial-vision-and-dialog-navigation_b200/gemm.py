@@ -102,12 +102,15 @@ class GemmPlan:
         _lib.check(self._run(self.buf, _lib.stream_ptr()), "avdn_gemm_run")
 
 
+BN_MAX = int(os.environ.get("AVDN_GEMM_BN_MAX", "128"))      # 128: two co-resident CTAs per SM beat one 256-wide tile
+
+
 def pick_bn(N):
     if N <= 32:
         return 32
     if N <= 64:
         return 64
-    if N <= 128 or N % 256 != 0:
+    if N <= 128 or N % 256 != 0 or BN_MAX < 256:
         return 128
     return 256
 
