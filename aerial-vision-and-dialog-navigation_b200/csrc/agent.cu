@@ -177,6 +177,145 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ out
   }
 }
 
+// ------------------------------------------------------- supervision geometry (N3)
+// compute_iou (src/xview_et/agent.py:46-78) and teacher_action with student feedback (agent.py:386-507), which the
+// reference evaluates per sample with shapely/GEOS on the host.  For the convex quadrilaterals of the simulator
+// those calls reduce to: convex hulls (monotone chain), the intersection of two convex polygons
+// (Sutherland-Hodgman), shoelace areas, and the point where the segment centre -> goal leaves the view quad.
+// One thread per sample, float64.
+struct P2 { double x, y; };
+__device__ __forceinline__ double cross3(P2 o, P2 a, P2 b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); }
+__device__ double poly_area(const P2* p, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) { const P2 a = p[i], b = p[(i + 1) % n]; s += a.x * b.y - b.x * a.y; }
+  return 0.5 * s;
+}
+// Andrew's monotone chain, counter-clockwise output; n <= 8
+__device__ int hull_ccw(const P2* in, int n, P2* out) {
+  P2 pts[8];
+  for (int i = 0; i < n; ++i) pts[i] = in[i];
+  for (int i = 1; i < n; ++i) {                       // insertion sort, lexicographic (x, y)
+    const P2 k = pts[i];
+    int j = i - 1;
+    while (j >= 0 && (pts[j].x > k.x || (pts[j].x == k.x && pts[j].y > k.y))) { pts[j + 1] = pts[j]; --j; }
+    pts[j + 1] = k;
+  }
+  if (n <= 2) { for (int i = 0; i < n; ++i) out[i] = pts[i]; return n; }
+  P2 h[18];
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    while (m >= 2 && cross3(h[m - 2], h[m - 1], pts[i]) <= 0) --m;
+    h[m++] = pts[i];
+  }
+  const int lo = m + 1;
+  for (int i = n - 2; i >= 0; --i) {
+    while (m >= lo && cross3(h[m - 2], h[m - 1], pts[i]) <= 0) --m;
+    h[m++] = pts[i];
+  }
+  --m;                                                // the last point repeats the first
+  for (int i = 0; i < m; ++i) out[i] = h[i];
+  return m;
+}
+// intersection of two CCW convex polygons (<= 8 vertices each) -> up to 16 vertices
+__device__ int clip_convex(const P2* subj, int ns, const P2* clip, int nc, P2* out) {
+  P2 a_[16], b_[16];
+  P2* cur = a_; P2* nxt = b_;
+  int n = ns;
+  for (int i = 0; i < ns; ++i) cur[i] = subj[i];
+  for (int e = 0; e < nc && n > 0; ++e) {
+    const P2 a = clip[e], b = clip[(e + 1) % nc];
+    int m = 0;
+    for (int j = 0; j < n; ++j) {
+      const P2 p = cur[j], q = cur[(j + 1) % n];
+      const double sp = (b.x - a.x) * (p.y - a.y) - (b.y - a.y) * (p.x - a.x);
+      const double sq = (b.x - a.x) * (q.y - a.y) - (b.y - a.y) * (q.x - a.x);
+      if (sp >= 0) nxt[m++] = p;
+      if ((sp >= 0) != (sq >= 0)) {
+        const double t = sp / (sp - sq);
+        nxt[m].x = p.x + t * (q.x - p.x);
+        nxt[m].y = p.y + t * (q.y - p.y);
+        ++m;
+      }
+    }
+    P2* tmp = cur; cur = nxt; nxt = tmp;
+    n = m;
+  }
+  for (int i = 0; i < n; ++i) out[i] = cur[i];
+  return n;
+}
+__device__ double quad_iou(const P2* a, const P2* b) {
+  P2 ha[8], hb[8], inter[16], all[8], hu[8];
+  const int na = hull_ccw(a, 4, ha), nb = hull_ccw(b, 4, hb);
+  const int ni = clip_convex(ha, na, hb, nb, inter);
+  if (ni < 3) return 0.0;
+  for (int i = 0; i < 4; ++i) { all[i] = a[i]; all[4 + i] = b[i]; }
+  const int nu = hull_ccw(all, 8, hu);
+  const double ua = fabs(poly_area(hu, nu));
+  return ua == 0.0 ? 0.0 : fabs(poly_area(inter, ni)) / ua;
+}
+
+__global__ void teacher_action_kernel(const double* __restrict__ corners, const double* __restrict__ gt, int pmax,
+                                      const int32_t* __restrict__ gt_len, const uint8_t* __restrict__ ended, int B,
+                                      float* __restrict__ ratio, float* __restrict__ altitude,
+                                      float* __restrict__ progress) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  P2 c[4], g[4];
+  for (int k = 0; k < 4; ++k) { c[k].x = corners[(i * 4 + k) * 2]; c[k].y = corners[(i * 4 + k) * 2 + 1]; }
+  const int n = gt_len[i];
+  const double* gl = gt + ((size_t)i * pmax + (n - 1)) * 8;
+  for (int k = 0; k < 4; ++k) { g[k].x = gl[2 * k]; g[k].y = gl[2 * k + 1]; }
+  P2 cur;
+  cur.x = (((c[0].x + c[1].x) + c[2].x) + c[3].x) / 4.0;
+  cur.y = (((c[0].y + c[1].y) + c[2].y) + c[3].y) / 4.0;
+  const float prog = (float)quad_iou(c, g);                       // progress[i] = np.float32(iou)
+  progress[i] = prog;
+  // teacher altitude: the ground-truth step whose centre is closest to the current position (later steps win ties)
+  double min_dis = 1000.0;
+  int closest = 0;
+  for (int j = n - 1; j >= 0; --j) {
+    const double* q = gt + ((size_t)i * pmax + j) * 8;
+    const double mx = (((q[0] + q[2]) + q[4]) + q[6]) / 4.0 - cur.x, my = (((q[1] + q[3]) + q[5]) + q[7]) / 4.0 - cur.y;
+    const double dis = sqrt(mx * mx + my * my);
+    if (dis + 0.00001 < min_dis) { min_dis = dis; closest = j; }
+  }
+  {
+    const double* q = gt + ((size_t)i * pmax + closest) * 8;
+    const double ex = q[0] - q[2], ey = q[1] - q[3];
+    altitude[i] = (float)((sqrt(ex * ex + ey * ey) * 11.13 * 1e4 - 40.0) / (400.0 - 40.0));
+  }
+  if (ended[i] || prog > 0.5f) { ratio[2 * i] = 0.f; ratio[2 * i + 1] = 0.f; return; }
+  // the part of the segment centre -> goal centre inside the view: its end point closest to the goal
+  P2 goal;
+  goal.x = (((g[0].x + g[1].x) + g[2].x) + g[3].x) / 4.0;
+  goal.y = (((g[0].y + g[1].y) + g[2].y) + g[3].y) / 4.0;
+  P2 poly[4];
+  const bool ccw = poly_area(c, 4) >= 0;
+  for (int k = 0; k < 4; ++k) poly[k] = ccw ? c[k] : c[3 - k];
+  double t_exit = 1.0;
+  for (int k = 0; k < 4; ++k) {
+    const P2 a = poly[k], b = poly[(k + 1) & 3];
+    const double ex = b.x - a.x, ey = b.y - a.y;
+    const double s0 = ex * (cur.y - a.y) - ey * (cur.x - a.x);
+    const double s1 = ex * (goal.y - a.y) - ey * (goal.x - a.x);
+    if (s1 < 0 && s0 >= 0) t_exit = fmin(t_exit, s0 / (s0 - s1));
+  }
+  const double xx = cur.x + t_exit * (goal.x - cur.x), xy = cur.y + t_exit * (goal.y - cur.y);
+  // local frame of the view (agent.py:481-487): integer-rounded half-edge vectors, 2x2 solve with partial pivoting
+  const double b0 = 1e5 * (xx - cur.x), b1 = 1e5 * (xy - cur.y);
+  const double ny0 = rint(1e5 * ((c[0].x + c[1].x) / 2 - cur.x)), ny1 = rint(1e5 * ((c[0].y + c[1].y) / 2 - cur.y));
+  const double nx0 = rint(1e5 * ((c[1].x + c[2].x) / 2 - cur.x)), nx1 = rint(1e5 * ((c[1].y + c[2].y) / 2 - cur.y));
+  double a00 = nx0, a01 = ny0, a10 = nx1, a11 = ny1, r0b = b0, r1b = b1;
+  if (fabs(a10) > fabs(a00)) { double t;  t = a00; a00 = a10; a10 = t;  t = a01; a01 = a11; a11 = t;  t = r0b; r0b = r1b; r1b = t; }
+  const double l = a10 / a00;
+  const double u11 = a11 - l * a01;
+  const double r1 = (r1b - l * r0b) / u11;
+  const double r0 = (r0b - a01 * r1) / a00;
+  const double m = fmax(fmax(fabs(r0), fabs(r1)), 1.0);
+  ratio[2 * i] = (float)(r0 / m);
+  ratio[2 * i + 1] = (float)(r1 / m);
+}
+
 // 8x8 -> 224x224 bilinear upsample (pred_saliency of the reference API)
 __global__ void upsample_kernel(const float* __restrict__ h_sali, int B, float* __restrict__ pred) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -285,6 +424,17 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 }
 
 }  // namespace
+
+extern "C" int avdn_teacher_action(const double* corners, const double* gt_path_corners, int pmax, const int32_t* gt_len,
+                                   const uint8_t* ended, int B, float* next_pos_ratio, float* altitude, float* progress,
+                                   avdn_stream_t stream) {
+  AVDN_REQUIRE(corners && gt_path_corners && gt_len && ended && next_pos_ratio && altitude && progress && pmax >= 1,
+               "avdn_teacher_action: bad argument");
+  if (B <= 0) return AVDN_OK;
+  teacher_action_kernel<<<(B + 63) / 64, 64, 0, avdn::to_cuda(stream)>>>(corners, gt_path_corners, pmax, gt_len, ended, B,
+                                                                       next_pos_ratio, altitude, progress);
+  return avdn::check_launch("avdn_teacher_action");
+}
 
 extern "C" int avdn_loss(const float* output, const float* h_sali, const float* gt_xy, const float* gt_alt,
                          const float* gt_prog, const uint8_t* att, const float* jitter, int B, float nss_w, int nss_r,

@@ -414,6 +414,37 @@ class NavCMTAgent:
             out.append(path)
         return out
 
+    def teacher_action(self, corners, gt_path_corners, ended):
+        """``teacher_action`` with student feedback (agent.py:386-507) for the whole batch on the device.
+        ``corners`` [B,4,2] f64 (lat,lng); ``gt_path_corners``: list (len B) of ``[n_i,4,2]`` arrays or a padded
+        ``[B,Pmax,4,2]`` tensor with ``gt_len``; ``ended`` [B].  Returns device tensors
+        ``(next_pos_ratio [B,2] f32, altitude [B] f32, progress [B] f32)`` -- the targets of ``output[:,0:2]``,
+        ``output[:,2]`` and ``output[:,3]`` (agent.py:655-671)."""
+        dev = self.device
+        c = torch.as_tensor(np.asarray(corners) if not torch.is_tensor(corners) else corners).to(dev, torch.float64).contiguous()
+        B = c.shape[0]
+        if isinstance(gt_path_corners, (list, tuple)) and not torch.is_tensor(gt_path_corners):
+            lens = [len(g) for g in gt_path_corners]
+            pmax = max(lens)
+            gt = np.zeros((B, pmax, 4, 2), dtype=np.float64)
+            for i, g in enumerate(gt_path_corners):
+                gt[i, :lens[i]] = np.asarray(g, dtype=np.float64)
+            gt_t = torch.from_numpy(gt).to(dev)
+            len_t = torch.tensor(lens, dtype=torch.int32, device=dev)
+        else:
+            gt_t, len_t = gt_path_corners
+            gt_t = gt_t.to(dev, torch.float64).contiguous()
+            len_t = len_t.to(dev, torch.int32).contiguous()
+            pmax = gt_t.shape[1]
+        e = torch.as_tensor(np.asarray(ended, dtype=np.uint8) if not torch.is_tensor(ended) else ended).to(dev, torch.uint8).contiguous()
+        ratio = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        alt = torch.empty(B, dtype=torch.float32, device=dev)
+        prog = torch.empty(B, dtype=torch.float32, device=dev)
+        _lib.call("avdn_teacher_action", _lib.ptr(c), _lib.ptr(gt_t), int(pmax), _lib.ptr(len_t), _lib.ptr(e), B,
+                  _lib.ptr(ratio), _lib.ptr(alt), _lib.ptr(prog))
+        self.launches += 1
+        return ratio, alt, prog
+
     # ------------------------------------------------------------ API helpers
     def NSS(self, sal, fix):
         """src/xview_et/agent.py:256-270 on device tensors (torch elementwise; off the hot
