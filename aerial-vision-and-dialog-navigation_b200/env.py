@@ -281,6 +281,99 @@ class ANDHNavBatch:
         return (int(round((gps[1] - ob["gps_botm_left"][1]) / lat_ratio)),
                 int(round((ob["gps_top_right"][0] - gps[0]) / lat_ratio)))
 
+    # ------------------------------------------------------------- evaluation
+    @staticmethod
+    def _contains(quad, point):
+        """shapely ``Polygon(quad).contains(Point(point))`` for the simulator's convex quads: strictly inside."""
+        q = np.asarray(quad, dtype=np.float64)
+        x, y = float(point[0]), float(point[1])
+        sign = 0
+        for i in range(len(q)):
+            a, b = q[i], q[(i + 1) % len(q)]
+            cr = (b[0] - a[0]) * (y - a[1]) - (b[1] - a[1]) * (x - a[0])
+            if cr == 0:
+                return False
+            s_ = 1 if cr > 0 else -1
+            if sign == 0:
+                sign = s_
+            elif s_ != sign:
+                return False
+        return True
+
+    def _eval_item(self, gt_path, gt_corners, path, corners, progress):
+        """src/env.py:335-374: trajectory length, goal progress, (oracle) success, SPL of one trajectory."""
+        scores = {}
+        scores["trajectory_lengths"] = np.sum([np.linalg.norm(a - b) for a, b in zip(path[:-1], path[1:])])
+        scores["trajectory_lengths"] = scores["trajectory_lengths"] * 11.13 * 1e4
+        gt_whole_lengths = np.sum([np.linalg.norm(a - b) for a, b in zip(gt_path[:-1], gt_path[1:])]) * 11.13 * 1e4
+        gt_net_lengths = np.linalg.norm(gt_path[0] - gt_path[-1]) * 11.13 * 1e4
+        scores["iou"] = progress[-1]
+        scores["gp"] = gt_net_lengths - np.linalg.norm(path[-1] - gt_path[-1]) * 11.13 * 1e4
+        scores["oracle_gp"] = gt_net_lengths - np.min([np.linalg.norm(path[x] - gt_path[-1])
+                                                       for x in range(len(path))]) * 11.13 * 1e4
+        scores["success"] = float(progress[-1] >= 0.4)
+        if not self._contains(corners[-1], np.mean(gt_corners[-1], axis=0)):
+            scores["success"] = float(0)
+        if not self._contains(gt_corners[-1], np.mean(corners[-1], axis=0)):
+            scores["success"] = float(0)
+        scores["oracle_success"] = float(any(np.array(progress) > 0.4))
+        scores["gt_length"] = gt_whole_lengths
+        scores["spl"] = scores["success"] * gt_net_lengths / max(scores["trajectory_lengths"], gt_net_lengths, 0.01)
+        return scores
+
+    def eval_metrics(self, preds, human_att_eval=False):
+        """src/env.py:376-475: averages over the trajectories of ``preds`` (``instr_id`` -> trajectory dict as
+        the rollouts produce them: ``path_corners``, ``gt_path_corners``, ``gt_progress``, ``num_dia`` ...)."""
+        from collections import defaultdict
+        metrics = defaultdict(list)
+        if human_att_eval:
+            for k in preds.keys():
+                if "human_att_performance" in preds[k].keys():
+                    metrics["human_att_performance"] += preds[k]["human_att_performance"]
+                    nss = np.mean(preds[k]["nss"])
+                    if nss == nss:
+                        metrics["nss"].append(nss)
+            metrics["human_att_performance"] = np.mean(metrics["human_att_performance"], axis=0)
+            metrics["nss"] = np.mean(metrics["nss"])
+            if metrics["nss"] == metrics["nss"]:
+                # (the reference reports precision under both keys, src/env.py:396-398)
+                avg = {"HA_precision": metrics["human_att_performance"][0],
+                       "HA_recall": metrics["human_att_performance"][0], "nss": metrics["nss"]}
+            else:
+                avg = {"HA_precision": 0, "HA_recall": 0, "nss": 0}
+            return avg, metrics
+        for k in preds.keys():
+            item = preds[k]
+            dia_number = item.get("num_dia", 0)
+            traj = [np.mean(x[0], axis=0) for x in item["path_corners"]]
+            corners = [np.array(x[0]) for x in item["path_corners"]]
+            progress = [x for x in item["gt_progress"]]
+            gt_corners = [np.array(x) for x in item["gt_path_corners"]]
+            gt_trajs = [np.mean(x, axis=0) for x in item["gt_path_corners"]]
+            sc = self._eval_item(gt_trajs, gt_corners, traj, corners, progress)
+            for kk, v in sc.items():
+                metrics[kk].append(v)
+            tag = {1: "1", 2: "2"}.get(dia_number, "else")
+            metrics["success_" + tag].append(sc["success"])
+            metrics["spl_" + tag].append(sc["spl"])
+            metrics["gp_" + tag].append(sc["gp"])
+            tag = "long" if sc["trajectory_lengths"] > 150 else "short"
+            metrics["success_" + tag].append(sc["success"])
+            metrics["spl_" + tag].append(sc["spl"])
+            metrics["gp_" + tag].append(sc["gp"])
+            metrics["instr_id"].append(item["instr_id"])
+        avg = {"lengths": np.mean(metrics["trajectory_lengths"]), "sr": np.mean(metrics["success"]) * 100,
+               "oracle_sr": np.mean(metrics["oracle_success"]) * 100, "spl": np.mean(metrics["spl"]) * 100,
+               "gp": np.mean(metrics["gp"]), "oracle_gp": np.mean(metrics["oracle_gp"]),
+               "gt_length": np.mean(metrics["gt_length"]), "iou": np.mean(metrics["iou"])}
+        for tag in ("1", "2", "else"):
+            if len(metrics["success_" + tag]) != 0:
+                avg["num_" + tag] = len(metrics["success_" + tag])
+                avg["spl_" + tag] = np.mean(metrics["spl_" + tag]) * 100
+                avg["sr_" + tag] = np.mean(metrics["success_" + tag]) * 100
+                avg["gp_" + tag] = np.mean(metrics["gp_" + tag])
+        return avg, metrics
+
     def _sync_maps(self):
         for name in list(self._uploaded):
             if name not in self.map_batch and name not in self._device_maps:

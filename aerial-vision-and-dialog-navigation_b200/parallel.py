@@ -45,3 +45,44 @@ def broadcast_(tensors, src=0, group=None):
     import torch.distributed as dist
     for t in tensors:
         dist.broadcast(t, src, group=group)
+
+
+# ---- result merging of multi-GPU evaluation (src/utils/distributed.py:90-164) ----
+def get_world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def all_gather(data, group=None):
+    """``all_gather`` of arbitrary picklable data (the per-rank trajectory dicts of ``agent.test``): returns
+    the list of every rank's object, in rank order (src/utils/distributed.py:90-130)."""
+    import torch.distributed as dist
+    world = get_world_size()
+    if world == 1:
+        return [data]
+    out = [None] * world
+    dist.all_gather_object(out, data, group=group)
+    return out
+
+
+def merge_dist_results(results):
+    """src/utils/distributed.py:160-164: concatenate the per-rank result lists."""
+    outs = []
+    for res in results:
+        outs.extend(res)
+    return outs
+
+
+def reduce_dict(input_dict, average=True, group=None):
+    """src/utils/distributed.py:133-157: sum (or average) a dict of scalar tensors over the ranks."""
+    import torch.distributed as dist
+    world = get_world_size()
+    if world < 2:
+        return input_dict
+    with torch.no_grad():
+        names = sorted(input_dict.keys())
+        values = torch.stack([input_dict[k] for k in names], dim=0)
+        dist.all_reduce(values, group=group)
+        if average:
+            values /= world
+        return {k: v for k, v in zip(names, values)}
