@@ -106,7 +106,8 @@ _SIGNATURES = {
     "avdn_waypoint_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_f32, c_int, c_void_p, c_void_p,
                            c_void_p, c_void_p],
     # ---- agent slice
-    "avdn_teacher_action": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "avdn_teacher_action": [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                            c_void_p],
     "avdn_loss": [c_void_p] * 7 + [c_int, c_f32, c_int, c_f64] + [c_void_p] * 4 + [c_void_p],
     "avdn_upsample_saliency": [c_void_p, c_int, c_void_p, c_void_p],
     "avdn_upsample_saliency_bwd": [c_void_p, c_int, c_void_p, c_void_p],

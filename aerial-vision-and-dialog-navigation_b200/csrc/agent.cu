@@ -256,7 +256,7 @@ __device__ double quad_iou(const P2* a, const P2* b) {
 
 __global__ void teacher_action_kernel(const double* __restrict__ corners, const double* __restrict__ gt, int pmax,
                                       const int32_t* __restrict__ gt_len, const uint8_t* __restrict__ ended, int B,
-                                      float* __restrict__ ratio, float* __restrict__ altitude,
+                                      int teacher_feedback, float* __restrict__ ratio, float* __restrict__ altitude,
                                       float* __restrict__ progress) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
@@ -292,15 +292,56 @@ __global__ void teacher_action_kernel(const double* __restrict__ corners, const 
   P2 poly[4];
   const bool ccw = poly_area(c, 4) >= 0;
   for (int k = 0; k < 4; ++k) poly[k] = ccw ? c[k] : c[3 - k];
-  double t_exit = 1.0;
-  for (int k = 0; k < 4; ++k) {
-    const P2 a = poly[k], b = poly[(k + 1) & 3];
-    const double ex = b.x - a.x, ey = b.y - a.y;
-    const double s0 = ex * (cur.y - a.y) - ey * (cur.x - a.x);
-    const double s1 = ex * (goal.y - a.y) - ey * (goal.x - a.x);
-    if (s1 < 0 && s0 >= 0) t_exit = fmin(t_exit, s0 / (s0 - s1));
+  double xx = 0.0, xy = 0.0;
+  bool found = false;
+  if (teacher_feedback) {
+    // the point of (ground-truth path  intersected with  view) closest to the goal (agent.py:441-466): the end
+    // points of the clipped path segments (Cyrus-Beck) are the boundary crossings and the path vertices inside
+    double best = 1.0;
+    P2 p;
+    {
+      const double* q0 = gt + (size_t)i * pmax * 8;
+      p.x = (((q0[0] + q0[2]) + q0[4]) + q0[6]) / 4.0; p.y = (((q0[1] + q0[3]) + q0[5]) + q0[7]) / 4.0;
+    }
+    for (int j = 1; j < n; ++j) {
+      const double* q1 = gt + ((size_t)i * pmax + j) * 8;
+      P2 q;
+      q.x = (((q1[0] + q1[2]) + q1[4]) + q1[6]) / 4.0; q.y = (((q1[1] + q1[3]) + q1[5]) + q1[7]) / 4.0;
+      double t0 = 0.0, t1 = 1.0;
+      bool miss = false;
+      const double dx = q.x - p.x, dy = q.y - p.y;
+      for (int k = 0; k < 4 && !miss; ++k) {
+        const P2 a = poly[k], b = poly[(k + 1) & 3];
+        const double ex = b.x - a.x, ey = b.y - a.y;
+        const double s0 = ex * (p.y - a.y) - ey * (p.x - a.x);
+        const double ds = ex * dy - ey * dx;
+        if (ds == 0.0) { if (s0 < 0) miss = true; continue; }
+        const double t = -s0 / ds;
+        if (ds > 0) t0 = fmax(t0, t); else t1 = fmin(t1, t);
+      }
+      if (!miss && t0 <= t1) {
+        const double tt[2] = {t0, t1};
+        for (int e = 0; e < 2; ++e) {
+          const double cx = p.x + tt[e] * dx, cy = p.y + tt[e] * dy;
+          const double dist = sqrt((cx - goal.x) * (cx - goal.x) + (cy - goal.y) * (cy - goal.y));
+          if (dist < best) { best = dist; xx = cx; xy = cy; found = true; }
+        }
+      }
+      p = q;
+    }
   }
-  const double xx = cur.x + t_exit * (goal.x - cur.x), xy = cur.y + t_exit * (goal.y - cur.y);
+  if (!found) {
+    double t_exit = 1.0;
+    for (int k = 0; k < 4; ++k) {
+      const P2 a = poly[k], b = poly[(k + 1) & 3];
+      const double ex = b.x - a.x, ey = b.y - a.y;
+      const double s0 = ex * (cur.y - a.y) - ey * (cur.x - a.x);
+      const double s1 = ex * (goal.y - a.y) - ey * (goal.x - a.x);
+      if (s1 < 0 && s0 >= 0) t_exit = fmin(t_exit, s0 / (s0 - s1));
+    }
+    xx = cur.x + t_exit * (goal.x - cur.x);
+    xy = cur.y + t_exit * (goal.y - cur.y);
+  }
   // local frame of the view (agent.py:481-487): integer-rounded half-edge vectors, 2x2 solve with partial pivoting
   const double b0 = 1e5 * (xx - cur.x), b1 = 1e5 * (xy - cur.y);
   const double ny0 = rint(1e5 * ((c[0].x + c[1].x) / 2 - cur.x)), ny1 = rint(1e5 * ((c[0].y + c[1].y) / 2 - cur.y));
@@ -426,13 +467,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 }  // namespace
 
 extern "C" int avdn_teacher_action(const double* corners, const double* gt_path_corners, int pmax, const int32_t* gt_len,
-                                   const uint8_t* ended, int B, float* next_pos_ratio, float* altitude, float* progress,
-                                   avdn_stream_t stream) {
+                                   const uint8_t* ended, int B, int teacher_feedback, float* next_pos_ratio,
+                                   float* altitude, float* progress, avdn_stream_t stream) {
   AVDN_REQUIRE(corners && gt_path_corners && gt_len && ended && next_pos_ratio && altitude && progress && pmax >= 1,
                "avdn_teacher_action: bad argument");
   if (B <= 0) return AVDN_OK;
   teacher_action_kernel<<<(B + 63) / 64, 64, 0, avdn::to_cuda(stream)>>>(corners, gt_path_corners, pmax, gt_len, ended, B,
-                                                                       next_pos_ratio, altitude, progress);
+                                                                       teacher_feedback, next_pos_ratio, altitude,
+                                                                       progress);
   return avdn::check_launch("avdn_teacher_action");
 }
 

@@ -414,8 +414,9 @@ class NavCMTAgent:
             out.append(path)
         return out
 
-    def teacher_action(self, corners, gt_path_corners, ended):
-        """``teacher_action`` with student feedback (agent.py:386-507) for the whole batch on the device.
+    def teacher_action(self, corners, gt_path_corners, ended, feedback=None):
+        """``teacher_action`` (agent.py:386-507) for the whole batch on the device; ``feedback`` 'student' /
+        'teacher' (default ``self.feedback`` or 'student').
         ``corners`` [B,4,2] f64 (lat,lng); ``gt_path_corners``: list (len B) of ``[n_i,4,2]`` arrays or a padded
         ``[B,Pmax,4,2]`` tensor with ``gt_len``; ``ended`` [B].  Returns device tensors
         ``(next_pos_ratio [B,2] f32, altitude [B] f32, progress [B] f32)`` -- the targets of ``output[:,0:2]``,
@@ -440,8 +441,11 @@ class NavCMTAgent:
         ratio = torch.empty((B, 2), dtype=torch.float32, device=dev)
         alt = torch.empty(B, dtype=torch.float32, device=dev)
         prog = torch.empty(B, dtype=torch.float32, device=dev)
+        fb = feedback if feedback is not None else getattr(self, "feedback", "student")
+        if fb not in ("student", "teacher"):
+            raise ValueError("Invalid feedback option")
         _lib.call("avdn_teacher_action", _lib.ptr(c), _lib.ptr(gt_t), int(pmax), _lib.ptr(len_t), _lib.ptr(e), B,
-                  _lib.ptr(ratio), _lib.ptr(alt), _lib.ptr(prog))
+                  int(fb == "teacher"), _lib.ptr(ratio), _lib.ptr(alt), _lib.ptr(prog))
         self.launches += 1
         return ratio, alt, prog
 

@@ -455,14 +455,17 @@ int avdn_heads_bwd(const float* x, int B, int S, int row_vis, int row_dir, const
  * ---------------------------------------------------------------------- */
 
 /* Supervision geometry of the training rollout: compute_iou (src/xview_et/agent.py:46-78) and
- * teacher_action with student feedback (agent.py:386-507), evaluated by the reference with shapely per sample.
+ * teacher_action (agent.py:386-507), evaluated by the reference with shapely per sample.  teacher_feedback = 0
+ * (self.feedback == 'student'): the target is where the segment view centre -> goal centre leaves the view;
+ * 1 ('teacher'): the point of (ground-truth path intersected with the view) closest to the goal, with the student
+ * rule as the fallback when the path misses the view (agent.py:451-456).
  *   corners [B,4,2] f64 (lat,lng) current view; gt_path_corners [B,pmax,4,2] f64 with gt_len[b] valid steps;
  *   ended [B] u8  ->  next_pos_ratio [B,2] f32 (target of output[:,0:2]; zero when ended or progress > 0.5),
  *   altitude [B] f32 (teacher_a[i][1]), progress [B] f32 = IoU with the last ground-truth view, where the
  *   reference's "IoU" is intersection area / area of the convex hull of the eight corners.                      */
 int avdn_teacher_action(const double* corners, const double* gt_path_corners, int pmax, const int32_t* gt_len,
-                        const uint8_t* ended, int B, float* next_pos_ratio, float* altitude, float* progress,
-                        avdn_stream_t stream);
+                        const uint8_t* ended, int B, int teacher_feedback, float* next_pos_ratio, float* altitude,
+                        float* progress, avdn_stream_t stream);
 
 /* Per-step loss and its gradient in one kernel (agent.py:663-681,883-885):
  *   loss_i = |p_xy-g_xy|^2 + (ang(p)-ang(g))^2 + (alt-g_alt)^2 + (prog-g_prog)^2

@@ -106,9 +106,47 @@ def segment_exit(poly, cur, goal):
     return cur + t_exit * d
 
 
-def teacher_action(corners, gt_path_corners, ended):
-    """agent.py:386-507 with ``self.feedback == 'student'`` for ONE sample.  corners [4,2] (lat, lng),
-    gt_path_corners [n,4,2].  Returns (next_pos_ratio float32 [2], altitude float, progress float32)."""
+def clip_segment(poly, p, q):
+    """The part of the segment p -> q inside the convex polygon: (a, b) or None (Cyrus-Beck)."""
+    poly = _ccw(np.asarray(poly, dtype=np.float64))
+    t0, t1 = 0.0, 1.0
+    d = q - p
+    for i in range(len(poly)):
+        a, b = poly[i], poly[(i + 1) % len(poly)]
+        e = b - a
+        s0 = e[0] * (p[1] - a[1]) - e[1] * (p[0] - a[0])
+        ds = e[0] * d[1] - e[1] * d[0]                    # d(side)/dt
+        if ds == 0:
+            if s0 < 0:
+                return None
+            continue
+        t = -s0 / ds
+        if ds > 0:
+            t0 = max(t0, t)                               # entering
+        else:
+            t1 = min(t1, t)                               # leaving
+    if t0 > t1:
+        return None
+    return p + t0 * d, p + t1 * d
+
+
+def path_candidates(poly, line):
+    """Coordinates of ``Polygon(poly).intersection(LineString(line))`` (agent.py:441-449): for a convex polygon the
+    union of the clipped segments -- their end points are the boundary crossings and the polyline vertices inside."""
+    out = []
+    for p, q in zip(line[:-1], line[1:]):
+        c = clip_segment(poly, np.asarray(p, dtype=np.float64), np.asarray(q, dtype=np.float64))
+        if c is not None:
+            out += [c[0], c[1]]
+    return out
+
+
+def teacher_action(corners, gt_path_corners, ended, feedback="student"):
+    """agent.py:386-507 for ONE sample.  corners [4,2] (lat, lng), gt_path_corners [n,4,2].
+    ``feedback == 'student'``: the target is where the segment view centre -> goal centre leaves the view (the goal
+    itself if it is inside); ``'teacher'``: the point of (ground-truth path ∩ view) closest to the goal, falling back
+    to the student rule when the path misses the view (agent.py:451-456).
+    Returns (next_pos_ratio float32 [2], altitude float, progress float32)."""
     corners = np.asarray(corners, dtype=np.float64)
     gt = np.asarray(gt_path_corners, dtype=np.float64)
     cur = np.mean(corners, axis=0)
@@ -122,7 +160,15 @@ def teacher_action(corners, gt_path_corners, ended):
     if ended or progress > 0.5:
         return np.array([0, 0], dtype=np.float32), altitude, progress
     goal = np.mean(gt[-1], axis=0)
-    x = segment_exit(corners, cur, goal)                  # the coords of the intersection closest to the goal
+    x = None
+    if feedback == "teacher":
+        best = 1.0                                         # min_distance = 1 (agent.py:461)
+        for c in path_candidates(corners, [np.mean(g, axis=0) for g in gt]):
+            dist = np.linalg.norm(c - goal)
+            if dist < best:
+                best, x = dist, c
+    if x is None:
+        x = segment_exit(corners, cur, goal)              # the coords of the intersection closest to the goal
     net_next = 1e5 * (x - cur)
     net_y = np.round(1e5 * ((corners[0] + corners[1]) / 2 - cur)).astype(np.int64)
     net_x = np.round(1e5 * ((corners[1] + corners[2]) / 2 - cur)).astype(np.int64)

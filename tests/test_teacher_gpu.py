@@ -15,7 +15,8 @@ def _quad(rng, c, side, th=None):
     return c + (np.array([[1, -1], [1, 1], [-1, 1], [-1, -1]]) * side / 2) @ R.T
 
 
-def test_teacher_action_kernel_vs_oracle(built_lib):
+@pytest.mark.parametrize("feedback", ["student", "teacher"])
+def test_teacher_action_kernel_vs_oracle(built_lib, feedback):
     from avdn_b200 import _lib
     rng = np.random.default_rng(0)
     B, pmax = 512, 7
@@ -42,12 +43,12 @@ def test_teacher_action_kernel_vs_oracle(built_lib):
     ptr = _lib.ptr
     args = (torch.from_numpy(corners).to(d), torch.from_numpy(gt).to(d), torch.from_numpy(lens.astype(np.int32)).to(d),
             torch.from_numpy(ended.astype(np.uint8)).to(d))
-    _lib.call("avdn_teacher_action", ptr(args[0]), ptr(args[1]), pmax, ptr(args[2]), ptr(args[3]), B, ptr(ratio), ptr(alt),
-              ptr(prog))
+    _lib.call("avdn_teacher_action", ptr(args[0]), ptr(args[1]), pmax, ptr(args[2]), ptr(args[3]), B,
+              int(feedback == "teacher"), ptr(ratio), ptr(alt), ptr(prog))
     ratio, alt, prog = ratio.cpu().numpy(), alt.cpu().numpy(), prog.cpu().numpy()
     n_zero = n_inside = 0
     for i in range(B):
-        r, a, p = to.teacher_action(corners[i], gt[i, :lens[i]], bool(ended[i]))
+        r, a, p = to.teacher_action(corners[i], gt[i, :lens[i]], bool(ended[i]), feedback=feedback)
         assert abs(prog[i] - p) <= 1e-6 * max(1.0, abs(p)) + 1e-7, (i, prog[i], p)
         assert abs(alt[i] - a) <= 1e-5 * max(1.0, abs(a)), (i, alt[i], a)
         np.testing.assert_allclose(ratio[i], r, rtol=1e-5, atol=1e-6, err_msg=str(i))
@@ -70,8 +71,8 @@ def test_agent_teacher_action_api(built_lib):
     base = np.array([40.01, -74.99])
     corners = [_quad(rng, base, 0.003) for _ in range(3)]
     paths = [[_quad(rng, base + rng.uniform(-0.004, 0.004, 2), 0.002) for _ in range(n)] for n in (1, 4, 2)]
-    ratio, alt, prog = agent.teacher_action(corners, paths, [False, False, True])
+    ratio, alt, prog = agent.teacher_action(corners, paths, [False, False, True], feedback="teacher")
     for i in range(3):
-        r, a, p = to.teacher_action(corners[i], paths[i], i == 2)
+        r, a, p = to.teacher_action(corners[i], paths[i], i == 2, feedback="teacher")
         np.testing.assert_allclose(ratio[i].cpu().numpy(), r, rtol=1e-5, atol=1e-6)
         assert abs(float(alt[i]) - a) < 1e-4 and abs(float(prog[i]) - p) < 1e-6

@@ -69,3 +69,33 @@ def test_teacher_action_semantics():
     r3, _, _ = to.teacher_action(q, [q, far], ended=True)
     assert np.all(r3 == 0)
     assert abs(alt - (np.linalg.norm(q[0] - q[1]) * 11.13e4 - 40) / 360) < 1e-9
+
+
+def test_clip_segment_and_teacher_feedback():
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        q = _quad(rng)
+        p0, p1 = rng.uniform(-2, 2, 2), rng.uniform(-2, 2, 2)
+        c = to.clip_segment(q, p0, p1)
+        ts = np.linspace(0, 1, 2001)
+        inside = np.array([to.inside_convex(q, p0 + t * (p1 - p0)) for t in ts])
+        if c is None:
+            assert inside.sum() <= 1
+            continue
+        a, b = c
+        ta, tb = np.dot(a - p0, p1 - p0) / np.dot(p1 - p0, p1 - p0), np.dot(b - p0, p1 - p0) / np.dot(p1 - p0, p1 - p0)
+        if inside.any():
+            assert abs(ts[inside].min() - ta) < 1e-3 and abs(ts[inside].max() - tb) < 1e-3
+    # teacher feedback: the path crosses the view; the target is the crossing nearest to the goal
+    base = np.array([40.01, -74.99])
+    view = base + _quad(rng, c=np.zeros(2), size=(0.004, 0.004))
+    g0 = view - np.array([0.006, 0.0])
+    g1 = view + np.array([0.006, 0.001])
+    rt, _, _ = to.teacher_action(view, [g0, g1], ended=False, feedback="teacher")
+    rs, _, _ = to.teacher_action(view, [g0, g1], ended=False, feedback="student")
+    assert np.max(np.abs(rt)) <= 1 + 1e-6 and np.max(np.abs(rs)) <= 1 + 1e-6
+    # a path that misses the view falls back to the student rule
+    far0, far1 = view + np.array([0.02, 0.02]), view + np.array([0.03, 0.02])
+    ft, _, _ = to.teacher_action(view, [far0, far1], ended=False, feedback="teacher")
+    fs, _, _ = to.teacher_action(view, [far0, far1], ended=False, feedback="student")
+    assert np.array_equal(ft, fs)
