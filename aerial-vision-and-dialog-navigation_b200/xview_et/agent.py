@@ -541,14 +541,20 @@ class NavCMTAgent:
         return np.array(moved), (cur + angle) % 360
 
     # ------------------------------------------------------------- checkpoints
+    def _checkpoint_items(self):
+        items = [("vision_model", self.vision_model, self.vision_model_optimizer),
+                 ("vln_model", self.vln_model, self.et_optimizer)]
+        if self.lang_model is not None:
+            items.insert(0, ("lang_model", self.lang_model, self.lang_optimizer))
+        return items
+
     def save(self, epoch, path):
-        """agent.py:899-916 (vision_model and vln_model; lang_model is outside the path)."""
+        """agent.py:899-916: vision_model, vln_model and (when attached) lang_model."""
         d = os.path.dirname(path)
         if d:
             os.makedirs(d, exist_ok=True)
         states = {}
-        for name, model, opt in (("vision_model", self.vision_model, self.vision_model_optimizer),
-                                 ("vln_model", self.vln_model, self.et_optimizer)):
+        for name, model, opt in self._checkpoint_items():
             states[name] = {"epoch": epoch + 1, "state_dict": model.state_dict(),
                             "optimizer": {"m": opt.m.clone(), "v": opt.v.clone(), "step": opt.step_count}}
         torch.save(states, path)
@@ -556,8 +562,7 @@ class NavCMTAgent:
     def load(self, path):
         """agent.py:918-940: parameters (and optimiser moments when ``args.resume_optimizer``)."""
         states = torch.load(path, map_location=self.device)
-        for name, model, opt in (("vision_model", self.vision_model, self.vision_model_optimizer),
-                                 ("vln_model", self.vln_model, self.et_optimizer)):
+        for name, model, opt in self._checkpoint_items():
             if name not in states:
                 continue
             state = model.state_dict()

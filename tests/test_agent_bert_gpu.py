@@ -79,3 +79,37 @@ def test_train_step_with_language_encoder(built_lib):
         opt.lr = 1e-4
     losses = [agent.train_step(batch, sync_loss=True) for _ in range(8)]
     assert np.isfinite(losses).all() and losses[-1] < ours, (ours, losses)
+
+
+def test_save_and_load_round_trip(built_lib, tmp_path):
+    """agent.py:899-940: a checkpoint restores every model (trunk, ET, attached language model) in place --
+    the parameters live in the optimiser arenas -- and, with ``resume_optimizer``, the AdamW moments."""
+    from transformers import BertConfig
+    from avdn_b200.models.bert import CustomBERTModel
+    from avdn_b200.xview_et.agent import NavCMTAgent
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(mo.tiny_trunk_cfg())
+    args = types.SimpleNamespace(demb=768, encoder_heads=12, encoder_layers=2, dropout_transformer_encoder=0.1,
+                                 num_input_actions=1, dropout_emb=0.0, darknet_model_file=f.name, darknet_weight_file=None,
+                                 lr=1e-5, resume_optimizer=True)
+    torch.manual_seed(0)
+    agent = NavCMTAgent(args, device="cuda")
+    os.unlink(f.name)
+    agent.attach_lang_model(CustomBERTModel(BertConfig(num_hidden_layers=1, vocab_size=50)))
+    for opt in agent.optimizers:
+        opt.m.normal_(); opt.v.uniform_(); opt.step_count = 7
+    ref = [{n: p.detach().clone() for n, p in opt.params.items()} for opt in agent.optimizers]
+    ref_m = [opt.m.clone() for opt in agent.optimizers]
+    path = str(tmp_path / "ckpt" / "latest.pt")
+    agent.save(4, path)
+    for opt in agent.optimizers:
+        opt.p.add_(1.0); opt.m.zero_(); opt.step_count = 0
+    assert agent.load(path) == 4
+    for opt, p0, m0 in zip(agent.optimizers, ref, ref_m):
+        for n, p in opt.params.items():                  # (the arena also holds alignment padding between tensors)
+            assert torch.equal(p.detach(), p0[n]), n
+        assert torch.equal(opt.m, m0) and opt.step_count == 7
+    # the modules still read the arenas (load copied in place)
+    w = agent.lang_model.linears[0].weight
+    assert w.data_ptr() >= agent.lang_optimizer.p.data_ptr()
+    assert w.data_ptr() < agent.lang_optimizer.p.data_ptr() + agent.lang_optimizer.p.numel() * 4
