@@ -263,6 +263,10 @@ __global__ void teacher_action_kernel(const double* __restrict__ corners, const 
   P2 c[4], g[4];
   for (int k = 0; k < 4; ++k) { c[k].x = corners[(i * 4 + k) * 2]; c[k].y = corners[(i * 4 + k) * 2 + 1]; }
   const int n = gt_len[i];
+  if (n < 1 || n > pmax) {                       // no ground-truth path: nothing to supervise
+    ratio[2 * i] = 0.f; ratio[2 * i + 1] = 0.f; altitude[i] = 0.f; progress[i] = 0.f;
+    return;
+  }
   const double* gl = gt + ((size_t)i * pmax + (n - 1)) * 8;
   for (int k = 0; k < 4; ++k) { g[k].x = gl[2 * k]; g[k].y = gl[2 * k + 1]; }
   P2 cur;
