@@ -414,6 +414,55 @@ class NavCMTAgent:
             out.append(path)
         return out
 
+    def test(self, batches, env_name="no_name_provided", feedback="student", **kwargs):
+        """``agent.test`` (agent.py:191-206): greedy rollouts over ``batches`` in eval mode, one trajectory dict per
+        episode in ``self.results[instr_id]`` -- the structure ``ANDHNavBatch.eval_metrics`` scores.
+
+        Every batch is the ``rollout_greedy`` input dict plus host metadata: ``instr_id`` list[str],
+        ``gt_path_corners`` list of ``[n_i,4,2]`` arrays (optional: without it ``gt_progress`` is omitted, as for
+        the unseen test split, agent.py:655) and ``num_dia`` list[int] (optional).  ``gt_progress`` is the
+        reference's per-step IoU of the current view with the goal (``teacher_action``'s progress, agent.py:660,
+        721), evaluated for all steps of the batch in one ``avdn_teacher_action`` launch."""
+        self.feedback, self.env_name = feedback, env_name
+        self.results, self.losses = {}, []
+        for batch in batches:
+            meta = {k: batch[k] for k in ("instr_id", "gt_path_corners", "num_dia") if k in batch}
+            res = self.rollout_greedy({k: v for k, v in batch.items() if k not in meta}, **kwargs)
+            steps = int(res["steps"])
+            corners = res["corners"]                                       # [T+1,B,4,2]
+            B = corners.shape[1]
+            ended = res["ended"].cpu().numpy().astype(bool)
+            prog = None
+            gts = meta.get("gt_path_corners")
+            if gts is not None:
+                flat = corners[:steps].reshape(steps * B, 4, 2)
+                _, _, pr = self.teacher_action(flat, [gts[i % B] for i in range(steps * B)],
+                                               np.zeros(steps * B, dtype=np.uint8), feedback="student")
+                prog = pr.view(steps, B).cpu().numpy()
+            c_host = corners.cpu().numpy()
+            d_host = res["directions"].cpu().numpy()
+            out_host = res["output"].cpu().numpy()
+            for i in range(B):
+                traj = {"instr_id": meta["instr_id"][i] if "instr_id" in meta else f"{env_name}_{len(self.results)}",
+                        "path_corners": [(c_host[0, i], d_host[0, i])], "actions": [], "progress": []}
+                if "num_dia" in meta:
+                    traj["num_dia"] = int(meta["num_dia"][i])
+                if gts is not None:
+                    traj["gt_path_corners"] = gts[i]
+                    traj["gt_progress"] = []
+                alive = True
+                for t in range(steps):
+                    if alive:                                              # logged while the episode has not ended
+                        traj["actions"].append(out_host[t, i, :3].copy())
+                        traj["progress"].append(float(out_host[t, i, 3]))
+                        if prog is not None:
+                            traj["gt_progress"].append(float(prog[t, i]))
+                    alive = not ended[t, i]
+                    if alive:
+                        traj["path_corners"].append((c_host[t + 1, i], d_host[t + 1, i]))
+                self.results[traj["instr_id"]] = traj
+        return self.results
+
     def teacher_action(self, corners, gt_path_corners, ended, feedback=None):
         """``teacher_action`` (agent.py:386-507) for the whole batch on the device; ``feedback`` 'student' /
         'teacher' (default ``self.feedback`` or 'student').

@@ -157,3 +157,41 @@ def test_incremental_rollout_matches_full_recompute(agent):
     full = agent.rollout_greedy(batch, max_action_len=T, stop_threshold=2.0, incremental=False)
     assert inc["steps"] == full["steps"] == T
     assert _rel(inc["output"][0], full["output"][0]) < 1e-6      # step 0 is the same computation
+
+
+def test_agent_test_produces_scorable_trajectories(agent):
+    """agent.test -> trajectory dicts -> ANDHNavBatch.eval_metrics (inference, supervision geometry and the
+    evaluation glue end to end)."""
+    from avdn_b200.env import ANDHNavBatch
+    from oracle import teacher_oracle as to
+    B, T, L = 4, 5, 12
+    size = 1024
+    lat_ratio = 0.02 / size
+    geo = np.tile(np.array([40.0, -75.0, 40.02, -74.98, lat_ratio]), (B, 1))
+    corners, dirs, _ = _poses(B, 3)
+    g = torch.Generator().manual_seed(2)
+    rng = np.random.default_rng(9)
+    gts = []
+    for i in range(B):
+        path = [corners[i]]
+        for _ in range(int(rng.integers(1, 4))):
+            path.append(path[-1] + rng.uniform(-0.001, 0.001, 2))
+        gts.append(np.stack(path))
+    batch = dict(corners_gps=torch.from_numpy(corners).cuda(), directions=torch.from_numpy(dirs).cuda(),
+                 geo=torch.from_numpy(geo).cuda(), tile_idx=None, lang=torch.randn(B, L, 768, generator=g).cuda(),
+                 lang_cls=torch.relu(torch.randn(B, 49, generator=g)).cuda(),
+                 instr_id=[f"ep{i}" for i in range(B)], gt_path_corners=gts, num_dia=[1, 2, 3, 1])
+    results = agent.test([batch], env_name="val_seen", max_action_len=T)
+    assert sorted(results) == [f"ep{i}" for i in range(B)]
+    for i in range(B):
+        tr = results[f"ep{i}"]
+        n = len(tr["gt_progress"])
+        assert 1 <= n <= T and len(tr["actions"]) == n and len(tr["progress"]) == n
+        assert len(tr["path_corners"]) in (n, n + 1) and np.array_equal(tr["path_corners"][0][0], corners[i])
+        for k in range(min(n, len(tr["path_corners"]))):
+            ref = to.compute_iou(tr["path_corners"][k][0], gts[i][-1])
+            assert abs(tr["gt_progress"][k] - ref) < 1e-5, (i, k)
+    env = ANDHNavBatch.__new__(ANDHNavBatch)
+    avg, metrics = env.eval_metrics(results)
+    assert set(("sr", "spl", "gp", "iou", "lengths")) <= set(avg) and len(metrics["instr_id"]) == B
+    assert all(np.isfinite(float(v)) for v in avg.values())
