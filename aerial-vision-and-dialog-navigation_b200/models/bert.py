@@ -353,8 +353,9 @@ class CustomBERTModel(nn.Module):
     def used_parameters(self):
         return {n: p for n, p in self.named_parameters()}
 
-    def engine(self, B, S, device):
-        key = (B, S, str(device))
+    def engine(self, B, S, device, slot=0):
+        """``slot`` separates engines of equal shape whose activations must coexist (the two passes of one rollout)."""
+        key = (B, S, str(device), slot)
         e = self._engines.get(key)
         if e is None:
             c = self.bert.config

@@ -97,7 +97,9 @@ class NavCMTAgent:
     # ------------------------------------------------------------ distributed
     def attach_lang_model(self, lang_model=None, lr=None):
         """Put ``CustomBERTModel`` into the training loop (src/xview_et/agent.py:125-126,155,249): ``train_step``
-        then takes ``input_ids`` / ``attention_mask`` instead of ``lang`` / ``lang_cls``, and the gradients of both
+        then takes ``input_ids`` / ``attention_mask`` (and optionally ``cls_input_ids`` / ``cls_attention_mask``: the
+        reference's second pass over pre_dialogs + instructions that produces ``linear_cls``, agent.py:530-538)
+        instead of ``lang`` / ``lang_cls``, and the gradients of both
         flow back into BERT and its head (one encoder pass per step = the reference's ``train_val_on_full`` mode,
         agent.py:530-538)."""
         from ..models.bert import CustomBERTModel
@@ -169,8 +171,18 @@ class NavCMTAgent:
             l0l = leng.launches
             seq, lin, _ = leng.forward(ids.long(), am)
             self.launches += leng.launches - l0l
-            batch = dict(batch, lang=seq, lang_cls=lin)
             self._lang_eng = leng
+            self._lang_eng_cls = None
+            if "cls_input_ids" in batch:
+                # agent.py:530-538: ``linear_cls`` comes from a second pass over pre_dialogs + instructions
+                ids2, am2 = batch["cls_input_ids"], batch["cls_attention_mask"]
+                leng2 = lm.engine(ids2.shape[0], ids2.shape[1], self.device, slot=1)
+                leng2.set_dropout(*lm.dropout_config())
+                l0l = leng2.launches
+                _, lin, _ = leng2.forward(ids2.long(), am2)
+                self.launches += leng2.launches - l0l
+                self._lang_eng_cls = leng2
+            batch = dict(batch, lang=seq, lang_cls=lin)
         lang, lang_cls, dirs = batch["lang"], batch["lang_cls"], batch["directions"]
         B, T = dirs.shape[0], dirs.shape[1]
         L = lang.shape[1]
@@ -247,8 +259,15 @@ class NavCMTAgent:
             d_cls = torch.zeros((eng.B, 49), dtype=torch.float32, device=self.device)
             _, d_lang = eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=bufs["d_frames"], need_lang_grad=True,
                                      d_lang_cls=d_cls)
+            leng2 = self._lang_eng_cls
             l0l = leng.launches
-            leng.backward(d_lang, d_cls, None)
+            if leng2 is None:
+                leng.backward(d_lang, d_cls, None)
+            else:                          # both passes accumulate into the one gradient arena
+                leng.backward(d_lang, None, None)
+                l1 = leng2.launches
+                leng2.backward(None, d_cls, None)
+                self.launches += leng2.launches - l1
             self.launches += leng.launches - l0l
         dp = self.world > 1
         if dp:

@@ -21,7 +21,10 @@ def _rel2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def test_train_step_with_language_encoder(built_lib):
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_train_step_with_language_encoder(built_lib, two_pass):
+    """``two_pass``: ``linear_cls`` from the reference's second BERT pass over pre_dialogs + instructions
+    (agent.py:530-538; same sequence length on purpose, so the two passes need separate activation slots)."""
     from transformers import BertConfig
     from avdn_b200.models.bert import CustomBERTModel
     from avdn_b200.xview_et.agent import NavCMTAgent
@@ -52,14 +55,33 @@ def test_train_step_with_language_encoder(built_lib):
     hb = dict(input_ids=ids, attention_mask=mask, directions=dirs, images=images.bfloat16(), att=torch.from_numpy(att),
               gt_xy=torch.rand(B, 2, generator=g) * 2 - 1, gt_alt=torch.rand(B, generator=g),
               gt_prog=torch.rand(B, generator=g), lenths=[T, T - 1])
+    sd_b = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in lm.state_dict().items()
+            if "position_ids" not in k}
+    ids2, mask2 = ids, mask
+    if two_pass:
+        mask2 = torch.ones(B, S, dtype=torch.long)
+        mask2[0, 9:] = 0
+        # the draw is chosen so that no ReLU of the 49-way head sits within bf16 noise of its kink: one flipped unit
+        # out of ~40 active ones moves the head gradients by tens of percent (seen: 26 %)
+        for seed in range(5, 40):
+            ids2 = torch.randint(0, V, (B, S), generator=torch.Generator().manual_seed(seed))
+            with torch.no_grad():
+                _, _, pooled = bo.custom_bert_forward(sd_b, ids2, mask2)
+                pre1 = pooled @ sd_b["linears.0.weight"].T + sd_b["linears.0.bias"]
+                pre3 = torch.relu(pre1) @ sd_b["linears.3.weight"].T + sd_b["linears.3.bias"]
+            if min(float(pre1.abs().min()), float(pre3.abs().min())) > 5e-4:
+                break
+        else:
+            pytest.skip("no well-conditioned draw")
+        hb.update(cls_input_ids=ids2, cls_attention_mask=mask2)
     batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in hb.items()}
     ours = agent.train_step(batch, sync_loss=True)
     frames = agent._ctx[2]["frames"].detach().cpu().view(B, T, 512, 49)
     # ---- oracle on the same weights, teacher-forced on our trunk features ----
-    sd_b = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in lm.state_dict().items()
-            if "position_ids" not in k}
     sd_e = {k: v.detach().cpu().clone() for k, v in agent.vln_model.state_dict().items()}
     seq, lin, _ = bo.custom_bert_forward(sd_b, ids, mask)
+    if two_pass:
+        _, lin, _ = bo.custom_bert_forward(sd_b, ids2, mask2)
     out, sal, _ = mo.et_forward(sd_e, dirs, frames, hb["lenths"], seq, lin)
     gt_sal = torch.from_numpy(att.astype(np.float64) / 255)
     loss = mo.step_loss(mo.et_loss(out, sal, hb["gt_xy"], hb["gt_alt"], hb["gt_prog"], gt_sal, 0.1), 0.2, B)
@@ -72,8 +94,8 @@ def test_train_step_with_language_encoder(built_lib):
               "bert.pooler.dense.weight", "linears.0.weight", "linears.3.weight", "linears.3.bias"):
         report[n] = _rel2(agent.lang_optimizer.grads[n], sd_b[n].grad)
         assert sd_b[n].grad.norm() > 0, n
-        assert report[n] < 0.1, (n, report[n])
     print({k: round(v, 4) for k, v in report.items()})
+    assert max(report.values()) < 0.1, report
     # and the encoder learns with the rest of the step
     for opt in agent.optimizers:
         opt.lr = 1e-4
