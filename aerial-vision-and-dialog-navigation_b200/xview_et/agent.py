@@ -292,6 +292,162 @@ class NavCMTAgent:
             return float(self.loss_total.item())
         return self.loss_total
 
+    def train_iteration(self, teacher_batch, student_batch, sync_loss=False):
+        """One iteration of ``train`` (agent.py:225-251): the teacher-feedback rollout and the student-feedback
+        rollout add their losses, ONE backward's worth of gradients (accumulated over both), clip, one step of every
+        optimiser.  ``student_batch`` comes from ``student_batch()``.  Returns the summed loss."""
+        l1 = self.train_rollout_step(teacher_batch, step=False)
+        l1 = l1.clone()
+        l2 = self.train_rollout_step(student_batch, zero=False)
+        total = l1 + l2
+        return float(total.item()) if sync_loss else total
+
+    def train_rollout_step(self, batch, sync_loss=False, zero=True, step=True):
+        """One teacher-forced training ROLLOUT (agent.py:580-760, 883-885, 245-251) as one batched pass: the loss is
+        taken at EVERY step t of every episode on the history ``[:t+1]``, summed over steps and samples and scaled
+        by ``ml_weight / B``, as the reference accumulates ``ml_loss`` over its step loop.
+
+        The poses of all steps are known before the pass (teacher feedback: the ground-truth path; student
+        feedback: a no-grad ``rollout_greedy`` -- see ``student_batch``), so the B*T views are rendered and pushed
+        through the trunk ONCE (forward and backward); the transformer then makes the reference's T encoder calls
+        over the growing history, each followed at once by its loss and its backward pass; the gradient of a
+        frame is the sum over the steps whose history contains it.  (The reference's train-mode trunk normalises each step's B
+        views with their own batch statistics; here the statistics are over all B*T views)
+
+        ``batch``: ``corners_px`` i32 [B,T,4,2] (or ``images``), ``tile_idx`` i32 [B,T] | None, ``lang`` [B,L,768],
+        ``lang_cls`` [B,49], ``directions`` f32 [B,T,2], ``gt_xy`` [B,T,2], ``gt_alt`` / ``gt_prog`` [B,T], optional
+        ``lenths`` host int [B][T] (history length seen at step t: stops growing once a sample has ended,
+        agent.py:603-620; default t+1), ``att`` u8 [B,T,224,224] (default: rendered from the poses), ``jitter``
+        f32 [B,T].  ``zero=False`` keeps the gradients already in the arenas, ``step=False`` leaves them there
+        without an optimiser step (``train_iteration`` chains the two rollouts of an iteration that way)."""
+        if "input_ids" in batch:
+            raise NotImplementedError("train_rollout_step takes language features (run the language model first)")
+        ptr = _lib.ptr
+        self.vision_model.train()
+        n = 0
+        if zero:
+            for opt in self.optimizers:
+                opt.zero_grad()
+            n += 2
+        dirs = batch["directions"].contiguous().float()
+        B, T = dirs.shape[0], dirs.shape[1]
+        BT = B * T
+        lang, lang_cls = batch["lang"].contiguous().float(), batch["lang_cls"].contiguous().float()
+        L = lang.shape[1]
+        dev = self.device
+        bufs = self._get_bufs(B, T)
+        key = ("rollout_train", B, T)
+        xb = self._bufs.get(key)
+        if xb is None:
+            xb = dict(att=torch.empty((BT, 224, 224), dtype=torch.uint8, device=dev),
+                      d_frames=torch.empty((BT, 512, 49), dtype=torch.float32, device=dev))
+            self._bufs[key] = xb
+        att = batch.get("att")
+        if "images" in batch:
+            x = batch["images"]
+        else:
+            r = self.renderer
+            ti = batch.get("tile_idx")
+            ti = None if ti is None else ti.reshape(-1)
+            minv = r.homography(batch["corners_px"].view(BT, 4, 2))
+            r.render(None, ti, views=False, norm_nhwc=True, minv=minv, out={"norm_nhwc": bufs["x"]})
+            n += 2
+            x = bufs["x"]
+            if att is None and self.nss_w != 0:
+                r.render(None, ti, views=False, att=True, minv=minv, out={"att": xb["att"]})
+                att = xb["att"]
+                n += 1
+        vm, et = self.vision_model, self.vln_model
+        teng = vm.engine(BT, 224, 224, dev)
+        l0 = teng.launches
+        DN._trunk_forward(vm, teng, x, True, out=bufs["frames"])
+        # ---- step t: the encoder over the history [:t+1], its loss, and straight back (the loss is a sum over steps,
+        #      so only one step's activations are alive at a time; every step adds into the one gradient arena) ----
+        frames = bufs["frames"].view(B, T, 512, 49)
+        d_frames = bufs["d_frames"].view(B, T, 512, 49)
+        d_frames.zero_()
+        lens = batch.get("lenths")
+        gt_xy = batch["gt_xy"].float().transpose(0, 1).contiguous()     # [T,B,2]
+        gt_alt = batch["gt_alt"].float().transpose(0, 1).contiguous()
+        gt_prog = batch["gt_prog"].float().transpose(0, 1).contiguous()
+        jit = batch.get("jitter")
+        jit = None if jit is None else jit.float().transpose(0, 1).contiguous()
+        att_t = None if att is None else att.view(B, T, 224, 224).transpose(0, 1).contiguous()
+        n += 6
+        et.train(not getattr(self.args, "no_dropout", False))
+        self.loss_total.zero_()
+        scale = float(self.train_ml) / B                               # agent.py:883-885
+        pe = et.encoder_vl.enc_pos.pe[0]
+        et_launches = 0
+        for t in range(T):
+            Tc = t + 1
+            eng = et.engine(B, L, Tc, dev)
+            e0 = eng.launches
+            eng.set_dropout(*et.dropout_config())
+            f_t = frames[:, :Tc].contiguous().view(B * Tc, 512, 49)
+            output, h_sali = eng.forward(f_t, lang, lang_cls, dirs[:, :Tc].contiguous(),
+                                         [int(lens[i][t]) for i in range(B)] if lens is not None else [Tc] * B, pe)
+            _lib.call("avdn_loss", ptr(output), ptr(h_sali), ptr(gt_xy[t]), ptr(gt_alt[t]), ptr(gt_prog[t]),
+                      ptr(None if att_t is None else att_t[t]), ptr(None if jit is None else jit[t]), B,
+                      float(self.nss_w), int(getattr(self.args, "nss_r", 0)), scale, ptr(self.loss_total),
+                      ptr(bufs["loss_i"]), ptr(bufs["d_output"]), ptr(bufs["d_h_sali"]))
+            df, _ = eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=xb["d_frames"][:B * Tc])
+            d_frames[:, :Tc] += df.view(B, Tc, 512, 49)
+            n += 5
+            et_launches += eng.launches - e0
+        e0 = eng.launches - et_launches
+        self._ctx = (teng, eng, bufs, l0, e0)
+        dp = self.world > 1 and step               # gradients are reduced once, after the iteration's last rollout
+        if dp:
+            self._allreduce_async(self.et_optimizer.g, 0, self.et_optimizer.n)
+            buckets = {c: (lo, hi) for c, lo, hi in self._trunk_buckets(teng)}
+            hook = lambda li: (self._allreduce_async(self.vision_model_optimizer.g, *buckets[li])
+                               if li in buckets else None)
+        else:
+            hook = None
+        DN._trunk_backward(vm, teng, bufs["d_frames"].view(-1, 512, 7, 7), after_layer=hook,
+                           flush_layers=set(buckets) if dp else None)
+        if dp:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        if step:
+            gs = 1.0 / self.world
+            for opt in self.optimizers:
+                if opt is not self.lang_optimizer:
+                    n += opt.step(grad_scale=gs)
+        self.launches += n + (teng.launches - l0) + (eng.launches - e0)
+        self.logs["IL_loss"].append(self.loss_total)
+        return float(self.loss_total.item()) if sync_loss else self.loss_total
+
+    @torch.no_grad()
+    def student_batch(self, batch, gt_path_corners, max_action_len=None):
+        """The student-feedback half of a training iteration (agent.py:245-251 runs ``rollout`` twice): a no-grad
+        greedy rollout fixes the poses, ``teacher_action`` supplies the target of every step (one launch), and the
+        result is a ``train_rollout_step`` batch.  ``batch`` as for ``rollout_greedy``; returns the training batch
+        (device tensors; ``lenths`` from the steps each sample was alive)."""
+        res = self.rollout_greedy(batch, max_action_len=max_action_len)
+        T = int(res["steps"])
+        corners = res["corners"][:T]                                   # [T,B,4,2] gps
+        B = corners.shape[1]
+        ended_before = torch.zeros((T, B), dtype=torch.uint8, device=self.device)
+        ended_before[1:] = res["ended"][:T - 1]
+        tgt_xy, tgt_alt, prog = self.teacher_action(corners.reshape(T * B, 4, 2),
+                                                    [gt_path_corners[k % B] for k in range(T * B)],
+                                                    ended_before.reshape(-1), feedback="student")
+        geo = batch["geo"].contiguous()
+        px = torch.empty((T * B, 4, 2), dtype=torch.int32, device=self.device)
+        _lib.call("avdn_gps_to_pixels", _lib.ptr(corners.reshape(T * B, 4, 2).contiguous()),
+                  _lib.ptr(geo.repeat(T, 1).contiguous()), T * B, _lib.ptr(px))
+        rad = res["directions"][:T].float() / 180 * PI_REF
+        alive = (ended_before == 0).cpu().numpy()
+        lens = np.cumsum(alive, axis=0).T                              # [B,T]: history length seen at step t
+        tb = lambda a: a.view(T, B, *a.shape[1:]).transpose(0, 1).contiguous()
+        ti = batch.get("tile_idx")
+        return dict(corners_px=tb(px), tile_idx=None if ti is None else ti.view(B, 1).expand(B, T).contiguous(),
+                    lang=batch["lang"], lang_cls=batch["lang_cls"],
+                    directions=torch.stack([torch.sin(rad), torch.cos(rad)], -1).transpose(0, 1).contiguous(),
+                    gt_xy=tb(tgt_xy.float()), gt_alt=tb(tgt_alt.float()), gt_prog=tb(prog.float()),
+                    lenths=np.maximum(lens, 1).tolist())
+
     # ----------------------------------------------------------------- inference
     STOP_THRESHOLD = 0.5               # agent.py:738-745 (the LSTM agent uses 0.25)
 

@@ -195,3 +195,97 @@ def test_agent_test_produces_scorable_trajectories(agent):
     avg, metrics = env.eval_metrics(results)
     assert set(("sr", "spl", "gp", "iou", "lengths")) <= set(avg) and len(metrics["instr_id"]) == B
     assert all(np.isfinite(float(v)) for v in avg.values())
+
+
+def test_student_batch_feeds_the_training_rollout(agent):
+    """agent.py:245-251: the student half of an iteration -- poses from a greedy rollout, per-step targets from
+    ``teacher_action`` (checked against the oracle's teacher), then ``train_rollout_step`` on that batch."""
+    from oracle import teacher_oracle as to
+    B, T, L = 4, 4, 12
+    size = 1024
+    geo = np.tile(np.array([40.0, -75.0, 40.02, -74.98, 0.02 / size]), (B, 1))
+    corners, dirs, _ = _poses(B, 3)
+    rng = np.random.default_rng(5)
+    gts = []
+    for i in range(B):
+        path = [corners[i]]
+        for _ in range(int(rng.integers(1, 4))):
+            path.append(path[-1] + rng.uniform(-0.001, 0.001, 2))
+        gts.append(np.stack(path))
+    g = torch.Generator().manual_seed(2)
+    batch = dict(corners_gps=torch.from_numpy(corners).cuda(), directions=torch.from_numpy(dirs).cuda(),
+                 geo=torch.from_numpy(geo).cuda(), tile_idx=None, lang=torch.randn(B, L, 768, generator=g).cuda(),
+                 lang_cls=torch.relu(torch.randn(B, 49, generator=g)).cuda())
+    tb = agent.student_batch(batch, gts, max_action_len=T)
+    Ts = tb["directions"].shape[1]
+    assert tb["corners_px"].shape == (B, Ts, 4, 2) and tb["gt_xy"].shape == (B, Ts, 2)
+    assert np.array_equal(np.asarray(tb["lenths"])[:, 0], np.ones(B, dtype=int))
+    res_corners = agent._bufs[("rollout", B, T)]["corners_hist"].cpu().numpy()
+    ended = agent._bufs[("rollout", B, T)]["ended_hist"].cpu().numpy().astype(bool)
+    for t in range(Ts):
+        eb = ended[t - 1] if t > 0 else np.zeros(B, dtype=bool)
+        for i in range(B):
+            r, a, p = to.teacher_action(res_corners[t, i], gts[i], bool(eb[i]), feedback="student")
+            assert np.allclose(tb["gt_xy"][i, t].cpu().numpy(), r, atol=1e-5), (t, i)
+            assert abs(float(tb["gt_alt"][i, t]) - a) < 1e-5 and abs(float(tb["gt_prog"][i, t]) - p) < 1e-5
+    agent.args.no_dropout = True
+    l0 = agent.train_rollout_step(tb, sync_loss=True)
+    losses = [agent.train_rollout_step(tb, sync_loss=True) for _ in range(6)]
+    assert np.isfinite([l0] + losses).all() and losses[-1] < l0, (l0, losses)
+
+
+def _shallow_cfg():
+    """Seven convolutions down to [512,7,7].  Run to run the batch statistics differ in the last bit (atomics), which
+    flips LeakyReLU masks of activations sitting at the kink: ~1e-3..1e-2 of gradient noise here, while the
+    random-init 52-layer trunk amplifies the same flips to ~0.2 of its features."""
+    out = ["[net]", "channels=3", "height=224", ""]
+    for f, k, st in ((32, 3, 1), (64, 3, 2), (128, 3, 2), (256, 3, 2), (512, 3, 2), (1024, 3, 2), (512, 1, 1)):
+        out.extend(["[convolutional]", "batch_normalize=1", f"filters={f}", f"size={k}", f"stride={st}", "pad=1",
+                    "activation=leaky", ""])
+    return "\n".join(out)
+
+
+def test_train_iteration_accumulates_both_rollouts(built_lib):
+    """agent.py:225-251: the gradients of the teacher and the student rollout add before the one optimiser step."""
+    from avdn_b200.xview_et.agent import NavCMTAgent
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(_shallow_cfg())
+    args = types.SimpleNamespace(demb=768, encoder_heads=12, encoder_layers=2, dropout_transformer_encoder=0.1,
+                                 num_input_actions=1, dropout_emb=0.0, darknet_model_file=f.name,
+                                 darknet_weight_file=None, lr=1e-5, nss_w=0.1, nss_r=0, ml_weight=0.2, no_dropout=True)
+    torch.manual_seed(0)
+    agent = NavCMTAgent(args, device="cuda")
+    os.unlink(f.name)
+    B, T, L = 2, 3, 8
+    g = torch.Generator().manual_seed(8)
+
+    def mk():
+        deg = torch.randint(0, 360, (B, T), generator=g).float()
+        images = torch.zeros(B * T, 224, 224, 4)
+        images[..., :3] = torch.randn(B * T, 224, 224, 3, generator=g)
+        return {k: v.cuda() for k, v in dict(
+            directions=torch.stack([torch.sin(deg / 180 * 3.14159), torch.cos(deg / 180 * 3.14159)], -1),
+            images=images.bfloat16(), lang=torch.randn(B, L, 768, generator=g),
+            lang_cls=torch.relu(torch.randn(B, 49, generator=g)), gt_xy=torch.rand(B, T, 2, generator=g) * 2 - 1,
+            gt_alt=torch.rand(B, T, generator=g), gt_prog=torch.rand(B, T, generator=g)).items()}
+    a, b = mk(), mk()
+    saved = [(o.lr, o.wd) for o in agent.optimizers]
+    for o in agent.optimizers:
+        o.lr, o.wd = 0.0, 0.0
+    try:
+        rel = lambda x, y: ((x - y).norm() / y.norm().clamp_min(1e-30)).item()
+        la = float(agent.train_rollout_step(a).item())
+        ga = [o.g.clone() for o in agent.optimizers]
+        agent.train_rollout_step(a)
+        noise = [rel(o.g, x) for o, x in zip(agent.optimizers, ga)]      # run-to-run (atomics)
+        lb = float(agent.train_rollout_step(b).item())
+        gb = [o.g.clone() for o in agent.optimizers]
+        tot = agent.train_iteration(a, b, sync_loss=True)
+        assert abs(tot - (la + lb)) <= 2e-3 * abs(la + lb)
+        errs = [rel(o.g, x + y) for o, x, y in zip(agent.optimizers, ga, gb)]
+        print("additivity", errs, "run-to-run", noise)
+        for e, nz in zip(errs, noise):
+            assert e < 0.15, (errs, noise)                               # a dropped rollout would show as ~0.5-1
+    finally:
+        for o, (lr, wd) in zip(agent.optimizers, saved):
+            o.lr, o.wd = lr, wd

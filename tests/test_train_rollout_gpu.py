@@ -1,0 +1,82 @@
+"""GPU: the teacher-forced training rollout (src/xview_et/agent.py:580-760, 883-885): a loss at every step on the
+growing history, summed, one backward.  ``train_rollout_step`` makes the reference's T encoder calls; the oracle
+does the same with autograd on OUR trunk features (teacher-forced), so loss, the gradient that reaches the trunk
+and the transformer's parameter gradients are compared."""
+import os
+import tempfile
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_rollout_step_matches_per_step_oracle(built_lib, ragged):
+    from avdn_b200.xview_et.agent import NavCMTAgent
+    B, T, L = 2, 3, 8
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(mo.yolov3_trunk_cfg())
+    args = types.SimpleNamespace(demb=768, encoder_heads=12, encoder_layers=2, dropout_transformer_encoder=0.1,
+                                 num_input_actions=1, dropout_emb=0.0, darknet_model_file=f.name, darknet_weight_file=None,
+                                 lr=1e-5, nss_w=0.1, nss_r=0, ml_weight=0.2, no_dropout=True)
+    torch.manual_seed(0)
+    agent = NavCMTAgent(args, device="cuda")
+    os.unlink(f.name)
+    for opt in agent.optimizers:
+        opt.lr, opt.wd = 0.0, 0.0
+    g = torch.Generator().manual_seed(4)
+    deg = torch.randint(0, 360, (B, T), generator=g).float()
+    dirs = torch.stack([torch.sin(deg / 180 * 3.14159), torch.cos(deg / 180 * 3.14159)], -1)
+    images = torch.zeros(B * T, 224, 224, 4)
+    images[..., :3] = torch.randn(B * T, 224, 224, 3, generator=g)
+    att = np.zeros((B, T, 224, 224), np.uint8)
+    att[0, :, 60:120, 80:160] = 255
+    att[1, 1, 10:50, 150:200] = 255                      # steps without a fixation map carry no NSS term
+    lens = [[1, 2, 3], [1, 2, 2]] if ragged else None     # sample 1 ended after its second step
+    hb = dict(directions=dirs, images=images.bfloat16(), att=torch.from_numpy(att),
+              lang=torch.randn(B, L, 768, generator=g), lang_cls=torch.relu(torch.randn(B, 49, generator=g)),
+              gt_xy=torch.rand(B, T, 2, generator=g) * 2 - 1, gt_alt=torch.rand(B, T, generator=g),
+              gt_prog=torch.rand(B, T, generator=g))
+    batch = {k: v.cuda() for k, v in hb.items()}
+    if lens is not None:
+        batch["lenths"] = lens
+    ours = agent.train_rollout_step(batch, sync_loss=True)
+    bufs = agent._ctx[2]
+    frames = bufs["frames"].detach().cpu().view(B, T, 512, 49).clone().requires_grad_(True)
+    sd_e = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point())
+            for k, v in agent.vln_model.state_dict().items()}
+    total = 0
+    for t in range(T):
+        lt = [lens[i][t] for i in range(B)] if lens is not None else [t + 1] * B
+        out, sal, _ = mo.et_forward(sd_e, dirs[:, :t + 1], frames[:, :t + 1], lt, hb["lang"], hb["lang_cls"])
+        gt_sal = torch.from_numpy(att[:, t].astype(np.float64) / 255)
+        total = total + mo.step_loss(mo.et_loss(out, sal, hb["gt_xy"][:, t], hb["gt_alt"][:, t], hb["gt_prog"][:, t],
+                                                gt_sal, 0.1), 0.2, B)
+    total.backward()
+    ref = float(total.detach())
+    assert abs(ours - ref) <= 1e-2 * abs(ref), (ours, ref)
+    d_frames = bufs["d_frames"].view(B, T, 512, 49)
+    assert _rel2(d_frames, frames.grad) < 5e-2
+    report = {}
+    for n in ("encoder_vl.enc_transformer.layers.0.self_attn.in_proj_weight",
+              "encoder_vl.enc_transformer.layers.1.linear2.weight", "direction_embedding.weight",
+              "decoder_2_action_full.0.weight", "fc.0.weight"):
+        if n in agent.et_optimizer.grads and sd_e[n].grad is not None:
+            report[n] = _rel2(agent.et_optimizer.grads[n], sd_e[n].grad)
+    print({k: round(v, 4) for k, v in report.items()})
+    assert len(report) >= 3 and max(report.values()) < 0.1, report
+    # the rollout step learns
+    for opt in agent.optimizers:
+        opt.lr = 1e-4
+    losses = [agent.train_rollout_step(batch, sync_loss=True) for _ in range(8)]
+    assert np.isfinite(losses).all() and losses[-1] < ours, (ours, losses)
