@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the AVDN hot path on B200 (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout|et_rollout|bert|train_bert|mapprep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|render|rollout|et_rollout|bert|train_bert|train_rollout|mapprep]
     python bench.py --impl reference ...        # the reference's CPU path, same metric
 
 One JSON line on stdout (rank 0).  Under torchrun (N>1) every rank runs its shard
@@ -269,9 +269,10 @@ class MapPrepWorkload:
 
 WORKLOADS = {"render": RenderWorkload, "mapprep": MapPrepWorkload}
 try:
-    from bench_train import TrainWorkload, TrainBertWorkload      # noqa: E402
+    from bench_train import TrainWorkload, TrainBertWorkload, TrainRolloutWorkload      # noqa: E402
     WORKLOADS["train"] = TrainWorkload
     WORKLOADS["train_bert"] = TrainBertWorkload
+    WORKLOADS["train_rollout"] = TrainRolloutWorkload
 except ImportError:
     TrainWorkload = None
 

@@ -234,6 +234,77 @@ class TrainWorkload:
                         "BASELINE configs[0] shape (batch 4, 10 views, 250 tokens)"}
 
 
+class TrainRolloutWorkload(TrainWorkload):
+    """The teacher-forced training rollout (src/xview_et/agent.py:580-760): the loss at every one of the 10 steps on
+    the growing history -- views and trunk once over the 640 poses, then the reference's 10 encoder calls (history
+    1..10), each with its loss and backward -- one optimiser step."""
+    name = "train_rollout"
+    metric = "HAA-Transformer train rollout episodes/s"
+
+    def config(self):
+        c = super().config()
+        c["workload"] = c["workload"].replace("et_haa training step bf16", "et_haa teacher-forced training rollout "
+                                              "(loss at each of the 10 steps on the history so far; 10 encoder "
+                                              "forward+backward passes per step), bf16")
+        return c
+
+    def setup_gpu(self, dev):
+        super().setup_gpu(dev)
+        rng = np.random.default_rng(200 + self.rank)
+        B, T = self.B, T_STEPS
+        xy = torch.from_numpy(rng.uniform(-1, 1, size=(B, T, 2)).astype(np.float32))
+        self.host.update(gt_xy=(xy / torch.clamp(xy.abs().amax(dim=2, keepdim=True), min=1.0)).contiguous(),
+                         gt_alt=torch.from_numpy(rng.uniform(0, 1, size=(B, T)).astype(np.float32)),
+                         gt_prog=torch.from_numpy(rng.uniform(0, 1, size=(B, T)).astype(np.float32)))
+        self.host.pop("lenths")
+        self.pinned = {k: v.pin_memory() for k, v in self.host.items() if torch.is_tensor(v)}
+        self.batch = {k: v.to(dev) for k, v in self.host.items() if torch.is_tensor(v)}
+
+    def step(self):
+        l0 = self.agent.launches
+        self.agent.train_rollout_step(self.batch)
+        return self.agent.launches - l0
+
+    def step_e2e(self):
+        h2d = 0
+        b = {}
+        for k, v in self.pinned.items():
+            b[k] = v.to(self.dev, non_blocking=True)
+            h2d += v.numel() * v.element_size()
+        loss = self.agent.train_rollout_step(b)
+        self.loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.last_loss = float(self.loss_host.item())
+        return h2d, 8
+
+    def profile_step(self):
+        from avdn_b200 import _lib
+        _lib.PROFILE = []
+        self.agent.train_rollout_step(self.batch)
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, fl, nb in _lib.PROFILE:
+            a = agg.setdefault(name, [0, 0.0, 0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += fl
+        _lib.PROFILE = None
+        self.profile = agg
+        return agg
+
+    def flops_per_step(self):
+        et = sum(et_flops_fwd(S=L_LANG + 2 * t) for t in range(1, T_STEPS + 1))
+        return (DARKNET_GFLOP_IMG * 1e9 * self.B * T_STEPS + et * self.B) * 3
+
+    def roofline(self, peaks, ms_per_step=None):
+        r = super().roofline(peaks, ms_per_step)
+        r["traffic"], r["traffic_source"] = None, None
+        return r
+
+    def cpu_step(self, n):
+        raise SystemExit("the train_rollout workload has no CPU leg: use --no-cpu-baseline")
+
+
 class TrainBertWorkload(TrainWorkload):
     """The training step with the language encoder in the loop (src/xview_et/agent.py:125-126,155,249,527-543):
     token ids in, BERT-base forward + backward + AdamW inside the step."""
