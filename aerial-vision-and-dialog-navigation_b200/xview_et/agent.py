@@ -315,13 +315,13 @@ class NavCMTAgent:
         views with their own batch statistics; here the statistics are over all B*T views)
 
         ``batch``: ``corners_px`` i32 [B,T,4,2] (or ``images``), ``tile_idx`` i32 [B,T] | None, ``lang`` [B,L,768],
-        ``lang_cls`` [B,49], ``directions`` f32 [B,T,2], ``gt_xy`` [B,T,2], ``gt_alt`` / ``gt_prog`` [B,T], optional
+        ``lang_cls`` [B,49] (or, with an attached language model, ``input_ids`` / ``attention_mask`` and optionally
+        ``cls_input_ids`` / ``cls_attention_mask``: the encoder runs once per rollout and receives the gradients of
+        every step), ``directions`` f32 [B,T,2], ``gt_xy`` [B,T,2], ``gt_alt`` / ``gt_prog`` [B,T], optional
         ``lenths`` host int [B][T] (history length seen at step t: stops growing once a sample has ended,
         agent.py:603-620; default t+1), ``att`` u8 [B,T,224,224] (default: rendered from the poses), ``jitter``
         f32 [B,T].  ``zero=False`` keeps the gradients already in the arenas, ``step=False`` leaves them there
         without an optimiser step (``train_iteration`` chains the two rollouts of an iteration that way)."""
-        if "input_ids" in batch:
-            raise NotImplementedError("train_rollout_step takes language features (run the language model first)")
         ptr = _lib.ptr
         self.vision_model.train()
         n = 0
@@ -329,6 +329,27 @@ class NavCMTAgent:
             for opt in self.optimizers:
                 opt.zero_grad()
             n += 2
+        leng = leng2 = None
+        if "input_ids" in batch:
+            # the language encoder runs once per rollout (agent.py:519-538) and collects the gradients of all steps
+            if self.lang_model is None:
+                raise RuntimeError("batch carries input_ids but no language model is attached (attach_lang_model)")
+            lm = self.lang_model
+            lm.train(not getattr(self.args, "no_dropout", False))
+            ids, am = batch["input_ids"], batch["attention_mask"]
+            leng = lm.engine(ids.shape[0], ids.shape[1], self.device)
+            leng.set_dropout(*lm.dropout_config())
+            l0l = leng.launches
+            seq, lin, _ = leng.forward(ids.long(), am)
+            n += leng.launches - l0l
+            if "cls_input_ids" in batch:
+                ids2, am2 = batch["cls_input_ids"], batch["cls_attention_mask"]
+                leng2 = lm.engine(ids2.shape[0], ids2.shape[1], self.device, slot=1)
+                leng2.set_dropout(*lm.dropout_config())
+                l0l = leng2.launches
+                _, lin, _ = leng2.forward(ids2.long(), am2)
+                n += leng2.launches - l0l
+            batch = dict(batch, lang=seq, lang_cls=lin)
         dirs = batch["directions"].contiguous().float()
         B, T = dirs.shape[0], dirs.shape[1]
         BT = B * T
@@ -379,6 +400,9 @@ class NavCMTAgent:
         scale = float(self.train_ml) / B                               # agent.py:883-885
         pe = et.encoder_vl.enc_pos.pe[0]
         et_launches = 0
+        if leng is not None:
+            d_lang_sum = torch.zeros((B, L, 768), dtype=torch.float32, device=dev)
+            d_cls_sum = torch.zeros((B, 49), dtype=torch.float32, device=dev)      # every step adds into it
         for t in range(T):
             Tc = t + 1
             eng = et.engine(B, L, Tc, dev)
@@ -391,14 +415,32 @@ class NavCMTAgent:
                       ptr(None if att_t is None else att_t[t]), ptr(None if jit is None else jit[t]), B,
                       float(self.nss_w), int(getattr(self.args, "nss_r", 0)), scale, ptr(self.loss_total),
                       ptr(bufs["loss_i"]), ptr(bufs["d_output"]), ptr(bufs["d_h_sali"]))
-            df, _ = eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=xb["d_frames"][:B * Tc])
+            if leng is None:
+                df, _ = eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=xb["d_frames"][:B * Tc])
+            else:
+                df, d_lang = eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=xb["d_frames"][:B * Tc],
+                                          need_lang_grad=True, d_lang_cls=d_cls_sum)
+                d_lang_sum += d_lang.view(B, L, 768)
+                n += 1
             d_frames[:, :Tc] += df.view(B, Tc, 512, 49)
             n += 5
             et_launches += eng.launches - e0
         e0 = eng.launches - et_launches
+        if leng is not None:
+            l0l = leng.launches
+            if leng2 is None:
+                leng.backward(d_lang_sum, d_cls_sum, None)
+            else:
+                leng.backward(d_lang_sum, None, None)
+                l1 = leng2.launches
+                leng2.backward(None, d_cls_sum, None)
+                n += leng2.launches - l1
+            n += leng.launches - l0l
         self._ctx = (teng, eng, bufs, l0, e0)
         dp = self.world > 1 and step               # gradients are reduced once, after the iteration's last rollout
         if dp:
+            if self.lang_optimizer is not None:
+                self._allreduce_async(self.lang_optimizer.g, 0, self.lang_optimizer.n)
             self._allreduce_async(self.et_optimizer.g, 0, self.et_optimizer.n)
             buckets = {c: (lo, hi) for c, lo, hi in self._trunk_buckets(teng)}
             hook = lambda li: (self._allreduce_async(self.vision_model_optimizer.g, *buckets[li])
@@ -412,8 +454,7 @@ class NavCMTAgent:
         if step:
             gs = 1.0 / self.world
             for opt in self.optimizers:
-                if opt is not self.lang_optimizer:
-                    n += opt.step(grad_scale=gs)
+                n += opt.step(grad_scale=gs)
         self.launches += n + (teng.launches - l0) + (eng.launches - e0)
         self.logs["IL_loss"].append(self.loss_total)
         return float(self.loss_total.item()) if sync_loss else self.loss_total

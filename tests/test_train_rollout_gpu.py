@@ -80,3 +80,57 @@ def test_rollout_step_matches_per_step_oracle(built_lib, ragged):
         opt.lr = 1e-4
     losses = [agent.train_rollout_step(batch, sync_loss=True) for _ in range(8)]
     assert np.isfinite(losses).all() and losses[-1] < ours, (ours, losses)
+
+
+def test_rollout_step_trains_the_language_encoder(built_lib):
+    """The language encoder runs once per rollout (agent.py:519-538) and receives the gradients of every step."""
+    from transformers import BertConfig
+    from oracle import bert_oracle as bo
+    from avdn_b200.models.bert import CustomBERTModel
+    from avdn_b200.xview_et.agent import NavCMTAgent
+    B, T, S, V = 2, 3, 12, 300
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(mo.yolov3_trunk_cfg())
+    args = types.SimpleNamespace(demb=768, encoder_heads=12, encoder_layers=2, dropout_transformer_encoder=0.1,
+                                 num_input_actions=1, dropout_emb=0.0, darknet_model_file=f.name, darknet_weight_file=None,
+                                 lr=1e-5, nss_w=0.0, nss_r=0, ml_weight=0.2, no_dropout=True)
+    torch.manual_seed(0)
+    agent = NavCMTAgent(args, device="cuda")
+    os.unlink(f.name)
+    lm = agent.attach_lang_model(CustomBERTModel(BertConfig(num_hidden_layers=2, vocab_size=V)))
+    for opt in agent.optimizers:
+        opt.lr, opt.wd = 0.0, 0.0
+    g = torch.Generator().manual_seed(6)
+    ids = torch.randint(0, V, (B, S), generator=g)
+    mask = torch.ones(B, S, dtype=torch.long)
+    mask[1, 8:] = 0
+    deg = torch.randint(0, 360, (B, T), generator=g).float()
+    dirs = torch.stack([torch.sin(deg / 180 * 3.14159), torch.cos(deg / 180 * 3.14159)], -1)
+    images = torch.zeros(B * T, 224, 224, 4)
+    images[..., :3] = torch.randn(B * T, 224, 224, 3, generator=g)
+    hb = dict(input_ids=ids, attention_mask=mask, directions=dirs, images=images.bfloat16(),
+              gt_xy=torch.rand(B, T, 2, generator=g) * 2 - 1, gt_alt=torch.rand(B, T, generator=g),
+              gt_prog=torch.rand(B, T, generator=g))
+    batch = {k: v.cuda() for k, v in hb.items()}
+    ours = agent.train_rollout_step(batch, sync_loss=True)
+    frames = agent._ctx[2]["frames"].detach().cpu().view(B, T, 512, 49)
+    sd_b = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in lm.state_dict().items()
+            if "position_ids" not in k}
+    sd_e = {k: v.detach().cpu().clone() for k, v in agent.vln_model.state_dict().items()}
+    seq, lin, _ = bo.custom_bert_forward(sd_b, ids, mask)
+    total = 0
+    zero_sal = torch.zeros(B, 224, 224, dtype=torch.float64)
+    for t in range(T):
+        out, sal, _ = mo.et_forward(sd_e, dirs[:, :t + 1], frames[:, :t + 1], [t + 1] * B, seq, lin)
+        total = total + mo.step_loss(mo.et_loss(out, sal, hb["gt_xy"][:, t], hb["gt_alt"][:, t], hb["gt_prog"][:, t],
+                                                zero_sal, 0.0), 0.2, B)
+    total.backward()
+    ref = float(total.detach())
+    assert abs(ours - ref) <= 1e-2 * abs(ref), (ours, ref)
+    report = {}
+    for n in ("bert.embeddings.word_embeddings.weight", "bert.encoder.layer.0.attention.self.query.weight",
+              "bert.encoder.layer.1.output.dense.weight", "bert.encoder.layer.1.output.LayerNorm.weight"):
+        report[n] = _rel2(agent.lang_optimizer.grads[n], sd_b[n].grad)
+        assert sd_b[n].grad.norm() > 0, n
+    print({k: round(v, 4) for k, v in report.items()})
+    assert max(report.values()) < 0.1, report
