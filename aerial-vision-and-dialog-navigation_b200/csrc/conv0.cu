@@ -64,9 +64,8 @@ __global__ void __launch_bounds__(THREADS) conv0_fwd_kernel(const uint2* __restr
   uint8_t* outs = smem + ((size_t)(F_ROWS + 2) * (W + 2) + 2) * 8;              // [WARPS][16][OUT_PITCH]
   // the 16-wide patch window of the last pixels runs 2 pixels past the last staged row (zero weights)
   if (threadIdx.x < 2) xs[(F_ROWS + 2) * (W + 2) + threadIdx.x] = make_uint2(0u, 0u);
-  __shared__ float s_stat[2 * C0_OUT];
+  __shared__ float s_stat[WARPS][2 * C0_OUT];          // one set per warp: summed in warp order (reproducible)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  if (threadIdx.x < 2 * C0_OUT) s_stat[threadIdx.x] = 0.f;
 
   // weight fragments: B[k = kw*4 + ci][n = co] per filter row kh, n-tile nt (co = nt*8 + g)
   uint32_t wf[3][4][2];
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(THREADS) conv0_fwd_kernel(const uint2* __restr
     }
   }
   if (stats) {
-    // lanes with the same t hold the same channels: reduce over g, then one smem atomic per channel
+    // lanes with the same t hold the same channels: reduce over g, then one slot per (warp, channel)
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -167,12 +166,15 @@ __global__ void __launch_bounds__(THREADS) conv0_fwd_kernel(const uint2* __restr
         float a = st1[nt][e], b = st2[nt][e];
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-        if (g == 0) { atomicAdd(&s_stat[nt * 8 + 2 * t + e], a); atomicAdd(&s_stat[C0_OUT + nt * 8 + 2 * t + e], b); }
+        if (g == 0) { s_stat[warp][nt * 8 + 2 * t + e] = a; s_stat[warp][C0_OUT + nt * 8 + 2 * t + e] = b; }
       }
     __syncthreads();
     if (threadIdx.x < 2 * C0_OUT) {
       const int which = threadIdx.x / C0_OUT, c = threadIdx.x % C0_OUT;
-      atomicAdd(stats + which * C0_PAD + c, (double)s_stat[threadIdx.x]);
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) v += s_stat[w][threadIdx.x];
+      atomicAdd(stats + which * C0_PAD + c, (double)v);
     }
   }
 }

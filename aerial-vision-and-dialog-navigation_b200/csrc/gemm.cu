@@ -260,7 +260,9 @@ struct Tiles {
   static constexpr int B_BYTES = (BN / CTAS) * BKT * 2;        // this CTA's part of B
   static constexpr int SUB_BYTES = A_BYTES + B_BYTES;          // one k-block
   static constexpr int NUM_BARS = 2 * MAX_STAGES + 4;
-  static constexpr int TAIL_BYTES = 2 * BN * 4 + NUM_BARS * 8 + 16 + 1024;   // stats + barriers + slot + align slack
+  static constexpr int STAT_GRP = (BN == 32) ? 8 : 4;          // row groups of the statistics pass: one accumulator set each
+  static constexpr int STAT_BYTES = STAT_GRP * 2 * BN * 4;
+  static constexpr int TAIL_BYTES = STAT_BYTES + NUM_BARS * 8 + 16 + 1024;   // stats + barriers + slot + align slack
 };
 
 // Thin tiles (BN <= 64: the <= 64-channel blocks of the trunk) are bound by the latency of one CTA's
@@ -281,7 +283,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
   const uint32_t stage_bytes = (uint32_t)KPS * L::SUB_BYTES;
   const uint32_t slab_off = (uint32_t)STAGES * stage_bytes;
   const uint32_t stat_off = slab_off + (uint32_t)NSLAB * SLAB_BYTES;
-  const uint32_t bar_off = stat_off + 2 * BN * 4;
+  const uint32_t bar_off = stat_off + L::STAT_BYTES;
   const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -383,7 +385,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
     }
   }
   if (warp >= 2)
-    for (int i = threadIdx.x - 64; i < 2 * BN; i += EPI_THREADS) s_stat[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < L::STAT_GRP * 2 * BN; i += EPI_THREADS) s_stat[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   if (CTAS == 2) cluster_sync_all();          // peer barriers initialised before anyone signals them
@@ -558,8 +560,10 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
       for (int i = et; i < 2 * BN; i += EPI_THREADS) {
         const int j = i % BN, which = i / BN;
         const int col = stat_nt * BN + j;
-        if (col < c.N) atomicAdd(c.stats + (size_t)which * c.N + col, (double)s_stat[i]);
-        s_stat[i] = 0.f;
+        float v = 0.f;                               // the row groups' partial sums, always in the same order
+#pragma unroll
+        for (int g = 0; g < L::STAT_GRP; ++g) { v += s_stat[g * 2 * BN + i]; s_stat[g * 2 * BN + i] = 0.f; }
+        if (col < c.N) atomicAdd(c.stats + (size_t)which * c.N + col, (double)v);
       }
       epi_bar_sync();
     };
@@ -766,10 +770,13 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
                 s1a += x0; s2a = fmaf(x0, x0, s2a);
                 s1b += x1; s2b = fmaf(x1, x1, s2b);
               }
-              atomicAdd(&s_stat[cc + 2 * jp], s1a);
-              atomicAdd(&s_stat[cc + 2 * jp + 1], s1b);
-              atomicAdd(&s_stat[BN + cc + 2 * jp], s2a);
-              atomicAdd(&s_stat[BN + cc + 2 * jp + 1], s2b);
+              // (column pair, row group) belongs to this thread alone: plain adds, and a summation order that
+              // does not depend on warp timing (run-to-run reproducible statistics up to the f64 global adds)
+              float* sg = s_stat + grp * 2 * BN + cc + 2 * jp;
+              sg[0] += s1a;
+              sg[1] += s1b;
+              sg[BN] += s2a;
+              sg[BN + 1] += s2b;
             }
             if (++slab_ctr == (uint32_t)NSLAB) slab_ctr = 0;
           }
@@ -1128,7 +1135,7 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   // ---- shared-memory plan: slabs, k-blocks per stage, ring depth ----
   {
     const int sub = BM * d->bk * 2 + (d->bn / d->ctas) * d->bk * 2;         // one k-block (this CTA)
-    const int tail = 2 * d->bn * 4 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
+    const int tail = (d->bn == 32 ? 8 : 4) * 2 * d->bn * 4 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
     // k-blocks per stage: one barrier round trip + commit costs the issuing thread ~300 cycles, a k-block of
     // MMAs (bn/256 * 512 cycles at bk = 64) should not be much shorter than that
     int kps = 1;

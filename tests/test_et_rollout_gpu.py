@@ -235,9 +235,8 @@ def test_student_batch_feeds_the_training_rollout(agent):
 
 
 def _shallow_cfg():
-    """Seven convolutions down to [512,7,7].  Run to run the batch statistics differ in the last bit (atomics), which
-    flips LeakyReLU masks of activations sitting at the kink: ~1e-3..1e-2 of gradient noise here, while the
-    random-init 52-layer trunk amplifies the same flips to ~0.2 of its features."""
+    """Seven convolutions down to [512,7,7]: a trunk shallow enough that differences between two of our own runs
+    (reduce order of the weight-gradient adds) are not amplified."""
     out = ["[net]", "channels=3", "height=224", ""]
     for f, k, st in ((32, 3, 1), (64, 3, 2), (128, 3, 2), (256, 3, 2), (512, 3, 2), (1024, 3, 2), (512, 1, 1)):
         out.extend(["[convolutional]", "batch_normalize=1", f"filters={f}", f"size={k}", f"stride={st}", "pad=1",
@@ -285,7 +284,7 @@ def test_train_iteration_accumulates_both_rollouts(built_lib):
         errs = [rel(o.g, x + y) for o, x, y in zip(agent.optimizers, ga, gb)]
         print("additivity", errs, "run-to-run", noise)
         for e, nz in zip(errs, noise):
-            assert e < 0.15, (errs, noise)                               # a dropped rollout would show as ~0.5-1
+            assert nz < 1e-3 and e < 2e-2, (errs, noise)                 # a dropped rollout would show as ~0.5-1
     finally:
         for o, (lr, wd) in zip(agent.optimizers, saved):
             o.lr, o.wd = lr, wd
