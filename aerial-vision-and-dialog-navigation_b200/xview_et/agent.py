@@ -311,8 +311,9 @@ class NavCMTAgent:
         feedback: a no-grad ``rollout_greedy`` -- see ``student_batch``), so the B*T views are rendered and pushed
         through the trunk ONCE (forward and backward); the transformer then makes the reference's T encoder calls
         over the growing history, each followed at once by its loss and its backward pass; the gradient of a
-        frame is the sum over the steps whose history contains it.  (The reference's train-mode trunk normalises each step's B
-        views with their own batch statistics; here the statistics are over all B*T views)
+        frame is the sum over the steps whose history contains it.  (The reference's train-mode trunk normalises
+        each step's B views with their own batch statistics; here the statistics are over all B*T views,
+        DESIGN.md §8.)
 
         ``batch``: ``corners_px`` i32 [B,T,4,2] (or ``images``), ``tile_idx`` i32 [B,T] | None, ``lang`` [B,L,768],
         ``lang_cls`` [B,49] (or, with an attached language model, ``input_ids`` / ``attention_mask`` and optionally
