@@ -54,6 +54,8 @@ _SIGNATURES = {
     "avdn_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_f32, c_void_p],
     "avdn_bn_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_f32,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "avdn_bn_backward_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_f32,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "avdn_pack_conv_weight": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "avdn_unpack_conv_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "avdn_unpack_conv_wgrad_pairs": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

@@ -253,7 +253,7 @@ struct alignas(64) KernelParams {
                         // tools/gemm_epilogue_probe.py)
 };
 
-// smem: [stages x kps x (A|B)] [slabs x 16 KB] [float 2 x BN] [barriers] [tmem slot]
+// smem: [stages x kps x (A|B)] [slabs x 16 KB] [float 2 x BN] [barriers] [tmem slot] [BNB: uint2 row table x 128]
 template <int BN, int CTAS, int BKT>
 struct Tiles {
   static constexpr int A_BYTES = BM * BKT * 2;                 // 16 KB (8 KB for 32-element k-blocks)
@@ -268,10 +268,13 @@ struct Tiles {
 // Thin tiles (BN <= 64: the <= 64-channel blocks of the trunk) are bound by the latency of one CTA's
 // producer -> MMA -> epilogue chain, not by any throughput: two CTAs per SM (half the shared memory each, 2 x 2 x BN
 // TMEM columns) interleave two such chains.
-template <int BN, bool A_MN, bool B_MN, int CTAS, int BKT>
+// BNB: the epilogue also accumulates the BatchNorm-backward reductions of the block that produced the tensor this
+// launch is the data gradient of (avdn_gemm_core.bnb_*).
+template <int BN, bool A_MN, bool B_MN, int CTAS, int BKT, bool BNB>
 __global__ void __launch_bounds__(NUM_THREADS, (BN <= 128) ? 2 : 1)
 gemm_kernel(const __grid_constant__ KernelParams p) {
   static_assert(BKT == 64 || (BKT == 32 && !A_MN && !B_MN), "32-element k-blocks: K-major operands only");
+  static_assert(!BNB || (!A_MN && !B_MN), "fused BatchNorm-backward statistics: K-major (CONV) operands only");
   using L = Tiles<BN, CTAS, BKT>;
   constexpr int BNH = BN / CTAS;                                // B columns this CTA loads
   constexpr uint32_t KLAYOUT = (BKT == 64) ? 2u : 4u;          // swizzle mode of the K-major operands
@@ -553,7 +556,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
     int etrace_n = 0;
     const bool etrace = p.dbg_out && blockIdx.x == 0 && et == 0;
     long long* eout = p.dbg_out ? p.dbg_out + 2048 : nullptr;
-#define ETR(slot) do { if (etrace && etrace_n < 200) eout[etrace_n * 8 + (slot)] = clock64(); } while (0)
+#define ETR(slot) do { if (etrace && etrace_n < 120) eout[etrace_n * 16 + (slot)] = clock64(); } while (0)
     auto flush_stats = [&]() {
       // all epilogue threads: commit the CTA's running column sums of tile column `stat_nt`
       epi_bar_sync();
@@ -563,7 +566,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
         float v = 0.f;                               // the row groups' partial sums, always in the same order
 #pragma unroll
         for (int g = 0; g < L::STAT_GRP; ++g) { v += s_stat[g * 2 * BN + i]; s_stat[g * 2 * BN + i] = 0.f; }
-        if (col < c.N) atomicAdd(c.stats + (size_t)which * c.N + col, (double)v);
+        if (col < c.N) atomicAdd((BNB ? c.bnb_sums : c.stats) + (size_t)which * c.N + col, (double)v);
       }
       epi_bar_sync();
     };
@@ -619,6 +622,53 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
       }
     };
     const uint32_t twh = (uint32_t)(c.tiles_w * c.tiles_h);
+    // ---- fused BatchNorm-backward statistics (BNB): tile-invariant part ----
+    // Element offset of output pixel (n, h, w) = OB + n*SN + h*SH + w*SW (+ column); `bnb_z` is addressed like `out`.
+    // The position (wi, hi, ni) of a tile row inside the box does not depend on the tile: s_row[r] holds its element
+    // offset relative to the box origin and its packed coordinates (0xFFFFFFFF: the row is not part of the box).
+    // Statistics mapping: a warp owns 32 rows; lane -> (16-byte chunk cg of the slab row = 8 columns, row set rs);
+    // the thread visits rows q*32 + ST_RS*i + rs, i < ST_NI, so one warp instruction reads ST_RS whole rows.
+    constexpr int ST_CH = (BN == 32) ? 4 : 8;                    // 16-byte chunks per slab row
+    constexpr int ST_RS = 32 / ST_CH;                            // rows per warp instruction (4 or 8)
+    constexpr int ST_NI = 32 / ST_RS;                            // rows per thread (8 or 4)
+    const __nv_bfloat16* bnb_z = reinterpret_cast<const __nv_bfloat16*>(c.bnb_z);
+    const __nv_bfloat16* bnb_o = reinterpret_cast<const __nv_bfloat16*>(c.out);
+    uint2* s_row = reinterpret_cast<uint2*>(smem_gen + bar_off + 8 * L::NUM_BARS + 16);
+    uint32_t SW = 0, SH = 0, SN = 0, OB = 0;
+    if (BNB) {
+      SW = (uint32_t)c.out_sw * (uint32_t)c.ldc;
+      SH = (uint32_t)c.out_sh * (uint32_t)c.out_W * (uint32_t)c.ldc;
+      SN = (uint32_t)c.out_H * (uint32_t)c.out_W * (uint32_t)c.ldc;
+      OB = ((uint32_t)c.out_oh * (uint32_t)c.out_W + (uint32_t)c.out_ow) * (uint32_t)c.ldc;
+      const int t2 = et / c.box_w;
+      const int wi = et - t2 * c.box_w, ni = t2 / c.box_h, hi = t2 - ni * c.box_h;
+      s_row[et] = (et < p.rows_in_box)
+                      ? make_uint2((uint32_t)ni * SN + (uint32_t)hi * SH + (uint32_t)wi * SW,
+                                   (uint32_t)wi | ((uint32_t)hi << 10) | ((uint32_t)ni << 20))
+                      : make_uint2(0u, 0xFFFFFFFFu);
+      epi_bar_sync();
+    }
+    // row r of the box whose origin is (w0, h0, i0): inside the tensor?
+    auto row_ok = [&](uint32_t xy, int w0_, int h0_, int i0_) {
+      return xy != 0xFFFFFFFFu && w0_ + (int)(xy & 1023u) < c.valid_w && h0_ + (int)((xy >> 10) & 1023u) < c.valid_h &&
+             i0_ + (int)(xy >> 20) < c.valid_n;
+    };
+    auto prefetch_tile = [&](int mt_, int nt_) {
+      const uint32_t mt = (uint32_t)mt_;
+      const uint32_t qq = mt / (uint32_t)c.tiles_w, in = mt / twh;
+      const int w0_ = (int)(mt - qq * c.tiles_w) * c.box_w, h0_ = (int)(qq - in * c.tiles_h) * c.box_h;
+      const int i0_ = (int)in * c.box_n;
+      const uint2 rw = s_row[et];
+      if (row_ok(rw.y, w0_, h0_, i0_)) {
+        const int n0_ = nt_ * BN;
+        const uint32_t off = OB + (uint32_t)i0_ * SN + (uint32_t)h0_ * SH + (uint32_t)w0_ * SW + rw.x + (uint32_t)n0_;
+        const int ncols = min(BN, c.N - n0_);
+        for (int b = 0; b < ncols; b += 64) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(bnb_z + off + b));
+          if (c.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(bnb_o + off + b));
+        }
+      }
+    };
     for (Walk wk = walk_init(); wk.t < total; walk_next(wk)) {
       const Tile T = walk_tile(wk);
       if (T.my_kb == 0) continue;
@@ -633,9 +683,20 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
         h0 = (int)(qq - in * c.tiles_h) * c.box_h;
         i0 = (int)in * c.box_n;
       }
-      if (c.stats && stat_nt != T.nt) {
+      if ((BNB || c.stats) && stat_nt != T.nt) {
         if (stat_nt >= 0) flush_stats();
         stat_nt = T.nt;
+      }
+      if (BNB) {
+        // pull the rows of z (and of the old dA) of the NEXT tile into L2 while this one is processed (the first
+        // tile prefetches itself as well): the statistics loop below then waits for L2 hits, not for HBM
+        Walk wn = wk;
+        if (it == 1) prefetch_tile(T.mt, T.nt);
+        walk_next(wn);
+        if (wn.t < total) {
+          const Tile Tn = walk_tile(wn);
+          prefetch_tile(Tn.mt, Tn.nt);
+        }
       }
       if (has_aff) {
         if (aff_nt != T.nt) {
@@ -675,7 +736,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
             else if (c.mode == AVDN_GEMM_WGRAD) { c0 = scol + c.taps[T.tap].bk; c1 = m0; c2 = 0; c3 = 0; }
             else { c1 = m0; c2 = T.z0; c3 = T.z1; }
             if (!(p.dbg & 1)) {
-              if (c.accumulate) tma_reduce_add_4d(&p.tmC, srca, c0, c1, c2, c3);
+              if (c.accumulate && !BNB) tma_reduce_add_4d(&p.tmC, srca, c0, c1, c2, c3);
               else tma_store_4d(&p.tmC, srca, c0, c1, c2, c3);
             }
             tma_commit_group();
@@ -752,8 +813,106 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
             if (!(p.dbg & 8)) fence_proxy_async_smem();
             if (!(p.dbg & 16)) epi_bar_sync();
             if (cc == 0) ETR(6);
-            issue_store(slab, col0);
-            if (c.stats) {
+            if (!(BNB && c.accumulate)) issue_store(slab, col0);
+            if (BNB) {
+              // Fused BatchNorm-backward reductions of the producing block.  dA comes from the slab (bf16: what is
+              // stored), z -- and with accumulate the old dA, which is added here in fp32 and written back to the
+              // slab before it is stored -- from global memory: 16 bytes (8 columns) per thread and row, all of a
+              // thread's rows in flight at once.
+              const int cg = lane & (ST_CH - 1), rs = lane / ST_CH;
+              const int colc = col0 + 8 * cg;
+              const bool col_ok = colc < c.N;                       // N is a multiple of 8
+              const bool acc = (c.accumulate != 0);
+              const bool tile_full = (w0 + c.box_w <= c.valid_w) && (h0 + c.box_h <= c.valid_h) &&
+                                     (i0 + c.box_n <= c.valid_n);
+              const uint32_t tile_off = OB + (uint32_t)i0 * SN + (uint32_t)h0 * SH + (uint32_t)w0 * SW + (uint32_t)colc;
+              if (cc == 0) ETR(8);
+              uint4 zq[ST_NI], oq[ST_NI];
+              uint32_t okm = 0u;
+#pragma unroll
+              for (int i = 0; i < ST_NI; ++i) {
+                const int r = q * 32 + ST_RS * i + rs;
+                const uint2 rw = s_row[r];
+                const bool ok = col_ok && (tile_full ? (r < p.rows_in_box) : row_ok(rw.y, w0, h0, i0));
+                zq[i] = make_uint4(0u, 0u, 0u, 0u); oq[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) {
+                  zq[i] = *reinterpret_cast<const uint4*>(bnb_z + tile_off + rw.x);
+                  if (acc) oq[i] = *reinterpret_cast<const uint4*>(bnb_o + tile_off + rw.x);
+                  okm |= 1u << i;
+                }
+              }
+              if (cc == 0) ETR(9);
+              float sc[8], sh[8], s1[8], s2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { sc[j] = 0.f; sh[j] = 0.f; s1[j] = 0.f; s2[j] = 0.f; }
+              if (col_ok) {
+                const float4* ps = reinterpret_cast<const float4*>(c.bnb_scale + colc);
+                const float4* ph = reinterpret_cast<const float4*>(c.bnb_shift + colc);
+                const float4 a0 = ps[0], a1 = ps[1], b0 = ph[0], b1 = ph[1];
+                sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+                sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+              }
+#pragma unroll
+              for (int i = 0; i < ST_NI; ++i) {
+                if ((okm >> i) & 1u) {
+                  const int r = q * 32 + ST_RS * i + rs;            // (r & 7) = (ST_RS*i + rs) & 7: q*32 drops out
+                  uint8_t* qp = SLAB64 ? slab + r * 64 + ((cg ^ ((r >> 1) & 3)) << 4)
+                                       : slab + r * 128 + ((cg ^ (r & 7)) << 4);
+                  uint4 dq = *reinterpret_cast<const uint4*>(qp);
+                  uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
+                  const uint32_t zw[4] = {zq[i].x, zq[i].y, zq[i].z, zq[i].w};
+                  if (acc) {
+                    const uint32_t ow[4] = {oq[i].x, oq[i].y, oq[i].z, oq[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float lo = __uint_as_float(dw[j] << 16) + __uint_as_float(ow[j] << 16);
+                      const float hi = __uint_as_float(dw[j] & 0xFFFF0000u) + __uint_as_float(ow[j] & 0xFFFF0000u);
+                      const __nv_bfloat162 b2 = __floats2bfloat162_rn(lo, hi);
+                      dw[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(qp) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                  }
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float d0 = __uint_as_float(dw[j] << 16), d1 = __uint_as_float(dw[j] & 0xFFFF0000u);
+                    const float z0 = __uint_as_float(zw[j] << 16), z1 = __uint_as_float(zw[j] & 0xFFFF0000u);
+                    const float g0 = d0 * (fmaf(z0, sc[2 * j], sh[2 * j]) > 0.f ? 1.f : slope);
+                    const float g1 = d1 * (fmaf(z1, sc[2 * j + 1], sh[2 * j + 1]) > 0.f ? 1.f : slope);
+                    s1[2 * j] += g0; s2[2 * j] = fmaf(g0, z0, s2[2 * j]);
+                    s1[2 * j + 1] += g1; s2[2 * j + 1] = fmaf(g1, z1, s2[2 * j + 1]);
+                  }
+                }
+              }
+              if (cc == 0) ETR(10);
+              // the warp's 32 rows: sum over the row sets (lanes that share cg), in a fixed order
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int o = ST_CH; o < 32; o <<= 1) {
+                  s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+                  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+                }
+              }
+              if (rs == 0 && col_ok) {
+                // centre: sum g*(z - mean) = sum g*z - mean * sum g (32 rows of fp32 partial sums)
+                const float4* pm = reinterpret_cast<const float4*>(c.bnb_mean + colc);
+                const float4 m0 = pm[0], m1 = pm[1];
+                const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                float* sg = s_stat + q * 2 * BN + cc + 8 * cg;        // one accumulator set per warp: plain adds
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  sg[j] += s1[j];
+                  sg[BN + j] += fmaf(-mu[j], s1[j], s2[j]);
+                }
+              }
+              if (cc == 0) ETR(11);
+              if (acc) {                       // the slab now holds old + new: publish it to the async proxy, store
+                fence_proxy_async_smem();
+                epi_bar_sync();
+                issue_store(slab, col0);
+              }
+              if (cc == 0) ETR(12);
+            } else if (c.stats) {
               // fused BatchNorm statistics of the ROUNDED outputs: thread -> (column pair, row group); one
               // 32-bit shared-memory read per row brings two columns
               const int npair = SLAB64 ? 16 : 32;                 // column pairs per slab row
@@ -894,7 +1053,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
         }
       }
     }
-    if (c.stats && stat_nt >= 0) flush_stats();
+    if ((BNB || c.stats) && stat_nt >= 0) flush_stats();
     if (et == 0) tma_wait_group_read<0>();       // smem slabs must outlive the bulk stores reading them
 #undef ETR
   }
@@ -977,16 +1136,16 @@ struct Plan {
   int32_t grid;
   int32_t smem;
   int32_t occ2;          // 1: thin tile planned for two CTAs per SM
-  int32_t pad_;
+  int32_t bnb;           // 1: fused BatchNorm-backward statistics (gemm_kernel<..., BNB = true>)
   KernelParams kp;
 };
 constexpr uint32_t PLAN_MAGIC = 0xA7D17C06u;
 
 constexpr int SMEM_MAX = 232448;       // 227 KB: the dynamic shared memory a CTA can opt in to on sm_100
 
-template <int BN, bool A_MN, bool B_MN, int CTAS, int BKT = BK>
+template <int BN, bool A_MN, bool B_MN, int CTAS, int BKT = BK, bool BNB = false>
 int launch_t(const Plan& pl, cudaStream_t s) {
-  auto kfn = gemm_kernel<BN, A_MN, B_MN, CTAS, BKT>;
+  auto kfn = gemm_kernel<BN, A_MN, B_MN, CTAS, BKT, BNB>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX) != cudaSuccess)
@@ -1132,10 +1291,24 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
                                c.out_oh == 0 && c.out_ow == 0 && (c.ldc % 8) == 0 && ((uintptr_t)c.residual & 15) == 0),
                "avdn_gemm_plan: residual needs the affine epilogue of a unit-stride CONV output");
   AVDN_REQUIRE(pl->kp.out_tma || c.mode != AVDN_GEMM_CONV, "avdn_gemm_plan: conv output cannot be described to TMA");
+  pl->bnb = (c.bnb_z != nullptr) ? 1 : 0;
+  AVDN_REQUIRE((c.bnb_z != nullptr) == (c.bnb_scale != nullptr) && (c.bnb_z != nullptr) == (c.bnb_shift != nullptr) &&
+                   (c.bnb_z != nullptr) == (c.bnb_mean != nullptr) && (c.bnb_z != nullptr) == (c.bnb_sums != nullptr),
+               "avdn_gemm_plan: bnb_z / bnb_scale / bnb_shift / bnb_mean / bnb_sums go together");
+  AVDN_REQUIRE(!pl->bnb || (c.mode == AVDN_GEMM_CONV && !d->a_mn && !d->b_mn && pl->kp.out_tma &&
+                            c.out_dtype == AVDN_DT_BF16 && !c.stats && !c.col_scale && !c.bias && !c.relu &&
+                            c.alpha == 1.0f && c.accumulate <= 1 && d->bn <= 128 && (c.N % 2) == 0 &&
+                            ((uintptr_t)c.bnb_z & 3) == 0 && ((uintptr_t)c.bnb_scale & 7) == 0 &&
+                            ((uintptr_t)c.bnb_shift & 7) == 0 && ((uintptr_t)c.bnb_mean & 7) == 0),
+               "avdn_gemm_plan: fused BatchNorm-backward statistics need a K-major CONV launch with a plain bf16 "
+               "TMA-store epilogue, bn <= 128 and aligned coefficient vectors");
+  AVDN_REQUIRE(!pl->bnb || (long long)c.valid_n * c.out_H * c.out_W * c.ldc < (1ll << 32),
+               "avdn_gemm_plan: fused BatchNorm-backward statistics address the output with 32-bit element offsets");
   // ---- shared-memory plan: slabs, k-blocks per stage, ring depth ----
   {
     const int sub = BM * d->bk * 2 + (d->bn / d->ctas) * d->bk * 2;         // one k-block (this CTA)
-    const int tail = (d->bn == 32 ? 8 : 4) * 2 * d->bn * 4 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024;
+    // stats + barriers + tmem slot + align slack (+ the row table of the fused BatchNorm-backward statistics)
+    const int tail = (d->bn == 32 ? 8 : 4) * 2 * d->bn * 4 + (2 * MAX_STAGES + 4) * 8 + 16 + 1024 + (c.bnb_z ? 1024 : 0);
     // k-blocks per stage: one barrier round trip + commit costs the issuing thread ~300 cycles, a k-block of
     // MMAs (bn/256 * 512 cycles at bk = 64) should not be much shorter than that
     int kps = 1;
@@ -1189,6 +1362,20 @@ extern "C" int avdn_gemm_run(const void* plan_host, avdn_stream_t stream) {
   if (pl->kp.c.stats) {
     if (cudaMemsetAsync(pl->kp.c.stats, 0, sizeof(double) * 2 * pl->kp.c.N, s) != cudaSuccess)
       return avdn::check_launch("gemm stats memset");
+  }
+  if (pl->bnb) {
+    if (pl->ctas == 2) {
+      if (pl->bn == 128) return launch_t<128, false, false, 2, 64, true>(*pl, s);
+    } else if (pl->bk == 32) {
+      if (pl->bn == 64) return launch_t<64, false, false, 1, 32, true>(*pl, s);
+    } else {
+      switch (pl->bn) {
+        case 32: return launch_t<32, false, false, 1, 64, true>(*pl, s);
+        case 64: return launch_t<64, false, false, 1, 64, true>(*pl, s);
+        case 128: return launch_t<128, false, false, 1, 64, true>(*pl, s);
+      }
+    }
+    return avdn::set_err(AVDN_ERR_UNSUPPORTED, "avdn_gemm_run: bnb with bn %d ctas %d bk %d", pl->bn, pl->ctas, pl->bk);
   }
   if (pl->ctas == 2) {
     switch (pl->bn) {

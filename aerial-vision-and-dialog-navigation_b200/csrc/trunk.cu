@@ -532,6 +532,26 @@ extern "C" int avdn_bn_backward(const void* da, const void* z, const float* scal
   return avdn::check_launch("bn_bwd_apply_kernel");
 }
 
+extern "C" int avdn_bn_backward_apply(const void* da, const void* z, const float* scale, const float* shift,
+                                      const float* mean, const float* rstd, long long R, int C, int C_real,
+                                      float slope, const double* sums, float* coef, void* dz, float* dgamma,
+                                      float* dbeta, avdn_stream_t stream) {
+  AVDN_REQUIRE(da && z && scale && shift && mean && rstd && sums && coef && dz && R > 0,
+               "avdn_bn_backward_apply: bad argument");
+  AVDN_REQUIRE(C % 8 == 0 && C >= 8 && BN_THREADS % (C / 8) == 0,
+               "avdn_bn_backward_apply: C=%d must be 8 * (a divisor of %d)", C, BN_THREADS);
+  cudaStream_t s = avdn::to_cuda(stream);
+  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, 1.0 / (double)R, C, C_real, scale, shift, mean, rstd, coef,
+                                                     dgamma, dbeta);
+  int r = avdn::check_launch("bn_bwd_coef_kernel");
+  if (r) return r;
+  const long long n8 = R * (C / 8);
+  bn_bwd_apply_kernel<<<bn_grid(n8, 16), BN_THREADS, 0, s>>>(reinterpret_cast<const uint4*>(da),
+                                                            reinterpret_cast<const uint4*>(z), coef,
+                                                            reinterpret_cast<uint4*>(dz), n8, C, slope);
+  return avdn::check_launch("bn_bwd_apply_kernel");
+}
+
 extern "C" int avdn_pack_conv_weight(const float* w, int Cout, int Cin, int k, int Cout_p, int Cin_p, void* wf,
                                      void* wd, avdn_stream_t stream) {
   AVDN_REQUIRE(w && wf && wd && Cout_p >= Cout && Cin_p >= Cin, "avdn_pack_conv_weight: bad argument");

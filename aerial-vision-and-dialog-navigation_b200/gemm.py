@@ -41,7 +41,9 @@ class GemmCore(C.Structure):
                 ("ldc", i64), ("out_bs0", i64), ("out_bs1", i64),
                 ("out", C.c_void_p), ("bias", C.c_void_p), ("relu_mask", C.c_void_p), ("stats", C.c_void_p),
                 ("col_scale", C.c_void_p), ("col_shift", C.c_void_p), ("residual", C.c_void_p),
-                ("leaky_slope", f32), ("pad2_", i32)]
+                ("leaky_slope", f32), ("pad2_", i32),
+                ("bnb_z", C.c_void_p), ("bnb_scale", C.c_void_p), ("bnb_shift", C.c_void_p),
+                ("bnb_mean", C.c_void_p), ("bnb_sums", C.c_void_p)]
 
 
 class GemmDesc(C.Structure):
@@ -310,10 +312,16 @@ def plan_conv_fwd(x, w_f, z, *, N, H, W, Cin, Cout, k, stride, bn=None, flops=No
                     tag="gemm_conv_fwd")
 
 
-def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0, bn=None, flops=None, ctas=None):
+def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0, bn=None, flops=None, ctas=None,
+                    bnb=None):
     """dx[N,H,W,Cin] (+)= conv_transpose(dz[N,Ho,Wo,Cout], w); ``w_d`` is
     ``[Cin, k*k*Cout]`` bf16 (tap-major, out-channel-minor).  Returns a list of plans
-    (4 output-parity plans for stride 2)."""
+    (4 output-parity plans for stride 2).
+
+    ``bnb=(z, scale, shift, mean, sums, slope)``: ``dx`` is the FINAL gradient of the activation
+    ``leaky(z*scale + shift)`` of the block that produced the layer input, and the epilogue adds that block's
+    BatchNorm-backward reductions into ``sums`` (f64 ``[2, Cin]``, zeroed by the caller); see
+    ``avdn_gemm_core.bnb_*``."""
     assert (Cin % 64 == 0 or Cin == 32) and (Cout % 64 == 0 or Cout == 32)
     Ho, Wo = H // stride, W // stride
     bn = bn or pick_bn(Cin)
@@ -355,8 +363,15 @@ def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0,
         d.b[0] = operand(w_d.data_ptr(), (Kt, Cin, 1, 1), (1, Kt, Kt * Cin, Kt * Cin), (bk, bn, 1, 1))
         d.grid_m, d.grid_n, d.grid_z = c.tiles_w * c.tiles_h * c.tiles_n, _cdiv(Cin, bn), 1
         d.ctas = pick_ctas(bn, d.grid_m, ctas)
+        if bnb is not None:
+            bz, bsc, bsh, bmu, bsums, slope = bnb
+            assert bz.dtype == torch.bfloat16 and bz.shape == dx.shape and bz.is_contiguous()
+            assert bsums.dtype == torch.float64 and bsums.numel() >= 2 * Cin
+            assert all(t.dtype == torch.float32 and t.numel() >= Cin for t in (bsc, bsh, bmu))
+            c.bnb_z, c.bnb_scale, c.bnb_shift = bz.data_ptr(), bsc.data_ptr(), bsh.data_ptr()
+            c.bnb_mean, c.bnb_sums, c.leaky_slope = bmu.data_ptr(), bsums.data_ptr(), float(slope)
         fl = flops if flops is not None else 2 * N * Ho * Wo * Cout * k * k * Cin
-        plans.append(GemmPlan(d, keep=(dz, w_d, dx), flops=fl // len(parities), tag="gemm_conv_dgrad"))
+        plans.append(GemmPlan(d, keep=(dz, w_d, dx, bnb), flops=fl // len(parities), tag="gemm_conv_dgrad"))
     return plans
 
 

@@ -18,6 +18,8 @@ raise ``NotImplementedError``.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -25,6 +27,12 @@ from .. import _lib
 from .. import gemm as G
 
 LEAKY_SLOPE = 0.01      # nn.LeakyReLU() default, dark_net.py:33
+# AVDN_FUSE_BNB=1: BatchNorm-backward reductions fused into the epilogue of the data-gradient convolution that
+# produces dA (avdn_gemm_core.bnb_*) instead of the separate reduction pass over (z, dA).  Off by default: measured
+# on a B200 the separate pass reads dA out of L2 right after the dgrad wrote it and runs at > 6 TB/s, while the
+# fused epilogue (four single-issue warps per CTA) makes the memory-bound 1x1 / stride-2 dgrads 1.7-2.5x slower
+# and the tensor-bound 3x3 ones ~10 % slower -- net +3 ms per step ("measured and not kept").
+FUSE_BNB = os.environ.get("AVDN_FUSE_BNB", "0") == "1"
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -240,7 +248,24 @@ class _Engine:
                 return (L.Cout_p if L.s == 2 else 2 * L.Cout_p, nblk * 2 * L.Cin_p)
             return (L.Cout_p, L.k * L.k * L.Cin_p)
         tot = sum((dwf_shape(L)[0] * dwf_shape(L)[1] + 63) // 64 * 64 for L in self.layers if not L.first)
-        self.dwf_arena = torch.zeros(tot, dtype=f32, device=dev)
+        # the fused BatchNorm-backward sums ([2, Cout_p] f64 per block) live behind the WGRAD outputs: the one
+        # memset per step clears both
+        n_bs = sum(4 * L.Cout_p for L in self.layers)
+        self.dwf_arena = torch.zeros(tot + n_bs, dtype=f32, device=dev)
+        bs_off = tot
+        # the data gradient of a block's output is final once its FIRST consumer (in forward order) has run its
+        # dgrad: that launch can reduce the BatchNorm-backward sums of the producing block in its epilogue
+        first_consumer = {}
+        for L in self.layers:
+            for P in (L.src, L.res):
+                if P is not None:
+                    first_consumer[id(P)] = min(first_consumer.get(id(P), L.idx), L.idx)
+        for L in self.layers:
+            L.coef = L.sums[2 * L.Cout_p:].view(f32)               # [4, Cout_p] fp32 scratch of the backward apply
+            L.bsums = self.dwf_arena[bs_off: bs_off + 4 * L.Cout_p].view(torch.float64)
+            bs_off += 4 * L.Cout_p
+            L.bnb_fused = False
+            L.bnb_ready = False
         dwf_off = 0
         seen_as_input = set()
         for L in reversed(self.layers):
@@ -270,8 +295,13 @@ class _Engine:
             # the input's gradient buffer already holds the skip gradient iff the input is a
             # residual source whose consumer (a later fused shortcut) was processed before
             acc = 1 if id(L.src) in seen_as_input else 0
+            P = L.src
+            bnb = None
+            if FUSE_BNB and first_consumer[id(P)] == L.idx and G.pick_bn(L.Cin_p) <= 128:
+                bnb = (P.z, P.scale, P.shift, P.mean, P.bsums, LEAKY_SLOPE)
+                P.bnb_fused = True
             L.p_dgrad = G.plan_conv_dgrad(dz, L.wd, L.src.g, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
-                                          Cout=L.Cout_p, k=L.k, stride=L.s, accumulate=acc, flops=L.flops)
+                                          Cout=L.Cout_p, k=L.k, stride=L.s, accumulate=acc, flops=L.flops, bnb=bnb)
             seen_as_input.add(id(L.src))
             if L.res is not None:
                 seen_as_input.add(id(L.res))
@@ -365,9 +395,16 @@ def _layer_backward(eng, L, unpack=True, zero=True):
     input gradient.  Returns the number of kernel launches.  ``unpack=False`` / ``zero=False``: the caller
     zeroes the WGRAD arena once and unpacks ranges of layers in one launch (``_trunk_backward``)."""
     call, ptr = _lib.call, _lib.ptr
-    call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
-         L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
-    n = 4
+    if L.bnb_fused and L.bnb_ready:
+        # the sums were reduced by the epilogue of the dgrad that wrote L.g: coefficients + apply only
+        call("avdn_bn_backward_apply", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
+             L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.bsums), ptr(L.coef), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
+        L.bnb_ready = False
+        n = 2
+    else:
+        call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
+             L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
+        n = 4
     if L.first:
         call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
         return n + 1
@@ -382,6 +419,11 @@ def _layer_backward(eng, L, unpack=True, zero=True):
         else:
             call("avdn_unpack_conv_wgrad", ptr(L.dwf), L.Cout, L.Cin, L.k, L.Cin_p, ptr(L.dw))
         n += 1
+    if L.src.bnb_fused:
+        if zero:
+            L.src.bsums.zero_()
+            n += 1
+        L.src.bnb_ready = True
     for p in L.p_dgrad:
         p.run()
     return n + len(L.p_dgrad)

@@ -184,6 +184,21 @@ typedef struct avdn_gemm_core {
   const void* residual;
   float leaky_slope;
   int32_t pad2_;
+  /* Fused train-mode BatchNorm BACKWARD statistics (dark_net.py:31 under autograd): this launch is the data
+   * gradient `out` = dA of the activation a = leaky(z*scale + shift) of the PRODUCING block, and once a tile of dA
+   * is final the epilogue adds, per output column c,
+   *     bnb_sums[0][c] += sum g          bnb_sums[1][c] += sum g * (z - mean[c]),   g = dA * leaky'(z*scale+shift)
+   * -- the two reductions nn.BatchNorm2d's backward needs -- so no separate pass over (z, dA) runs.
+   * bnb_z: bf16 tensor addressed like `out` (the block's stored pre-activation), bnb_scale/shift/mean [N] fp32,
+   * bnb_sums [2][N] f64, NOT zeroed by avdn_gemm_run (the parity launches of a stride-2 layer add into one
+   * buffer).  With accumulate == 1 the epilogue reads the old dA tile, adds in fp32 and stores (no bf16 TMA
+   * reduce-add), so the statistics see the final value.  CONV mode, K-major operands, bf16 TMA-store epilogue;
+   * excludes stats / col_scale.  All five NULL = off.                                                     */
+  const void* bnb_z;
+  const float* bnb_scale;
+  const float* bnb_shift;
+  const float* bnb_mean;
+  double* bnb_sums;
 } avdn_gemm_core;
 
 typedef struct avdn_gemm_desc {
@@ -252,6 +267,12 @@ int avdn_bn_apply(const void* z, const float* scale, const float* shift, const v
 int avdn_bn_backward(const void* da, const void* z, const float* scale, const float* shift, const float* mean,
                      const float* rstd, long long R, int C, int C_real, float slope, double* sums, void* dz,
                      float* dgamma, float* dbeta, avdn_stream_t stream);
+/* The second half of avdn_bn_backward alone: `sums` [2,C] f64 (sum g, sum g*(z-mean)) were produced by the
+ * epilogue of the data-gradient convolution that wrote `da` (avdn_gemm_core.bnb_*); `coef` [4,C] fp32 scratch. */
+int avdn_bn_backward_apply(const void* da, const void* z, const float* scale, const float* shift,
+                           const float* mean, const float* rstd, long long R, int C, int C_real, float slope,
+                           const double* sums, float* coef, void* dz, float* dgamma, float* dbeta,
+                           avdn_stream_t stream);
 
 /* nn.Conv2d weight [Cout,Cin,k,k] fp32 -> GEMM operands (bf16, zero padded):
  * wf [Cout_p][k*k][Cin_p] (forward / wgrad layout), wd [Cin_p][k*k][Cout_p] (dgrad). */

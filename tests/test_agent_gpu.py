@@ -253,3 +253,36 @@ def test_step_gradients_vs_oracle(agent):
         report[n] = (e, e16)
         assert e <= 1.5 * e16 + 8e-2, (n, e, e16)
     print({k: (round(a, 4), round(b, 4)) for k, (a, b) in report.items()})
+
+
+@pytest.mark.parametrize("nss_r", [0, 1, -1])
+def test_loss_kernel_nss_vs_reference_agent_golden(built_lib, golden_dir, nss_r):
+    """The NSS term of ``avdn_loss`` against the REFERENCE's ``NavCMTAgent.NSS`` values
+    (tests/golden/nss_golden.pt, written by make_nss_golden.py from src/xview_et/agent.py:256-270): with zero
+    waypoint error the per-sample loss is ``scale * nss_w * NSS_i``."""
+    import os
+    from avdn_b200 import _lib
+    g = torch.load(os.path.join(golden_dir, "nss_golden.pt"), weights_only=False)
+    B = g["h_sali"].shape[0]
+    att = torch.from_numpy(np.unpackbits(g["fix_packed"])[:B * 224 * 224].reshape(B, 224, 224)) * 255
+    dev = "cuda"
+    # output == targets (up to the angular term's own convention): xy on the unit axis, alt / prog equal
+    output = torch.tensor([[0.0, 1.0, 0.5, 0.25]] * B)
+    gt_xy, gt_alt, gt_prog = output[:, :2].clone(), output[:, 2].clone(), output[:, 3].clone()
+    jitter = torch.zeros(B)
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    loss_i = torch.zeros(B, dtype=torch.float64, device=dev)
+    d_o = torch.zeros(B, 4, device=dev)
+    d_h = torch.zeros(B, 64, device=dev)
+    t = [x.to(dev).contiguous() for x in (output, g["h_sali"], gt_xy, gt_alt, gt_prog, att.to(torch.uint8), jitter)]
+    nss_w, scale = 0.1, 0.2 / B
+    _lib.call("avdn_loss", *[_lib.ptr(x) for x in t], B, nss_w, nss_r, scale, _lib.ptr(loss), _lib.ptr(loss_i),
+              _lib.ptr(d_o), _lib.ptr(d_h))
+    ref_i = g["per_sample"][nss_r] * nss_w
+    got_i = loss_i.cpu()
+    # loss_i may or may not carry the step scale: accept the kernel's convention, pin the NSS values
+    ratio = (got_i / ref_i)
+    k = ratio[0].item()
+    assert abs(k - 1.0) < 1e-4 or abs(k - scale) < 1e-4 * scale, k
+    assert torch.allclose(got_i, ref_i * k, rtol=1e-4, atol=1e-9), (got_i, ref_i * k)
+    assert abs(loss.item() - (ref_i.sum() * scale).item()) <= 1e-4 * abs((ref_i.sum() * scale).item())

@@ -143,3 +143,62 @@ def test_conv_fwd_dgrad_wgrad(G, N, H, Cin, Cout, k, stride):
     G.plan_conv_wgrad(dz, x, dw, N=N, H=H, W=W, Cin=Cin, Cout=Cout, k=k, stride=stride).run()
     ref_dw = wr.grad.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)
     _close(dw, ref_dw, rtol=3e-3)
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,k,stride,acc", [
+    (4, 14, 128, 256, 3, 1, 0),      # 128-column tiles, CTA pairs
+    (5, 28, 256, 128, 1, 1, 1),      # 1x1 into a residual source: old dA read, added in fp32, stored
+    (3, 28, 64, 128, 3, 2, 0),       # stride 2: four parity launches add into one sums buffer
+    (3, 56, 32, 64, 3, 1, 0),        # 32-channel gradient (64-byte slab rows)
+    (2, 56, 64, 32, 1, 1, 1),        # 32-channel dZ operand (32-element k-blocks), accumulate
+    (20, 7, 128, 256, 3, 1, 0),      # 7x7 boxes spanning images, 98 of 128 tile rows used
+    (5, 7, 512, 1024, 3, 1, 1),      # odd tile count under CTA pairs (phantom tile)
+    (2, 112, 32, 64, 3, 2, 0)])      # first stride-2 block: 224x224x32 gradient
+def test_conv_dgrad_fused_bn_backward_sums(G, N, H, Cin, Cout, k, stride, acc):
+    """avdn_gemm_core.bnb_*: the dgrad epilogue reduces sum g and sum g*(z-mean), g = dA*leaky'(z*scale+shift), of the
+    block that produced the layer input -- checked against torch on the dA the launch actually stored (bit-exact
+    inputs, fp32 partial sums => 1e-4), and dA itself against the unfused launch."""
+    W = H
+    Ho, Wo = H // stride, W // stride
+    dz = _rand(N, Ho, Wo, Cout, seed=31)
+    w = _rand(Cout, Cin, k, k, seed=32, scale=0.05)
+    w_d = w.permute(1, 2, 3, 0).reshape(Cin, k * k * Cout).contiguous()
+    z = _rand(N, H, W, Cin, seed=33)
+    g = torch.Generator(device="cuda").manual_seed(34)
+    scale = torch.randn(Cin, device="cuda", generator=g)
+    shift = torch.randn(Cin, device="cuda", generator=g) * 0.5
+    mean = torch.randn(Cin, device="cuda", generator=g) * 0.3
+    slope = 0.01
+    base = _rand(N, H, W, Cin, seed=35) if acc else torch.full((N, H, W, Cin), float("nan"), device="cuda",
+                                                                 dtype=torch.bfloat16)
+    kw = dict(N=N, H=H, W=W, Cin=Cin, Cout=Cout, k=k, stride=stride, accumulate=acc)
+    dx_ref = base.clone()
+    for p in G.plan_conv_dgrad(dz, w_d, dx_ref, **kw):
+        p.run()
+    dx = base.clone()
+    sums = torch.zeros(2 * Cin, device="cuda", dtype=torch.float64)
+    plans = G.plan_conv_dgrad(dz, w_d, dx, bnb=(z, scale, shift, mean, sums, slope), **kw)
+    assert all(p.desc.core.bnb_z for p in plans)
+    for p in plans:
+        p.run()
+    torch.cuda.synchronize()
+    assert torch.isfinite(dx.float()).all()
+    # the fused launch adds old + new in fp32 and rounds once; the TMA reduce-add rounds twice
+    _close(dx, dx_ref, rtol=1e-2 if acc else 0.0)
+    da, zf = dx.double(), z.double()
+    # z*scale + shift in float64 is exact up to one rounding: its sign is the sign of the kernel's fp32 fma
+    y = zf * scale.double() + shift.double()
+    gg = torch.where(y > 0, da, (dx.float() * slope).double())
+    hh = gg * (zf - mean.double())
+    s1, s2 = gg.sum(dim=(0, 1, 2)), hh.sum(dim=(0, 1, 2))
+    got = sums.view(2, Cin).clone()
+    tol1 = 2e-4 * gg.abs().sum(dim=(0, 1, 2)) + 1e-6
+    tol2 = 2e-4 * hh.abs().sum(dim=(0, 1, 2)) + 1e-6
+    assert ((got[0] - s1).abs() <= tol1).all(), ((got[0] - s1).abs() / tol1).max().item()
+    assert ((got[1] - s2).abs() <= tol2).all(), ((got[1] - s2).abs() / tol2).max().item()
+    if not acc:
+        # the caller owns the zeroing: a second run adds the same sums again (and they are reproducible)
+        for p in plans:
+            p.run()
+        torch.cuda.synchronize()
+        assert torch.allclose(sums.view(2, Cin), 2 * got, rtol=1e-12, atol=0)

@@ -55,3 +55,17 @@ def test_postprocess_waypoints_integers():
     assert alt.tolist() == [400, 130, 40]
     assert stop.tolist() == [True, False, False]
     assert ang.tolist() == [63, 180, 315]
+
+
+def test_nss_matches_reference_agent(golden_dir):
+    """``mo.nss`` against the values the reference's own ``NavCMTAgent.NSS`` (src/xview_et/agent.py:256-270)
+    returned for the same maps (tests/golden/make_nss_golden.py), for all three nss_r variants."""
+    g = torch.load(os.path.join(golden_dir, "nss_golden.pt"), weights_only=False)
+    B = g["h_sali"].shape[0]
+    sal = torch.nn.functional.interpolate(g["h_sali"].view(B, 1, 8, 8), size=(224, 224), mode="bilinear",
+                                          align_corners=False)
+    fix = torch.from_numpy(np.unpackbits(g["fix_packed"])[:B * 224 * 224].reshape(B, 224, 224).astype(np.float64))
+    for nss_r in (0, 1, -1):
+        per = torch.stack([mo.nss(sal[i], fix[i], nss_r) for i in range(B)])
+        assert torch.allclose(per, g["per_sample"][nss_r], rtol=1e-9, atol=0), nss_r
+        assert torch.allclose(mo.nss(sal.view(B, 224, 224), fix, nss_r), g["batch"][nss_r], rtol=1e-9, atol=0)

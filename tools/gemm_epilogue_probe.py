@@ -40,7 +40,7 @@ if os.environ.get("PROBE_TRACE"):
         bench("L13 1x1 256->128 @28", N, 28, 256, 128, 1, 1, reps=1)
     else:
         bench("L14 3x3 128->256 @28", N, 28, 128, 256, 3, 1, reps=1)
-    e = buf.cpu()[2048:2048 + 8 * 40].view(-1, 8)
+    e = buf.cpu()[2048:2048 + 16 * 40].view(-1, 16)      # 16 clock slots per tile (8..12: fused BN-backward phase)
     eb = int(e[0, 0])
     print("epilogue (thread 0) per tile: t_wait_start | +tfull | +wait_group | +bar1 | slab0: +ld/cvt/sts | +fence | +bar2 | tile_end")
     for i in range(2, 30):
