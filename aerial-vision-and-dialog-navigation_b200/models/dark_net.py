@@ -33,6 +33,9 @@ LEAKY_SLOPE = 0.01      # nn.LeakyReLU() default, dark_net.py:33
 # fused epilogue (four single-issue warps per CTA) makes the memory-bound 1x1 / stride-2 dgrads 1.7-2.5x slower
 # and the tensor-bound 3x3 ones ~10 % slower -- net +3 ms per step ("measured and not kept").
 FUSE_BNB = os.environ.get("AVDN_FUSE_BNB", "0") == "1"
+# Block 0 in train mode: recompute path (avdn_conv0_fwd_stats / _fwd_apply / _bwd) -- its pre-activation z and its
+# gradient dz (2 GB each at 640 views) are never stored.  AVDN_CONV0_RECOMPUTE=0 keeps the stored-z path.
+CONV0_RECOMPUTE = os.environ.get("AVDN_CONV0_RECOMPUTE", "1") != "0"
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -104,6 +107,8 @@ class _Engine:
 
     def __init__(self, net: "Darknet", N: int, H: int, W: int, device):
         self.N, self.H, self.W, self.device = N, H, W, device
+        import weakref
+        self.net_ref = weakref.ref(net)
         bf, f32 = torch.bfloat16, torch.float32
         dev = device
         self.layers = []
@@ -153,9 +158,15 @@ class _Engine:
         # ---- buffers ----
         for L in self.layers:
             n_el = L.R * L.Cout_p
-            max_elems = max(max_elems, n_el)
-            L.z = torch.empty((N, L.Hout, L.Wout, L.Cout_p), dtype=bf, device=dev)
+            if not (L.first and CONV0_RECOMPUTE):              # the recompute path of block 0 forms no dz
+                max_elems = max(max_elems, n_el)
+            L.recompute = bool(L.first and CONV0_RECOMPUTE)
+            L.z = None if L.recompute else torch.empty((N, L.Hout, L.Wout, L.Cout_p), dtype=bf, device=dev)
             L.a = torch.empty((N, L.Hout, L.Wout, L.Cout_p), dtype=bf, device=dev)
+            if L.recompute:
+                L.zw = torch.zeros(L.Cout * 27, dtype=f32, device=dev)         # sum z * x  (forward pass 1)
+                L.gw = torch.zeros(L.Cout * 27, dtype=f32, device=dev)         # sum g * x  (backward)
+                L.xs9 = torch.zeros(36, dtype=torch.float64, device=dev)       # total / border sums of x
             L.scale = torch.zeros(L.Cout_p, dtype=f32, device=dev)
             L.shift = torch.zeros(L.Cout_p, dtype=f32, device=dev)
             L.mean = torch.zeros(L.Cout_p, dtype=f32, device=dev)
@@ -269,7 +280,7 @@ class _Engine:
         dwf_off = 0
         seen_as_input = set()
         for L in reversed(self.layers):
-            dz = self.dz[: L.R * L.Cout_p].view(self.N, L.Hout, L.Wout, L.Cout_p)
+            dz = None if L.recompute else self.dz[: L.R * L.Cout_p].view(self.N, L.Hout, L.Wout, L.Cout_p)
             L.dz = dz
             if arena is not None:
                 i = L.idx
@@ -297,7 +308,7 @@ class _Engine:
             acc = 1 if id(L.src) in seen_as_input else 0
             P = L.src
             bnb = None
-            if FUSE_BNB and first_consumer[id(P)] == L.idx and G.pick_bn(L.Cin_p) <= 128:
+            if FUSE_BNB and P.z is not None and first_consumer[id(P)] == L.idx and G.pick_bn(L.Cin_p) <= 128:
                 bnb = (P.z, P.scale, P.shift, P.mean, P.bsums, LEAKY_SLOPE)
                 P.bnb_fused = True
             L.p_dgrad = G.plan_conv_dgrad(dz, L.wd, L.src.g, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
@@ -343,7 +354,12 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
                 L.p_fwd_eval.run()
                 n += 1
             continue
-        if L.first:
+        if L.first and L.recompute:
+            # pass 1: batch statistics (+ the z-weighted input sums the backward needs); pass 2 below recomputes z
+            call("avdn_conv0_fwd_stats", ptr(x_nhwc4), ptr(conv.weight), eng.N, L.Hin, L.Win, ptr(L.sums), ptr(L.zw),
+                 ptr(L.xs9))
+            n += 5
+        elif L.first:
             call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win, ptr(L.sums))
             n += 2
         else:
@@ -353,8 +369,12 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
              ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.scale),
              ptr(L.shift), ptr(L.mean), ptr(L.rstd))
         n += 1 if L.first else 2    # finalize (+ the stats memset inside avdn_gemm_run)
-        call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.res.a) if L.res is not None else None,
-             ptr(L.a), L.R, L.Cout_p, LEAKY_SLOPE)
+        if L.first and L.recompute:
+            call("avdn_conv0_fwd_apply", ptr(x_nhwc4), ptr(conv.weight), ptr(L.scale), ptr(L.shift), LEAKY_SLOPE,
+                 ptr(L.a), eng.N, L.Hin, L.Win)
+        else:
+            call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.res.a) if L.res is not None else None,
+                 ptr(L.a), L.R, L.Cout_p, LEAKY_SLOPE)
         n += 1
     if train:
         net._bump_batches_tracked()
@@ -395,6 +415,13 @@ def _layer_backward(eng, L, unpack=True, zero=True):
     input gradient.  Returns the number of kernel launches.  ``unpack=False`` / ``zero=False``: the caller
     zeroes the WGRAD arena once and unpacks ranges of layers in one launch (``_trunk_backward``)."""
     call, ptr = _lib.call, _lib.ptr
+    if L.first and L.recompute:
+        # one pass over (x, dA): BatchNorm-backward sums and the weight gradient, z recomputed, dz never formed
+        conv = eng.net_ref().module_list[L.idx][0]
+        call("avdn_conv0_bwd", ptr(eng.x_in), ptr(conv.weight), ptr(L.g), ptr(L.scale), ptr(L.shift), ptr(L.mean),
+             ptr(L.rstd), LEAKY_SLOPE, eng.N, L.Hin, L.Win, ptr(L.zw), ptr(L.xs9), ptr(L.sums), ptr(L.gw), ptr(L.dw),
+             ptr(L.dgamma), ptr(L.dbeta))
+        return 4
     if L.bnb_fused and L.bnb_ready:
         # the sums were reduced by the epilogue of the dgrad that wrote L.g: coefficients + apply only
         call("avdn_bn_backward_apply", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,

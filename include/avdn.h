@@ -238,6 +238,25 @@ int avdn_conv0_fwd_eval(const void* x_nhwc4, const float* w, const float* scale,
                         void* a, int N, int H, int W, avdn_stream_t stream);
 /* dw [32,3,3,3] fp32 += sum_pixels dz * x (weight gradient of the same layer). */
 int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int H, int W, avdn_stream_t stream);
+/* Train-mode RECOMPUTE path of the same block (nn.Conv2d + nn.BatchNorm2d(train) + nn.LeakyReLU and their autograd
+ * backward, dark_net.py:22-33): the block moves the trunk's largest tensors for 0.6 % of its FLOPs, so neither its
+ * pre-activation z nor dz is ever stored.
+ *   avdn_conv0_fwd_stats  pass 1: stats [2,32] f64 = BatchNorm batch statistics of z (rounded to bf16, i.e. of the z a
+ *                         stored tensor would hold; finish with avdn_bn_finalize), zw [32,3,3,3] fp32 =
+ *                         sum_px z[px][co] * x[px+tap][ci], xs9 [9,4] f64 = total / border sums of x.  All three are
+ *                         zeroed by the call and feed avdn_conv0_bwd.
+ *   avdn_conv0_fwd_apply  pass 2: a [N,H,W,32] bf16 = leaky(bf16(conv(x)) * scale + shift).
+ *   avdn_conv0_bwd        da [N,H,W,32] bf16 -> dw += scale*Gw + A*Zw + B*Xw (the weight gradient of
+ *                         dz = scale*g + A*z + B without forming dz), dgamma += rstd*S2, dbeta += S1;
+ *                         sums [2,32] f64 and gw [32,3,3,3] fp32 are scratch.   W % 16 == 0, H % 2 == 0.            */
+int avdn_conv0_fwd_stats(const void* x_nhwc4, const float* w, int N, int H, int W, double* stats, float* zw,
+                         double* xs9, avdn_stream_t stream);
+int avdn_conv0_fwd_apply(const void* x_nhwc4, const float* w, const float* scale, const float* shift, float slope,
+                         void* a, int N, int H, int W, avdn_stream_t stream);
+int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* da, const float* scale, const float* shift,
+                   const float* mean, const float* rstd, float slope, int N, int H, int W, const float* zw,
+                   const double* xs9, double* sums, float* gw, float* dw, float* dgamma, float* dbeta,
+                   avdn_stream_t stream);
 
 /* nn.BatchNorm2d in train mode (dark_net.py:31; eps 1e-5, momentum 0.1): batch
  * statistics of z [R,C] bf16 -> per-channel affine scale = gamma*rstd,

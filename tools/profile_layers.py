@@ -45,7 +45,9 @@ take()  # nchw->nhwc
 bw = {}
 for L in reversed(eng.layers):
     d = {"bn_bwd": take()}
-    if L.first:
+    if L.first and getattr(L, "recompute", False):
+        d["wgrad"] = ("", 0.0, 0)        # avdn_conv0_bwd is one record: sums + weight gradient
+    elif L.first:
         d["wgrad"] = take()
     else:
         d["wgrad"] = take()
