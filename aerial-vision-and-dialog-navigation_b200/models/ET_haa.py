@@ -89,7 +89,8 @@ class ET(nn.Module):
         if float(getattr(self.args, "dropout_emb", 0.0)) != 0.0:
             raise NotImplementedError("dropout_emb > 0 (EncoderVL's embedding dropout) is not implemented")
         self._drop_step = getattr(self, "_drop_step", 0) + 1
-        seed = (torch.initial_seed() * 1000003 + self._drop_step) & 0xFFFFFFFFFFFFFFFF
+        seed = (torch.initial_seed() * 1000003 + self._drop_step + 0x9E3779B97F4A7C15 * int(getattr(self, 'drop_rank', 0))) \
+            & 0xFFFFFFFFFFFFFFFF
         return float(self.args.dropout_transformer_encoder), self.HEAD_DROPOUT, seed
 
     def forward_features(self, **inputs):

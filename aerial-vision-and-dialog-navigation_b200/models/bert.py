@@ -347,7 +347,8 @@ class CustomBERTModel(nn.Module):
             return 0.0, 0.0, 0.0, 0
         c = self.bert.config
         self._drop_step += 1
-        seed = (torch.initial_seed() * 1000003 + 7919 * self._drop_step) & 0xFFFFFFFFFFFFFFFF
+        seed = (torch.initial_seed() * 1000003 + 7919 * self._drop_step
+                + 0x9E3779B97F4A7C15 * int(getattr(self, 'drop_rank', 0))) & 0xFFFFFFFFFFFFFFFF
         return float(c.hidden_dropout_prob), float(c.attention_probs_dropout_prob), float(self.linears[2].p), seed
 
     def used_parameters(self):

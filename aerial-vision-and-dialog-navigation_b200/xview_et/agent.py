@@ -20,9 +20,11 @@ What is here
   over the t+1 steps seen so far, discretises the waypoint and moves the view -- all on the device;
   the host reads the B stop flags once per step (the reference's ``lenths`` bookkeeping).
 
-What is not here: the dataset-driven ``rollout`` with the shapely teacher
-(``teacher_action``, agent.py:386-507) -- SURVEY.md §8f N3 ("next"); the language side (BERT ->
-``lang`` / ``lang_cls``, agent.py:527-543) is an input of the path (N1).
+* ``rollout(train_ml, not_in_train, nss_w)`` / ``train(loader, n_epochs, feedback, nss_w_weighting)`` /
+  ``test(loader, ...)``: the reference's agent loop with its signatures over ``self.env`` (an ``ANDHNavBatch``):
+  tokenizer -> ``CustomBERTModel`` -> poses of the rollout (teacher: ground-truth actions, ``avdn_teacher_action`` +
+  ``avdn_waypoint_step`` on the device; student: a no-grad greedy rollout) -> ``train_rollout_step`` (views, trunk,
+  T encoder passes with loss and backward) -> trajectory dicts, ``self.loss``, ``self.logs['IL_loss']``.
 """
 from __future__ import annotations
 
@@ -75,7 +77,17 @@ class NavCMTAgent:
             state.update({k: v for k, v in new_state["model"].items() if k in state})
             self.vision_model.load_state_dict(state)
         self.vln_model = ET(args).to(self.device)
+        self.vln_model.drop_rank = rank              # data-parallel replicas draw different dropout masks
+        self.tokenizer = getattr(args, "tokenizer", None)     # agent.py:124 (BertTokenizerFast; no vocabulary offline)
+        self.feedback = "student"
+        self.env_name = ""
+        self.loss = 0
+        self.exposed_events = None                   # bench: [(event, event)] around the wait for the last gradient bucket
         lr = getattr(args, "lr", 1e-5)
+        if getattr(args, "optim", "adamW") not in ("adamW", "adam"):
+            raise ValueError("optim must be 'adam' or 'adamW' (agent.py:151)")
+        if getattr(args, "optim", "adamW") == "adam":
+            raise NotImplementedError("optim='adam' (no decoupled weight decay) is not implemented: use 'adamW'")
         # agent.py:153-156: one AdamW per model, default weight decay; only ET is clipped (agent.py:247)
         self.et_optimizer = FusedAdamW(self.vln_model.used_parameters(), lr=lr, max_norm=40.0)
         self.vision_model_optimizer = FusedAdamW(dict(self.vision_model.named_parameters()), lr=lr)
@@ -108,7 +120,12 @@ class NavCMTAgent:
                                          lr=lr if lr is not None else getattr(self.args, "lr", 1e-5))
         self.lang_model._grad_arena = self.lang_optimizer.grads
         self.lang_model._engines.clear()
+        self.lang_model.drop_rank = self.rank
         self.optimizers = (self.et_optimizer, self.vision_model_optimizer, self.lang_optimizer)
+        if self.world > 1:
+            # every rank built (and randomly initialised) its own encoder: replicas start from rank 0's, like the
+            # other two models in __init__
+            parallel.broadcast_([self.lang_optimizer.p], 0, self.pg)
         return self.lang_model
 
     def broadcast_parameters(self):
@@ -231,17 +248,36 @@ class NavCMTAgent:
 
     @property
     def nss_w(self):
-        return float(getattr(self.args, "nss_w", 0.1))
+        ov = getattr(self, "_nss_w_override", None)
+        return float(ov if ov is not None else getattr(self.args, "nss_w", 1.0))        # parser.py:38 default 1
 
     @property
     def train_ml(self):
-        return float(getattr(self.args, "ml_weight", 0.2))
+        ov = getattr(self, "_train_ml_override", None)
+        return float(ov if ov is not None else getattr(self.args, "ml_weight", 0.2))     # parser.py:54
+
+    class _Weights:
+        """``with agent._weights(nss_w, train_ml):`` -- the per-rollout loss weights the reference passes to
+        ``rollout(train_ml=..., nss_w=...)`` (agent.py:229-235); ``None`` keeps the value from ``args``."""
+
+        def __init__(self, agent, nss_w, train_ml):
+            self.a, self.v = agent, (nss_w, train_ml)
+
+        def __enter__(self):
+            self.old = (getattr(self.a, "_nss_w_override", None), getattr(self.a, "_train_ml_override", None))
+            self.a._nss_w_override, self.a._train_ml_override = self.v
+
+        def __exit__(self, *exc):
+            self.a._nss_w_override, self.a._train_ml_override = self.old
+
+    def _weights(self, nss_w=None, train_ml=None):
+        return NavCMTAgent._Weights(self, nss_w, train_ml)
 
     def forward_loss(self, batch):
         """Validation: forward + loss (trunk in eval mode).  Returns (loss, output, h_sali)."""
         self.vision_model.eval()
         output, h_sali = self._forward(batch, False)
-        return self.loss_total, output, h_sali
+        return self.loss_total.clone(), output, h_sali
 
     def train_step(self, batch, sync_loss=False):
         """One training iteration (see the module docstring).  Returns the device
@@ -282,27 +318,69 @@ class NavCMTAgent:
         DN._trunk_backward(self.vision_model, teng, bufs["d_frames"].view(-1, 512, 7, 7), after_layer=hook,
                            flush_layers=set(buckets) if dp else None)
         if dp:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._wait_comm()
         gs = 1.0 / self.world
         for opt in self.optimizers:
             self.launches += opt.step(grad_scale=gs)
         self.launches += (teng.launches - l0) + (eng.launches - e0)
-        self.logs["IL_loss"].append(self.loss_total)
+        self._log_loss()
         if sync_loss:
             return float(self.loss_total.item())
         return self.loss_total
 
-    def train_iteration(self, teacher_batch, student_batch, sync_loss=False):
-        """One iteration of ``train`` (agent.py:225-251): the teacher-feedback rollout and the student-feedback
-        rollout add their losses, ONE backward's worth of gradients (accumulated over both), clip, one step of every
-        optimiser.  ``student_batch`` comes from ``student_batch()``.  Returns the summed loss."""
-        l1 = self.train_rollout_step(teacher_batch, step=False)
-        l1 = l1.clone()
-        l2 = self.train_rollout_step(student_batch, zero=False)
-        total = l1 + l2
-        return float(total.item()) if sync_loss else total
+    def _wait_comm(self):
+        """The optimiser waits for the last gradient bucket; with ``exposed_events`` set (bench) the wait is bracketed
+        by CUDA events: the all-reduce time the backward pass did not hide."""
+        cur = torch.cuda.current_stream()
+        if self.exposed_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            cur.wait_stream(self._comm_stream)
+            e1.record(cur)
+            self.exposed_events.append((e0, e1))
+        else:
+            cur.wait_stream(self._comm_stream)
 
-    def train_rollout_step(self, batch, sync_loss=False, zero=True, step=True):
+    LOG_KEEP = 4096
+
+    def _log_loss(self):
+        """``self.logs['IL_loss']`` (agent.py:885): one entry per rollout.  Device scalars (a copy: ``loss_total`` is
+        rewritten every step), converted lazily by ``il_losses()``; bounded."""
+        log = self.logs["IL_loss"]
+        log.append(self.loss_total.clone())
+        if len(log) > self.LOG_KEEP:
+            del log[: len(log) - self.LOG_KEEP]
+
+    def il_losses(self):
+        """The logged losses as host floats (one synchronisation)."""
+        log = self.logs["IL_loss"]
+        return torch.stack([x.reshape(()) for x in log]).cpu().tolist() if log else []
+
+    def train_iteration(self, teacher_batch, student_batch=None, sync_loss=False, feedback="student",
+                        nss_w_weighting=1):
+        """One iteration of ``train`` (agent.py:225-251).  ``feedback='student'`` (the reference's recipe): the
+        teacher-feedback rollout with ``train_ml = args.ml_weight`` and **nss_w = 0** (agent.py:232), then the
+        student-feedback rollout with ``nss_w = args.nss_w * nss_w_weighting`` (agent.py:235); the two add their
+        losses, ONE backward's worth of gradients (accumulated over both), clip, one step of every optimiser.
+        ``feedback='teacher'``: the teacher rollout alone with ``train_ml = args.teacher_weight`` and the NSS term
+        (agent.py:229).  ``student_batch`` comes from ``student_batch()``.  Returns the summed loss."""
+        nss = float(getattr(self.args, "nss_w", 1.0)) * nss_w_weighting
+        if feedback == "teacher":
+            tot = self.train_rollout_step(teacher_batch, nss_w=nss,
+                                          train_ml=float(getattr(self.args, "teacher_weight", 1.0))).clone()
+        elif feedback == "student":
+            l1 = self.train_rollout_step(teacher_batch, step=False, nss_w=0.0).clone()
+            tot = l1 + self.train_rollout_step(student_batch, zero=False, nss_w=nss)
+        else:
+            raise ValueError("Invalid feedback option")
+        return float(tot.item()) if sync_loss else tot
+
+    def train_rollout_step(self, batch, sync_loss=False, zero=True, step=True, nss_w=None, train_ml=None,
+                           collect=None):
+        with self._weights(nss_w, train_ml):
+            return self._train_rollout_step(batch, sync_loss, zero, step, collect)
+
+    def _train_rollout_step(self, batch, sync_loss=False, zero=True, step=True, collect=None):
         """One teacher-forced training ROLLOUT (agent.py:580-760, 883-885, 245-251) as one batched pass: the loss is
         taken at EVERY step t of every episode on the history ``[:t+1]``, summed over steps and samples and scaled
         by ``ml_weight / B``, as the reference accumulates ``ml_loss`` over its step loop.
@@ -322,7 +400,10 @@ class NavCMTAgent:
         ``lenths`` host int [B][T] (history length seen at step t: stops growing once a sample has ended,
         agent.py:603-620; default t+1), ``att`` u8 [B,T,224,224] (default: rendered from the poses), ``jitter``
         f32 [B,T].  ``zero=False`` keeps the gradients already in the arenas, ``step=False`` leaves them there
-        without an optimiser step (``train_iteration`` chains the two rollouts of an iteration that way)."""
+        without an optimiser step (``train_iteration`` chains the two rollouts of an iteration that way).
+        ``nss_w`` / ``train_ml`` (``train_rollout_step``): this rollout's loss weights (default: ``args.nss_w``,
+        ``args.ml_weight``); with ``nss_w == 0`` no human-attention maps are rendered.  ``collect``: a list that
+        receives the per-step ``output`` [B,4] tensors (the trajectory log of ``rollout``)."""
         ptr = _lib.ptr
         self.vision_model.train()
         n = 0
@@ -416,6 +497,8 @@ class NavCMTAgent:
                       ptr(None if att_t is None else att_t[t]), ptr(None if jit is None else jit[t]), B,
                       float(self.nss_w), int(getattr(self.args, "nss_r", 0)), scale, ptr(self.loss_total),
                       ptr(bufs["loss_i"]), ptr(bufs["d_output"]), ptr(bufs["d_h_sali"]))
+            if collect is not None:
+                collect.append(output.detach().clone())
             if leng is None:
                 df, _ = eng.backward(bufs["d_output"], bufs["d_h_sali"], d_frames=xb["d_frames"][:B * Tc])
             else:
@@ -451,13 +534,13 @@ class NavCMTAgent:
         DN._trunk_backward(vm, teng, bufs["d_frames"].view(-1, 512, 7, 7), after_layer=hook,
                            flush_layers=set(buckets) if dp else None)
         if dp:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._wait_comm()
         if step:
             gs = 1.0 / self.world
             for opt in self.optimizers:
                 n += opt.step(grad_scale=gs)
         self.launches += n + (teng.launches - l0) + (eng.launches - e0)
-        self.logs["IL_loss"].append(self.loss_total)
+        self._log_loss()
         return float(self.loss_total.item()) if sync_loss else self.loss_total
 
     @torch.no_grad()
@@ -631,9 +714,12 @@ class NavCMTAgent:
             out.append(path)
         return out
 
-    def test(self, batches, env_name="no_name_provided", feedback="student", **kwargs):
-        """``agent.test`` (agent.py:191-206): greedy rollouts over ``batches`` in eval mode, one trajectory dict per
+    def test(self, batches, env_name="no_name_provided", feedback="student", not_in_train=False, **kwargs):
+        """``agent.test`` (agent.py:191-206): greedy rollouts in eval mode, one trajectory dict per
         episode in ``self.results[instr_id]`` -- the structure ``ANDHNavBatch.eval_metrics`` scores.
+
+        With ``self.env`` set to an ``ANDHNavBatch`` this is the reference's loop: ``batches`` is the data loader (it
+        fills ``self.env`` as it is iterated) and every item triggers ``self.rollout(not_in_train=True)``.  Otherwise:
 
         Every batch is the ``rollout_greedy`` input dict plus host metadata: ``instr_id`` list[str],
         ``gt_path_corners`` list of ``[n_i,4,2]`` arrays (optional: without it ``gt_progress`` is omitted, as for
@@ -642,6 +728,16 @@ class NavCMTAgent:
         721), evaluated for all steps of the batch in one ``avdn_teacher_action`` launch."""
         self.feedback, self.env_name = feedback, env_name
         self.results, self.losses = {}, []
+        if hasattr(self.env, "_get_obs"):
+            self.vln_model.eval(); self.vision_model.eval()
+            if self.lang_model is not None:
+                self.lang_model.eval()
+            self.loss = 0
+            for _ in batches:
+                for traj in self.rollout(not_in_train=True, **kwargs):
+                    self.loss = 0
+                    self.results[traj["instr_id"]] = traj
+            return self.results
         for batch in batches:
             meta = {k: batch[k] for k in ("instr_id", "gt_path_corners", "num_dia") if k in batch}
             res = self.rollout_greedy({k: v for k, v in batch.items() if k not in meta}, **kwargs)
@@ -690,7 +786,8 @@ class NavCMTAgent:
         dev = self.device
         c = torch.as_tensor(np.asarray(corners) if not torch.is_tensor(corners) else corners).to(dev, torch.float64).contiguous()
         B = c.shape[0]
-        if isinstance(gt_path_corners, (list, tuple)) and not torch.is_tensor(gt_path_corners):
+        packed = isinstance(gt_path_corners, tuple) and len(gt_path_corners) == 2 and torch.is_tensor(gt_path_corners[0])
+        if isinstance(gt_path_corners, (list, tuple)) and not packed:
             lens = [len(g) for g in gt_path_corners]
             pmax = max(lens)
             gt = np.zeros((B, pmax, 4, 2), dtype=np.float64)
@@ -806,6 +903,338 @@ class NavCMTAgent:
             return np.array(rotated), (cur + angle) % 360
         return np.array(moved), (cur + angle) % 360
 
+    # ------------------------------------------------- the reference's agent loop (drop-in signatures)
+    def _language_batch(self, items):
+        """agent.py:519-538: the dialog of every episode through the tokenizer -- ``instructions`` for the
+        transformer's language rows, ``pre_dialogs + instructions`` for ``linear_cls`` unless
+        ``args.train_val_on_full``.  Needs ``self.tokenizer`` (the reference's ``BertTokenizerFast``: any callable
+        ``tok(list[str], padding=True, return_tensors='pt')`` -> ``input_ids`` / ``attention_mask``) and an attached
+        language model."""
+        if self.lang_model is None or self.tokenizer is None:
+            raise RuntimeError("rollout() tokenises the dialogs and runs CustomBERTModel (agent.py:124-126,519-538): "
+                               "set agent.tokenizer and call attach_lang_model() first")
+        vis_only = bool(getattr(self.args, "vision_only", False))
+        texts = ["" if vis_only else it["instructions"] for it in items]
+        enc = self.tokenizer(texts, padding=True, return_tensors="pt")
+        out = {"input_ids": enc["input_ids"].to(self.device), "attention_mask": enc["attention_mask"].to(self.device)}
+        lang_inputs = texts
+        if not bool(getattr(self.args, "train_val_on_full", False)):
+            lang_inputs = [it["pre_dialogs"] + it["instructions"] for it in items]
+            enc2 = self.tokenizer(lang_inputs, padding=True, return_tensors="pt")
+            out["cls_input_ids"] = enc2["input_ids"].to(self.device)
+            out["cls_attention_mask"] = enc2["attention_mask"].to(self.device)
+        return out, lang_inputs
+
+    @torch.no_grad()
+    def _teacher_rollout_poses(self, corners0, dirs0, geo, gt_paths, T):
+        """The pose sequence of a teacher-feedback rollout (agent.py:580-770 with ``feedback == 'teacher'``): the
+        action of every step is the ground-truth action, so the sequence does not depend on the model.  Per step:
+        ``teacher_action`` (target waypoint / altitude / progress at the current view) and the simulator update with
+        that target -- stop once the ground-truth progress exceeds 0.5 or at the last step.  All on the device; the
+        host reads the stop flags once at the end.  Returns a dict of ``[T, B, ...]`` tensors and the step count."""
+        ptr, call = _lib.ptr, _lib.call
+        dev = self.device
+        B = corners0.shape[0]
+        f64, i32 = torch.float64, torch.int32
+        corners = corners0.to(dev, f64).contiguous().clone()
+        cur = dirs0.to(dev, f64).contiguous().clone()
+        ended = torch.zeros(B, dtype=torch.uint8, device=dev)
+        bounds = geo[:, :4].contiguous()
+        H = dict(corners=torch.empty((T + 1, B, 4, 2), dtype=f64, device=dev), dirs=torch.empty((T + 1, B), dtype=f64, device=dev),
+                 ended=torch.empty((T, B), dtype=torch.uint8, device=dev), xy=torch.empty((T, B, 2), device=dev),
+                 alt=torch.empty((T, B), device=dev), prog=torch.empty((T, B), device=dev))
+        ang = torch.empty(B, dtype=i32, device=dev); dist = torch.empty(B, dtype=f64, device=dev); alt_i = torch.empty(B, dtype=i32, device=dev)
+        gts = [gt_paths[i] for i in range(B)]
+        lens = [len(g) for g in gts]
+        gt = np.zeros((B, max(lens), 4, 2), dtype=np.float64)
+        for i, g in enumerate(gts):
+            gt[i, :lens[i]] = np.asarray(g, dtype=np.float64)
+        gt_pack = (torch.from_numpy(gt).to(dev), torch.tensor(lens, dtype=i32, device=dev))
+        for t in range(T):
+            H["corners"][t].copy_(corners); H["dirs"][t].copy_(cur)
+            xy, alt, prog = self.teacher_action(corners, gt_pack, ended, feedback="teacher")
+            H["xy"][t].copy_(xy); H["alt"][t].copy_(alt); H["prog"][t].copy_(prog)
+            out = torch.cat((xy, alt[:, None], prog[:, None]), 1).contiguous()
+            call("avdn_waypoint_step", ptr(out), ptr(corners), ptr(bounds), ptr(cur), ptr(ended), B,
+                 float(self.STOP_THRESHOLD), int(t == T - 1), ptr(ang), ptr(dist), ptr(alt_i))
+            H["ended"][t].copy_(ended)
+            self.launches += 8
+        H["corners"][T].copy_(corners); H["dirs"][T].copy_(cur)
+        e = H["ended"].cpu().numpy().astype(bool)
+        steps = T
+        for t in range(T):
+            if e[t].all():                                   # agent.py:773-774: early exit once every sample has ended
+                steps = t + 1
+                break
+        return H, steps
+
+    def rollout(self, train_ml=None, not_in_train=False, nss_w=0, **kwargs):
+        """Drop-in for ``NavCMTAgent.rollout`` (src/xview_et/agent.py:512-894) over ``self.env`` (an
+        ``ANDHNavBatch`` whose ``batch`` / maps the data loader has filled): one rollout of the current batch under
+        ``self.feedback``; returns the list of trajectory dicts the reference returns.
+
+        * training (``not_in_train`` false): the rollout's loss ``ml_loss * train_ml / B`` is added to ``self.loss`` and
+          its gradients to the optimiser arenas -- the reference builds an autograd graph here and calls
+          ``self.loss.backward()`` in ``train``; this implementation has no graph, so the backward of a rollout runs
+          inside it and ``train`` only clips and steps.  Teacher feedback: the poses come from the ground-truth
+          actions; student feedback: from a no-grad greedy rollout (``student_batch``).  Language: tokenizer +
+          ``CustomBERTModel``, trained in the loop.
+        * ``not_in_train``: no gradients; student feedback is ``rollout_greedy``; teacher feedback additionally logs
+          ``human_att_performance`` / ``nss`` per step (agent.py:683-693)."""
+        env = self.env
+        items = list(env.batch)
+        B = len(items)
+        dev = self.device
+        env._sync_maps()
+        T = int(getattr(self.args, "max_action_len", 15))
+        lb, lang_inputs = self._language_batch(items)
+        gps0 = np.stack([np.asarray(it["gt_path_corners"][0], dtype=np.float64) for it in items])
+        _, geo_h, tidx_h = env._gather_poses(None, 0)
+        geo = torch.from_numpy(geo_h).to(dev)
+        tidx = torch.from_numpy(tidx_h).to(dev)
+        dirs0 = torch.tensor([float(it["angle"]) for it in items], dtype=torch.float64, device=dev)
+        gt_paths = [np.asarray(it["gt_path_corners"], dtype=np.float64) for it in items]
+        has_gt = "test" not in self.env_name
+        traj = []
+        for i, it in enumerate(items):
+            rounds = lang_inputs[i].split("[QUE]")
+            remove = sum(1 for r in rounds if "Yes" in r[0:5])
+            traj.append({"instr_id": it["map_name"] + "__" + it["route_index"], "num_dia": len(rounds) - remove,
+                         "path_corners": [(np.array(it["gt_path_corners"][0]), it["angle"])],
+                         "gt_path_corners": it["gt_path_corners"], "actions": [], "gt_actions": [], "gt_progress": [],
+                         "progress": []})
+        prev_r, self.renderer = self.renderer, env.renderer
+        try:
+            if not_in_train and self.feedback == "student":
+                lm = self.lang_model
+                lm.eval()
+                with torch.no_grad():
+                    leng = lm.engine(lb["input_ids"].shape[0], lb["input_ids"].shape[1], dev)
+                    leng.set_dropout(*lm.dropout_config())
+                    seq, lin, _ = leng.forward(lb["input_ids"].long(), lb["attention_mask"])
+                    if "cls_input_ids" in lb:
+                        leng2 = lm.engine(lb["cls_input_ids"].shape[0], lb["cls_input_ids"].shape[1], dev, slot=1)
+                        leng2.set_dropout(*lm.dropout_config())
+                        _, lin, _ = leng2.forward(lb["cls_input_ids"].long(), lb["cls_attention_mask"])
+                res = self.rollout_greedy(dict(corners_gps=torch.from_numpy(gps0).to(dev), directions=dirs0, geo=geo,
+                                               tile_idx=tidx, lang=seq.float(), lang_cls=lin.float()), max_action_len=T)
+                steps = int(res["steps"])
+                ended = res["ended"][:steps].cpu().numpy().astype(bool)
+                c_h, d_h = res["corners"].cpu().numpy(), res["directions"].cpu().numpy()
+                outs = res["output"][:steps].cpu().numpy()
+                tgt = None
+                if has_gt:
+                    flat = res["corners"][:steps].reshape(steps * B, 4, 2)
+                    eb = np.zeros((steps, B), dtype=np.uint8)
+                    eb[1:] = ended[:steps - 1]
+                    xy, alt, pr = self.teacher_action(flat, [gt_paths[k % B] for k in range(steps * B)], eb.reshape(-1),
+                                                      feedback="student")
+                    tgt = (xy.view(steps, B, 2).cpu().numpy(), alt.view(steps, B).cpu().numpy(),
+                           pr.view(steps, B).cpu().numpy())
+                self._log_traj(traj, outs, tgt, ended, c_h, d_h, steps)
+                return traj
+            # ---- poses of the rollout ----
+            if self.feedback == "teacher":
+                Hh, steps = self._teacher_rollout_poses(torch.from_numpy(gps0), dirs0, geo, gt_paths, T)
+                corners = Hh["corners"][:steps]
+                ended = Hh["ended"][:steps]
+                tgt_xy, tgt_alt, tgt_prog = Hh["xy"][:steps], Hh["alt"][:steps], Hh["prog"][:steps]
+                heads = Hh["dirs"][:steps]
+                c_all, d_all = Hh["corners"], Hh["dirs"]
+            elif self.feedback == "student":
+                # the student's own (no-grad, eval-mode) greedy rollout fixes the poses; the teacher supplies the
+                # target of every visited pose (agent.py:655-661)
+                with torch.no_grad():
+                    lm = self.lang_model
+                    lm.eval()
+                    leng = lm.engine(lb["input_ids"].shape[0], lb["input_ids"].shape[1], dev)
+                    leng.set_dropout(*lm.dropout_config())
+                    seq, lin, _ = leng.forward(lb["input_ids"].long(), lb["attention_mask"])
+                    if "cls_input_ids" in lb:
+                        leng2 = lm.engine(lb["cls_input_ids"].shape[0], lb["cls_input_ids"].shape[1], dev, slot=1)
+                        leng2.set_dropout(*lm.dropout_config())
+                        _, lin, _ = leng2.forward(lb["cls_input_ids"].long(), lb["cls_attention_mask"])
+                    res = self.rollout_greedy(dict(corners_gps=torch.from_numpy(gps0).to(dev), directions=dirs0, geo=geo,
+                                                   tile_idx=tidx, lang=seq.float().clone(), lang_cls=lin.float().clone()),
+                                              max_action_len=T)
+                steps = int(res["steps"])
+                corners, ended, heads = res["corners"][:steps], res["ended"][:steps], res["directions"][:steps]
+                c_all, d_all = res["corners"], res["directions"]
+                eb = torch.zeros((steps, B), dtype=torch.uint8, device=dev)
+                eb[1:] = ended[:steps - 1]
+                xy, alt, pr = self.teacher_action(corners.reshape(steps * B, 4, 2),
+                                                  [gt_paths[k % B] for k in range(steps * B)], eb.reshape(-1),
+                                                  feedback="student")
+                tgt_xy, tgt_alt, tgt_prog = xy.view(steps, B, 2), alt.view(steps, B), pr.view(steps, B)
+            else:
+                raise SystemExit("Invalid feedback option")
+            ended_h = ended.cpu().numpy().astype(bool)
+            alive = np.ones((steps, B), dtype=bool)
+            alive[1:] = ~ended_h[:steps - 1]
+            lens = np.maximum(np.cumsum(alive, axis=0).T, 1)             # [B, steps]: history length seen at step t
+            px = torch.empty((steps * B, 4, 2), dtype=torch.int32, device=dev)
+            _lib.call("avdn_gps_to_pixels", _lib.ptr(corners.reshape(steps * B, 4, 2).contiguous()),
+                      _lib.ptr(geo.repeat(steps, 1).contiguous()), steps * B, _lib.ptr(px))
+            rad = heads.float() / 180 * PI_REF                            # agent.py:605-606
+            tb = lambda a: a.reshape(steps, B, *a.shape[2:]).transpose(0, 1).contiguous()
+            batch = dict(lb, corners_px=tb(px.view(steps, B, 4, 2)), tile_idx=tidx.view(B, 1).expand(B, steps).contiguous(),
+                         directions=tb(torch.stack([torch.sin(rad), torch.cos(rad)], -1)),
+                         gt_xy=tb(tgt_xy.float()), gt_alt=tb(tgt_alt.float()), gt_prog=tb(tgt_prog.float()),
+                         lenths=lens.tolist())
+            if getattr(self.args, "no_direction", False):
+                batch["directions"] = torch.zeros_like(batch["directions"])
+            outs = []
+            if not_in_train:
+                loss = self._eval_rollout(batch, traj, outs)
+            else:
+                loss = self.train_rollout_step(batch, zero=False, step=False, nss_w=float(nss_w),
+                                               train_ml=train_ml if train_ml is not None else 0.0, collect=outs)
+            tgt = (tgt_xy.cpu().numpy(), tgt_alt.cpu().numpy(), tgt_prog.cpu().numpy()) if has_gt else None
+            # what the rollout was made of (inspection / tests): poses, stop flags, targets, the training batch
+            self._last_rollout = dict(corners=corners, ended=ended, steps=steps, tgt_xy=tgt_xy, tgt_alt=tgt_alt,
+                                      tgt_prog=tgt_prog, batch=batch, lenths=lens)
+            self._log_traj(traj, torch.stack(outs).cpu().numpy(), tgt, ended_h, c_all.cpu().numpy(), d_all.cpu().numpy(), steps)
+            if train_ml is not None:
+                l = loss.clone()
+                self.loss = l if isinstance(self.loss, (int, float)) else self.loss + l
+                self.losses.append(l)
+            else:
+                self.losses.append(0.0)
+        finally:
+            self.renderer = prev_r
+        return traj
+
+    @staticmethod
+    def _log_traj(traj, outs, tgt, ended, corners, dirs, steps):
+        """agent.py:637-653,725-770: per alive step the clipped prediction, the ground-truth action / progress and the
+        pose the simulator moved to."""
+        B = len(traj)
+        for i in range(B):
+            alive = True
+            for t in range(steps):
+                if alive:
+                    o = outs[t, i]
+                    m = max(abs(float(o[0])), abs(float(o[1])), 1.0)
+                    traj[i]["actions"].append([np.array([o[0] / m, o[1] / m], dtype=np.float32),
+                                               np.float32(min(1.0, max(0.0, float(o[2]))))])
+                    traj[i]["progress"].append(float(o[3]))
+                    if tgt is not None:
+                        traj[i]["gt_actions"].append([tgt[0][t, i].copy(), float(tgt[1][t, i])])
+                        traj[i]["gt_progress"].append(float(tgt[2][t, i]))
+                alive = not ended[t, i]
+                if alive:
+                    traj[i]["path_corners"].append((corners[t + 1, i].copy(), float(dirs[t + 1, i])))
+
+    @torch.no_grad()
+    def _eval_rollout(self, batch, traj, outs):
+        """``not_in_train`` with teacher feedback (validation of the human-attention head, agent.py:673-693): the ET in
+        eval mode over the growing history of the given poses; per step the loss terms and, for samples with a
+        fixation map, precision / recall of the clipped saliency map and the NSS value.  Returns the loss."""
+        ptr = _lib.ptr
+        dev = self.device
+        self.vision_model.eval()
+        et = self.vln_model
+        et.eval()
+        lm = self.lang_model
+        lm.eval()
+        ids, am = batch["input_ids"], batch["attention_mask"]
+        leng = lm.engine(ids.shape[0], ids.shape[1], dev)
+        leng.set_dropout(*lm.dropout_config())
+        seq, lin, _ = leng.forward(ids.long(), am)
+        if "cls_input_ids" in batch:
+            leng2 = lm.engine(batch["cls_input_ids"].shape[0], batch["cls_input_ids"].shape[1], dev, slot=1)
+            leng2.set_dropout(*lm.dropout_config())
+            _, lin, _ = leng2.forward(batch["cls_input_ids"].long(), batch["cls_attention_mask"])
+        lang, lang_cls = seq.float().contiguous(), lin.float().contiguous()
+        dirs = batch["directions"].contiguous().float()
+        B, T = dirs.shape[:2]
+        L = lang.shape[1]
+        r = self.renderer
+        ti = batch["tile_idx"].reshape(-1)
+        minv = r.homography(batch["corners_px"].view(B * T, 4, 2))
+        x = torch.empty((B * T, 224, 224, 4), dtype=torch.bfloat16, device=dev)
+        att = torch.empty((B * T, 224, 224), dtype=torch.uint8, device=dev)
+        r.render(None, ti, views=False, norm_nhwc=True, minv=minv, out={"norm_nhwc": x})
+        r.render(None, ti, views=False, att=True, minv=minv, out={"att": att})
+        att = att.view(B, T, 224, 224)
+        xs = x.view(B, T, 224, 224, 4)
+        fr = torch.empty((B, T, 512, 49), dtype=torch.float32, device=dev)
+        for t in range(T):                                   # the reference's eval-mode trunk sees B views per call
+            teng = self.vision_model.engine(B, 224, 224, dev)
+            o = torch.empty((B, 512, 7, 7), dtype=torch.float32, device=dev)
+            DN._trunk_forward(self.vision_model, teng, xs[:, t].contiguous(), False, out=o)
+            fr[:, t] = o.view(B, 512, 49)
+        lens = batch["lenths"]
+        pe = et.encoder_vl.enc_pos.pe[0]
+        total = torch.zeros(1, dtype=torch.float64, device=dev)
+        loss_i = torch.empty(B, dtype=torch.float64, device=dev)
+        d_o = torch.empty((B, 4), device=dev); d_h = torch.empty((B, 64), device=dev)
+        scale = float(self.train_ml) / B
+        for t in range(T):
+            Tc = t + 1
+            eng = et.engine(B, L, Tc, dev)
+            eng.set_dropout(0.0, 0.0, 0)
+            output, h_sali = eng.forward(fr[:, :Tc].contiguous().view(B * Tc, 512, 49), lang, lang_cls,
+                                         dirs[:, :Tc].contiguous(), [int(lens[i][t]) for i in range(B)], pe)
+            outs.append(output.detach().clone())
+            att_t = att[:, t].contiguous()
+            _lib.call("avdn_loss", ptr(output), ptr(h_sali), ptr(batch["gt_xy"][:, t].contiguous()),
+                      ptr(batch["gt_alt"][:, t].contiguous()), ptr(batch["gt_prog"][:, t].contiguous()), ptr(att_t), None, B,
+                      float(self.nss_w), int(getattr(self.args, "nss_r", 0)), scale, ptr(total), ptr(loss_i), ptr(d_o), ptr(d_h))
+            if self.feedback == "teacher":
+                sal = torch.empty((B, 224, 224), dtype=torch.float32, device=dev)
+                _lib.call("avdn_upsample_saliency", ptr(h_sali.contiguous()), B, ptr(sal))
+                gt = att_t.double() / 255
+                for i in range(B):
+                    if float(gt[i].sum()) > 0:
+                        nss = self.NSS(sal[i].double(), gt[i])
+                        p = sal[i].clip(0, 1).double()
+                        tp = float((p * gt[i]).sum())
+                        sp = float(p.sum())
+                        traj[i].setdefault("human_att_performance", []).append([tp / sp if sp != 0 else 0.0,
+                                                                                tp / float(gt[i].sum())])
+                        traj[i].setdefault("nss", []).append(float(nss))
+        return total
+
+    def train(self, loader, n_epochs, feedback="student", nss_w_weighting=1, **kwargs):
+        """Drop-in for ``NavCMTAgent.train`` (src/xview_et/agent.py:208-254): for every batch the loader yields (the
+        loader fills ``self.env`` as a side effect, as the reference's ``num_workers=0`` DataLoader does): zero the
+        gradients, one teacher rollout (``feedback='teacher'``) or a teacher rollout without the NSS term followed by
+        a student rollout (``'student'``), clip the ET gradients to 40, one step of every optimiser."""
+        self.vision_model.train(); self.vln_model.train()
+        if self.lang_model is not None:
+            self.lang_model.train()
+        self.losses = []
+        for epoch in range(1, n_epochs + 1):
+            for _ in loader:
+                for opt in self.optimizers:
+                    opt.zero_grad()
+                self.loss = 0
+                if feedback == "teacher":
+                    self.feedback = "teacher"
+                    self.rollout(train_ml=float(getattr(self.args, "teacher_weight", 1.0)), train_rl=False,
+                                 nss_w=float(getattr(self.args, "nss_w", 1.0)) * nss_w_weighting, **kwargs)
+                elif feedback == "student":
+                    self.feedback = "teacher"
+                    self.rollout(train_ml=float(getattr(self.args, "ml_weight", 0.2)), train_rl=False, nss_w=0, **kwargs)
+                    self.feedback = "student"
+                    self.rollout(train_ml=float(getattr(self.args, "ml_weight", 0.2)), train_rl=False,
+                                 nss_w=float(getattr(self.args, "nss_w", 1.0)) * nss_w_weighting, **kwargs)
+                else:
+                    assert False
+                # (the reference calls self.loss.backward() here; the rollouts above already left their gradients in
+                #  the arenas)  gradient all-reduce, clip (ET only, agent.py:247), step
+                self._reduce_and_step()
+
+    def _reduce_and_step(self):
+        if self.world > 1:
+            for opt in self.optimizers:
+                self._allreduce_async(opt.g, 0, opt.n)
+            self._wait_comm()
+        gs = 1.0 / self.world
+        for opt in self.optimizers:
+            self.launches += opt.step(grad_scale=gs)
+
     # ------------------------------------------------------------- checkpoints
     def _checkpoint_items(self):
         items = [("vision_model", self.vision_model, self.vision_model_optimizer),
@@ -831,11 +1260,16 @@ class NavCMTAgent:
         for name, model, opt in self._checkpoint_items():
             if name not in states:
                 continue
-            state = model.state_dict()
-            state.update({k: v for k, v in states[name]["state_dict"].items() if k in state})
-            for k, v in state.items():                       # copy IN PLACE: parameters live in the arena
-                model.state_dict()[k].copy_(v)
-            if getattr(self.args, "resume_optimizer", False) and "m" in states[name].get("optimizer", {}):
-                o = states[name]["optimizer"]
+            state = model.state_dict()                       # tensors alias the arena: copy IN PLACE
+            with torch.no_grad():
+                for k, v in states[name]["state_dict"].items():
+                    if k in state:
+                        state[k].copy_(v)
+            if getattr(self.args, "resume_optimizer", False):
+                o = states[name].get("optimizer", {})
+                if "m" not in o:
+                    raise ValueError(f"checkpoint '{name}': optimiser state is not in the flat-arena format this agent "
+                                     "writes ({'m', 'v', 'step'}); torch per-parameter optimiser states (the reference's "
+                                     "format) cannot be resumed -- load with resume_optimizer=False")
                 opt.m.copy_(o["m"]); opt.v.copy_(o["v"]); opt.step_count = int(o["step"])
         return states.get("vln_model", {}).get("epoch", 0) - 1

@@ -326,6 +326,9 @@ def use_all_host_threads():
 
 
 def run_reference(args, W):
+    """``--impl reference``: the reference's CPU implementation of the path (cv2 for the renderer; the oracle port
+    pinned to the reference modules for the training step -- /root/reference does not exist on the GPU box) on the
+    box's host cores, on a bounded sample of the workload.  The line states ITS OWN configuration."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
@@ -341,15 +344,109 @@ def run_reference(args, W):
     dt = time.perf_counter() - t0
     val = units / dt
     info = wl.cpu_info()
+    cfg = dict(wl.config())
+    cfg.update(getattr(wl, "cpu_config", lambda: {})())
+    cfg["device"] = "cpu"
+    cfg["gpu_arm_workload"] = wl.config()["workload"]
     line = {"impl": "reference", "metric": wl.metric, "value": val, "unit": wl.unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
-            "data": "synthetic", "config": wl.config(),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": getattr(wl, "cpu_dtype", wl.dtype), "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": wl.unit, "cores": info["cores"], "kind": info["kind"],
                              "sample": f"{n} units per step of the workload, {info['what']}"},
             "e2e": {"value": val, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def measure(wl, dev, rank, world, local, steps, warmup, with_cpu, dist):
+    """One workload, the bench contract: W untimed warm-up steps, exactly K timed steps bracketed by barrier +
+    synchronize, CUDA events on the launching stream, L2 flushed between timed steps, max over ranks; then the same
+    metric end to end through the public API with host buffers; then the roofline of the dominant kernel and (rank 0)
+    the CPU leg.  Returns the result dict on every rank (the CPU leg and the formatting only matter on rank 0)."""
+    use_dist = dist is not None
+    peaks = load_peaks()
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
+    launches = 0
+    for _ in range(warmup):
+        wl.step()
+        wl.after_step(False)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with ClockSampler(local) as clk:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()                                   # L2 flush between timed iterations (untimed)
+            evs[i][0].record()
+            launches += wl.step()
+            evs[i][1].record()
+            wl.after_step(True)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if use_dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    units = wl.units_per_step() * world * steps
+    value = units / (ms * 1e-3)
+
+    # end-to-end through the public API with host buffers
+    for _ in range(2):
+        wl.step_e2e()
+    barrier()
+    e_steps = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        h2d, d2h = wl.step_e2e()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if use_dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = wl.units_per_step() * world * e_steps / float(te.item())
+
+    # collective parts of the roofline measurement (the instrumented training step all-reduces) and the
+    # multi-GPU proofs run on every rank; only rank 0 formats the result
+    prep = getattr(wl, "prepare_roofline", None)
+    if prep is not None:
+        prep()
+    barrier()
+    multi = None
+    mg = getattr(wl, "multi_gpu_checks", None)
+    if mg is not None and use_dist:
+        multi = mg(dist)
+    barrier()
+    del flush
+    cpu = None
+    if rank == 0 and with_cpu:
+        use_all_host_threads()
+        n = wl.CPU_SAMPLE
+        wl.cpu_step(max(1, n // 8))
+        t0 = time.perf_counter()
+        done = wl.cpu_step(n)
+        dt = time.perf_counter() - t0
+        info = wl.cpu_info()
+        cpu = {"value": done / dt, "unit": wl.unit, "cores": info["cores"], "kind": info["kind"],
+               "sample": f"{n} units of the workload, {info['what']}; {dt:.1f} s of CPU time"}
+    line = {"metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+            "config": wl.config(), "roofline": wl.roofline(peaks) if rank == 0 else None, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clk.summary(), "wall_s_timed_region": t_wall}
+    if multi:
+        line.update(multi)
+    extra = getattr(wl, "extra", None)
+    if extra and rank == 0:
+        line.update(extra(ms / steps))
+    return line
 
 
 def main():
@@ -360,6 +457,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train" if "train" in WORKLOADS else "render", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="train workload only: skip the render (configs[2]) and rollout (configs[4]) entries")
+    ap.add_argument("--no-library-bar", action="store_true",
+                    help="train workload only: skip the stock torch / cuDNN / cuBLAS timing of the same step")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON result): anything libraries print on file descriptor 1
     # (e.g. NCCL's version banner) is sent to stderr instead
@@ -382,88 +483,39 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    use_dist = world > 1
-    if use_dist:
+    dist = None
+    if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    peaks = load_peaks()
     wl = W(rank, world)
     wl.setup_gpu(dev)
+    line = measure(wl, dev, rank, world, local, args.steps, args.warmup, not args.no_cpu_baseline, dist)
 
-    def barrier():
-        if use_dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
-    launches = 0
-    for _ in range(args.warmup):
-        wl.step()
-        wl.after_step(False)
-    barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clk:
-        barrier()
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            flush.zero_()                                   # L2 flush between timed iterations (untimed)
-            evs[i][0].record()
-            launches += wl.step()
-            evs[i][1].record()
-            wl.after_step(True)
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if use_dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    units = wl.units_per_step() * world * args.steps
-    value = units / (ms * 1e-3)
-
-    # end-to-end through the public API with host buffers
-    for _ in range(2):
-        wl.step_e2e()
-    barrier()
-    e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        h2d, d2h = wl.step_e2e()
-    barrier()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if use_dist:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = wl.units_per_step() * world * e_steps / float(te.item())
-
-    # collective parts of the roofline measurement (the instrumented training step all-reduces) run on
-    # every rank; only rank 0 formats the result
-    prep = getattr(wl, "prepare_roofline", None)
-    if prep is not None:
-        prep()
-    barrier()
+    if args.workload == "train":
+        # BASELINE.json's metric names two more numbers -- "rendered views/s" (configs[2]) and the greedy rollout
+        # of configs[4] "at 1 and 8 B200": measured here, in the same run, as `secondary` entries of the one line.
+        # Under torchrun every rank renders / rolls out its own shard (pose- / episode-sharded, no collective).
+        if not args.no_library_bar and world == 1:
+            line["library_bar"] = wl.library_bar(line["ms_per_step"])
+        del wl
+        torch.cuda.empty_cache()
+        if not args.no_secondary:
+            sec = {}
+            for name, st, wu in (("render", 10, 3), ("rollout", 3, 3)):
+                if name not in WORKLOADS:
+                    continue
+                w2 = WORKLOADS[name](rank, world)
+                w2.setup_gpu(dev)
+                r = measure(w2, dev, rank, world, local, st, wu, not args.no_cpu_baseline and world == 1, dist)
+                sec[name] = {k: r[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                                               "dtype", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches",
+                                               "clocks")}
+                del w2
+                torch.cuda.empty_cache()
+            line["secondary"] = sec
     if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline:
-            use_all_host_threads()
-            n = wl.CPU_SAMPLE
-            wl.cpu_step(max(1, n // 8))
-            t0 = time.perf_counter()
-            done = wl.cpu_step(n)
-            dt = time.perf_counter() - t0
-            info = wl.cpu_info()
-            cpu = {"value": done / dt, "unit": wl.unit, "cores": info["cores"], "kind": info["kind"],
-                   "sample": f"{n} units of the workload, {info['what']}; {dt:.1f} s of CPU time"}
-        line = {"metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-                "config": wl.config(), "roofline": wl.roofline(peaks), "cpu_baseline": cpu,
-                "e2e": {"value": e2e_val, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "clocks": clk.summary(), "wall_s_timed_region": t_wall}
-        extra = getattr(wl, "extra", None)
-        if extra:
-            line.update(extra(ms / args.steps))
         emit(line)
-    if use_dist:
+    if dist is not None:
         dist.destroy_process_group()
 
 

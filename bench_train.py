@@ -78,7 +78,23 @@ class TrainWorkload:
                 "global_batch": self.B * self.world, "per_gpu_batch": self.B, "views_per_step_per_gpu": self.B * T_STEPS,
                 "seq_len": L_LANG + 2 * T_STEPS, "dropout": "train mode: 0.1 at the 4 sites of each encoder layer, 0.2 in the heads (stateless hash masks)",
                 "cache": "per-step working set (~40 GB of activations) far exceeds L2; L2 is also flushed between steps",
+                "parity_mode": "ET logits / loss / every gradient vs the fp32 oracle at the configs[0] shape (1e-2 / 5e-2); "
+                               "trunk per block 1e-2 forward, 8e-2 backward (teacher-forced); trunk END TO END only by the "
+                               "bf16-storage envelope (the random-init 57-block train-mode-BN chain amplifies a "
+                               "perturbation ~100x, so no bf16 pipeline sits within 1e-2 of fp32 there); fused step loss "
+                               "1e-2 at B=4, T=10, L=250 on conditioned weights (tests/test_agent_gpu.py)",
                 "parallelism": f"dp{self.world} by episode, NCCL all-reduce of gradients" if self.world > 1 else "dp1"}
+
+    cpu_dtype = "fp32"
+
+    def cpu_config(self):
+        """What the CPU leg (``--impl reference`` / ``cpu_baseline``) actually runs: BASELINE configs[0]."""
+        return {"workload": "et_haa forward + loss + backward + clip + AdamW on the host cores, fp32, batch 4 "
+                            "(BASELINE configs[0]): 40 views rendered with cv2.warpPerspective, Darknet (train-mode BN) "
+                            "+ ET + both heads; torch CPU restatement pinned to the reference modules",
+                "global_batch": self.CPU_SAMPLE, "per_gpu_batch": self.CPU_SAMPLE,
+                "views_per_step_per_gpu": self.CPU_SAMPLE * T_STEPS, "dropout": "off (oracle arithmetic)",
+                "cache": "n/a (host)", "parallelism": "none (one process, all host threads)"}
 
     # --------------------------------------------------------------------- GPU
     def setup_gpu(self, dev):
@@ -160,19 +176,9 @@ class TrainWorkload:
         peak = peaks["bf16_sustained"]
         self._peak = peak
         top = sorted(self.profile.items(), key=lambda kv: -kv[1][1])[:14]
-        # DRAM bytes of the step's gemm_kernel launches from the committed ncu capture of this same command
-        # (profiles/r01_train_step_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum, single GPU)
-        traffic, traffic_src = None, None
-        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_train_step_traffic.json")
-        if self.world == 1 and os.path.exists(tp):
-            try:
-                with open(tp) as f:
-                    tj = json.load(f)["gemm_kernel"]
-                if tj["n"] == g_n:
-                    traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
-                    traffic_src = "profiles/r01_train_step_traffic.json (ncu, sum over the step's gemm_kernel launches)"
-            except (KeyError, ValueError):
-                pass
+        # DRAM traffic is not measurable from inside the run (it needs ncu): null here; the ncu capture of this
+        # command is summarised under profiles/ (r02_*).
+        traffic, traffic_src = None, "not measured in-run (ncu summaries under profiles/)"
         return {"kernel": "gemm_kernel (tcgen05 implicit-GEMM conv fwd/dgrad/wgrad + transformer GEMMs)",
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
@@ -190,6 +196,162 @@ class TrainWorkload:
             out["mfu_vs_sustained_bf16"] = out["step_tflops_per_s"] / self._peak if getattr(self, "_peak", None) else None
         return out
 
+    # ------------------------------------------------------------ multi-GPU proofs
+    def multi_gpu_checks(self, dist):
+        """Under torchrun, on every rank, after the timed steps: (1) the replicas hold bit-identical parameters
+        (all-reduce MAX and MIN of per-arena checksums agree), (2) how long the optimiser waited for the last
+        gradient bucket (CUDA events around the wait on the communication stream, mean over instrumented steps)."""
+        ag = self.agent
+        sums = []
+        for opt in ag.optimizers:
+            p = opt.p
+            sums += [p.double().sum(), p.double().abs().sum(), p.view(torch.int32).double().sum()]
+        v = torch.stack(sums)
+        hi, lo = v.clone(), v.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        in_sync = bool(torch.equal(hi, lo))
+        ag.exposed_events = []
+        for _ in range(3):
+            ag.train_step(self.batch)
+        torch.cuda.synchronize()
+        ex = [a.elapsed_time(b) for a, b in ag.exposed_events]
+        ag.exposed_events = None
+        t = torch.tensor([float(np.mean(ex)) if ex else 0.0], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"replicas_in_sync": in_sync, "allreduce_exposed_ms": float(t.item()),
+                "allreduce": {"bytes_per_step": int(sum(o.n for o in ag.optimizers) * 4), "dtype": "fp32",
+                              "buckets": 1 + len(ag._buckets or [])}}
+
+    # ---------------------------------------------------------------- library bar
+    def library_bar(self, ours_ms):
+        """The same B = 64 step on stock torch 2.x kernels (cuDNN convolutions / BatchNorm, cuBLAS GEMMs, SDPA inside
+        nn.TransformerEncoderLayer, fused AdamW): nn modules of the reference's architecture (random init), bf16
+        autocast, channels-last, cudnn.benchmark -- the best stock configuration.  Test infrastructure like the CPU
+        leg: nothing of it is on the product path.  View rendering is NOT included (the reference renders on the
+        host), so the comparison favours the library side by the ~0.3 ms the renderer takes."""
+        import torch.nn as nn
+        import torch.nn.functional as F
+        from avdn_b200.utils import synthetic as syn
+        dev = self.dev
+        B, T, L = self.B, T_STEPS, L_LANG
+
+        class Trunk(nn.Module):
+            def __init__(s_, cfg_text):
+                super().__init__()
+                s_.defs = []
+                cur = None
+                for line in cfg_text.split("\n"):
+                    line = line.strip()
+                    if line.startswith("["):
+                        cur = {"type": line[1:-1]}
+                        s_.defs.append(cur)
+                    elif "=" in line and cur is not None:
+                        k, v = line.split("=")
+                        cur[k.strip()] = v.strip()
+                s_.defs = s_.defs[1:]
+                s_.mods = nn.ModuleList()
+                ch = [3]
+                for d in s_.defs:
+                    if d["type"] == "convolutional":
+                        f, k, st = int(d["filters"]), int(d["size"]), int(d["stride"])
+                        s_.mods.append(nn.Sequential(nn.Conv2d(ch[-1], f, k, st, (k - 1) // 2, bias=False),
+                                                     nn.BatchNorm2d(f), nn.LeakyReLU(0.01)))
+                        ch.append(f)
+                    else:
+                        s_.mods.append(nn.Identity())
+                        ch.append(ch[int(d["from"])])
+
+            def forward(s_, x):
+                outs = []
+                for d, m in zip(s_.defs, s_.mods):
+                    x = m(x) if d["type"] == "convolutional" else outs[-1] + outs[int(d["from"])]
+                    outs.append(x)
+                return x
+
+        class ETLike(nn.Module):
+            def __init__(s_):
+                super().__init__()
+                s_.w_in = nn.Linear(49, 49, bias=False); s_.w_out = nn.Linear(98, 49, bias=False)
+                s_.fc2 = nn.Linear(49, 768); s_.demb = nn.Linear(2, 768); s_.ln = nn.LayerNorm(768)
+                s_.enc = nn.TransformerEncoder(nn.TransformerEncoderLayer(768, 12, 768, 0.1), 2,
+                                               enable_nested_tensor=False)
+                s_.head = nn.Sequential(nn.Linear(768, 256), nn.ReLU(), nn.Dropout(0.2), nn.Linear(256, 32), nn.ReLU(),
+                                        nn.Dropout(0.2), nn.Linear(32, 4))
+                s_.fc = nn.Sequential(nn.Linear(768, 64), nn.Dropout(0.2), nn.ReLU())
+
+            def forward(s_, frames, lang, lang_cls, dirs, mask, pe):
+                Bq, Tq = dirs.shape[:2]
+                ctx = frames.view(Bq, Tq, 512, 49)
+                tgt = s_.w_in(lang_cls)                                                   # SoftDotAttention(49)
+                attn = torch.softmax(torch.einsum("btcp,bp->btc", ctx, tgt), dim=2)
+                wc = torch.einsum("btc,btcp->btp", attn, ctx)
+                h = torch.tanh(s_.w_out(torch.cat((wc, lang_cls[:, None].expand(-1, Tq, -1)), -1)))
+                x = torch.cat((lang + pe[:L], s_.fc2(h) + pe[L:L + Tq], s_.demb(dirs) + pe[L:L + Tq]), 1)
+                x = s_.enc(s_.ln(x).transpose(0, 1), mask=mask).transpose(0, 1)
+                out = s_.head(x[:, L + 2 * Tq - 1])
+                sal = F.interpolate(s_.fc(x[:, L + Tq - 1]).view(-1, 1, 8, 8), size=(224, 224), mode="bilinear",
+                                    align_corners=False)
+                return out, sal
+
+        prev = torch.backends.cudnn.benchmark
+        torch.backends.cudnn.benchmark = True
+        try:
+            torch.manual_seed(0)
+            trunk = Trunk(syn.yolov3_trunk_cfg()).to(dev).to(memory_format=torch.channels_last).train()
+            et = ETLike().to(dev).train()
+            opt_t = torch.optim.AdamW(trunk.parameters(), lr=1e-5, fused=True)
+            opt_e = torch.optim.AdamW(et.parameters(), lr=1e-5, fused=True)
+            images = torch.randn(B * T, 3, 224, 224, device=dev).contiguous(memory_format=torch.channels_last)
+            S = L + 2 * T
+            mask = torch.zeros(S, S, device=dev)
+            mask[:L, L:] = float("-inf")
+            tri = torch.triu(torch.full((T, T), float("-inf"), device=dev), 1)
+            mask[L:L + T, L:L + T] = tri; mask[L:L + T, L + T:] = tri
+            mask[L + T:, L:L + T] = tri; mask[L + T:, L + T:] = tri
+            pe = torch.randn(S, 768, device=dev) * 0.02
+            bt = self.batch
+            fix = torch.zeros(B, 1, 224, 224, device=dev)
+            fix[:, :, 60:120, 80:160] = 1.0
+
+            def step():
+                opt_t.zero_grad(set_to_none=True)
+                opt_e.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    feats = trunk(images)
+                    out, sal = et(feats.float().reshape(B * T, 512, 49), bt["lang"], bt["lang_cls"], bt["directions"],
+                                  mask, pe)
+                out, sal = out.float(), sal.float()
+                loss = ((out[:, :2] - bt["gt_xy"]) ** 2).sum() + ((out[:, 2] - bt["gt_alt"]) ** 2).sum() + \
+                       ((out[:, 3] - bt["gt_prog"]) ** 2).sum()
+                m, sd_ = sal.mean((1, 2, 3), keepdim=True), sal.std((1, 2, 3), keepdim=True)
+                loss = loss - 0.1 * ((((sal - m) / sd_) * fix).sum((1, 2, 3)) / (fix.sum((1, 2, 3)) + 1e-3)).sum()
+                (loss * 0.2 / B).backward()
+                torch.nn.utils.clip_grad_norm_(et.parameters(), 40.0)
+                opt_t.step()
+                opt_e.step()
+
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            n = 5
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            for a, b in evs:
+                a.record(); step(); b.record()
+            torch.cuda.synchronize()
+            ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        finally:
+            torch.backends.cudnn.benchmark = prev
+        del trunk, et, opt_t, opt_e, images
+        torch.cuda.empty_cache()
+        return {"what": "stock torch " + torch.__version__ + " modules of the same architecture (nn.Conv2d + "
+                        "nn.BatchNorm2d(train) + nn.LeakyReLU x57 with shortcuts; SoftDotAttention + nn.TransformerEncoder "
+                        "(2 x 768, 12 heads, ff 768) + both heads, upsample + NSS-style loss), bf16 autocast, channels-last, "
+                        "cudnn.benchmark, fused AdamW on both models, clip on ET; batch 64 x 10 views; view rendering "
+                        "excluded",
+                "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "episodes/s", "steps": n, "warmup": 3,
+                "ours_ms_per_step": ours_ms, "ours_over_library_speedup": ms / ours_ms}
+
     # --------------------------------------------------------------------- CPU
     def _cpu_setup(self):
         if getattr(self, "_cpu", None) is not None:
@@ -205,33 +367,54 @@ class TrainWorkload:
                 if v.is_floating_point() and "running" not in k and not k.endswith(".pe"):
                     v.requires_grad_(True)
         hb = synthetic_batch(B, T, L, seed=0)
-        images = torch.randn(B * T, 3, 224, 224)
-        gt_sal = torch.zeros(B, 224, 224, dtype=torch.float64)
-        gt_sal[:, 60:120, 80:160] = 1.0
-        self._cpu = (mo, cfg, sd, et_sd, hb, images, gt_sal)
+        from avdn_b200.utils import synthetic as syn
+        tile = syn.synthetic_tile(seed=0, size=SIZE)
+        att = syn.synthetic_attention_tile(seed=0, size=SIZE)
+        opt_t = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=1e-5)
+        opt_e = torch.optim.AdamW([v for v in et_sd.values() if v.requires_grad], lr=1e-5)
+        self._cpu = (mo, cfg, sd, et_sd, hb, tile, att, opt_t, opt_e)
         return self._cpu
 
     def cpu_step(self, n):
         """The oracle's restatement of the reference step (torch CPU fp32 autograd: Darknet
         train-mode forward, ET forward, loss, backward) on ``CPU_SAMPLE`` episodes."""
-        mo, cfg, sd, et_sd, hb, images, gt_sal = self._cpu_setup()
+        import cv2
+        mo, cfg, sd, et_sd, hb, tile, att, opt_t, opt_e = self._cpu_setup()
         B, T = self.CPU_SAMPLE, T_STEPS
+        dst = np.array([[0, 0], [223, 0], [223, 223], [0, 223]], dtype=np.float32)
+        mean = np.array([60.134, 49.697, 40.746], dtype=np.float32).reshape(3, 1, 1)       # agent.py:115-116
+        std = np.array([29.99, 24.498, 22.046], dtype=np.float32).reshape(3, 1, 1)
         done = 0
         while done < n:
-            for d in (sd, et_sd):
-                for v in d.values():
-                    v.grad = None
-            feats = mo.darknet_forward(images, sd, cfg, train=True).view(B, T, 512, 49)
-            out, sal, _ = mo.et_forward(et_sd, hb["directions"], feats, hb["lenths"], hb["lang"], hb["lang_cls"])
-            loss = mo.step_loss(mo.et_loss(out, sal, hb["gt_xy"], hb["gt_alt"], hb["gt_prog"], gt_sal, 0.1), 0.2, B)
+            opt_t.zero_grad(set_to_none=True)
+            opt_e.zero_grad(set_to_none=True)
+            # the observations: cv2 calls of src/env.py:287-293, normalisation of agent.py:586-592
+            views, sal = [], []
+            cpx = hb["corners_px"].numpy().astype(np.float32)
+            for b in range(B):
+                for t in range(T):
+                    M = cv2.getPerspectiveTransform(cpx[b, t], dst)
+                    views.append(cv2.warpPerspective(tile, M, (224, 224)))
+                    if t == T - 1:
+                        sal.append(cv2.warpPerspective(att, M, (224, 224))[:, :, 0].astype(np.float64) / 255)
+            images = np.ascontiguousarray(np.stack(views)[:, :, :, ::-1].transpose(0, 3, 1, 2), dtype=np.float32)
+            images -= mean
+            images /= std
+            gt_sal = torch.from_numpy(np.stack(sal))
+            feats = mo.darknet_forward(torch.from_numpy(images), sd, cfg, train=True).view(B, T, 512, 49)
+            out, sal_p, _ = mo.et_forward(et_sd, hb["directions"], feats, hb["lenths"], hb["lang"], hb["lang_cls"])
+            loss = mo.step_loss(mo.et_loss(out, sal_p, hb["gt_xy"], hb["gt_alt"], hb["gt_prog"], gt_sal, 0.1), 0.2, B)
             loss.backward()
+            torch.nn.utils.clip_grad_norm_([v for v in et_sd.values() if v.requires_grad], 40.0)      # agent.py:247
+            opt_t.step()
+            opt_e.step()
             done += B
         return done
 
     def cpu_info(self):
         return {"kind": "port", "cores": int(torch.get_num_threads()),
-                "what": "oracle/model_oracle.py (torch CPU fp32 restatement of Darknet + ET + loss, fwd+bwd), "
-                        "BASELINE configs[0] shape (batch 4, 10 views, 250 tokens)"}
+                "what": "cv2 view rendering + oracle/model_oracle.py (torch CPU fp32 restatement of Darknet + ET + loss, "
+                        "fwd+bwd) + clip_grad_norm_ + AdamW, BASELINE configs[0] shape (batch 4, 10 views, 250 tokens)"}
 
 
 class TrainRolloutWorkload(TrainWorkload):

@@ -200,6 +200,41 @@ def test_train_step_loss_matches_oracle_and_learns(agent):
     assert losses[-1] < first, (first, losses)
 
 
+def test_train_step_loss_at_config1_shape_vs_oracle(agent):
+    """The fused ``train_step`` at BASELINE configs[0]'s shape (B = 4 episodes, T = 10 views each, L = 250 tokens,
+    ragged ``lenths``) against the oracle pipeline on the same weights: cv2-exact views of all 40 poses -> fp32
+    Darknet with train-mode BatchNorm over the 40 views -> ET -> loss incl. NSS.  Step loss within 1e-2 relative
+    (bf16 path, north_star tolerance; conditioned synthetic trunk weights, see the ``agent`` fixture)."""
+    B, T, L = 4, 10, 250
+    hb = _small_batch(B, T, L, 31)
+    hb["lenths"] = [10, 4, 7, 1]
+    batch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in hb.items()}
+    sd_t = {k: v.detach().cpu().clone() for k, v in agent.vision_model.state_dict().items()}
+    sd_e = {k: v.detach().cpu().clone() for k, v in agent.vln_model.state_dict().items()}
+    views, atts = [], []
+    for b in range(B):
+        for t in range(T):
+            Mi = wo.inverse_homography(hb["corners_px"][b, t].numpy())
+            views.append(wo.warp_fixed_point(agent._tile, Mi))
+            if t == T - 1:
+                atts.append(wo.warp_fixed_point(agent._att, Mi)[:, :, 0])
+    x = torch.from_numpy(wo.normalise_views(np.stack(views)))
+    with torch.no_grad():
+        feats = mo.darknet_forward(x, sd_t, mo.yolov3_trunk_cfg(), train=True).view(B, T, 512, 49)
+        out, sal, _ = mo.et_forward(sd_e, hb["directions"], feats, hb["lenths"], hb["lang"], hb["lang_cls"])
+        gt_sal = torch.from_numpy(np.stack(atts).astype(np.float64) / 255)
+        ref = float(mo.step_loss(mo.et_loss(out, sal, hb["gt_xy"], hb["gt_alt"], hb["gt_prog"], gt_sal, 0.1), 0.2, B))
+    for opt in agent.optimizers:
+        opt.lr = 0.0
+        opt.wd = 0.0
+    ours = agent.train_step(batch, sync_loss=True)
+    assert abs(ours - ref) <= 1e-2 * abs(ref), (ours, ref)
+    # and the forward-only entry point (trunk in eval mode is a different function: compare train_step's own output)
+    o_dev = agent._ctx[1].output if hasattr(agent._ctx[1], "output") else None
+    if o_dev is not None:
+        assert (o_dev.float().cpu() - out).abs().max() <= 1e-2 * out.abs().max() + 5e-3
+
+
 def test_step_gradients_vs_oracle(agent):
     """Gradients the fused step leaves in the arenas vs autograd of the oracle pipeline, run twice:
     float32 end to end (the reference arithmetic) and with the trunk's tensors stored in bf16

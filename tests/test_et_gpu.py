@@ -145,6 +145,65 @@ def test_all_gradients_vs_oracle_ragged(et):
     assert _rel2(c2.grad, lc.grad) < 5e-2          # linear_cls feeds the trained BERT head in the reference
 
 
+def test_config1_shape_forward_loss_and_all_gradients_vs_oracle(et):
+    """BASELINE configs[0] shape -- B = 4, L = 250 dialog tokens, T = 10 views, S = 270 (padded to 288 rows inside the
+    engine), ragged ``lenths`` with Tmax = 10: logits, saliency head, loss (fused ``avdn_loss`` incl. NSS) within 1e-2
+    and EVERY used parameter's gradient (plus the gradients of frames / lang / lang_cls) within 5e-2 relative L2 of
+    the fp32 oracle (oracle/model_oracle.py, pinned to the reference's ``ET`` by make_model_golden.py)."""
+    from avdn_b200 import _lib
+    torch.manual_seed(21)
+    B, L, T = 4, 250, 10
+    lens = [10, 3, 7, 1]
+    lang = torch.randn(B, L, 768)
+    lang_cls = torch.relu(torch.randn(B, 49))
+    frames = torch.randn(B, T, 512, 49) * 0.5
+    deg = torch.randint(0, 360, (B, T)).float()
+    dirs = torch.stack([torch.sin(deg / 180 * 3.14159), torch.cos(deg / 180 * 3.14159)], -1)
+    gt_xy = torch.rand(B, 2) * 2 - 1
+    gt_xy = gt_xy / gt_xy.abs().amax(1, keepdim=True).clamp_min(1.0)
+    gt_alt, gt_prog = torch.rand(B), torch.rand(B)
+    rng = np.random.default_rng(21)
+    att = np.zeros((B, 224, 224), dtype=np.uint8)
+    for i in range(B - 1):                                   # the last sample has no attention: NSS skipped
+        cy, cx, r = rng.integers(40, 180), rng.integers(40, 180), rng.integers(10, 50)
+        yy, xx = np.ogrid[:224, :224]
+        att[i][(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 255
+    gt_sal = torch.from_numpy(att.astype(np.float64) / 255)
+    # ---- oracle ----
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in et.state_dict().items()}
+    fr = frames.clone().requires_grad_(True)
+    lg = lang.clone().requires_grad_(True)
+    lc = lang_cls.clone().requires_grad_(True)
+    oo, so, hs_o = mo.et_forward(sd, dirs, fr, lens, lg, lc)
+    ref = mo.step_loss(mo.et_loss(oo, so, gt_xy, gt_alt, gt_prog, gt_sal, nss_w=0.1), 0.2, B)
+    ref.backward()
+    # ---- device ----
+    f2 = frames.cuda().requires_grad_(True)
+    l2 = lang.cuda().requires_grad_(True)
+    c2 = lang_cls.cuda().requires_grad_(True)
+    et.zero_grad()
+    out, hs = et.forward_features(directions=dirs.cuda(), frames=f2, lenths=lens, lang=l2, lang_cls=c2)
+    assert _rel(out, oo) < 1e-2, _rel(out, oo)
+    assert _rel(hs, hs_o) < 1e-2, _rel(hs, hs_o)
+    loss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    loss_i = torch.zeros(B, dtype=torch.float64, device="cuda")
+    d_out = torch.zeros(B, 4, device="cuda")
+    d_hs = torch.zeros(B, 64, device="cuda")
+    ptr = _lib.ptr
+    o_d, h_d = out.detach().contiguous(), hs.detach().contiguous()
+    xy_d, alt_d, prog_d, att_d = gt_xy.cuda(), gt_alt.cuda(), gt_prog.cuda(), torch.from_numpy(att).cuda()
+    _lib.call("avdn_loss", ptr(o_d), ptr(h_d), ptr(xy_d), ptr(alt_d), ptr(prog_d), ptr(att_d), None, B, 0.1, 0,
+              0.2 / B, ptr(loss), ptr(loss_i), ptr(d_out), ptr(d_hs))
+    assert abs(loss.item() - ref.item()) <= 1e-2 * abs(ref.item()), (loss.item(), ref.item())
+    torch.autograd.backward([out, hs], [d_out, d_hs])
+    for n, p in et.used_parameters().items():
+        r = _rel2(p.grad, sd[n].grad)
+        assert r < 5e-2, (n, r)
+    assert _rel2(f2.grad, fr.grad) < 5e-2
+    assert _rel2(l2.grad, lg.grad) < 5e-2
+    assert _rel2(c2.grad, lc.grad) < 5e-2
+
+
 def test_encoder_vl_standalone(et):
     torch.manual_seed(7)
     B, L, T = 2, 20, 4
