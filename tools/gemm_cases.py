@@ -1,0 +1,38 @@
+"""Runs single conv GEMM launches of the training step's shapes (for `ncu --set full -k regex:gemm_kernel`):
+  L14 fwd   3x3 128->256 @28x28   (tensor-bound, the bulk of the step)      gemm_kernel<128,0,0,2,64>
+  L3  fwd   3x3  32->64  @112x112 (thin: L2->SM bandwidth / latency bound)  gemm_kernel<64,0,0,1,32>
+  L13 fwd   1x1 256->128 @28x28   (HBM-bound)
+  L14 wgrad                        gemm_kernel<128,1,1,2,64>
+Usage (GPU box): python tools/gemm_cases.py [reps]"""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from avdn_b200 import gemm as G
+
+N = int(os.environ.get("PROBE_N", "640"))
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+dev = "cuda"
+
+
+def conv_case(H, Cin, Cout, k, s, wgrad=False):
+    x = torch.randn(N, H, H, Cin, device=dev).bfloat16()
+    w = (torch.randn(Cout, k * k * Cin, device=dev) * 0.05).bfloat16()
+    z = torch.empty(N, H // s, H // s, Cout, device=dev, dtype=torch.bfloat16)
+    st = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+    if wgrad:
+        dz = torch.randn(N, H // s, H // s, Cout, device=dev).bfloat16()
+        dw = torch.zeros(Cout, k * k * Cin, device=dev)
+        return G.plan_conv_wgrad(dz, x, dw, N=N, H=H, W=H, Cin=Cin, Cout=Cout, k=k, stride=s)
+    return G.plan_conv_fwd(x, w, z, N=N, H=H, W=H, Cin=Cin, Cout=Cout, k=k, stride=s, stats=st)
+
+
+cases = [("L14 fwd 3x3 128->256 @28", conv_case(28, 128, 256, 3, 1)), ("L3 fwd 3x3 32->64 @112", conv_case(112, 32, 64, 3, 1)),
+         ("L13 fwd 1x1 256->128 @28", conv_case(28, 256, 128, 1, 1)), ("L14 wgrad", conv_case(28, 128, 256, 3, 1, wgrad=True))]
+for name, p in cases:
+    for _ in range(reps):
+        p.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); p.run(); e1.record(); torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1):.3f} ms  {p.flops / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
