@@ -240,7 +240,7 @@ constexpr int MAX_SLABS = 4;
 struct alignas(64) KernelParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB[4];
-  CUtensorMap tmC;      // output map (out_tma == 1)
+  CUtensorMap tmC[4];   // output map (out_tma == 1); one per output class (avdn_gemm_core.n_classes)
   avdn_gemm_core c;     // plain-data description shared with the host (avdn.h)
   int32_t grid_m, grid_n, grid_z;   // tile space (grid_m counts 128-row tiles)
   int32_t out_tma;      // 1: epilogue goes through smem slabs + TMA store / reduce-add
@@ -307,14 +307,21 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
   const uint32_t pm = (uint32_t)(p.grid_m + CTAS - 1) / CTAS;
   const uint32_t gn = (uint32_t)p.grid_n;
   const uint32_t total = pm * gn * (uint32_t)p.grid_z;
-  const uint32_t t_begin = blockIdx.x / CTAS, t_step = gridDim.x / CTAS;
+  // Output classes (CONV, n_classes > 1): the launch index of a CTA (pair) is class-fastest, NC * r + q.  The host
+  // makes the number of CTA (pair)s a multiple of NC, so q is a constant of the CTA and all NC tiles of a spatial
+  // tile r are visited in the same iteration by NC neighbouring CTAs; the class of the tile is (q + iteration) % NC:
+  // a bijection for every r, and every CTA cycles through the classes (their work differs: 1, 2, 2, 4 taps).
+  const uint32_t NC = (c.mode == AVDN_GEMM_CONV && c.n_classes > 1) ? (uint32_t)c.n_classes : 1u;
+  const uint32_t cq = (blockIdx.x / CTAS) % NC;
+  const uint32_t t_begin = (blockIdx.x / CTAS) / NC, t_step = (gridDim.x / CTAS) / NC;
   const int kb_per = (c.num_kb + c.split_k - 1) / c.split_k;
 
-  struct Tile { int mt, nt, z0, z1, tap, kb_begin, my_kb; };
+  struct Tile { int mt, nt, z0, z1, tap, kb_begin, my_kb, cls; };
   struct Walk {
     uint32_t t, nt, mtp, z;          // current tile
     uint32_t dn, dm, dz;             // t_step decomposed
     uint32_t zc; int z0, z1, tap, kb_begin, my_kb;   // cached decomposition of z
+    uint32_t it;                     // iteration count (class rotation)
   };
   auto walk_init = [&]() {
     Walk w;
@@ -329,6 +336,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
     w.dz = r / pm;
     w.zc = 0xFFFFFFFFu;
     w.z0 = w.z1 = w.tap = w.kb_begin = w.my_kb = 0;
+    w.it = 0;
     return w;
   };
   auto walk_tile = [&](Walk& w) {
@@ -353,9 +361,17 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
     T.nt = (int)w.nt;
     T.mt = (int)w.mtp * CTAS + (int)rank;
     T.z0 = w.z0; T.z1 = w.z1; T.tap = w.tap; T.kb_begin = w.kb_begin; T.my_kb = w.my_kb;
+    T.cls = 0;
+    if (NC > 1) {                    // this class's taps: T.tap is their first index, all of them in one pass
+      T.cls = (int)((cq + w.it) % NC);
+      T.tap = c.cls_tap0[T.cls];
+      T.kb_begin = 0;
+      T.my_kb = (c.cls_tap0[T.cls + 1] - T.tap) * c.cblocks;
+    }
     return T;
   };
   auto walk_next = [&](Walk& w) {
+    ++w.it;
     w.t += t_step;
     w.nt += w.dn;
     uint32_t carry = (w.nt >= gn) ? 1u : 0u;
@@ -419,6 +435,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
           i0 = (int)in * c.box_n;                           // phantom tile of an odd pair: out of bounds -> zeros
           tp_i = T.kb_begin / c.cblocks;
           cb = T.kb_begin - tp_i * c.cblocks;
+          if (NC > 1) tp_i += T.tap;                        // first tap of this tile's output class
           tp = c.taps[tp_i];
         } else if (c.mode == AVDN_GEMM_WGRAD) {
           tp = c.taps[T.tap];
@@ -653,7 +670,11 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
       return xy != 0xFFFFFFFFu && w0_ + (int)(xy & 1023u) < c.valid_w && h0_ + (int)((xy >> 10) & 1023u) < c.valid_h &&
              i0_ + (int)(xy >> 20) < c.valid_n;
     };
-    auto prefetch_tile = [&](int mt_, int nt_) {
+    // origin of the output class of a tile (its parity offset inside the strided output)
+    auto cls_origin = [&](int cls) -> uint32_t {
+      return (NC > 1) ? ((uint32_t)c.cls_oh[cls] * (uint32_t)c.out_W + (uint32_t)c.cls_ow[cls]) * (uint32_t)c.ldc : OB;
+    };
+    auto prefetch_tile = [&](int mt_, int nt_, int cls_) {
       const uint32_t mt = (uint32_t)mt_;
       const uint32_t qq = mt / (uint32_t)c.tiles_w, in = mt / twh;
       const int w0_ = (int)(mt - qq * c.tiles_w) * c.box_w, h0_ = (int)(qq - in * c.tiles_h) * c.box_h;
@@ -661,7 +682,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
       const uint2 rw = s_row[et];
       if (row_ok(rw.y, w0_, h0_, i0_)) {
         const int n0_ = nt_ * BN;
-        const uint32_t off = OB + (uint32_t)i0_ * SN + (uint32_t)h0_ * SH + (uint32_t)w0_ * SW + rw.x + (uint32_t)n0_;
+        const uint32_t off = cls_origin(cls_) + (uint32_t)i0_ * SN + (uint32_t)h0_ * SH + (uint32_t)w0_ * SW + rw.x + (uint32_t)n0_;
         const int ncols = min(BN, c.N - n0_);
         for (int b = 0; b < ncols; b += 64) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(bnb_z + off + b));
@@ -691,11 +712,11 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
         // pull the rows of z (and of the old dA) of the NEXT tile into L2 while this one is processed (the first
         // tile prefetches itself as well): the statistics loop below then waits for L2 hits, not for HBM
         Walk wn = wk;
-        if (it == 1) prefetch_tile(T.mt, T.nt);
+        if (it == 1) prefetch_tile(T.mt, T.nt, T.cls);
         walk_next(wn);
         if (wn.t < total) {
           const Tile Tn = walk_tile(wn);
-          prefetch_tile(Tn.mt, Tn.nt);
+          prefetch_tile(Tn.mt, Tn.nt, Tn.cls);
         }
       }
       if (has_aff) {
@@ -736,8 +757,8 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
             else if (c.mode == AVDN_GEMM_WGRAD) { c0 = scol + c.taps[T.tap].bk; c1 = m0; c2 = 0; c3 = 0; }
             else { c1 = m0; c2 = T.z0; c3 = T.z1; }
             if (!(p.dbg & 1)) {
-              if (c.accumulate && !BNB) tma_reduce_add_4d(&p.tmC, srca, c0, c1, c2, c3);
-              else tma_store_4d(&p.tmC, srca, c0, c1, c2, c3);
+              if (c.accumulate && !BNB) tma_reduce_add_4d(&p.tmC[T.cls], srca, c0, c1, c2, c3);
+              else tma_store_4d(&p.tmC[T.cls], srca, c0, c1, c2, c3);
             }
             tma_commit_group();
           }
@@ -825,7 +846,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
               const bool acc = (c.accumulate != 0);
               const bool tile_full = (w0 + c.box_w <= c.valid_w) && (h0 + c.box_h <= c.valid_h) &&
                                      (i0 + c.box_n <= c.valid_n);
-              const uint32_t tile_off = OB + (uint32_t)i0 * SN + (uint32_t)h0 * SH + (uint32_t)w0 * SW + (uint32_t)colc;
+              const uint32_t tile_off = cls_origin(T.cls) + (uint32_t)i0 * SN + (uint32_t)h0 * SH + (uint32_t)w0 * SW + (uint32_t)colc;
               if (cc == 0) ETR(8);
               uint4 zq[ST_NI], oq[ST_NI];
               uint32_t okm = 0u;
@@ -1277,12 +1298,29 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
       box[0] = slab_cols; box[1] = BM; box[2] = 1; box[3] = 1;
     }
     if (ok && encode_map(base, eb, dim, str, box, nullptr, true) == AVDN_OK) {
-      int r = encode_map(base, eb, dim, str, box, &pl->kp.tmC);
+      int r = encode_map(base, eb, dim, str, box, &pl->kp.tmC[0]);
       if (r) return r;
       pl->kp.out_tma = 1;
+      if (c.mode == AVDN_GEMM_CONV && c.n_classes > 1) {       // one map per output class (parity offset)
+        const uint8_t* base0 = reinterpret_cast<const uint8_t*>(c.out);
+        for (int k = 0; k < c.n_classes; ++k) {
+          const uint8_t* bk = base0 + ((int64_t)c.cls_oh[k] * c.out_W + c.cls_ow[k]) * c.ldc * eb;
+          r = encode_map(bk, eb, dim, str, box, &pl->kp.tmC[k]);
+          if (r) return r;
+        }
+      }
     }
   }
   AVDN_REQUIRE(!c.stats || pl->kp.out_tma, "avdn_gemm_plan: fused statistics need the TMA epilogue");
+  if (c.n_classes > 1) {
+    AVDN_REQUIRE(c.mode == AVDN_GEMM_CONV && c.n_classes <= 4 && pl->kp.out_tma && c.split_k == 1 && !c.stats && !c.col_scale,
+                 "avdn_gemm_plan: output classes need a CONV launch with the TMA epilogue (no stats / affine / split-K)");
+    AVDN_REQUIRE(c.cls_tap0[0] == 0 && c.cls_tap0[c.n_classes] == c.n_taps, "avdn_gemm_plan: class tap ranges must cover the taps");
+    for (int k = 0; k < c.n_classes; ++k)
+      AVDN_REQUIRE(c.cls_tap0[k + 1] > c.cls_tap0[k] && c.cls_oh[k] >= 0 && c.cls_oh[k] < c.out_sh && c.cls_ow[k] >= 0 &&
+                       c.cls_ow[k] < c.out_sw,
+                   "avdn_gemm_plan: bad output class %d", k);
+  }
   AVDN_REQUIRE((c.col_scale == nullptr) == (c.col_shift == nullptr), "avdn_gemm_plan: col_scale and col_shift go together");
   AVDN_REQUIRE(!c.col_scale || (pl->kp.out_tma && c.out_dtype == AVDN_DT_BF16 && !c.stats && c.accumulate == 0 &&
                                 !c.bias && !c.relu && c.alpha == 1.0f),
@@ -1347,10 +1385,13 @@ extern "C" int avdn_gemm_plan(const avdn_gemm_desc* d, void* plan_host, size_t p
   }
   // ---- launch geometry: persistent, one CTA (pair) per SM ----
   const long long pm = (d->grid_m + d->ctas - 1) / d->ctas;
-  const long long tiles = pm * d->grid_n * d->grid_z;
+  const long long nc = (c.mode == AVDN_GEMM_CONV && c.n_classes > 1) ? c.n_classes : 1;
+  const long long tiles = pm * d->grid_n * d->grid_z * nc;
   AVDN_REQUIRE(tiles < (1ll << 31), "avdn_gemm_plan: too many tiles");
   const long long slots = (long long)avdn::sm_count() * (pl->occ2 ? 2 : 1) / d->ctas;
-  pl->grid = (int)((tiles < slots ? tiles : slots) * d->ctas);
+  long long g = tiles < slots ? tiles : slots;
+  g = g / nc * nc;                     // class-fastest walk: a whole number of class groups (tiles is a multiple of nc)
+  pl->grid = (int)(g * d->ctas);
   pl->magic = PLAN_MAGIC;
   return AVDN_OK;
 }

@@ -43,7 +43,8 @@ class GemmCore(C.Structure):
                 ("col_scale", C.c_void_p), ("col_shift", C.c_void_p), ("residual", C.c_void_p),
                 ("leaky_slope", f32), ("pad2_", i32),
                 ("bnb_z", C.c_void_p), ("bnb_scale", C.c_void_p), ("bnb_shift", C.c_void_p),
-                ("bnb_mean", C.c_void_p), ("bnb_sums", C.c_void_p)]
+                ("bnb_mean", C.c_void_p), ("bnb_sums", C.c_void_p),
+                ("n_classes", i32), ("cls_tap0", i32 * 5), ("cls_oh", i32 * 4), ("cls_ow", i32 * 4), ("pad4_", i32 * 2)]
 
 
 class GemmDesc(C.Structure):
@@ -105,6 +106,9 @@ class GemmPlan:
 
 
 BN_MAX = int(os.environ.get("AVDN_GEMM_BN_MAX", "128"))      # 128: two co-resident CTAs per SM beat one 256-wide tile
+# data gradient of a stride-2 convolution: 1 = one launch with the four output parities as tile classes
+# (avdn_gemm_core.n_classes), 0 = four launches that each re-read dZ
+DGRAD_CLASSES = os.environ.get("AVDN_DGRAD_CLASSES", "1") != "0"
 
 
 def pick_bn(N):
@@ -330,14 +334,27 @@ def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0,
     pad = (k - 1) // 2
     Kt = k * k * Cout
     plans = []
+    # dX[2i+a, 2j+b] = sum over taps with kh = a+1 (mod 2): a=0 -> kh=1 (d=0); a=1 -> kh=0 (d=+1), kh=2 (d=0)
+    sel = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}
     parities = [(0, 0)] if stride == 1 else [(0, 0), (0, 1), (1, 0), (1, 1)]
-    for (pa, pb) in parities:
+    one_launch = stride == 2 and DGRAD_CLASSES
+    if one_launch:
+        parities = [None]                      # one plan: the four output parities are classes of the same launch
+    for par in parities:
+        classes = None
         if stride == 1:
             taps = [(0, pad - kw, pad - kh, (kh * k + kw) * Cout) for kh in range(k) for kw in range(k)]
             gw, gh = W, H
+            pa = pb = 0
+        elif one_launch:
+            taps, classes = [], []
+            for (ca, cb) in [(0, 0), (0, 1), (1, 0), (1, 1)]:
+                classes.append((len(taps), ca, cb))
+                taps += [(0, dw, dh, (kh * k + kw) * Cout) for (kh, dh) in sel[ca] for (kw, dw) in sel[cb]]
+            gw, gh = Wo, Ho
+            pa = pb = 0
         else:
-            # dX[2i+a, 2j+b] = sum over taps with kh = a+1 (mod 2): a=0 -> kh=1 (d=0); a=1 -> kh=0 (d=+1), kh=2 (d=0)
-            sel = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}
+            pa, pb = par
             taps = [(0, dw, dh, (kh * k + kw) * Cout) for (kh, dh) in sel[pa] for (kw, dw) in sel[pb]]
             gw, gh = Wo, Ho
         bw, bh, bnn = conv_box(gw, gh, N, 128)
@@ -348,6 +365,11 @@ def plan_conv_dgrad(dz, w_d, dx, *, N, H, W, Cin, Cout, k, stride, accumulate=0,
         _fill_taps(c, taps)
         c.cblocks = Cout // bk
         c.num_kb = len(taps) * c.cblocks
+        if classes is not None:
+            c.n_classes = len(classes)
+            for i, (t0, ca, cb) in enumerate(classes):
+                c.cls_tap0[i], c.cls_oh[i], c.cls_ow[i] = t0, ca, cb
+            c.cls_tap0[len(classes)] = len(taps)
         c.split_k, c.batch0, c.batch1 = 1, 1, 1
         c.tiles_w, c.tiles_h, c.tiles_n = _cdiv(gw, bw), _cdiv(gh, bh), _cdiv(N, bnn)
         c.box_w, c.box_h, c.box_n = bw, bh, bnn

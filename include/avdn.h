@@ -199,6 +199,15 @@ typedef struct avdn_gemm_core {
   const float* bnb_shift;
   const float* bnb_mean;
   double* bnb_sums;
+  /* Output classes of a CONV launch (the data gradient of a stride-2 convolution): n_classes > 1 makes every spatial
+   * tile n_classes tiles, class k using taps [cls_tap0[k], cls_tap0[k+1]) and writing the output pixels
+   * (n, h*out_sh + cls_oh[k], w*out_sw + cls_ow[k]) -- the four output parities of dX = conv_transpose(dZ, w) in ONE
+   * launch, the class being the fastest-varying tile index so that the CTAs working side by side read the same dZ
+   * tile (once from HBM) and together complete whole output lines.  0 / 1: a single class (out_oh / out_ow above). */
+  int32_t n_classes;
+  int32_t cls_tap0[5];
+  int32_t cls_oh[4], cls_ow[4];
+  int32_t pad4_[2];
 } avdn_gemm_core;
 
 typedef struct avdn_gemm_desc {
