@@ -537,8 +537,10 @@ class Darknet(nn.Module):
                     self.module_list[i][1].num_batches_tracked += self._pending_batches
             self._pending_batches = 0
 
-    def engine(self, N, H, W, device):
-        return self._engine(N, H, W, device)
+    def engine(self, N, H, W, device, slot=0):
+        """``slot`` separates engines of equal shape whose activations must coexist (one trunk pass per time step of a
+        training rollout, each kept for its own backward pass)."""
+        return self._engine(N, H, W, device, slot)
 
     def _params(self):
         ps = []
@@ -547,8 +549,8 @@ class Darknet(nn.Module):
                 ps += [self.module_list[i][0].weight, self.module_list[i][1].weight, self.module_list[i][1].bias]
         return ps
 
-    def _engine(self, N, H, W, device):
-        key = (N, H, W, str(device))
+    def _engine(self, N, H, W, device, slot=0):
+        key = (N, H, W, str(device)) if slot == 0 else (N, H, W, str(device), slot)
         e = self._engines.get(key)
         if e is None:
             e = _Engine(self, N, H, W, device)

@@ -376,11 +376,11 @@ class NavCMTAgent:
         return float(tot.item()) if sync_loss else tot
 
     def train_rollout_step(self, batch, sync_loss=False, zero=True, step=True, nss_w=None, train_ml=None,
-                           collect=None):
+                           collect=None, bn_per_step=None):
         with self._weights(nss_w, train_ml):
-            return self._train_rollout_step(batch, sync_loss, zero, step, collect)
+            return self._train_rollout_step(batch, sync_loss, zero, step, collect, bn_per_step)
 
-    def _train_rollout_step(self, batch, sync_loss=False, zero=True, step=True, collect=None):
+    def _train_rollout_step(self, batch, sync_loss=False, zero=True, step=True, collect=None, bn_per_step=None):
         """One teacher-forced training ROLLOUT (agent.py:580-760, 883-885, 245-251) as one batched pass: the loss is
         taken at EVERY step t of every episode on the history ``[:t+1]``, summed over steps and samples and scaled
         by ``ml_weight / B``, as the reference accumulates ``ml_loss`` over its step loop.
@@ -403,7 +403,10 @@ class NavCMTAgent:
         without an optimiser step (``train_iteration`` chains the two rollouts of an iteration that way).
         ``nss_w`` / ``train_ml`` (``train_rollout_step``): this rollout's loss weights (default: ``args.nss_w``,
         ``args.ml_weight``); with ``nss_w == 0`` no human-attention maps are rendered.  ``collect``: a list that
-        receives the per-step ``output`` [B,4] tensors (the trajectory log of ``rollout``)."""
+        receives the per-step ``output`` [B,4] tensors (the trajectory log of ``rollout``).
+        ``bn_per_step`` (default ``args.bn_per_step``, false): the reference's BatchNorm semantics -- one train-mode
+        trunk pass per time step over that step's B views (its own batch statistics, one running-statistics update
+        per step, agent.py:593), each pass kept for its own backward -- instead of one pass over all B*T views."""
         ptr = _lib.ptr
         self.vision_model.train()
         n = 0
@@ -461,9 +464,32 @@ class NavCMTAgent:
                 att = xb["att"]
                 n += 1
         vm, et = self.vision_model, self.vln_model
-        teng = vm.engine(BT, 224, 224, dev)
-        l0 = teng.launches
-        DN._trunk_forward(vm, teng, x, True, out=bufs["frames"])
+        if bn_per_step is None:
+            bn_per_step = bool(getattr(self.args, "bn_per_step", False))
+        if bn_per_step:
+            # the reference's loop: Darknet sees the B views of one time step per call (agent.py:593)
+            key = ("rollout_steps", B, T)
+            sb = self._bufs.get(key)
+            if sb is None:
+                sb = dict(x=[torch.empty((B, 224, 224, 4), dtype=torch.bfloat16, device=dev) for _ in range(T)],
+                          f=torch.empty((B, 512, 7, 7), dtype=torch.float32, device=dev),
+                          df=torch.empty((B, 512, 7, 7), dtype=torch.float32, device=dev))
+                self._bufs[key] = sb
+            tengs = [vm.engine(B, 224, 224, dev, slot=1 + t) for t in range(T)]
+            l0 = sum(e.launches for e in tengs)
+            x5 = x.view(B, T, 224, 224, 4)
+            f5 = bufs["frames"].view(B, T, 512, 49)
+            for t in range(T):
+                sb["x"][t].copy_(x5[:, t])
+                DN._trunk_forward(vm, tengs[t], sb["x"][t], True, out=sb["f"])
+                f5[:, t].copy_(sb["f"].view(B, 512, 49))
+            n += 2 * T
+            teng = tengs[0]
+        else:
+            tengs = None
+            teng = vm.engine(BT, 224, 224, dev)
+            l0 = teng.launches
+            DN._trunk_forward(vm, teng, x, True, out=bufs["frames"])
         # ---- step t: the encoder over the history [:t+1], its loss, and straight back (the loss is a sum over steps,
         #      so only one step's activations are alive at a time; every step adds into the one gradient arena) ----
         frames = bufs["frames"].view(B, T, 512, 49)
@@ -531,15 +557,29 @@ class NavCMTAgent:
                                if li in buckets else None)
         else:
             hook = None
-        DN._trunk_backward(vm, teng, bufs["d_frames"].view(-1, 512, 7, 7), after_layer=hook,
-                           flush_layers=set(buckets) if dp else None)
+        if tengs is None:
+            DN._trunk_backward(vm, teng, bufs["d_frames"].view(-1, 512, 7, 7), after_layer=hook,
+                               flush_layers=set(buckets) if dp else None)
+            trunk_launches = teng.launches - l0
+        else:
+            # one backward pass per time step, each through the activations of its own forward pass; the parameter
+            # gradients accumulate, the last pass releases the data-parallel buckets
+            sb = self._bufs[("rollout_steps", B, T)]
+            d5 = bufs["d_frames"].view(B, T, 512, 49)
+            for t in reversed(range(T)):
+                sb["df"].view(B, 512, 49).copy_(d5[:, t])
+                last = (t == 0)
+                DN._trunk_backward(vm, tengs[t], sb["df"], after_layer=hook if last else None,
+                                   flush_layers=set(buckets) if (dp and last) else None)
+            n += T
+            trunk_launches = sum(e.launches for e in tengs) - l0
         if dp:
             self._wait_comm()
         if step:
             gs = 1.0 / self.world
             for opt in self.optimizers:
                 n += opt.step(grad_scale=gs)
-        self.launches += n + (teng.launches - l0) + (eng.launches - e0)
+        self.launches += n + trunk_launches + (eng.launches - e0)
         self._log_loss()
         return float(self.loss_total.item()) if sync_loss else self.loss_total
 
@@ -1088,7 +1128,8 @@ class NavCMTAgent:
                 loss = self._eval_rollout(batch, traj, outs)
             else:
                 loss = self.train_rollout_step(batch, zero=False, step=False, nss_w=float(nss_w),
-                                               train_ml=train_ml if train_ml is not None else 0.0, collect=outs)
+                                               train_ml=train_ml if train_ml is not None else 0.0, collect=outs,
+                                               bn_per_step=bool(getattr(self.args, "bn_per_step", True)))
             tgt = (tgt_xy.cpu().numpy(), tgt_alt.cpu().numpy(), tgt_prog.cpu().numpy()) if has_gt else None
             # what the rollout was made of (inspection / tests): poses, stop flags, targets, the training batch
             self._last_rollout = dict(corners=corners, ended=ended, steps=steps, tgt_xy=tgt_xy, tgt_alt=tgt_alt,

@@ -134,3 +134,56 @@ def test_rollout_step_trains_the_language_encoder(built_lib):
         assert sd_b[n].grad.norm() > 0, n
     print({k: round(v, 4) for k, v in report.items()})
     assert max(report.values()) < 0.1, report
+
+
+def test_rollout_step_bn_per_step_is_the_reference_trunk_schedule(built_lib):
+    """``bn_per_step=True``: one train-mode trunk pass per time step over that step's B views (src/xview_et/agent.py:593)
+    -- batch statistics of B images, T running-statistics updates per rollout -- instead of one pass over B*T views.
+    The features of step t must be bit-identical to a separate train-mode ``Darknet`` pass over the views of step t;
+    with T = 1 the two schedules are the same computation (loss and gradients agree)."""
+    from avdn_b200.models import dark_net as DN
+    from avdn_b200.xview_et.agent import NavCMTAgent
+    B, T, L = 3, 3, 8
+    with tempfile.NamedTemporaryFile("w", suffix=".cfg", delete=False) as f:
+        f.write(mo.yolov3_trunk_cfg())
+    args = types.SimpleNamespace(demb=768, encoder_heads=12, encoder_layers=2, dropout_transformer_encoder=0.1,
+                                 num_input_actions=1, dropout_emb=0.0, darknet_model_file=f.name, darknet_weight_file=None,
+                                 lr=1e-5, nss_w=0.0, nss_r=0, ml_weight=0.2, no_dropout=True)
+    torch.manual_seed(0)
+    agent = NavCMTAgent(args, device="cuda")
+    os.unlink(f.name)
+    for opt in agent.optimizers:
+        opt.lr, opt.wd = 0.0, 0.0
+    g = torch.Generator().manual_seed(9)
+    deg = torch.randint(0, 360, (B, T), generator=g).float()
+    dirs = torch.stack([torch.sin(deg / 180 * 3.14159), torch.cos(deg / 180 * 3.14159)], -1)
+    images = torch.zeros(B * T, 224, 224, 4)
+    images[..., :3] = torch.randn(B * T, 224, 224, 3, generator=g)
+    hb = dict(directions=dirs, images=images.bfloat16(), lang=torch.randn(B, L, 768, generator=g),
+              lang_cls=torch.relu(torch.randn(B, 49, generator=g)), gt_xy=torch.rand(B, T, 2, generator=g) * 2 - 1,
+              gt_alt=torch.rand(B, T, generator=g), gt_prog=torch.rand(B, T, generator=g))
+    batch = {k: v.cuda() for k, v in hb.items()}
+    vm = agent.vision_model
+    nb0 = int(vm.state_dict()["module_list.0.batch_norm_0.num_batches_tracked"])
+    l_step = agent.train_rollout_step(batch, sync_loss=True, bn_per_step=True)
+    assert np.isfinite(l_step)
+    frames = agent._ctx[2]["frames"].view(B, T, 512, 49).clone()
+    assert int(vm.state_dict()["module_list.0.batch_norm_0.num_batches_tracked"]) == nb0 + T
+    x5 = batch["images"].view(B, T, 224, 224, 4)
+    vm.train()
+    for t in range(T):
+        eng = vm.engine(B, 224, 224, "cuda", slot=100 + t)
+        ref = DN._trunk_forward(vm, eng, x5[:, t].contiguous(), True)
+        assert torch.equal(frames[:, t], ref.view(B, 512, 49)), t
+    l_fused = agent.train_rollout_step(batch, sync_loss=True, bn_per_step=False)
+    f_fused = agent._ctx[2]["frames"].view(B, T, 512, 49)
+    assert not torch.equal(f_fused, frames)                 # statistics over B*T views are a different function
+    # T = 1: the same computation under both schedules
+    b1 = {k: (v[:, :1].contiguous() if k in ("directions", "gt_xy", "gt_alt", "gt_prog") else v) for k, v in batch.items()}
+    b1["images"] = x5[:, 0].contiguous()
+    la = agent.train_rollout_step(b1, sync_loss=True, bn_per_step=False)
+    ga = agent.vision_model_optimizer.g.clone()
+    lb = agent.train_rollout_step(b1, sync_loss=True, bn_per_step=True)
+    gb = agent.vision_model_optimizer.g.clone()
+    assert abs(la - lb) <= 1e-6 * abs(la)
+    assert _rel2(gb, ga) < 1e-3, _rel2(gb, ga)
