@@ -399,12 +399,10 @@ __global__ void __launch_bounds__(THREADS, 2) conv0_train_kernel(const uint2* __
   uint8_t* stg_all = smem + 2 * buf_bytes;                                     // [WARPS][16][OUT_PITCH]
   __shared__ float s_acc[27 * C0_OUT];
   __shared__ float s_stat[WARPS][2 * C0_OUT];
-  __shared__ float s_coef[3 * C0_OUT];
+  __shared__ float4 s_coef[C0_OUT];          // (scale, shift, mean, -) per channel: one 16-byte load each
   for (int i = threadIdx.x; i < 27 * C0_OUT; i += THREADS) s_acc[i] = 0.f;
   if (BWD)
-    for (int i = threadIdx.x; i < C0_OUT; i += THREADS) {
-      s_coef[i] = bn_scale[i]; s_coef[C0_OUT + i] = bn_shift[i]; s_coef[2 * C0_OUT + i] = bn_mean[i];
-    }
+    for (int i = threadIdx.x; i < C0_OUT; i += THREADS) s_coef[i] = make_float4(bn_scale[i], bn_shift[i], bn_mean[i], 0.f);
   for (int b = 0; b < 2; ++b) zero_halo(reinterpret_cast<uint2*>(smem + b * buf_bytes), TR_ROWS + 2, W);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   uint32_t wf[3][4][2];
@@ -449,8 +447,13 @@ __global__ void __launch_bounds__(THREADS, 2) conv0_train_kernel(const uint2* __
     __syncthreads();                                   // ... for every thread
     const uint2* xs = reinterpret_cast<const uint2*>(smem + buf * buf_bytes);
     const uint8_t* dzs = smem + buf * buf_bytes + xs_bytes;
-    for (int tile = warp; tile < TR_ROWS * tiles_per_row; tile += WARPS) {
-      const int hr = tile / tiles_per_row, w0 = (tile % tiles_per_row) * 16;
+    // this warp's 16-pixel tiles of the strip: (row hr, tile column tc), advanced without divisions
+    int hr = 0, tc = warp;
+    while (tc >= tiles_per_row) { tc -= tiles_per_row; ++hr; }
+    for (; hr < TR_ROWS; tc += WARPS) {
+      while (tc >= tiles_per_row) { tc -= tiles_per_row; ++hr; }
+      if (hr >= TR_ROWS) break;
+      const int w0 = tc * 16;
       float acc[4][4];
       conv_tile(xs, pitch, hr, w0, g, t, wf, acc);
 #pragma unroll
@@ -465,8 +468,8 @@ __global__ void __launch_bounds__(THREADS, 2) conv0_train_kernel(const uint2* __
           st2[nt][1] = fmaf(z1, z1, fmaf(z3, z3, st2[nt][1]));
         } else {
           const int c0 = nt * 8 + 2 * t;
-          const float sc0 = s_coef[c0], sc1 = s_coef[c0 + 1], sh0 = s_coef[C0_OUT + c0], sh1 = s_coef[C0_OUT + c0 + 1];
-          const float mu0 = s_coef[2 * C0_OUT + c0], mu1 = s_coef[2 * C0_OUT + c0 + 1];
+          const float4 k0 = s_coef[c0], k1 = s_coef[c0 + 1];
+          const float sc0 = k0.x, sc1 = k1.x, sh0 = k0.y, sh1 = k1.y, mu0 = k0.z, mu1 = k1.z;
           const uint32_t dlo = *reinterpret_cast<const uint32_t*>(dzs + (size_t)(hr * W + w0 + g) * DZ_PITCH + c0 * 2);
           const uint32_t dhi = *reinterpret_cast<const uint32_t*>(dzs + (size_t)(hr * W + w0 + g + 8) * DZ_PITCH + c0 * 2);
           const float g0 = __uint_as_float(dlo << 16) * (fmaf(z0, sc0, sh0) > 0.f ? 1.f : slope);
@@ -516,6 +519,82 @@ __global__ void __launch_bounds__(THREADS, 2) conv0_train_kernel(const uint2* __
 #pragma unroll
     for (int wi = 0; wi < WARPS; ++wi) v += s_stat[wi][threadIdx.x];
     atomicAdd(sums + which * C0_PAD + c, (double)v);
+  }
+}
+
+// Forward pass that writes the activation: a = leaky(z*scale + shift), z recomputed (train mode pass 2: z rounded
+// to bf16 first, exactly what a stored z would hold; eval mode: the fp32 accumulator).  Lean (no statistics, the
+// affine coefficients in shared memory) so that four CTAs fit an SM, strips double-buffered with cp.async.
+constexpr int AP_ROWS = 4;
+__global__ void __launch_bounds__(THREADS, 4) conv0_apply_kernel(const uint2* __restrict__ x, const float* __restrict__ w,
+                                                                 uint4* __restrict__ out, int N, int H, int W,
+                                                                 const float* __restrict__ aff_scale,
+                                                                 const float* __restrict__ aff_shift, float slope,
+                                                                 int round_first) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int pitch = W + 2;
+  const size_t buf_bytes = ((((size_t)(AP_ROWS + 2) * pitch + 2) * 8) + 15) / 16 * 16;
+  uint8_t* stg_all = smem + 2 * buf_bytes;                                     // [WARPS][16][OUT_PITCH]
+  __shared__ float2 s_aff[C0_OUT];                                              // (scale, shift) per channel
+  for (int i = threadIdx.x; i < C0_OUT; i += THREADS) s_aff[i] = make_float2(aff_scale[i], aff_shift[i]);
+  for (int b = 0; b < 2; ++b) zero_halo(reinterpret_cast<uint2*>(smem + b * buf_bytes), AP_ROWS + 2, W);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t wf[3][4][2];
+  load_wfrag(w, g, t, wf);
+  const int strips_per_img = H / AP_ROWS, tiles_per_row = W / 16;
+  const long long total = (long long)N * strips_per_img;
+  uint8_t* my_stg = stg_all + warp * 16 * OUT_PITCH;
+  auto issue = [&](long long s, int b) {
+    const int n = (int)(s / strips_per_img), h0 = (int)(s % strips_per_img) * AP_ROWS;
+    stage_x_async(reinterpret_cast<uint2*>(smem + b * buf_bytes), x, n, h0 - 1, AP_ROWS + 2, H, W);
+  };
+  __syncthreads();
+  long long s = blockIdx.x;
+  int buf = 0;
+  if (s < total) issue(s, 0);
+  cp_async_commit();
+  for (; s < total; s += gridDim.x, buf ^= 1) {
+    const long long s2 = s + gridDim.x;
+    if (s2 < total) issue(s2, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait_1();
+    __syncthreads();
+    const uint2* xs = reinterpret_cast<const uint2*>(smem + buf * buf_bytes);
+    const int n = (int)(s / strips_per_img), h0 = (int)(s % strips_per_img) * AP_ROWS;
+    int hr = 0, tc = warp;
+    while (tc >= tiles_per_row) { tc -= tiles_per_row; ++hr; }
+    for (; hr < AP_ROWS; tc += WARPS) {
+      while (tc >= tiles_per_row) { tc -= tiles_per_row; ++hr; }
+      if (hr >= AP_ROWS) break;
+      const int w0 = tc * 16;
+      float acc[4][4];
+      conv_tile(xs, pitch, hr, w0, g, t, wf, acc);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 a0 = s_aff[nt * 8 + 2 * t], a1 = s_aff[nt * 8 + 2 * t + 1];
+        float v[4] = {acc[nt][0], acc[nt][1], acc[nt][2], acc[nt][3]};
+        if (round_first) {
+          const uint32_t lo = pack_bf16(v[0], v[1]), hi = pack_bf16(v[2], v[3]);
+          v[0] = __uint_as_float(lo << 16); v[1] = __uint_as_float(lo & 0xFFFF0000u);
+          v[2] = __uint_as_float(hi << 16); v[3] = __uint_as_float(hi & 0xFFFF0000u);
+        }
+        const float y0 = fmaf(v[0], a0.x, a0.y), y1 = fmaf(v[1], a1.x, a1.y);
+        const float y2 = fmaf(v[2], a0.x, a0.y), y3 = fmaf(v[3], a1.x, a1.y);
+        *reinterpret_cast<uint32_t*>(my_stg + g * OUT_PITCH + (nt * 8 + 2 * t) * 2) =
+            pack_bf16(fmaxf(y0, y0 * slope), fmaxf(y1, y1 * slope));
+        *reinterpret_cast<uint32_t*>(my_stg + (g + 8) * OUT_PITCH + (nt * 8 + 2 * t) * 2) =
+            pack_bf16(fmaxf(y2, y2 * slope), fmaxf(y3, y3 * slope));
+      }
+      __syncwarp();
+      uint4* dst = out + (((size_t)n * H + h0 + hr) * W + w0) * (C0_PAD / 8);      // 16 pixels x 64 bytes, contiguous
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int qd = i * 32 + lane, px = qd >> 2, part = qd & 3;
+        dst[qd] = *reinterpret_cast<const uint4*>(my_stg + px * OUT_PITCH + part * 16);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
   }
 }
 
@@ -628,10 +707,29 @@ extern "C" int avdn_conv0_fwd(const void* x_nhwc4, const float* w, void* z, int 
   return conv0_fwd_launch("avdn_conv0_fwd", x_nhwc4, w, z, N, H, W, stats, nullptr, nullptr, 0.f, stream);
 }
 
+static int conv0_apply_launch(const char* who, const void* x_nhwc4, const float* w, const float* scale, const float* shift,
+                              float slope, void* a, int N, int H, int W, int round_first, avdn_stream_t stream) {
+  AVDN_REQUIRE(x_nhwc4 && w && a && scale && shift && N > 0 && H > 0 && W > 0, "%s: bad argument", who);
+  if (W % 16 != 0 || H % AP_ROWS != 0 || W > 1024)
+    return avdn::set_err(AVDN_ERR_UNSUPPORTED, "%s: W %% 16 == 0, H %% 4 == 0, W <= 1024 required (%dx%d)", who, H, W);
+  const size_t buf_bytes = ((((size_t)(AP_ROWS + 2) * (W + 2) + 2) * 8) + 15) / 16 * 16;
+  const size_t smem = 2 * buf_bytes + (size_t)WARPS * 16 * OUT_PITCH;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    if (cudaFuncSetAttribute(conv0_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return avdn::check_launch("conv0_apply_kernel smem attribute");
+    attr = smem;
+  }
+  const long long strips = (long long)N * (H / AP_ROWS);
+  const long long cap = (long long)avdn::sm_count() * 4;
+  conv0_apply_kernel<<<(unsigned)(strips < cap ? strips : cap), THREADS, smem, avdn::to_cuda(stream)>>>(
+      reinterpret_cast<const uint2*>(x_nhwc4), w, reinterpret_cast<uint4*>(a), N, H, W, scale, shift, slope, round_first);
+  return avdn::check_launch(who);
+}
+
 extern "C" int avdn_conv0_fwd_eval(const void* x_nhwc4, const float* w, const float* scale, const float* shift,
                                    float slope, void* a, int N, int H, int W, avdn_stream_t stream) {
-  AVDN_REQUIRE(scale && shift, "avdn_conv0_fwd_eval: scale/shift are required");
-  return conv0_fwd_launch("avdn_conv0_fwd_eval", x_nhwc4, w, a, N, H, W, nullptr, scale, shift, slope, stream);
+  return conv0_apply_launch("avdn_conv0_fwd_eval", x_nhwc4, w, scale, shift, slope, a, N, H, W, 0, stream);
 }
 
 extern "C" int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int H, int W,
@@ -703,8 +801,7 @@ extern "C" int avdn_conv0_fwd_stats(const void* x_nhwc4, const float* w, int N, 
 
 extern "C" int avdn_conv0_fwd_apply(const void* x_nhwc4, const float* w, const float* scale, const float* shift,
                                     float slope, void* a, int N, int H, int W, avdn_stream_t stream) {
-  AVDN_REQUIRE(scale && shift, "avdn_conv0_fwd_apply: scale/shift are required");
-  return conv0_fwd_launch("avdn_conv0_fwd_apply", x_nhwc4, w, a, N, H, W, nullptr, scale, shift, slope, stream, 1);
+  return conv0_apply_launch("avdn_conv0_fwd_apply", x_nhwc4, w, scale, shift, slope, a, N, H, W, 1, stream);
 }
 
 extern "C" int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* da, const float* scale,
