@@ -299,6 +299,19 @@ __device__ __forceinline__ uint32_t blend(uint2 r0, uint2 r1, uint32_t ax, uint3
   return o;
 }
 
+// Word index of output pixel x inside a staged band row: the 16-byte chunks of every 16-pixel group are XOR-permuted
+// by the group's index so that the repack below (a thread reads the four chunks of ONE group, neighbouring threads
+// neighbouring groups: a 64-byte stride) is free of bank conflicts; the writers' pattern is unaffected.
+__device__ __forceinline__ int swz_px(int x) { return (((x >> 2) ^ ((x >> 5) & 3)) << 2) | (x & 3); }
+
+// 64-bit gather from the packed tile with an L2 evict-last policy: the tile (72 MB for a 3000 x 3000 map) is re-read
+// by every pose while 0.6 GB of views stream out through the same L2
+__device__ __forceinline__ uint2 ldg_tile(const uint2* p, uint64_t policy) {
+  uint2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(policy));
+  return v;
+}
+
 template <bool ATT>
 __global__ void __launch_bounds__(THREADS, 4)
 render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restrict__ tile_idx,
@@ -341,6 +354,8 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
   const double c6 = __dmul_rn(s_m[6], dx1);
   const int pitch = td.W + 2;
   const uint2* __restrict__ tile = reinterpret_cast<const uint2*>(td.tile8);
+  uint64_t keep_policy;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
 
   const int n_xb = (x1 < 32) ? 4 : 3;             // 224 = 3*64 + 32 (warp-uniform)
   for (int xbi = 0; xbi < n_xb; ++xbi) {
@@ -367,11 +382,11 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
       uint2 r0 = make_uint2(0u, 0u), r1 = make_uint2(0u, 0u);
       if ((unsigned)(sx + 1) <= (unsigned)td.W && (unsigned)(sy + 1) <= (unsigned)td.H) {
         const uint2* q = tile + (size_t)(sy + 1) * pitch + (sx + 1);
-        r0 = __ldg(q);
-        r1 = __ldg(q + 1);
+        r0 = ldg_tile(q, keep_policy);
+        r1 = ldg_tile(q + 1, keep_policy);
       }
-      s_px[r * SPITCH + x] = blend<ATT>(r0, r1, (uint32_t)(X & (INTER_TAB - 1)),
-                                      (uint32_t)(Y & (INTER_TAB - 1)));
+      s_px[r * SPITCH + swz_px(x)] = blend<ATT>(r0, r1, (uint32_t)(X & (INTER_TAB - 1)),
+                                              (uint32_t)(Y & (INTER_TAB - 1)));
     }
   }
   __syncthreads();
@@ -385,8 +400,9 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
     for (int g = t; g < BAND * VIEW / 16; g += THREADS) {
       const int row = g / (VIEW / 16), c16 = g - row * (VIEW / 16);
       uint4 q[4];
+      const int sw = (c16 >> 1) & 3;                       // swz_px: chunk k of group c16 sits at k ^ sw
 #pragma unroll
-      for (int k = 0; k < 4; ++k) q[k] = src[row * (SPITCH / 4) + c16 * 4 + k];
+      for (int k = 0; k < 4; ++k) q[k] = src[row * (SPITCH / 4) + c16 * 4 + (k ^ sw)];
       if (views) {
         uint32_t w[12];
 #pragma unroll
@@ -396,15 +412,15 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
           w[3 * k + 2] = __byte_perm(q[k].z, q[k].w, 0x6542);
         }
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-          vdst[g * 3 + k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+        for (int k = 0; k < 3; ++k)      // streaming stores: the views are not read back by this kernel
+          __stcs(vdst + g * 3 + k, make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
       }
       if (ATT && att) {
         uint32_t a4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           a4[k] = __byte_perm(__byte_perm(q[k].x, q[k].y, 0x0073), __byte_perm(q[k].z, q[k].w, 0x0073), 0x5410);
-        adst[g] = make_uint4(a4[0], a4[1], a4[2], a4[3]);
+        __stcs(adst + g, make_uint4(a4[0], a4[1], a4[2], a4[3]));
       }
     }
   }
@@ -413,7 +429,7 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
     uint2* dst = reinterpret_cast<uint2*>(norm_nhwc) + band_px;
     for (int i = t; i < BAND * VIEW; i += THREADS) {
       const int row = i / VIEW;
-      const uint32_t v = s_px[i + row * (SPITCH - VIEW)];
+      const uint32_t v = s_px[row * SPITCH + swz_px(i - row * VIEW)];
       const float r_ = s_lut[(v >> 16) & 255u];
       const float g_ = s_lut[256 + ((v >> 8) & 255u)];
       const float b_ = s_lut[512 + (v & 255u)];
@@ -431,7 +447,8 @@ render_kernel(const avdn_tile_desc* __restrict__ tiles, const int32_t* __restric
     for (int i = t; i < 3 * BAND * VIEW / 4; i += THREADS) {
       const int c = i / (BAND * VIEW / 4);
       const int j4 = i - c * (BAND * VIEW / 4);          // group of 4 pixels inside the band
-      const uint4 q = src[j4 + (j4 / (VIEW / 4)) * ((SPITCH - VIEW) / 4)];
+      const int rowq = j4 / (VIEW / 4), chq = j4 - rowq * (VIEW / 4);
+      const uint4 q = src[rowq * (SPITCH / 4) + (chq ^ ((chq >> 3) & 3))];
       const int sh = 8 * (2 - c);
       float4 o;
       o.x = s_lut[c * 256 + ((q.x >> sh) & 255u)];
