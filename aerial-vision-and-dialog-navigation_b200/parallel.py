@@ -20,7 +20,15 @@ def shard_range(n_total: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def bucket_edges(first_offsets, total, cut_fracs=(0.75, 0.5, 0.3, 0.18)):
+def _default_cuts():
+    import os
+    e = os.environ.get("AVDN_BUCKET_CUTS")          # e.g. "0.75,0.45" (experiments)
+    if e is None:
+        return (0.75, 0.5, 0.3, 0.18)
+    return tuple(float(x) for x in e.split(",") if x.strip())      # "" = one bucket, reduced after the backward pass
+
+
+def bucket_edges(first_offsets, total, cut_fracs=None):
     """Split a flat gradient arena laid out in FORWARD layer order into buckets that
     complete in BACKWARD order.  ``first_offsets[i]`` is the arena offset of the first
     parameter of layer ``i``.  Returns ``[(layer_pos, lo, hi), ...]``: once the backward
@@ -29,6 +37,8 @@ def bucket_edges(first_offsets, total, cut_fracs=(0.75, 0.5, 0.3, 0.18)):
     The default cuts are for the Darknet trunk: its deep blocks hold the parameters (and finish first), its first
     ten blocks hold a third of the backward TIME but < 1 MB of gradients -- so the last bucket, the only one the
     optimiser has to wait for, is a latency-sized all-reduce."""
+    if cut_fracs is None:
+        cut_fracs = _default_cuts()
     nl = len(first_offsets)
     cuts = sorted({min(nl - 1, max(0, int(nl * f))) for f in cut_fracs} | {0}, reverse=True)
     edges, hi = [], total

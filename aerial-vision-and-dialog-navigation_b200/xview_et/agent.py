@@ -102,6 +102,8 @@ class NavCMTAgent:
         self._bufs = {}
         self.launches = 0
         self._comm_stream = torch.cuda.Stream(self.device) if world_size > 1 else None
+        self._ar_bf16 = str(getattr(args, "allreduce_dtype", os.environ.get("AVDN_ALLREDUCE_DTYPE", "fp32"))) == "bf16"
+        self._ar_bufs = {}
         self._buckets = None
         if world_size > 1:
             self.broadcast_parameters()
@@ -144,10 +146,23 @@ class NavCMTAgent:
         return self._buckets
 
     def _allreduce_async(self, flat, lo, hi):
+        """Sum ``flat[lo:hi]`` (a slice of a gradient arena) over the ranks on the communication stream, behind
+        everything enqueued so far.  ``args.allreduce_dtype == 'bf16'`` (or AVDN_ALLREDUCE_DTYPE=bf16) ships the
+        bucket as bf16 -- half the NVLink bytes; every rank receives the same rounded sum, so the replicas stay
+        bit-identical -- the default is fp32."""
         cs = self._comm_stream
         cs.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cs):
-            parallel.allreduce_sum_(flat, lo, hi, self.pg)
+            if self._ar_bf16:
+                buf = self._ar_bufs.get(flat.data_ptr())
+                if buf is None:
+                    buf = torch.empty(flat.numel(), dtype=torch.bfloat16, device=flat.device)
+                    self._ar_bufs[flat.data_ptr()] = buf
+                buf[lo:hi].copy_(flat[lo:hi])
+                parallel.allreduce_sum_(buf, lo, hi, self.pg)
+                flat[lo:hi].copy_(buf[lo:hi])
+            else:
+                parallel.allreduce_sum_(flat, lo, hi, self.pg)
 
     # ----------------------------------------------------------------- buffers
     def _get_bufs(self, B, T):

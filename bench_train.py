@@ -219,9 +219,45 @@ class TrainWorkload:
         ag.exposed_events = None
         t = torch.tensor([float(np.mean(ex)) if ex else 0.0], dtype=torch.float64, device=self.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # (3) the same step with the collective switched off (every rank an independent replica, state snapshotted
+        # and restored around it): max over ranks = what the slowest GPU of this box does on its own, the floor a
+        # synchronous step cannot beat; the distance from ms_per_step to it is what data parallelism costs
+        k = 8
+
+        def back_to_back():
+            for _ in range(2):
+                ag.train_step(self.batch)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                ag.train_step(self.batch)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / k
+
+        synced = back_to_back()                       # same loop with the all-reduce on, for a like-for-like pair
+        snap = [(o, o.p.clone(), o.m.clone(), o.v.clone(), o.step_count) for o in ag.optimizers]
+        bn = [b.clone() for b in ag.vision_model.buffers()]
+        world, ag.world = ag.world, 1
+        try:
+            solo = back_to_back()
+        finally:
+            ag.world = world
+        for o, p_, m_, v_, sc in snap:
+            o.p.copy_(p_); o.m.copy_(m_); o.v.copy_(v_); o.step_count = sc
+        for b, b0 in zip(ag.vision_model.buffers(), bn):
+            b.copy_(b0)
+        per = [torch.zeros(2, dtype=torch.float64, device=self.dev) for _ in range(world)]
+        dist.all_gather(per, torch.tensor([solo, synced], dtype=torch.float64, device=self.dev))
+        synced = max(float(x[1].item()) for x in per)
+        per = [round(float(x[0].item()), 3) for x in per]
         return {"replicas_in_sync": in_sync, "allreduce_exposed_ms": float(t.item()),
-                "allreduce": {"bytes_per_step": int(sum(o.n for o in ag.optimizers) * 4), "dtype": "fp32",
-                              "buckets": 1 + len(ag._buckets or [])}}
+                "replica_ms_per_step_without_allreduce": {"per_rank": per, "max": max(per), "min": min(per),
+                                                          "steps": k, "same_loop_with_allreduce": round(synced, 3),
+                                                          "note": "back-to-back steps, no L2 flush between them"},
+                "allreduce": {"bytes_per_step": int(sum(o.n for o in ag.optimizers) * (2 if ag._ar_bf16 else 4)),
+                              "dtype": "bf16" if ag._ar_bf16 else "fp32", "buckets": 1 + len(ag._buckets or [])}}
 
     # ---------------------------------------------------------------- library bar
     def library_bar(self, ours_ms):
