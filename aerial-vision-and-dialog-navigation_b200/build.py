@@ -30,6 +30,7 @@ SOURCES = {
     "gemm.cu": [],
     "trunk.cu": [],
     "conv0.cu": [],
+    "conv0_tc.cu": [],
     "lstm.cu": ["-fmad=false"],
     "encoder.cu": [],
     "agent.cu": [],

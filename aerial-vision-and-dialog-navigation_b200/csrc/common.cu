@@ -38,7 +38,7 @@ int sm_count() {
 
 extern "C" const char* avdn_last_error_string(void) { return avdn::err_buf(); }
 
-extern "C" int avdn_abi_version(void) { return 6; }
+extern "C" int avdn_abi_version(void) { return 7; }
 
 extern "C" int avdn_device_supported(void) {
   int n = 0;

@@ -11,6 +11,9 @@
 //   forward : Z[pixel][co]   = sum_kh  P_kh[pixel][16] . W_kh[16][co]      (+ fused BN statistics)
 //   wgrad   : dW_kh[co][16] += sum_pixel dZ^T[co][pixel] . P_kh[pixel][16]
 #include "common.cuh"
+#include "conv0_tc.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -678,6 +681,25 @@ __global__ void conv0_bwd_finish_kernel(const double* __restrict__ sums, const f
 }  // namespace
 
 // ===================================================================== C ABI
+// Which kernels serve the recompute path and the eval forward: 1 = tcgen05 (conv0_tc.cu), 0 = warp-level mma.sync
+// (this file).  AVDN_CONV0_TC in the environment sets the initial value; avdn_conv0_set_tensor_path() changes it.
+static int& conv0_tc_flag() {
+  static int flag = [] {
+    const char* e = getenv("AVDN_CONV0_TC");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return flag;
+}
+static bool conv0_use_tc(int N, int H, int W) {
+  return conv0_tc_flag() && (long long)N * H * W <= avdn::CONV0_TC_MAX_PIXELS;
+}
+extern "C" int avdn_conv0_set_tensor_path(int on) {
+  int& f = conv0_tc_flag();
+  const int old = f;
+  if (on >= 0) f = on ? 1 : 0;
+  return old;
+}
+
 static int conv0_fwd_launch(const char* who, const void* x_nhwc4, const float* w, void* out, int N, int H, int W,
                             double* stats, const float* scale, const float* shift, float slope,
                             avdn_stream_t stream, int round_first = 0) {
@@ -729,6 +751,10 @@ static int conv0_apply_launch(const char* who, const void* x_nhwc4, const float*
 
 extern "C" int avdn_conv0_fwd_eval(const void* x_nhwc4, const float* w, const float* scale, const float* shift,
                                    float slope, void* a, int N, int H, int W, avdn_stream_t stream) {
+  if (conv0_use_tc(N, H, W)) {
+    AVDN_REQUIRE(x_nhwc4 && w && a && scale && shift && N > 0 && H > 0 && W > 0, "avdn_conv0_fwd_eval: bad argument");
+    return avdn::conv0_tc_apply(x_nhwc4, w, scale, shift, slope, a, N, H, W, 0, avdn::to_cuda(stream));
+  }
   return conv0_apply_launch("avdn_conv0_fwd_eval", x_nhwc4, w, scale, shift, slope, a, N, H, W, 0, stream);
 }
 
@@ -785,6 +811,7 @@ extern "C" int avdn_conv0_fwd_stats(const void* x_nhwc4, const float* w, int N, 
                                     double* xs9, avdn_stream_t stream) {
   AVDN_REQUIRE(x_nhwc4 && w && stats && zw && xs9 && N > 0 && H > 0 && W > 0, "avdn_conv0_fwd_stats: bad argument");
   cudaStream_t s = avdn::to_cuda(stream);
+  if (conv0_use_tc(N, H, W)) return avdn::conv0_tc_fwd_stats(x_nhwc4, w, N, H, W, stats, zw, xs9, s);
   if (cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C0_PAD, s) != cudaSuccess ||
       cudaMemsetAsync(zw, 0, sizeof(float) * 27 * C0_OUT, s) != cudaSuccess ||
       cudaMemsetAsync(xs9, 0, sizeof(double) * 9 * 4, s) != cudaSuccess)
@@ -801,6 +828,10 @@ extern "C" int avdn_conv0_fwd_stats(const void* x_nhwc4, const float* w, int N, 
 
 extern "C" int avdn_conv0_fwd_apply(const void* x_nhwc4, const float* w, const float* scale, const float* shift,
                                     float slope, void* a, int N, int H, int W, avdn_stream_t stream) {
+  if (conv0_use_tc(N, H, W)) {
+    AVDN_REQUIRE(x_nhwc4 && w && a && scale && shift && N > 0 && H > 0 && W > 0, "avdn_conv0_fwd_apply: bad argument");
+    return avdn::conv0_tc_apply(x_nhwc4, w, scale, shift, slope, a, N, H, W, 1, avdn::to_cuda(stream));
+  }
   return conv0_apply_launch("avdn_conv0_fwd_apply", x_nhwc4, w, scale, shift, slope, a, N, H, W, 1, stream);
 }
 
@@ -812,6 +843,9 @@ extern "C" int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* d
                    N > 0 && H > 0 && W > 0,
                "avdn_conv0_bwd: bad argument");
   cudaStream_t s = avdn::to_cuda(stream);
+  if (conv0_use_tc(N, H, W))
+    return avdn::conv0_tc_bwd(x_nhwc4, w, da, scale, shift, mean, rstd, slope, N, H, W, zw, xs9, sums, gw, dw, dgamma,
+                              dbeta, s);
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C0_PAD, s) != cudaSuccess ||
       cudaMemsetAsync(gw, 0, sizeof(float) * 27 * C0_OUT, s) != cudaSuccess)
     return avdn::check_launch("avdn_conv0_bwd memset");

@@ -257,7 +257,15 @@ int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int 
  *   avdn_conv0_fwd_apply  pass 2: a [N,H,W,32] bf16 = leaky(bf16(conv(x)) * scale + shift).
  *   avdn_conv0_bwd        da [N,H,W,32] bf16 -> dw += scale*Gw + A*Zw + B*Xw (the weight gradient of
  *                         dz = scale*g + A*z + B without forming dz), dgamma += rstd*S2, dbeta += S1;
- *                         sums [2,32] f64 and gw [32,3,3,3] fp32 are scratch.   W % 16 == 0, H % 2 == 0.            */
+ *                         sums [2,32] f64 and gw [32,3,3,3] fp32 are scratch.   W % 16 == 0, H % 2 == 0.
+ * The three passes (and avdn_conv0_fwd_eval) run on the tcgen05 tensor cores by default (csrc/conv0_tc.cu: one
+ * 128-pixel im2col tile per UMMA, every per-channel sum taken as a Gram product of the same tile; any H, W with
+ * N*H*W < 2^31).  On that path the statistics are those of the UNROUNDED z, xs9 carries Xw [3,3,3] f64 (sum of the
+ * input patches) instead of the border sums, and the library keeps 32 KB of per-device f64 scratch, so calls for
+ * one device must be issued on one stream.  avdn_conv0_set_tensor_path(0) (or AVDN_CONV0_TC=0 in the environment)
+ * selects the warp-level mma.sync kernels instead; the argument -1 only queries.  Returns the previous setting.
+ * fwd_stats and bwd of one step must run under the same setting.                                               */
+int avdn_conv0_set_tensor_path(int on);
 int avdn_conv0_fwd_stats(const void* x_nhwc4, const float* w, int N, int H, int W, double* stats, float* zw,
                          double* xs9, avdn_stream_t stream);
 int avdn_conv0_fwd_apply(const void* x_nhwc4, const float* w, const float* scale, const float* shift, float slope,

@@ -29,9 +29,13 @@ def run():
          ptr(sums), ptr(gw), ptr(dw), ptr(dg), ptr(db))
 
 
-run(); torch.cuda.synchronize()
-_lib.PROFILE = []
-run(); torch.cuda.synchronize()
-for name, e0, e1, fl, nb in _lib.PROFILE:
-    print(f"{name}: {e0.elapsed_time(e1):.3f} ms")
-_lib.PROFILE = None
+for path in (0, 1):
+    _lib.lib().avdn_conv0_set_tensor_path(path)
+    run(); torch.cuda.synchronize()
+    for rep in range(2):
+        _lib.PROFILE = []
+        run(); torch.cuda.synchronize()
+        for name, e0, e1, fl, nb in _lib.PROFILE:
+            print(f"{'tcgen05 ' if path else 'mma.sync'} {name}: {e0.elapsed_time(e1):.3f} ms")
+        _lib.PROFILE = None
+_lib.lib().avdn_conv0_set_tensor_path(1)
