@@ -753,7 +753,7 @@ extern "C" int avdn_conv0_fwd_eval(const void* x_nhwc4, const float* w, const fl
                                    float slope, void* a, int N, int H, int W, avdn_stream_t stream) {
   if (conv0_use_tc(N, H, W)) {
     AVDN_REQUIRE(x_nhwc4 && w && a && scale && shift && N > 0 && H > 0 && W > 0, "avdn_conv0_fwd_eval: bad argument");
-    return avdn::conv0_tc_apply(x_nhwc4, w, scale, shift, slope, a, N, H, W, 0, avdn::to_cuda(stream));
+    return avdn::conv0_tc_apply(x_nhwc4, w, scale, shift, slope, a, nullptr, N, H, W, avdn::to_cuda(stream));
   }
   return conv0_apply_launch("avdn_conv0_fwd_eval", x_nhwc4, w, scale, shift, slope, a, N, H, W, 0, stream);
 }
@@ -827,15 +827,16 @@ extern "C" int avdn_conv0_fwd_stats(const void* x_nhwc4, const float* w, int N, 
 }
 
 extern "C" int avdn_conv0_fwd_apply(const void* x_nhwc4, const float* w, const float* scale, const float* shift,
-                                    float slope, void* a, int N, int H, int W, avdn_stream_t stream) {
+                                    float slope, void* a, void* mask, int N, int H, int W, avdn_stream_t stream) {
   if (conv0_use_tc(N, H, W)) {
     AVDN_REQUIRE(x_nhwc4 && w && a && scale && shift && N > 0 && H > 0 && W > 0, "avdn_conv0_fwd_apply: bad argument");
-    return avdn::conv0_tc_apply(x_nhwc4, w, scale, shift, slope, a, N, H, W, 1, avdn::to_cuda(stream));
+    return avdn::conv0_tc_apply(x_nhwc4, w, scale, shift, slope, a, reinterpret_cast<uint32_t*>(mask), N, H, W,
+                                avdn::to_cuda(stream));
   }
   return conv0_apply_launch("avdn_conv0_fwd_apply", x_nhwc4, w, scale, shift, slope, a, N, H, W, 1, stream);
 }
 
-extern "C" int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* da, const float* scale,
+extern "C" int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* da, const void* mask, const float* scale,
                               const float* shift, const float* mean, const float* rstd, float slope, int N, int H, int W,
                               const float* zw, const double* xs9, double* sums, float* gw, float* dw, float* dgamma,
                               float* dbeta, avdn_stream_t stream) {
@@ -843,9 +844,11 @@ extern "C" int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* d
                    N > 0 && H > 0 && W > 0,
                "avdn_conv0_bwd: bad argument");
   cudaStream_t s = avdn::to_cuda(stream);
-  if (conv0_use_tc(N, H, W))
-    return avdn::conv0_tc_bwd(x_nhwc4, w, da, scale, shift, mean, rstd, slope, N, H, W, zw, xs9, sums, gw, dw, dgamma,
-                              dbeta, s);
+  if (conv0_use_tc(N, H, W)) {
+    AVDN_REQUIRE(mask, "avdn_conv0_bwd: the tensor-core path needs the sign mask avdn_conv0_fwd_apply wrote");
+    return avdn::conv0_tc_bwd(x_nhwc4, w, da, reinterpret_cast<const uint32_t*>(mask), scale, mean, rstd, slope, N, H, W,
+                              zw, xs9, sums, gw, dw, dgamma, dbeta, s);
+  }
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C0_PAD, s) != cudaSuccess ||
       cudaMemsetAsync(gw, 0, sizeof(float) * 27 * C0_OUT, s) != cudaSuccess)
     return avdn::check_launch("avdn_conv0_bwd memset");

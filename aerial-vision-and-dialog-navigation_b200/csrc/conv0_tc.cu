@@ -11,18 +11,24 @@
 //   im2col tile   one thread per pixel gathers its 3x3 patch (9 x 8-byte pixels R,G,B,0 -> 36 bf16, element
 //                 e = (kh*3 + kw)*4 + c) into ONE 128-byte row of a 128-row shared-memory tile, written in the
 //                 128-byte-swizzle layout tcgen05 reads (16-byte chunk j of row r at chunk j ^ (r & 7)); element
-//                 63 of every row is 1.0.  The SAME 16 KB image is a K-major A operand [128 px x 64 k] for the
-//                 convolution and an MN-major operand [K = 128 px x 64] for the pixel reductions.
-//   convolution   Z[128 px x 32] = X . W^T : 3 UMMAs (M 128, N 32, K 16) into TMEM.
+//                 39 of every row is 1.0.  The SAME 16 KB image is a K-major A operand [128 px x 48 k] for the
+//                 convolution and an MN-major operand [K = 128 px x 48] for the pixel reductions.
+//   convolution   Z[128 px x 32] = X . W^T : 3 UMMAs (M 128, N 32, K 16) into TMEM (pass 2 / eval only).
 //   reductions    every sum over pixels the block needs is a Gram product on the same tile:
-//                   pass 1   G  += X^T X  (64 x 64): sum z = W.G[:,63], sum z^2 = w^T G w, Zw = W.G, Xw = G[:,63]
-//                   backward Gw += G'^T X (32 x 64), G' = da * leaky'(bn(z)) written to a second tile by the
-//                            epilogue: sum g' = Gw[:,63], sum g' z = <w, Gw>, and Gw itself is the raw weight gradient
-//                 8 UMMAs (M 128, N 64, K 16) per tile, accumulated in TMEM over the CTA's tiles and flushed to f64
-//                 every FLUSH tiles.  Pass 1 therefore has NO per-pixel epilogue at all.
+//                   pass 1   G  += X^T X  (48 x 48): sum z = W.G[:,39], sum z^2 = w^T G w, Zw = W.G, Xw = G[:,39]
+//                   backward Gw += G'^T X (32 x 48), G' = da * leaky' from the sign mask pass 2 left (one bit per
+//                            element): sum g' = Gw[:,39], sum g' z = <w, Gw>, and Gw itself is the raw weight gradient
+//                 8 UMMAs (M 64, N 48, K 16) per tile, accumulated in TMEM over the CTA's tiles and flushed to f64
+//                 every FLUSH tiles.  Neither reduction pass has a per-pixel epilogue, and the backward never
+//                 recomputes z.
 //
-// Per step at B = 64 (32.1 M pixels): pass 1 reads x (257 MB), pass 2 reads x and writes a (2.06 GB), the
-// backward reads x and da (2.06 GB).
+// All three kernels are bound by shared-memory bandwidth (LSU wavefronts + the tensor core's operand reads add up
+// to ~100 % in ncu), so the data movement is what is trimmed: BatchNorm coefficients sit in the constant bank, the
+// activation leaves through a linear staging slab and one bulk copy per warp, da arrives by bulk copy, and the next
+// tile's gather is in flight while the current one is processed.
+//
+// Per step at B = 64 (32.1 M pixels): pass 1 reads x (257 MB), pass 2 reads x and writes a (2.06 GB) + the mask
+// (128 MB), the backward reads x, da (2.06 GB) and the mask.
 #include "common.cuh"
 #include "tcgen05.cuh"
 #include "conv0_tc.cuh"
@@ -32,12 +38,17 @@ namespace {
 using namespace avdn_tc;
 
 constexpr int C0 = 32;                 // output channels (= stored channels)
-constexpr int TILE = 128;              // pixels per tile = UMMA M
+constexpr int TILE = 128;              // pixels per tile = UMMA M of the convolution, K of the reductions
 constexpr int TILE_BYTES = TILE * 128; // 16 KB: 128 rows of 64 bf16
 constexpr int THREADS = 128;           // one thread per pixel of the tile; warp w owns TMEM lanes 32w..32w+31
 constexpr int NE = 36;                 // patch elements that carry data (9 taps x 4 channels, the 4th is zero)
-constexpr int ONE = 63;                // the element of every patch row that is 1.0 (column sums)
+constexpr int ONE = 39;                // the element of every patch row that is 1.0 (column sums)
+constexpr int GN = 48;                 // columns of the Gram accumulators (elements 0..39 used)
 constexpr int FLUSH = 64;              // tiles between two f64 flushes of a TMEM accumulator (8192 pixels in fp32)
+constexpr int OUT_BYTES = TILE * 64;   // one tile of a / da: 128 pixels x 32 bf16
+
+__constant__ float c_scale[C0];        // BatchNorm scale / shift of the running apply kernel (constant bank operands)
+__constant__ float c_shift[C0];
 
 // byte offset of 16-byte chunk `c` of row `r` in a 128-byte-swizzled tile of 128-byte rows
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
@@ -58,11 +69,21 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&b);
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// linear shared -> global / global -> shared bulk copies (16-byte granularity)
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 // instruction descriptors: D f32, A = B = bf16; bit 15 / 16 = A / B MN-major; N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t IDESC_CONV = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C0 >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-constexpr uint32_t IDESC_GRAM = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
-                                ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t IDESC_GRAM = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GN >> 3) << 17) |
+                                ((uint32_t)(64 >> 4) << 24);
 
 struct Pix {              // the pixel a thread owns in the current tile
   long long p;            // flat index n*H*W + y*W + x   (< 2^31: checked by the host)
@@ -91,16 +112,15 @@ __device__ __forceinline__ void gather(const uint2* __restrict__ x, const Pix& q
     v[kh * 3 + 2] = (rok && q.x < W - 1) ? __ldg(r + 2) : z;
   }
 }
-// patch row of this thread's pixel: chunks 0..4 (elements 0..39) and chunk 7 (the ones column; 0 for a pixel
-// past the end so that it drops out of every sum).  Chunks 5, 6 stay zero from the set-up.
+// patch row of this thread's pixel: chunks 0..4 = elements 0..39; element 39 is the ones column (0 for a pixel past
+// the end, which therefore drops out of every sum).  Chunk 5 stays zero from the set-up, 6 and 7 are never read.
 __device__ __forceinline__ void store_patch(uint32_t tile_addr, const uint2 (&v)[9], bool valid) {
   const uint32_t r = threadIdx.x;
   sts128(tile_addr + sw128(r, 0), v[0].x, v[0].y, v[1].x, v[1].y);
   sts128(tile_addr + sw128(r, 1), v[2].x, v[2].y, v[3].x, v[3].y);
   sts128(tile_addr + sw128(r, 2), v[4].x, v[4].y, v[5].x, v[5].y);
   sts128(tile_addr + sw128(r, 3), v[6].x, v[6].y, v[7].x, v[7].y);
-  sts128(tile_addr + sw128(r, 4), v[8].x, v[8].y, 0u, 0u);
-  sts128(tile_addr + sw128(r, 7), 0u, 0u, 0u, valid ? 0x3F800000u : 0u);      // element 63 = bf16(1.0)
+  sts128(tile_addr + sw128(r, 4), v[8].x, v[8].y, 0u, valid ? 0x3F800000u : 0u);      // element 39 = bf16(1.0)
 }
 __device__ __forceinline__ void zero_chunks(uint32_t tile_addr, int c_lo, int c_hi) {
   for (int c = c_lo; c <= c_hi; ++c) sts128(tile_addr + sw128(threadIdx.x, c), 0u, 0u, 0u, 0u);
@@ -136,8 +156,9 @@ __device__ __forceinline__ uint8_t* align1k(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
 
-// G (+)= [A0 | A1]^T X over the 128 pixels of a tile: A = two MN-major atoms (64 columns each, 16 KB apart),
-// B = X (MN-major, 64 columns): 8 UMMAs of K = 16 pixels.  `acc` = 0 overwrites the accumulator with the first.
+// D[64 x 48] (+)= A^T X over the 128 pixels of a tile: A and B = X are MN-major 64-column atoms (one 128-byte row per
+// pixel): 8 UMMAs of K = 16 pixels.  `acc` = 0 overwrites the accumulator with the first.
+// TMEM layout of an M = 64 accumulator: row m sits in lane (m % 16) + 32 * (m / 16).
 __device__ __forceinline__ void gram_mma(uint32_t tmem_d, uint32_t a_addr, uint32_t x_addr, uint32_t acc) {
   const uint64_t ad = make_smem_desc(a_addr, TILE_BYTES, 1024), bd = make_smem_desc(x_addr, TILE_BYTES, 1024);
 #pragma unroll
@@ -146,7 +167,24 @@ __device__ __forceinline__ void gram_mma(uint32_t tmem_d, uint32_t a_addr, uint3
     acc = 1u;
   }
 }
-// Z = X . W^T : K = 48 covers the 36 patch elements
+// rows of an M = 64 accumulator this warp holds: lane l < 16 of warp w has row 16 w + l; columns 0..35 and ONE of it
+// are added to dst[row][.] (row stride 64)
+__device__ __forceinline__ void flush_rows(uint32_t tmem_d, double* __restrict__ dst, int n_rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t lo[32], hi[32];
+  tmem_ld32_async(tmem_d + ((uint32_t)(warp * 32) << 16), lo);            // columns 0..31
+  tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + 16, hi);             // columns 16..47
+  const int r = warp * 16 + lane;
+  if (lane < 16 && r < n_rows && (r < NE || r == ONE || n_rows == C0)) {
+    double* g = dst + r * 64;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) atomicAdd(g + c, (double)__uint_as_float(lo[c]));
+#pragma unroll
+    for (int c = 32; c < NE; ++c) atomicAdd(g + c, (double)__uint_as_float(hi[c - 16]));
+    atomicAdd(g + ONE, (double)__uint_as_float(hi[ONE - 16]));
+  }
+}
+// Z = X . W^T : K = 48 covers the 36 patch elements (the weights of elements 36..47 are zero)
 __device__ __forceinline__ void conv_mma(uint32_t tmem_d, uint32_t x_addr, uint32_t w_addr) {
   const uint64_t ad = make_smem_desc(x_addr, 16, 1024), bd = make_smem_desc(w_addr, 16, 1024);
 #pragma unroll
@@ -154,29 +192,29 @@ __device__ __forceinline__ void conv_mma(uint32_t tmem_d, uint32_t x_addr, uint3
 }
 
 // ------------------------------------------------------------------ pass 1: Gram matrix of the patches
-// gram [64][64] f64 += sum over pixels x_patch x_patch^T (rows / columns < 36 and 63 are written).
+// gram [64][64] f64 += sum over pixels x_patch x_patch^T (rows / columns < 36 and 39 are written).
 __global__ void __launch_bounds__(THREADS, 4) conv0_tc_gram_kernel(const uint2* __restrict__ x, int H, int W, long long P,
                                                                    long long n_tiles, double* __restrict__ gram) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = align1k(smem_raw);
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
-  const uint32_t xs = smem_u32(sm);                    // [2 tiles][16 KB] + 16 KB that only the unused rows read
+  const uint32_t xs = smem_u32(sm);                    // 2 tiles of 16 KB
   const uint32_t bar0 = smem_u32(&bars[0]);
   if (threadIdx.x == 0) {
     mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int b = 0; b < 3; ++b) zero_chunks(xs + b * TILE_BYTES, b < 2 ? 5 : 0, b < 2 ? 6 : 7);
+  for (int b = 0; b < 2; ++b) zero_chunks(xs + b * TILE_BYTES, 5, 7);
   const uint32_t tmem = tmem_alloc(&tmem_slot, 64);
-  const int warp = threadIdx.x >> 5;
 
-  uint32_t it = 0, since_flush = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  long long tile = blockIdx.x;
+  Pix q = locate(tile, P, H, W);
+  uint2 v[9];
+  if (tile < n_tiles) gather(x, q, H, W, v);
+  uint32_t since_flush = 0;
+  for (uint32_t it = 0; tile < n_tiles; ++it) {
     const uint32_t b = it & 1u;
-    const Pix q = locate(tile, P, H, W);
-    uint2 v[9];
-    gather(x, q, H, W, v);
     if (it >= 2) mbar_wait(bar0 + 8 * b, ((it >> 1) - 1u) & 1u);        // the UMMAs of tile it-2 have read buffer b
     store_patch(xs + b * TILE_BYTES, v, q.valid);
     fence_proxy_async_smem();
@@ -188,24 +226,16 @@ __global__ void __launch_bounds__(THREADS, 4) conv0_tc_gram_kernel(const uint2* 
     }
     __syncwarp();
     ++since_flush;
-    const bool last = tile + gridDim.x >= n_tiles;
+    tile += gridDim.x;
+    const bool last = tile >= n_tiles;
+    if (!last) {                                                        // the next tile's loads fly under the UMMAs
+      q = locate(tile, P, H, W);
+      gather(x, q, H, W, v);
+    }
     if (since_flush == FLUSH || last) {
       mbar_wait(bar0 + 8 * b, (it >> 1) & 1u);                          // everything issued so far has completed
       tcgen05_fence_after();
-      if (warp < 2) {                                                   // rows 0..63 of the accumulator
-        uint32_t lo[32], hi[32];
-        tmem_ld32_async(tmem + ((uint32_t)(warp * 32) << 16), lo);
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32, hi);
-        const int r = threadIdx.x;
-        if (r < NE || r == ONE) {
-          double* g = gram + r * 64;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) atomicAdd(g + c, (double)__uint_as_float(lo[c]));
-#pragma unroll
-          for (int c = 0; c < NE - 32; ++c) atomicAdd(g + 32 + c, (double)__uint_as_float(hi[c]));
-          atomicAdd(g + ONE, (double)__uint_as_float(hi[ONE - 32]));
-        }
-      }
+      flush_rows(tmem, gram, ONE + 1);
       tcgen05_fence_before();
       __syncthreads();
       since_flush = 0;
@@ -247,28 +277,26 @@ __global__ void __launch_bounds__(256) conv0_tc_stats_finish_kernel(const double
 }
 
 // ------------------------------------------------------------------ pass 2 / eval: a = leaky(bn(conv(x)))
-__global__ void __launch_bounds__(THREADS, 6) conv0_tc_apply_kernel(const uint2* __restrict__ x, const float* __restrict__ w,
-                                                                    const float* __restrict__ scale,
-                                                                    const float* __restrict__ shift, float slope,
-                                                                    uint4* __restrict__ a, int H, int W, long long P,
-                                                                    long long n_tiles, int round_first) {
+// mask (NULL or [P] u32): bit 31 - c of mask[p] = (a[p][c] > 0), for the backward.
+__global__ void __launch_bounds__(THREADS, 5) conv0_tc_apply_kernel(const uint2* __restrict__ x, const float* __restrict__ w,
+                                                                    float slope, uint8_t* __restrict__ a,
+                                                                    uint32_t* __restrict__ mask, int H, int W, long long P,
+                                                                    long long n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = align1k(smem_raw);
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float2 s_coef[C0];
-  const uint32_t xs = smem_u32(sm), ws = xs + TILE_BYTES, outs = ws + C0 * 128;     // X 16 KB | W 4 KB | staging 8 KB
+  const uint32_t xs = smem_u32(sm), ws = xs + TILE_BYTES, outs = ws + C0 * 128;     // X 16 KB | W 4 KB | 2 x staging 8 KB
   const uint32_t bar_a = smem_u32(&bar);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < C0) s_coef[threadIdx.x] = make_float2(scale[threadIdx.x], shift[threadIdx.x]);
-  zero_chunks(xs, 5, 6);
+  zero_chunks(xs, 5, 5);
   build_w_tile(sm + TILE_BYTES, w);
   const uint32_t tmem = tmem_alloc(&tmem_slot, 32);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t my_out = outs + warp * 2048;          // this warp's 32 pixels x 64 B
+  const uint32_t rot = (uint32_t)(lane >> 1) & 3u;     // chunk rotation that makes the 64-byte-row stores conflict-free
 
   long long tile = blockIdx.x;
   Pix q = locate(tile, P, H, W);
@@ -285,6 +313,7 @@ __global__ void __launch_bounds__(THREADS, 6) conv0_tc_apply_kernel(const uint2*
     }
     __syncwarp();
     const long long cur = tile;
+    const bool cur_valid = q.valid;
     tile += gridDim.x;
     if (tile < n_tiles) {                               // the next tile's loads fly under this tile's epilogue
       q = locate(tile, P, H, W);
@@ -295,138 +324,143 @@ __global__ void __launch_bounds__(THREADS, 6) conv0_tc_apply_kernel(const uint2*
     uint32_t z[32];
     tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), z);
     tcgen05_fence_before();
-    uint32_t o[16];
+    uint32_t o[16], sign = 0u;
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {
-      float z0 = __uint_as_float(z[c]), z1 = __uint_as_float(z[c + 1]);
-      if (round_first) { z0 = bf16_round(z0); z1 = bf16_round(z1); }
-      const float2 k0 = s_coef[c], k1 = s_coef[c + 1];
-      float a0 = fmaf(z0, k0.x, k0.y), a1 = fmaf(z1, k1.x, k1.y);
-      a0 = a0 > 0.f ? a0 : a0 * slope;
-      a1 = a1 > 0.f ? a1 : a1 * slope;
+      float a0 = fmaf(__uint_as_float(z[c]), c_scale[c], c_shift[c]);
+      float a1 = fmaf(__uint_as_float(z[c + 1]), c_scale[c + 1], c_shift[c + 1]);
+      a0 = fmaxf(a0, a0 * slope);                       // leaky, 0 < slope < 1
+      a1 = fmaxf(a1, a1 * slope);
+      sign = __funnelshift_l(__float_as_uint(a0), sign, 1);
+      sign = __funnelshift_l(__float_as_uint(a1), sign, 1);
       o[c >> 1] = pack2(a0, a1);
     }
-    // 64-byte pixel rows -> the warp's 2 KB staging slab (chunk c of row l at c ^ ((l >> 1) & 3)) -> 4 coalesced
-    // 512-byte stores
-    const uint32_t sx = (uint32_t)(lane >> 1) & 3u;
+    const long long pix = cur * TILE + threadIdx.x;
+    if (mask != nullptr && cur_valid) mask[pix] = ~sign;
+    // rotate the four 16-byte chunks of the pixel row left by `rot`: chunk (j + rot) & 3 ends up in slot j
+    if (rot & 1u) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      sts128(my_out + lane * 64 + (((uint32_t)c ^ sx) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t t = o[k];
+        o[k] = o[4 + k]; o[4 + k] = o[8 + k]; o[8 + k] = o[12 + k]; o[12 + k] = t;
+      }
+    }
+    if (rot & 2u) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t t = o[k]; o[k] = o[8 + k]; o[8 + k] = t;
+        t = o[4 + k]; o[4 + k] = o[12 + k]; o[12 + k] = t;
+      }
+    }
+    // the warp's 32 pixels x 64 B go to its linear 2 KB slab and leave with one bulk copy
+    const uint32_t slab = outs + (it & 1u) * OUT_BYTES + warp * 2048;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(slab + lane * 64 + ((((uint32_t)j + rot) & 3u) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    fence_proxy_async_smem();
     __syncwarp();
-    const long long base16 = (cur * TILE + warp * 32) * 4;          // in 16-byte units
-    const long long end16 = P * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t off = (uint32_t)j * 512u + (uint32_t)lane * 16u;
-      const uint32_t row = off >> 6, c = (off >> 4) & 3u;
-      const uint4 val = lds128(my_out + row * 64 + ((c ^ ((row >> 1) & 3u)) << 4));
-      const long long g = base16 + j * 32 + lane;
-      if (g < end16) a[g] = val;
+    if (lane == 0) {
+      const long long first = cur * TILE + warp * 32;
+      long long n = P - first;
+      n = n > 32 ? 32 : n;
+      if (n > 0) bulk_store(a + first * 64, slab, (uint32_t)n * 64u);
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the other slab (tile it-1) has been read
     }
     __syncwarp();
   }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tmem_free(tmem, 32);
 }
 
 // ------------------------------------------------------------------ backward
-// gwacc [32][64] f64 += sum over pixels g'[co] * x_patch[e], g' = da * leaky'(scale * bf16(z) + shift).
-__global__ void __launch_bounds__(THREADS, 4) conv0_tc_bwd_kernel(const uint2* __restrict__ x, const float* __restrict__ w,
-                                                                  const uint4* __restrict__ da,
-                                                                  const float* __restrict__ scale,
-                                                                  const float* __restrict__ shift, float slope, int H,
+// gwacc [32][64] f64 += sum over pixels g'[co] * x_patch[e], g' = da where mask says a > 0, slope * da elsewhere.
+__global__ void __launch_bounds__(THREADS, 4) conv0_tc_bwd_kernel(const uint2* __restrict__ x, const uint8_t* __restrict__ da,
+                                                                  const uint32_t* __restrict__ mask, float slope, int H,
                                                                   int W, long long P, long long n_tiles,
                                                                   double* __restrict__ gwacc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = align1k(smem_raw);
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[3];
   __shared__ uint32_t tmem_slot;
-  __shared__ float2 s_coef[C0];
-  const uint32_t xs = smem_u32(sm), gs = xs + TILE_BYTES, ws = gs + TILE_BYTES;     // X 16 KB | G' 16 KB | W 4 KB
-  const uint32_t bar1 = smem_u32(&bars[0]), bar2 = bar1 + 8;
+  const uint32_t xs = smem_u32(sm), gs = xs + TILE_BYTES, ds = gs + TILE_BYTES;     // X 16 KB | G' 16 KB | 2 x da 8 KB
+  const uint32_t bar_mma = smem_u32(&bars[0]), bar_da = bar_mma + 8;
   if (threadIdx.x == 0) {
-    mbar_init(bar1, 1); mbar_init(bar2, 1);
+    mbar_init(bar_mma, 1); mbar_init(bar_da, 1); mbar_init(bar_da + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < C0) s_coef[threadIdx.x] = make_float2(scale[threadIdx.x], shift[threadIdx.x]);
-  zero_chunks(xs, 5, 6);
-  zero_chunks(gs, 4, 7);
-  build_w_tile(sm + 2 * TILE_BYTES, w);
-  const uint32_t tmem = tmem_alloc(&tmem_slot, 128);
-  const uint32_t tmem_z = tmem, tmem_g = tmem + 64;
-  const int warp = threadIdx.x >> 5;
+  zero_chunks(xs, 5, 7);
+  zero_chunks(gs, 4, 7);                               // channels 32..63 of the A atom: accumulator rows 32..63 = 0
+  const uint32_t tmem = tmem_alloc(&tmem_slot, 64);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rot = (uint32_t)(lane >> 1) & 3u;
 
-  uint32_t it = 0, since_flush = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const Pix q = locate(tile, P, H, W);
-    uint2 v[9];
+  auto load_da = [&](long long t, uint32_t stage) {    // thread 0: one bulk copy of the tile's 128 x 64 B
+    long long n = P - t * TILE;
+    n = n > TILE ? TILE : n;
+    mbar_expect_tx(bar_da + 8 * stage, (uint32_t)n * 64u);
+    bulk_load(ds + stage * OUT_BYTES, da + t * TILE * 64, (uint32_t)n * 64u, bar_da + 8 * stage);
+  };
+
+  long long tile = blockIdx.x;
+  Pix q = locate(tile, P, H, W);
+  uint2 v[9];
+  uint32_t m = 0u;
+  if (tile < n_tiles) {
+    if (threadIdx.x == 0) load_da(tile, 0);
     gather(x, q, H, W, v);
-    uint4 d[4];
-    {
-      const uint4* dp = da + q.p * 4;
-      const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) d[c] = q.valid ? __ldg(dp + c) : zz;
-    }
-    if (it > 0) mbar_wait(bar2, (it - 1u) & 1u);      // the Gram UMMAs of the previous tile have read X and G'
+    if (q.valid) m = __ldg(mask + q.p);
+  }
+  uint32_t since_flush = 0;
+  for (uint32_t it = 0; tile < n_tiles; ++it) {
+    const uint32_t s = it & 1u;
+    if (it > 0) mbar_wait(bar_mma, (it - 1u) & 1u);    // the UMMAs of the previous tile have read X and G'
     store_patch(xs, v, q.valid);
+    mbar_wait(bar_da + 8 * s, (it >> 1) & 1u);         // this tile's da has landed
+    const uint32_t row = ds + s * OUT_BYTES + threadIdx.x * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t c = ((uint32_t)j + rot) & 3u;     // rotated chunk order: conflict-free 64-byte-row loads
+      uint4 d = q.valid ? lds128(row + (c << 4)) : make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t bits = m << (8u * c);             // bit 31 = channel 8c, bit 30 = channel 8c + 1, ...
+      uint32_t dw_[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float g0 = __uint_as_float(dw_[k] << 16), g1 = __uint_as_float(dw_[k] & 0xFFFF0000u);
+        const bool p0 = (bits << (2 * k)) & 0x80000000u, p1 = (bits << (2 * k + 1)) & 0x80000000u;
+        dw_[k] = pack2(p0 ? g0 : g0 * slope, p1 ? g1 : g1 * slope);
+      }
+      sts128(gs + sw128(threadIdx.x, c), dw_[0], dw_[1], dw_[2], dw_[3]);
+    }
     fence_proxy_async_smem();
     __syncthreads();
+    tile += gridDim.x;
+    const bool last = tile >= n_tiles;
     if (threadIdx.x == 0) {
       tcgen05_fence_after();
-      conv_mma(tmem_z, xs, ws);
-      tcgen05_commit<1>(bar1);
-    }
-    __syncwarp();
-    mbar_wait(bar1, it & 1u);
-    tcgen05_fence_after();
-    uint32_t z[32];
-    tmem_ld32(tmem_z + ((uint32_t)(warp * 32) << 16), z);
-    tcgen05_fence_before();
-    const uint32_t dw_[16] = {d[0].x, d[0].y, d[0].z, d[0].w, d[1].x, d[1].y, d[1].z, d[1].w,
-                              d[2].x, d[2].y, d[2].z, d[2].w, d[3].x, d[3].y, d[3].z, d[3].w};
-    uint32_t o[16];
-#pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      const float z0 = bf16_round(__uint_as_float(z[c])), z1 = bf16_round(__uint_as_float(z[c + 1]));
-      const float2 k0 = s_coef[c], k1 = s_coef[c + 1];
-      const float g0 = __uint_as_float(dw_[c >> 1] << 16), g1 = __uint_as_float(dw_[c >> 1] & 0xFFFF0000u);
-      o[c >> 1] = pack2(fmaf(z0, k0.x, k0.y) > 0.f ? g0 : g0 * slope, fmaf(z1, k1.x, k1.y) > 0.f ? g1 : g1 * slope);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) sts128(gs + sw128(threadIdx.x, c), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      tcgen05_fence_after();
-      gram_mma(tmem_g, xs, xs, since_flush ? 1u : 0u);               // rows 64..95 of the accumulator = G'^T X
-      tcgen05_commit<1>(bar2);
+      gram_mma(tmem, gs, xs, since_flush ? 1u : 0u);
+      tcgen05_commit<1>(bar_mma);
+      if (!last) load_da(tile, s ^ 1u);                // stage s^1 was consumed before the barrier above
     }
     __syncwarp();
     ++since_flush;
-    const bool last = tile + gridDim.x >= n_tiles;
+    if (!last) {
+      q = locate(tile, P, H, W);
+      gather(x, q, H, W, v);
+      m = q.valid ? __ldg(mask + q.p) : 0u;
+    }
     if (since_flush == FLUSH || last) {
-      mbar_wait(bar2, it & 1u);
+      mbar_wait(bar_mma, it & 1u);
       tcgen05_fence_after();
-      if (warp == 2) {                                                // TMEM lanes 64..95 = output channel
-        uint32_t lo[32], hi[32];
-        tmem_ld32_async(tmem_g + ((uint32_t)64 << 16), lo);
-        tmem_ld32(tmem_g + ((uint32_t)64 << 16) + 32, hi);
-        double* g = gwacc + (threadIdx.x - 64) * 64;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) atomicAdd(g + c, (double)__uint_as_float(lo[c]));
-#pragma unroll
-        for (int c = 0; c < NE - 32; ++c) atomicAdd(g + 32 + c, (double)__uint_as_float(hi[c]));
-        atomicAdd(g + ONE, (double)__uint_as_float(hi[ONE - 32]));
-      }
+      flush_rows(tmem, gwacc, C0);
       tcgen05_fence_before();
       __syncthreads();
       since_flush = 0;
     }
   }
-  tmem_free(tmem, 128);
+  tmem_free(tmem, 64);
 }
 
-// dW = scale*Gw + A*Zw + B*Xw ; dgamma += rstd*S2 ; dbeta += S1, with S1 = sum g' = Gw[:,63] and
+// dW = scale*Gw + A*Zw + B*Xw ; dgamma += rstd*S2 ; dbeta += S1, with S1 = sum g' = Gw[:,39] and
 // S2 = sum g' (z - mean) = <w, Gw> - mean * S1                       (one thread per weight element)
 __global__ void conv0_tc_bwd_finish_kernel(const double* __restrict__ gwacc, const float* __restrict__ w,
                                            const float* __restrict__ zw, const double* __restrict__ xw, double invR,
@@ -455,7 +489,7 @@ __global__ void conv0_tc_bwd_finish_kernel(const double* __restrict__ gwacc, con
   }
 }
 
-// per-device f64 scratch: the Gram matrix [64][64] and the backward accumulator [32][64]
+// per-device f64 scratch: the Gram matrix [64][64] / the backward accumulator [32][64]
 double* scratch(cudaStream_t s) {
   static double* buf[64] = {};
   int dev = 0;
@@ -479,7 +513,7 @@ int conv0_tc_fwd_stats(const void* x, const float* w, int N, int H, int W, doubl
   const long long P = (long long)N * H * W, n_tiles = (P + TILE - 1) / TILE;
   double* gram = scratch(s);
   if (!gram) return set_err(AVDN_ERR_LAUNCH, "conv0 tensor path: no scratch");
-  const size_t smem = 3 * TILE_BYTES + 1024;
+  const size_t smem = 2 * TILE_BYTES + 1024;
   static bool attr = false;
   if (!attr) {
     if (set_smem(conv0_tc_gram_kernel, smem)) return check_launch("conv0_tc_gram_kernel smem attribute");
@@ -494,29 +528,32 @@ int conv0_tc_fwd_stats(const void* x, const float* w, int N, int H, int W, doubl
   return check_launch("conv0_tc_stats_finish_kernel");
 }
 
-int conv0_tc_apply(const void* x, const float* w, const float* scale, const float* shift, float slope, void* a, int N,
-                   int H, int W, int round_first, cudaStream_t s) {
+int conv0_tc_apply(const void* x, const float* w, const float* scale, const float* shift, float slope, void* a,
+                   uint32_t* mask, int N, int H, int W, cudaStream_t s) {
+  if (!(slope > 0.f && slope < 1.f)) return set_err(AVDN_ERR_UNSUPPORTED, "conv0 tensor path: 0 < slope < 1 required");
   const long long P = (long long)N * H * W, n_tiles = (P + TILE - 1) / TILE;
-  const size_t smem = TILE_BYTES + C0 * 128 + 4 * 2048 + 1024;
+  if (cudaMemcpyToSymbolAsync(c_scale, scale, sizeof(float) * C0, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+      cudaMemcpyToSymbolAsync(c_shift, shift, sizeof(float) * C0, 0, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    return check_launch("conv0 tensor path: coefficient upload");
+  const size_t smem = TILE_BYTES + C0 * 128 + 2 * OUT_BYTES + 1024;
   static bool attr = false;
   if (!attr) {
     if (set_smem(conv0_tc_apply_kernel, smem)) return check_launch("conv0_tc_apply_kernel smem attribute");
     attr = true;
   }
-  const long long cap = (long long)sm_count() * 6;
+  const long long cap = (long long)sm_count() * 5;
   conv0_tc_apply_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), THREADS, smem, s>>>(
-      reinterpret_cast<const uint2*>(x), w, scale, shift, slope, reinterpret_cast<uint4*>(a), H, W, P, n_tiles,
-      round_first);
+      reinterpret_cast<const uint2*>(x), w, slope, reinterpret_cast<uint8_t*>(a), mask, H, W, P, n_tiles);
   return check_launch("conv0_tc_apply_kernel");
 }
 
-int conv0_tc_bwd(const void* x, const float* w, const void* da, const float* scale, const float* shift,
+int conv0_tc_bwd(const void* x, const float* w, const void* da, const uint32_t* mask, const float* scale,
                  const float* mean, const float* rstd, float slope, int N, int H, int W, const float* zw,
                  const double* xs9, double* sums, float* gw, float* dw, float* dgamma, float* dbeta, cudaStream_t s) {
   const long long P = (long long)N * H * W, n_tiles = (P + TILE - 1) / TILE;
   double* gwacc = scratch(s);
   if (!gwacc) return set_err(AVDN_ERR_LAUNCH, "conv0 tensor path: no scratch");
-  const size_t smem = 2 * TILE_BYTES + C0 * 128 + 1024;
+  const size_t smem = 2 * TILE_BYTES + 2 * OUT_BYTES + 1024;
   static bool attr = false;
   if (!attr) {
     if (set_smem(conv0_tc_bwd_kernel, smem)) return check_launch("conv0_tc_bwd_kernel smem attribute");
@@ -524,8 +561,7 @@ int conv0_tc_bwd(const void* x, const float* w, const void* da, const float* sca
   }
   const long long cap = (long long)sm_count() * 4;
   conv0_tc_bwd_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), THREADS, smem, s>>>(
-      reinterpret_cast<const uint2*>(x), w, reinterpret_cast<const uint4*>(da), scale, shift, slope, H, W, P, n_tiles,
-      gwacc);
+      reinterpret_cast<const uint2*>(x), reinterpret_cast<const uint8_t*>(da), mask, slope, H, W, P, n_tiles, gwacc);
   int r = check_launch("conv0_tc_bwd_kernel");
   if (r) return r;
   conv0_tc_bwd_finish_kernel<<<(27 * C0 + 127) / 128, 128, 0, s>>>(gwacc, w, zw, xs9, 1.0 / (double)P, scale, mean, rstd,

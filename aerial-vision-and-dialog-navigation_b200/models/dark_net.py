@@ -166,7 +166,8 @@ class _Engine:
             if L.recompute:
                 L.zw = torch.zeros(L.Cout * 27, dtype=f32, device=dev)         # sum z * x  (forward pass 1)
                 L.gw = torch.zeros(L.Cout * 27, dtype=f32, device=dev)         # sum g * x  (backward)
-                L.xs9 = torch.zeros(36, dtype=torch.float64, device=dev)       # total / border sums of x
+                L.xs9 = torch.zeros(36, dtype=torch.float64, device=dev)       # patch sums (tcgen05) / border sums of x
+                L.mask = torch.zeros(L.R, dtype=torch.int32, device=dev)       # sign bits of a, one word per pixel
             L.scale = torch.zeros(L.Cout_p, dtype=f32, device=dev)
             L.shift = torch.zeros(L.Cout_p, dtype=f32, device=dev)
             L.mean = torch.zeros(L.Cout_p, dtype=f32, device=dev)
@@ -371,7 +372,7 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
         n += 1 if L.first else 2    # finalize (+ the stats memset inside avdn_gemm_run)
         if L.first and L.recompute:
             call("avdn_conv0_fwd_apply", ptr(x_nhwc4), ptr(conv.weight), ptr(L.scale), ptr(L.shift), LEAKY_SLOPE,
-                 ptr(L.a), eng.N, L.Hin, L.Win)
+                 ptr(L.a), ptr(L.mask), eng.N, L.Hin, L.Win)
         else:
             call("avdn_bn_apply", ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.res.a) if L.res is not None else None,
                  ptr(L.a), L.R, L.Cout_p, LEAKY_SLOPE)
@@ -418,7 +419,7 @@ def _layer_backward(eng, L, unpack=True, zero=True):
     if L.first and L.recompute:
         # one pass over (x, dA): BatchNorm-backward sums and the weight gradient, z recomputed, dz never formed
         conv = eng.net_ref().module_list[L.idx][0]
-        call("avdn_conv0_bwd", ptr(eng.x_in), ptr(conv.weight), ptr(L.g), ptr(L.scale), ptr(L.shift), ptr(L.mean),
+        call("avdn_conv0_bwd", ptr(eng.x_in), ptr(conv.weight), ptr(L.g), ptr(L.mask), ptr(L.scale), ptr(L.shift), ptr(L.mean),
              ptr(L.rstd), LEAKY_SLOPE, eng.N, L.Hin, L.Win, ptr(L.zw), ptr(L.xs9), ptr(L.sums), ptr(L.gw), ptr(L.dw),
              ptr(L.dgamma), ptr(L.dbeta))
         return 4

@@ -260,17 +260,21 @@ int avdn_conv0_wgrad(const void* dz, const void* x_nhwc4, float* dw, int N, int 
  *                         sums [2,32] f64 and gw [32,3,3,3] fp32 are scratch.   W % 16 == 0, H % 2 == 0.
  * The three passes (and avdn_conv0_fwd_eval) run on the tcgen05 tensor cores by default (csrc/conv0_tc.cu: one
  * 128-pixel im2col tile per UMMA, every per-channel sum taken as a Gram product of the same tile; any H, W with
- * N*H*W < 2^31).  On that path the statistics are those of the UNROUNDED z, xs9 carries Xw [3,3,3] f64 (sum of the
- * input patches) instead of the border sums, and the library keeps 32 KB of per-device f64 scratch, so calls for
- * one device must be issued on one stream.  avdn_conv0_set_tensor_path(0) (or AVDN_CONV0_TC=0 in the environment)
+ * N*H*W < 2^31).  On that path z is never rounded to bf16 (statistics, activation and the LeakyReLU mask all come
+ * from the fp32 accumulator), xs9 carries Xw [3,3,3] f64 (sum of the input patches) instead of the border sums,
+ * avdn_conv0_fwd_apply writes mask [N*H*W] u32 (bit 31-c = a[c] > 0; may be NULL when no backward follows) and
+ * avdn_conv0_bwd reads it instead of recomputing z (the mma.sync kernels ignore mask), and the library keeps 32 KB
+ * of per-device f64 scratch plus the coefficients in constant memory, so calls for one device must be issued on
+ * one stream.  avdn_conv0_set_tensor_path(0) (or AVDN_CONV0_TC=0 in the environment)
  * selects the warp-level mma.sync kernels instead; the argument -1 only queries.  Returns the previous setting.
  * fwd_stats and bwd of one step must run under the same setting.                                               */
 int avdn_conv0_set_tensor_path(int on);
 int avdn_conv0_fwd_stats(const void* x_nhwc4, const float* w, int N, int H, int W, double* stats, float* zw,
                          double* xs9, avdn_stream_t stream);
 int avdn_conv0_fwd_apply(const void* x_nhwc4, const float* w, const float* scale, const float* shift, float slope,
-                         void* a, int N, int H, int W, avdn_stream_t stream);
-int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* da, const float* scale, const float* shift,
+                         void* a, void* mask, int N, int H, int W, avdn_stream_t stream);
+int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* da, const void* mask, const float* scale,
+                   const float* shift,
                    const float* mean, const float* rstd, float slope, int N, int H, int W, const float* zw,
                    const double* xs9, double* sums, float* gw, float* dw, float* dgamma, float* dbeta,
                    avdn_stream_t stream);

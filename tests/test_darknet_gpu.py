@@ -360,9 +360,10 @@ def test_conv0_recompute_path_matches_stored_path(built_lib, N, H, conv0_path):
          ptr(mu_b), ptr(rs_b))
     a_b = torch.empty_like(z)
     # the stored path's coefficients, so that the activations can be compared bit for bit
-    call("avdn_conv0_fwd_apply", ptr(x), ptr(w), ptr(sc_a), ptr(sh_a), 0.01, ptr(a_b), N, H, W)
+    mask = torch.zeros(R, dtype=torch.int32, device=dev)
+    call("avdn_conv0_fwd_apply", ptr(x), ptr(w), ptr(sc_a), ptr(sh_a), 0.01, ptr(a_b), ptr(mask), N, H, W)
     dw_b, dg_b, db_b = torch.zeros(32, 3, 3, 3, device=dev), torch.zeros(32, device=dev), torch.zeros(32, device=dev)
-    call("avdn_conv0_bwd", ptr(x), ptr(w), ptr(da), ptr(sc_a), ptr(sh_a), ptr(mu_a), ptr(rs_a), 0.01, N, H, W, ptr(zw),
+    call("avdn_conv0_bwd", ptr(x), ptr(w), ptr(da), ptr(mask), ptr(sc_a), ptr(sh_a), ptr(mu_a), ptr(rs_a), 0.01, N, H, W, ptr(zw),
          ptr(xs9), ptr(sums_b), ptr(gw), ptr(dw_b), ptr(dg_b), ptr(db_b))
     torch.cuda.synchronize()
     if not tc:
@@ -375,9 +376,10 @@ def test_conv0_recompute_path_matches_stored_path(built_lib, N, H, conv0_path):
         assert ((stats_b[:32] - stats_a[:32]).abs() / R <= 1e-3 * var_a.sqrt()).all()
         assert torch.allclose(var_b, var_a, rtol=1e-3)
         assert torch.allclose(sc_b, sc_a, rtol=1e-3) and torch.allclose(sh_b, sh_a, rtol=1e-3, atol=1e-3)
+        # the stored path rounds z to bf16 before the affine map, the tensor path does not
         d = (a_b.float() - a_a.float()).abs()
-        assert (d <= 2.0 ** -7 * a_a.float().abs() + 2e-3).all(), d.max()
-        assert (d > 0).float().mean() < 2e-3, (d > 0).float().mean()
+        zs = (z.float() * sc_a.view(1, 1, 1, 32)).abs()
+        assert (d <= 2.0 ** -7 * a_a.float().abs() + 2.0 ** -8 * zs + 1e-6).all(), d.max()
     # z-weighted / plain input sums against torch on the stored z
     zf = z.float().permute(0, 3, 1, 2)
     xf = x[..., :3].float().permute(0, 3, 1, 2)
@@ -385,8 +387,11 @@ def test_conv0_recompute_path_matches_stored_path(built_lib, N, H, conv0_path):
     zw_ref = torch.einsum("ncp,nkp->ck", zf.reshape(N, 32, H * W).double(), cols.double()).reshape(-1)
     assert _rel2(zw, zw_ref.float()) < (1e-3 if tc else 1e-4)
     # gradients
-    assert _rel2(db_b, db_a) < (1e-3 if tc else 1e-4) and _rel2(dg_b, dg_a) < (5e-3 if tc else 1e-4)
-    assert _rel2(dw_b, dw_a) < 2e-2, _rel2(dw_b, dw_a)
+    # (tensor path: its LeakyReLU mask comes from the unrounded z, the stored path's from bf16(z): ~0.1 % of the pixels
+    # of a channel whose pre-activation straddles zero take the other slope -- the strict check of that path, against
+    # fp64 with its own mask, is test_conv0_tensor_path_vs_torch_fp64)
+    assert _rel2(db_b, db_a) < (3e-2 if tc else 1e-4) and _rel2(dg_b, dg_a) < (3e-2 if tc else 1e-4)
+    assert _rel2(dw_b, dw_a) < (3e-2 if tc else 2e-2), _rel2(dw_b, dw_a)
     # and against fp64 torch: dz = scale*g + A*z + B on the stored z, dW = sum dz * x (no bf16 rounding of dz)
     y = zf.double() * sc_a.double().view(1, 32, 1, 1) + sh_a.double().view(1, 32, 1, 1)
     gg = torch.where(y > 0, da.double().permute(0, 3, 1, 2), (da.float() * 0.01).double().permute(0, 3, 1, 2))
@@ -396,7 +401,7 @@ def test_conv0_recompute_path_matches_stored_path(built_lib, N, H, conv0_path):
     B = -sc_a.double() * S1 / R - A * mu_a.double()
     dzr = sc_a.double().view(1, 32, 1, 1) * gg + A.view(1, 32, 1, 1) * zf.double() + B.view(1, 32, 1, 1)
     dw_ref = torch.einsum("ncp,nkp->ck", dzr.reshape(N, 32, H * W), cols.double()).reshape(32, 3, 3, 3)
-    assert _rel2(dw_b, dw_ref.float()) < 1e-2, _rel2(dw_b, dw_ref.float())
+    assert _rel2(dw_b, dw_ref.float()) < (3e-2 if tc else 1e-2), _rel2(dw_b, dw_ref.float())
     assert _rel2(dw_a, dw_ref.float()) < 1e-2
 
 
@@ -430,11 +435,12 @@ def test_conv0_tensor_path_vs_torch_fp64(built_lib, N, H, W):
         call("avdn_bn_finalize", ptr(sums), R, 32, 32, ptr(gamma), ptr(beta), None, None, 0.1, 1e-5, ptr(sc), ptr(sh),
              ptr(mu), ptr(rs))
         a = torch.empty(N, H, W, 32, device=dev, dtype=torch.bfloat16)
-        call("avdn_conv0_fwd_apply", ptr(x), ptr(w), ptr(sc), ptr(sh), 0.01, ptr(a), N, H, W)
+        mask = torch.zeros(R, dtype=torch.int32, device=dev)
+        call("avdn_conv0_fwd_apply", ptr(x), ptr(w), ptr(sc), ptr(sh), 0.01, ptr(a), ptr(mask), N, H, W)
         a_eval = torch.empty_like(a)
         call("avdn_conv0_fwd_eval", ptr(x), ptr(w), ptr(sc), ptr(sh), 0.01, ptr(a_eval), N, H, W)
         dw, dg, db = torch.zeros(32, 3, 3, 3, device=dev), torch.zeros(32, device=dev), torch.zeros(32, device=dev)
-        call("avdn_conv0_bwd", ptr(x), ptr(w), ptr(da), ptr(sc), ptr(sh), ptr(mu), ptr(rs), 0.01, N, H, W, ptr(zw),
+        call("avdn_conv0_bwd", ptr(x), ptr(w), ptr(da), ptr(mask), ptr(sc), ptr(sh), ptr(mu), ptr(rs), 0.01, N, H, W, ptr(zw),
              ptr(xs9), ptr(sums), ptr(gw), ptr(dw), ptr(dg), ptr(db))
         torch.cuda.synchronize()
         # ---- fp64 reference on the bf16 operands ----
@@ -447,18 +453,16 @@ def test_conv0_tensor_path_vs_torch_fp64(built_lib, N, H, W):
         zw_ref = torch.einsum("ncp,nkp->ck", z.reshape(N, 32, H * W), cols).reshape(-1)
         assert _rel2(zw, zw_ref.float()) < 1e-4
         assert torch.allclose(xs9[:27], cols.sum(dim=(0, 2)), rtol=1e-5, atol=1e-5 * R ** 0.5)
-        zr = z.to(torch.bfloat16).double()
-        y = zr * sc.double().view(1, 32, 1, 1) + sh.double().view(1, 32, 1, 1)
-        a_ref = torch.where(y > 0, y, 0.01 * y).permute(0, 2, 3, 1)
-        d = (a.double() - a_ref).abs()
-        assert (d <= 2.0 ** -6 * a_ref.abs() + 4e-3).all(), d.max()          # one bf16 step of z or of a
-        assert d.mean() < 2e-3 * a_ref.abs().mean()
         y2 = z * sc.double().view(1, 32, 1, 1) + sh.double().view(1, 32, 1, 1)
         e_ref = torch.where(y2 > 0, y2, 0.01 * y2).permute(0, 2, 3, 1)
-        assert ((a_eval.double() - e_ref).abs() <= 2.0 ** -8 * e_ref.abs() + 1e-6).all()
+        tol = 2.0 ** -8 * e_ref.abs() + 1e-5 * (z.abs() * sc.double().abs().view(1, 32, 1, 1)).permute(0, 2, 3, 1) + 1e-6
+        assert ((a.double() - e_ref).abs() <= tol).all(), (a.double() - e_ref).abs().max()      # half a bf16 step of a
+        assert torch.equal(a_eval, a)                      # eval and train apply are the same kernel on this path
+        bits = torch.stack([(mask >> (31 - c)) & 1 for c in range(32)], dim=-1).view(N, H, W, 32).bool()
+        assert torch.equal(bits, a.float() >= 0)           # sign bits; a == 0 only for an exactly zero pre-activation
         # backward: the mask from the kernel's own activation sign (a == 0 cannot happen for leaky), so that a z on
         # the boundary does not count as an error
-        gg = torch.where(a.double().permute(0, 3, 1, 2) > 0, da.double().permute(0, 3, 1, 2),
+        gg = torch.where(bits.permute(0, 3, 1, 2), da.double().permute(0, 3, 1, 2),
                          (da.float() * 0.01).double().permute(0, 3, 1, 2))
         S1 = gg.sum(dim=(0, 2, 3))
         S2 = (gg * (z - mu.double().view(1, 32, 1, 1))).sum(dim=(0, 2, 3))

@@ -19,13 +19,14 @@ da = torch.randn(N, H, W, 32, device=dev).to(torch.bfloat16)
 sums = torch.zeros(128, dtype=torch.float64, device=dev)
 zw, gw = torch.zeros(864, device=dev), torch.zeros(864, device=dev)
 xs9 = torch.zeros(36, dtype=torch.float64, device=dev)
+mask = torch.zeros(N * H * W, dtype=torch.int32, device=dev)
 dw, dg, db = torch.zeros(32, 3, 3, 3, device=dev), torch.zeros(32, device=dev), torch.zeros(32, device=dev)
 
 
 def run():
     call("avdn_conv0_fwd_stats", ptr(x), ptr(w), N, H, W, ptr(sums), ptr(zw), ptr(xs9))
-    call("avdn_conv0_fwd_apply", ptr(x), ptr(w), ptr(sc), ptr(sh), 0.01, ptr(a), N, H, W)
-    call("avdn_conv0_bwd", ptr(x), ptr(w), ptr(da), ptr(sc), ptr(sh), ptr(mu), ptr(rs), 0.01, N, H, W, ptr(zw), ptr(xs9),
+    call("avdn_conv0_fwd_apply", ptr(x), ptr(w), ptr(sc), ptr(sh), 0.01, ptr(a), ptr(mask), N, H, W)
+    call("avdn_conv0_bwd", ptr(x), ptr(w), ptr(da), ptr(mask), ptr(sc), ptr(sh), ptr(mu), ptr(rs), 0.01, N, H, W, ptr(zw), ptr(xs9),
          ptr(sums), ptr(gw), ptr(dw), ptr(dg), ptr(db))
 
 
