@@ -99,6 +99,27 @@ __device__ __forceinline__ Pix locate(long long tile, long long P, int H, int W)
   q.y = (int)(row % (uint32_t)H);
   return q;
 }
+// the same pixel slot one grid stride (gridDim.x tiles) further on, without divisions
+struct Stride {
+  int dp, dx, dy;         // gridDim.x * TILE pixels = dy' rows + dx pixels, dy = dy' % H
+};
+__device__ __forceinline__ Stride make_stride(int H, int W) {
+  Stride st;
+  st.dp = (int)gridDim.x * TILE;
+  const int rows = st.dp / W;
+  st.dx = st.dp - rows * W;
+  st.dy = rows % H;
+  return st;
+}
+__device__ __forceinline__ void advance(Pix& q, const Stride& st, long long P, int H, int W) {
+  q.p += st.dp;
+  q.valid = q.p < P;
+  q.x += st.dx;
+  const int carry = q.x >= W ? 1 : 0;
+  q.x -= carry * W;
+  q.y += st.dy + carry;
+  q.y -= q.y >= H ? H : 0;
+}
 // the 3x3 neighbourhood of the pixel (zero outside the image): v[kh*3 + kw] = x[y + kh - 1][x + kw - 1]
 __device__ __forceinline__ void gather(const uint2* __restrict__ x, const Pix& q, int H, int W, uint2 (&v)[9]) {
 #pragma unroll
@@ -210,6 +231,7 @@ __global__ void __launch_bounds__(THREADS, 4) conv0_tc_gram_kernel(const uint2* 
 
   long long tile = blockIdx.x;
   Pix q = locate(tile, P, H, W);
+  const Stride st = make_stride(H, W);
   uint2 v[9];
   if (tile < n_tiles) gather(x, q, H, W, v);
   uint32_t since_flush = 0;
@@ -229,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, 4) conv0_tc_gram_kernel(const uint2* 
     tile += gridDim.x;
     const bool last = tile >= n_tiles;
     if (!last) {                                                        // the next tile's loads fly under the UMMAs
-      q = locate(tile, P, H, W);
+      advance(q, st, P, H, W);
       gather(x, q, H, W, v);
     }
     if (since_flush == FLUSH || last) {
@@ -300,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, 5) conv0_tc_apply_kernel(const uint2*
 
   long long tile = blockIdx.x;
   Pix q = locate(tile, P, H, W);
+  const Stride st = make_stride(H, W);
   uint2 v[9];
   if (tile < n_tiles) gather(x, q, H, W, v);
   for (uint32_t it = 0; tile < n_tiles; ++it) {
@@ -316,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 5) conv0_tc_apply_kernel(const uint2*
     const bool cur_valid = q.valid;
     tile += gridDim.x;
     if (tile < n_tiles) {                               // the next tile's loads fly under this tile's epilogue
-      q = locate(tile, P, H, W);
+      advance(q, st, P, H, W);
       gather(x, q, H, W, v);
     }
     mbar_wait(bar_a, it & 1u);
@@ -403,6 +426,7 @@ __global__ void __launch_bounds__(THREADS, 4) conv0_tc_bwd_kernel(const uint2* _
 
   long long tile = blockIdx.x;
   Pix q = locate(tile, P, H, W);
+  const Stride st = make_stride(H, W);
   uint2 v[9];
   uint32_t m = 0u;
   if (tile < n_tiles) {
@@ -419,7 +443,8 @@ __global__ void __launch_bounds__(THREADS, 4) conv0_tc_bwd_kernel(const uint2* _
     const uint32_t row = ds + s * OUT_BYTES + threadIdx.x * 64;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t c = ((uint32_t)j + rot) & 3u;     // rotated chunk order: conflict-free 64-byte-row loads
+      const uint32_t c = (uint32_t)j ^ rot;            // permuted chunk order: neither the loads from the linear
+                                                       // 64-byte rows nor the swizzled stores below conflict
       uint4 d = q.valid ? lds128(row + (c << 4)) : make_uint4(0u, 0u, 0u, 0u);
       const uint32_t bits = m << (8u * c);             // bit 31 = channel 8c, bit 30 = channel 8c + 1, ...
       uint32_t dw_[4] = {d.x, d.y, d.z, d.w};
@@ -444,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, 4) conv0_tc_bwd_kernel(const uint2* _
     __syncwarp();
     ++since_flush;
     if (!last) {
-      q = locate(tile, P, H, W);
+      advance(q, st, P, H, W);
       gather(x, q, H, W, v);
       m = q.valid ? __ldg(mask + q.p) : 0u;
     }
