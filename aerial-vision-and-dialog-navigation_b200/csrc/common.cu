@@ -1,6 +1,8 @@
 // Error plumbing and device queries for libavdn.so.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace avdn {
 
 static thread_local char g_err[512] = "ok";
@@ -32,6 +34,14 @@ int sm_count() {
     n = p.multiProcessorCount;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("AVDN_PDL");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 }  // namespace avdn

@@ -21,7 +21,36 @@ inline cudaStream_t to_cuda(avdn_stream_t s) { return reinterpret_cast<cudaStrea
 
 int sm_count();
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains (its CTAs
+// become resident and run their prologue as SM resources free up) and blocks in avdn_pdl_wait() until the
+// predecessor has completed and flushed, so the fill/drain gap between two dependent launches -- 660 launches per
+// training step -- overlaps with the tail of the previous kernel.  OFF by default: measured on the B = 64 training
+// step (power-capped at ~1.7 GHz) it changes nothing, 58.3-58.9 ms with and without;
+// AVDN_PDL=1 in the environment turns the attribute on for the tcgen05 GEMM and the BatchNorm kernels.  Kernels
+// launched this way must call avdn_pdl_wait() before their first global-memory access that depends on earlier work.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace avdn
+
+// first statement of a kernel launched with avdn::launch_pdl: let the successor start its own prologue, then wait
+// for the predecessor's results (both are no-ops in a plain launch)
+__device__ __forceinline__ void avdn_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void avdn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Stateless dropout: element `idx` of dropout site `site` in the step with seed `seed` is kept iff a
 // 24-bit hash of (seed, site, idx) is >= p * 2^24.  Forward and backward kernels re-evaluate the same

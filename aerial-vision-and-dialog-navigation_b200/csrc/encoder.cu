@@ -142,12 +142,7 @@ __global__ void __launch_bounds__(256) frame_attn_bwd_kernel(
     for (int j = 0; j < NSP; ++j) a = fmaf(w_in[tid * NSP + j], s_h[j], a);
     s_t[tid] = a;
   }
-  // fc2: d_fc2_b += d_emb ; d_fc2_w[o][j] += d_emb[o]*e[j] ; d_e[j] = sum_o fc2_w[o][j] d_emb[o]
-  for (int o = tid; o < E; o += 256) {
-    const float g = s_demb[o];
-    atomicAdd(&d_fc2_b[o], g);
-    for (int j = 0; j < NSP; ++j) atomicAdd(&d_fc2_w[o * NSP + j], g * s_e[j]);
-  }
+  // fc2: d_e[j] = sum_o fc2_w[o][j] d_emb[o]   (d_fc2_w / d_fc2_b: frame_attn_fc2_grad_kernel)
   {
     float a0 = 0.f, a1 = 0.f;       // warp w: rows o = w, w+8, ... ; lanes over j
     for (int o = warp; o < E; o += 8) {
@@ -227,6 +222,28 @@ __global__ void __launch_bounds__(256) frame_attn_bwd_kernel(
     for (int i = 0; i < NSP; ++i) a = fmaf(w_in[i * NSP + tid], s_dt[i], fmaf(w_out[i * 2 * NSP + NSP + tid], s_dpre[i], a));
     atomicAdd(&d_lang_cls[b * NSP + tid], a);
   }
+}
+
+// d_fc2_w[o][j] += sum_bt d_emb[bt][o] * e49[bt][j] ; d_fc2_b[o] += sum_bt d_emb[bt][o].  A block owns 16 output rows
+// and a slice of the frames; one thread per (o, j), column 49 = the bias.  (Summed by every (b,t) CTA of
+// frame_attn_bwd_kernel with global atomics this was 24 M atomic adds per step at B = 64.)
+constexpr int FC2_ROWS = 16, FC2_SLICES = 4;
+__global__ void __launch_bounds__(FC2_ROWS * (NSP + 1)) frame_attn_fc2_grad_kernel(const float* __restrict__ d_emb,
+                                                                                  const float* __restrict__ e49, int BT,
+                                                                                  float* __restrict__ d_fc2_w,
+                                                                                  float* __restrict__ d_fc2_b) {
+  const int o = blockIdx.x * FC2_ROWS + threadIdx.x / (NSP + 1), j = threadIdx.x % (NSP + 1);
+  const int per = (BT + FC2_SLICES - 1) / FC2_SLICES;
+  const int lo = blockIdx.y * per, hi = min(BT, lo + per);
+  float a0 = 0.f, a1 = 0.f;
+  int bt = lo;
+  for (; bt + 1 < hi; bt += 2) {
+    a0 = fmaf(d_emb[(size_t)bt * E + o], j < NSP ? e49[(size_t)bt * NSP + j] : 1.f, a0);
+    a1 = fmaf(d_emb[(size_t)(bt + 1) * E + o], j < NSP ? e49[(size_t)(bt + 1) * NSP + j] : 1.f, a1);
+  }
+  if (bt < hi) a0 = fmaf(d_emb[(size_t)bt * E + o], j < NSP ? e49[(size_t)bt * NSP + j] : 1.f, a0);
+  if (j < NSP) atomicAdd(&d_fc2_w[o * NSP + j], a0 + a1);
+  else atomicAdd(&d_fc2_b[o], a0 + a1);
 }
 
 // ------------------------------------------------------------------ embedding
@@ -425,6 +442,76 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
   }
 }
 
+// The same, one pass: a lane keeps its NP column pairs (k = 2*lane + 64*i) in registers, so a row is read once
+// (float2) and written once (bf16x2); the mask of a column costs a compare, not a modulo.  Sp <= 64 * NP, Sp even.
+template <int NP>
+__global__ void __launch_bounds__(256) softmax_fwd_regs_kernel(const float* __restrict__ scores,
+                                                               const int* __restrict__ lens, int B, int H, int L, int T,
+                                                               int Sp, __nv_bfloat16* __restrict__ P,
+                                                               __nv_bfloat16* __restrict__ P_full, unsigned int dthr,
+                                                               float dscale, unsigned long long seed, unsigned int site) {
+  const int S = L + 2 * T;
+  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= (long long)B * H * S) return;
+  const int lane = threadIdx.x & 31;
+  const int q = (int)(row % S), b = (int)(row / ((long long)S * H));
+  const int len = lens[b];
+  // columns a query may attend: [0, k_all) all of them, then k in [L, S) with step(k) <= tq and step(k) < len
+  int k_all, tq = -1;
+  if (T == 0) k_all = len;                               // key-padding mask only
+  else {
+    k_all = L;
+    if (q >= L) tq = (q - L) >= T ? q - L - T : q - L;
+  }
+  const int tmax = tq < len - 1 ? tq : len - 1;          // largest step that may be attended (-1: none)
+  auto allowed = [&](int k) -> bool {
+    if (k < k_all) return true;
+    if (T == 0 || k >= S) return false;
+    const int d = k - L, tk = d >= T ? d - T : d;
+    return tk <= tmax;
+  };
+  const float2* sr = reinterpret_cast<const float2*>(scores + row * Sp);
+  float2 v[NP];
+  unsigned int ok = 0u;
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int k = 2 * lane + 64 * i;
+    v[i] = make_float2(0.f, 0.f);
+    if (k < Sp) {
+      v[i] = sr[lane + 32 * i];
+      if (allowed(k)) { ok |= 1u << (2 * i); m = fmaxf(m, v[i].x); }
+      if (allowed(k + 1)) { ok |= 2u << (2 * i); m = fmaxf(m, v[i].y); }
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    v[i].x = (ok >> (2 * i)) & 1u ? __expf(v[i].x - m) : 0.f;
+    v[i].y = (ok >> (2 * i)) & 2u ? __expf(v[i].y - m) : 0.f;
+    sum += v[i].x + v[i].y;
+  }
+  sum = 1.f / warp_sum(sum);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(P + row * Sp);
+  __nv_bfloat162* pf = reinterpret_cast<__nv_bfloat162*>(P_full + row * Sp);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int k = 2 * lane + 64 * i;
+    if (k < Sp) {
+      const float p0f = (ok >> (2 * i)) & 1u ? v[i].x * sum : 0.f, p1f = (ok >> (2 * i)) & 2u ? v[i].y * sum : 0.f;
+      float p0 = p0f, p1 = p1f;
+      if (dthr) {
+        pf[lane + 32 * i] = __floats2bfloat162_rn(p0, p1);
+        const unsigned long long idx = (unsigned long long)(row * Sp + k);
+        p0 = avdn_drop_keep(seed, site, idx, dthr) ? p0 * dscale : 0.f;
+        p1 = avdn_drop_keep(seed, site, idx + 1, dthr) ? p1 * dscale : 0.f;
+      }
+      pr[lane + 32 * i] = __floats2bfloat162_rn(p0, p1);
+    }
+  }
+}
+
 // dS = alpha * P * (dP - sum_k P*dP)  (bf16 out, 0 in the padding)
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P,
                                                           const float* __restrict__ dP, long long rows, int S, int Sp,
@@ -451,6 +538,48 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
     dS[row * Sp + k] = __float2bfloat16_rn(o);
   }
 }
+
+template <int NP>
+__global__ void __launch_bounds__(256) softmax_bwd_regs_kernel(const __nv_bfloat16* __restrict__ P,
+                                                               const float* __restrict__ dP, long long rows, int S, int Sp,
+                                                               float alpha, __nv_bfloat16* __restrict__ dS,
+                                                               unsigned int dthr, float dscale, unsigned long long seed,
+                                                               unsigned int site) {
+  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(P + row * Sp);
+  const float2* dr = reinterpret_cast<const float2*>(dP + row * Sp);
+  float2 p[NP], d[NP];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int k = 2 * lane + 64 * i;
+    p[i] = make_float2(0.f, 0.f);
+    d[i] = make_float2(0.f, 0.f);
+    if (k < Sp) {
+      p[i] = __bfloat1622float2(pr[lane + 32 * i]);
+      d[i] = dr[lane + 32 * i];
+      if (dthr) {
+        const unsigned long long idx = (unsigned long long)(row * Sp + k);
+        d[i].x = avdn_drop_keep(seed, site, idx, dthr) ? d[i].x * dscale : 0.f;
+        d[i].y = avdn_drop_keep(seed, site, idx + 1, dthr) ? d[i].y * dscale : 0.f;
+      }
+      if (k >= S) p[i].x = d[i].x = 0.f;          // the padding columns of dP hold whatever the GEMM left there
+      if (k + 1 >= S) p[i].y = d[i].y = 0.f;
+      dot = fmaf(p[i].x, d[i].x, dot);
+      dot = fmaf(p[i].y, d[i].y, dot);
+    }
+  }
+  dot = warp_sum(dot);
+  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dS + row * Sp);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int k = 2 * lane + 64 * i;
+    if (k < Sp) o[lane + 32 * i] = __floats2bfloat162_rn(alpha * p[i].x * (d[i].x - dot), alpha * p[i].y * (d[i].y - dot));
+  }
+}
+
 
 // Incremental ("decode") attention of the ET inference path.  Rows of earlier steps never change (the mask is
 // causal over steps and LayerNorm / FFN are row-wise), so a rollout step only computes its R = 2 new rows per
@@ -716,6 +845,9 @@ extern "C" int avdn_frame_attn_bwd_cls(const float* frames, const float* lang_cl
                    d_w_out && d_fc2_w && d_fc2_b,
                "avdn_frame_attn_bwd: null pointer");
   if (B * T == 0) return AVDN_OK;
+  static_assert(E % FC2_ROWS == 0, "fc2 gradient blocks tile the 768 rows");
+  frame_attn_fc2_grad_kernel<<<dim3(E / FC2_ROWS, FC2_SLICES), FC2_ROWS * (NSP + 1), 0, avdn::to_cuda(stream)>>>(
+      d_emb, e49, B * T, d_fc2_w, d_fc2_b);
   frame_attn_bwd_kernel<<<B * T, 256, 0, avdn::to_cuda(stream)>>>(frames, lang_cls, w_in, w_out, fc2_w, T, attn, wc,
                                                                 e49, d_emb, d_frames, d_w_in, d_w_out, d_fc2_w,
                                                                 d_fc2_b, d_lang_cls);
@@ -786,9 +918,17 @@ extern "C" int avdn_softmax_fwd_drop(const float* scores, const int* lens, int B
                                      avdn_stream_t stream) {
   AVDN_REQUIRE(scores && lens && P && T >= 0 && Sp >= L + 2 * T, "avdn_softmax_fwd: bad argument");
   AVDN_REQUIRE(drop_ok(p) && (p == 0.f || P_full), "avdn_softmax_fwd: dropout p in [0,1) and needs P_full");
-  softmax_fwd_kernel<<<rows_grid((long long)B * H * (L + 2 * T)), 256, 0, avdn::to_cuda(stream)>>>(
-      scores, lens, B, H, L, T, Sp, reinterpret_cast<__nv_bfloat16*>(P), reinterpret_cast<__nv_bfloat16*>(P_full),
-      avdn_drop_thresh(p), drop_scale(p), seed, site);
+  const unsigned grid = rows_grid((long long)B * H * (L + 2 * T));
+  cudaStream_t s = avdn::to_cuda(stream);
+  __nv_bfloat16 *Pb = reinterpret_cast<__nv_bfloat16*>(P), *Pf = reinterpret_cast<__nv_bfloat16*>(P_full);
+  const unsigned int dthr = avdn_drop_thresh(p);
+  const float dsc = drop_scale(p);
+  const bool vec = Sp % 2 == 0 && (reinterpret_cast<uintptr_t>(scores) % 8 == 0) && (reinterpret_cast<uintptr_t>(P) % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(P_full) % 4 == 0);
+  if (vec && Sp <= 128) softmax_fwd_regs_kernel<2><<<grid, 256, 0, s>>>(scores, lens, B, H, L, T, Sp, Pb, Pf, dthr, dsc, seed, site);
+  else if (vec && Sp <= 320) softmax_fwd_regs_kernel<5><<<grid, 256, 0, s>>>(scores, lens, B, H, L, T, Sp, Pb, Pf, dthr, dsc, seed, site);
+  else if (vec && Sp <= 512) softmax_fwd_regs_kernel<8><<<grid, 256, 0, s>>>(scores, lens, B, H, L, T, Sp, Pb, Pf, dthr, dsc, seed, site);
+  else softmax_fwd_kernel<<<grid, 256, 0, s>>>(scores, lens, B, H, L, T, Sp, Pb, Pf, dthr, dsc, seed, site);
   return avdn::check_launch("avdn_softmax_fwd");
 }
 
@@ -802,9 +942,18 @@ extern "C" int avdn_softmax_bwd_drop(const void* P, const float* dP, long long r
                                      avdn_stream_t stream) {
   AVDN_REQUIRE(P && dP && dS && rows > 0, "avdn_softmax_bwd: bad argument");
   AVDN_REQUIRE(drop_ok(p), "avdn_softmax_bwd: dropout p must be in [0,1)");
-  softmax_bwd_kernel<<<rows_grid(rows), 256, 0, avdn::to_cuda(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(P), dP, rows, S, Sp, alpha, reinterpret_cast<__nv_bfloat16*>(dS),
-      avdn_drop_thresh(p), drop_scale(p), seed, site);
+  const unsigned grid = rows_grid(rows);
+  cudaStream_t s = avdn::to_cuda(stream);
+  const __nv_bfloat16* Pb = reinterpret_cast<const __nv_bfloat16*>(P);
+  __nv_bfloat16* dSb = reinterpret_cast<__nv_bfloat16*>(dS);
+  const unsigned int dthr = avdn_drop_thresh(p);
+  const float dsc = drop_scale(p);
+  const bool vec = Sp % 2 == 0 && (reinterpret_cast<uintptr_t>(dP) % 8 == 0) && (reinterpret_cast<uintptr_t>(P) % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(dS) % 4 == 0);
+  if (vec && Sp <= 128) softmax_bwd_regs_kernel<2><<<grid, 256, 0, s>>>(Pb, dP, rows, S, Sp, alpha, dSb, dthr, dsc, seed, site);
+  else if (vec && Sp <= 320) softmax_bwd_regs_kernel<5><<<grid, 256, 0, s>>>(Pb, dP, rows, S, Sp, alpha, dSb, dthr, dsc, seed, site);
+  else if (vec && Sp <= 512) softmax_bwd_regs_kernel<8><<<grid, 256, 0, s>>>(Pb, dP, rows, S, Sp, alpha, dSb, dthr, dsc, seed, site);
+  else softmax_bwd_kernel<<<grid, 256, 0, s>>>(Pb, dP, rows, S, Sp, alpha, dSb, dthr, dsc, seed, site);
   return avdn::check_launch("avdn_softmax_bwd");
 }
 

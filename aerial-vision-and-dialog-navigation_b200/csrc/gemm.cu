@@ -99,6 +99,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
   constexpr int BNH = BN / CTAS;                                // B columns this CTA loads
   constexpr uint32_t KLAYOUT = (BKT == 64) ? 2u : 4u;          // swizzle mode of the K-major operands
   constexpr uint32_t KSBO = 8u * BKT * 2u;                     // 8 rows of BKT bf16
+  avdn_pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -230,6 +231,7 @@ gemm_kernel(const __grid_constant__ KernelParams p) {
   if (CTAS == 2) cluster_sync_all();          // peer barriers initialised before anyone signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  avdn_pdl_wait();                             // barriers, TMEM and tables are set up: now wait for the inputs
 
   if (warp == 0) {
     // =========================== TMA producer ===============================
@@ -998,13 +1000,15 @@ int launch_t(const Plan& pl, cudaStream_t s) {
   cfg.blockDim = dim3(NUM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = (size_t)pl.smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see avdn::launch_pdl (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = avdn::pdl_enabled() ? 2 : 1;
   if (cudaLaunchKernelEx(&cfg, kfn, pl.kp) != cudaSuccess) return avdn::check_launch("gemm_kernel launch");
   return avdn::check_launch("gemm_kernel");
 }

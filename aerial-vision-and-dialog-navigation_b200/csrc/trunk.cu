@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const uint4* __re
                                                                const float* __restrict__ shift,
                                                                const float* __restrict__ mean, float slope,
                                                                long long n8, int C, double* __restrict__ sums) {
+  avdn_pdl_trigger();
+  avdn_pdl_wait();
   extern __shared__ float sred[];           // [2][RY][C]
   const int C8 = C >> 3;
   const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
@@ -117,6 +119,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long R,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float momentum, float eps, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean, float* __restrict__ rstd) {
+  avdn_pdl_trigger();
+  avdn_pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (c >= C_real) { scale[c] = 0.f; shift[c] = 0.f; mean[c] = 0.f; rstd[c] = 0.f; return; }
@@ -154,6 +158,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4* __res
                                                               const float* __restrict__ shift,
                                                               const uint4* __restrict__ residual, uint4* __restrict__ a,
                                                               long long n8, int C8, float slope) {
+  avdn_pdl_trigger();
+  avdn_pdl_wait();
   const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
   const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8
   const int cx = (int)(tid % C8);
@@ -198,6 +204,8 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double invR,
                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                    float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  avdn_pdl_trigger();
+  avdn_pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double sc = scale[c], rs = rstd[c], mu = mean[c];
@@ -217,6 +225,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* _
                                                                   const float* __restrict__ coef,
                                                                   uint4* __restrict__ dz, long long n8, int C,
                                                                   float slope) {
+  avdn_pdl_trigger();
+  avdn_pdl_wait();
   const int C8 = C >> 3;
   const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
   const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8
@@ -461,12 +471,11 @@ static int bn_reduce_launch(bool bwd, const void* z, const void* da, const float
   const size_t smem = (size_t)2 * RY * C * sizeof(float);      // = 2 * 256 * 8 * 4 = 16 KB
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s) != cudaSuccess) return avdn::check_launch("bn reduce memset");
   if (bwd)
-    bn_reduce_kernel<true><<<blocks, BN_THREADS, smem, s>>>(reinterpret_cast<const uint4*>(z),
-                                                            reinterpret_cast<const uint4*>(da), scale, shift, mean,
-                                                            slope, n8, C, sums);
+    avdn::launch_pdl(bn_reduce_kernel<true>, dim3(blocks), dim3(BN_THREADS), smem, s, reinterpret_cast<const uint4*>(z),
+                     reinterpret_cast<const uint4*>(da), scale, shift, mean, slope, n8, C, sums);
   else
-    bn_reduce_kernel<false><<<blocks, BN_THREADS, smem, s>>>(reinterpret_cast<const uint4*>(z), nullptr, nullptr,
-                                                             nullptr, nullptr, slope, n8, C, sums);
+    avdn::launch_pdl(bn_reduce_kernel<false>, dim3(blocks), dim3(BN_THREADS), smem, s, reinterpret_cast<const uint4*>(z),
+                     nullptr, nullptr, nullptr, nullptr, slope, n8, C, sums);
   return avdn::check_launch("bn_reduce_kernel");
 }
 
@@ -477,8 +486,8 @@ extern "C" int avdn_bn_stats(const void* z, long long R, int C, int C_real, cons
   cudaStream_t s = avdn::to_cuda(stream);
   int r = bn_reduce_launch(false, z, nullptr, nullptr, nullptr, nullptr, 0.f, R, C, sums, s);
   if (r) return r;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, C_real, gamma, beta, running_mean, running_var,
-                                                     momentum, eps, scale, shift, mean, rstd);
+  avdn::launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, s, sums, R, C, C_real, gamma, beta,
+                   running_mean, running_var, momentum, eps, scale, shift, mean, rstd);
   return avdn::check_launch("bn_finalize_kernel");
 }
 
@@ -487,9 +496,8 @@ extern "C" int avdn_bn_finalize(const double* sums, long long R, int C, int C_re
                                 float eps, float* scale, float* shift, float* mean, float* rstd,
                                 avdn_stream_t stream) {
   AVDN_REQUIRE(sums && gamma && beta && scale && shift && mean && rstd && R > 0, "avdn_bn_finalize: bad argument");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, avdn::to_cuda(stream)>>>(sums, R, C, C_real, gamma, beta, running_mean,
-                                                                         running_var, momentum, eps, scale, shift,
-                                                                         mean, rstd);
+  avdn::launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, avdn::to_cuda(stream), sums, R, C, C_real,
+                   gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean, rstd);
   return avdn::check_launch("bn_finalize_kernel");
 }
 
@@ -507,9 +515,9 @@ extern "C" int avdn_bn_apply(const void* z, const float* scale, const float* shi
   AVDN_REQUIRE(z && scale && shift && a && R > 0 && C % 8 == 0 && BN_THREADS % (C / 8) == 0,
                "avdn_bn_apply: bad argument (C=%d)", C);
   const long long n8 = R * (C / 8);
-  bn_apply_kernel<<<bn_grid(n8, 16), BN_THREADS, 0, avdn::to_cuda(stream)>>>(
-      reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<const uint4*>(residual),
-      reinterpret_cast<uint4*>(a), n8, C / 8, slope);
+  avdn::launch_pdl(bn_apply_kernel, dim3(bn_grid(n8, 16)), dim3(BN_THREADS), 0, avdn::to_cuda(stream),
+                   reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<const uint4*>(residual),
+                   reinterpret_cast<uint4*>(a), n8, C / 8, slope);
   return avdn::check_launch("avdn_bn_apply");
 }
 
@@ -521,14 +529,13 @@ extern "C" int avdn_bn_backward(const void* da, const void* z, const float* scal
   int r = bn_reduce_launch(true, z, da, scale, shift, mean, slope, R, C, sums, s);
   if (r) return r;
   float* coef = reinterpret_cast<float*>(sums + 2 * C);         // second half of the [4,C] f64 scratch
-  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, 1.0 / (double)R, C, C_real, scale, shift, mean, rstd, coef,
-                                                     dgamma, dbeta);
+  avdn::launch_pdl(bn_bwd_coef_kernel, dim3((C + 127) / 128), dim3(128), 0, s, sums, 1.0 / (double)R, C, C_real, scale,
+                   shift, mean, rstd, coef, dgamma, dbeta);
   r = avdn::check_launch("bn_bwd_coef_kernel");
   if (r) return r;
   const long long n8 = R * (C / 8);
-  bn_bwd_apply_kernel<<<bn_grid(n8, 16), BN_THREADS, 0, s>>>(reinterpret_cast<const uint4*>(da),
-                                                            reinterpret_cast<const uint4*>(z), coef,
-                                                            reinterpret_cast<uint4*>(dz), n8, C, slope);
+  avdn::launch_pdl(bn_bwd_apply_kernel, dim3(bn_grid(n8, 16)), dim3(BN_THREADS), 0, s, reinterpret_cast<const uint4*>(da),
+                   reinterpret_cast<const uint4*>(z), coef, reinterpret_cast<uint4*>(dz), n8, C, slope);
   return avdn::check_launch("bn_bwd_apply_kernel");
 }
 
@@ -541,14 +548,13 @@ extern "C" int avdn_bn_backward_apply(const void* da, const void* z, const float
   AVDN_REQUIRE(C % 8 == 0 && C >= 8 && BN_THREADS % (C / 8) == 0,
                "avdn_bn_backward_apply: C=%d must be 8 * (a divisor of %d)", C, BN_THREADS);
   cudaStream_t s = avdn::to_cuda(stream);
-  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, 1.0 / (double)R, C, C_real, scale, shift, mean, rstd, coef,
-                                                     dgamma, dbeta);
+  avdn::launch_pdl(bn_bwd_coef_kernel, dim3((C + 127) / 128), dim3(128), 0, s, sums, 1.0 / (double)R, C, C_real, scale,
+                   shift, mean, rstd, coef, dgamma, dbeta);
   int r = avdn::check_launch("bn_bwd_coef_kernel");
   if (r) return r;
   const long long n8 = R * (C / 8);
-  bn_bwd_apply_kernel<<<bn_grid(n8, 16), BN_THREADS, 0, s>>>(reinterpret_cast<const uint4*>(da),
-                                                            reinterpret_cast<const uint4*>(z), coef,
-                                                            reinterpret_cast<uint4*>(dz), n8, C, slope);
+  avdn::launch_pdl(bn_bwd_apply_kernel, dim3(bn_grid(n8, 16)), dim3(BN_THREADS), 0, s, reinterpret_cast<const uint4*>(da),
+                   reinterpret_cast<const uint4*>(z), coef, reinterpret_cast<uint4*>(dz), n8, C, slope);
   return avdn::check_launch("bn_bwd_apply_kernel");
 }
 

@@ -440,6 +440,7 @@ class ETEngine:
                    ptr(Gd["attention_layer_vision.linear_in.weight"]),
                    ptr(Gd["attention_layer_vision.linear_out.weight"]), ptr(Gd["fc2.weight"]), ptr(Gd["fc2.bias"]),
                    ptr(d_lang_cls))
+        self.launches += 1                       # fc2 weight-gradient reduction + the per-frame kernel
         d_lang = dv0[:, :L].contiguous() if need_lang_grad else None
         return d_frames, d_lang
 
