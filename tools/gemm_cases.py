@@ -28,6 +28,8 @@ def conv_case(H, Cin, Cout, k, s, wgrad=False):
 
 
 cases = [("L14 fwd 3x3 128->256 @28", conv_case(28, 128, 256, 3, 1)), ("L3 fwd 3x3 32->64 @112", conv_case(112, 32, 64, 3, 1)),
+         ("L1 fwd 3x3 32->64 s2 @224", conv_case(224, 32, 64, 3, 2)), ("L2 fwd 1x1 64->32 @112", conv_case(112, 64, 32, 1, 1)),
+         ("L7 fwd 3x3 64->128 @56", conv_case(56, 64, 128, 3, 1)),
          ("L13 fwd 1x1 256->128 @28", conv_case(28, 256, 128, 1, 1)), ("L14 wgrad", conv_case(28, 128, 256, 3, 1, wgrad=True))]
 for name, p in cases:
     for _ in range(reps):
