@@ -23,7 +23,7 @@ int sm_count();
 
 // Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains (its CTAs
 // become resident and run their prologue as SM resources free up) and blocks in avdn_pdl_wait() until the
-// predecessor has completed and flushed, so the fill/drain gap between two dependent launches -- 660 launches per
+// predecessor has completed and flushed, so the fill/drain gap between two dependent launches -- ~550 kernels per
 // training step -- overlaps with the tail of the previous kernel.  OFF by default: measured on the B = 64 training
 // step (power-capped at ~1.7 GHz) it changes nothing, 58.3-58.9 ms with and without;
 // AVDN_PDL=1 in the environment turns the attribute on for the tcgen05 GEMM and the BatchNorm kernels.  Kernels

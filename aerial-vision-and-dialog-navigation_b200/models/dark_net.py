@@ -359,17 +359,17 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
             # pass 1: batch statistics (+ the z-weighted input sums the backward needs); pass 2 below recomputes z
             call("avdn_conv0_fwd_stats", ptr(x_nhwc4), ptr(conv.weight), eng.N, L.Hin, L.Win, ptr(L.sums), ptr(L.zw),
                  ptr(L.xs9))
-            n += 5
+            n += 2                  # kernels only (memsets / symbol copies inside the ABI calls are not counted)
         elif L.first:
             call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win, ptr(L.sums))
-            n += 2
+            n += 1
         else:
             L.p_fwd_stats.run()
             n += 1
         call("avdn_bn_finalize", ptr(L.sums), L.R, L.Cout_p, L.Cout, ptr(bn.weight), ptr(bn.bias),
              ptr(bn.running_mean), ptr(bn.running_var), BN_MOMENTUM, BN_EPS, ptr(L.scale),
              ptr(L.shift), ptr(L.mean), ptr(L.rstd))
-        n += 1 if L.first else 2    # finalize (+ the stats memset inside avdn_gemm_run)
+        n += 1                      # finalize
         if L.first and L.recompute:
             call("avdn_conv0_fwd_apply", ptr(x_nhwc4), ptr(conv.weight), ptr(L.scale), ptr(L.shift), LEAKY_SLOPE,
                  ptr(L.a), ptr(L.mask), eng.N, L.Hin, L.Win)
@@ -422,7 +422,7 @@ def _layer_backward(eng, L, unpack=True, zero=True):
         call("avdn_conv0_bwd", ptr(eng.x_in), ptr(conv.weight), ptr(L.g), ptr(L.mask), ptr(L.scale), ptr(L.shift), ptr(L.mean),
              ptr(L.rstd), LEAKY_SLOPE, eng.N, L.Hin, L.Win, ptr(L.zw), ptr(L.xs9), ptr(L.sums), ptr(L.gw), ptr(L.dw),
              ptr(L.dgamma), ptr(L.dbeta))
-        return 4
+        return 2
     if L.bnb_fused and L.bnb_ready:
         # the sums were reduced by the epilogue of the dgrad that wrote L.g: coefficients + apply only
         call("avdn_bn_backward_apply", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
@@ -432,7 +432,7 @@ def _layer_backward(eng, L, unpack=True, zero=True):
     else:
         call("avdn_bn_backward", ptr(L.g), ptr(L.z), ptr(L.scale), ptr(L.shift), ptr(L.mean), ptr(L.rstd), L.R,
              L.Cout_p, L.Cout, LEAKY_SLOPE, ptr(L.sums), ptr(L.dz), ptr(L.dgamma), ptr(L.dbeta))
-        n = 4
+        n = 3                       # reduce, coefficients, apply
     if L.first:
         call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
         return n + 1
