@@ -31,6 +31,7 @@ SOURCES = {
     "trunk.cu": [],
     "conv0.cu": [],
     "conv0_tc.cu": [],
+    "conv3_halo.cu": [],
     "lstm.cu": ["-fmad=false"],
     "encoder.cu": [],
     "agent.cu": [],

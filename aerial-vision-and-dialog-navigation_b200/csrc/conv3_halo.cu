@@ -1,0 +1,253 @@
+// 3x3, stride-1, pad-1 convolution for the THIN layers of the trunk (<= 64 input channels, e.g. module_list.3:
+// 32 -> 64 at 112 x 112; nn.Conv2d at src/models/dark_net.py:22-28) with halo-tile reuse of the input.
+//
+// In the general implicit-GEMM kernel (gemm.cu) every one of the nine taps of a 128-pixel tile is its own TMA box:
+// the input travels L2 -> shared memory nine times, in 64-byte rows, and those layers are bound by that fill
+// (38 B/clk/SM delivered, epilogue and filter traffic irrelevant).  Here an output tile is 8 pixels wide
+// and 16 rows tall and the input arrives as THREE boxes of 8 x 18 pixels -- one per horizontal tap kw, shifted by
+// kw - 1 pixels -- so that
+//   * a box row (8 pixels x CIN bf16) is exactly one swizzle atom (8 rows of 64 / 128 bytes), and
+//   * the A operand of tap (kh, kw) is box kw advanced by kh whole atoms: a plain K-major descriptor, no sub-atom
+//     start address.
+// The input is read 3.4x (3 boxes x 18/16 rows) instead of 9x, the whole filter bank (9 x COUT x CIN bf16) stays
+// resident in shared memory, and the tile leaves through a 128-byte-swizzled staging slab and one TMA store; the
+// BatchNorm batch statistics (sum, sum of squares of the bf16-rounded outputs per channel) are read back from that
+// slab, as in gemm.cu.  One CTA = 128 threads = 128 TMEM lanes = the 128 pixels of a tile; two CTAs per SM overlap
+// each other's load / UMMA / epilogue phases.
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include "conv3_halo.cuh"
+
+namespace {
+
+using namespace avdn_tc;
+
+constexpr int TW = 8, TH = 16;            // output tile: 8 pixels x 16 rows = 128 = UMMA M
+constexpr int THREADS = 128;
+
+template <int CIN, int COUT>
+struct Cfg {
+  static constexpr int ROW = CIN * 2;                    // bytes per pixel = K-major row (64 or 128)
+  static constexpr int ATOM = 8 * ROW;                   // 8 pixels = one box row = one swizzle atom
+  static constexpr int XBOX = (TH + 2) * ATOM;           // one horizontal-tap box: 18 rows
+  static constexpr int XBUF = 3 * XBOX;                  // the three boxes of a tile
+  static constexpr int WTAP = COUT * ROW;                // filters of one tap: COUT rows
+  static constexpr int WBYTES = 9 * WTAP;
+  static constexpr int OUT_ROW = COUT * 2;               // bytes per output pixel (64 / 128 / 256)
+  static constexpr int OUT_SLABS = (OUT_ROW + 127) / 128;   // 128-byte-wide slabs of the staging tile
+  static constexpr int OUT_BYTES = 128 * OUT_ROW;
+  static constexpr uint32_t LAYOUT = (CIN == 64) ? 2u : 4u;  // SWIZZLE_128B / SWIZZLE_64B
+  static constexpr int SMEM = 2 * XBUF + WBYTES + OUT_BYTES + 1024;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static constexpr uint32_t TMEM_COLS = COUT < 32 ? 32 : COUT;
+};
+
+struct alignas(64) Params {
+  CUtensorMap tmX, tmW, tmZ;
+  int32_t tiles_x, tiles_y, n_tiles;
+  double* stats;          // NULL or [2][COUT] f64, accumulated
+};
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&b);
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_constant__ Params p) {
+  using C = Cfg<CIN, COUT>;
+  static_assert(COUT == 64, "the epilogue below is written for 128-byte output pixels");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t xs = base, ws = xs + 2 * C::XBUF, outs = ws + C::WBYTES;
+  __shared__ __align__(8) uint64_t bars[4];              // X buffer 0 / 1, filters, UMMAs done
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar_x = smem_u32(&bars[0]), bar_w = bar_x + 16, bar_mma = bar_x + 24;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar_x, 1); mbar_init(bar_x + 8, 1); mbar_init(bar_w, 1); mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const int per_img = p.tiles_x * p.tiles_y;
+  auto load_x = [&](int tile, uint32_t buf) {            // thread 0: the three boxes of a tile
+    const int n = tile / per_img, r = tile - n * per_img, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+    mbar_expect_tx(bar_x + 8 * buf, (uint32_t)C::XBUF);
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+      tma_load_4d<1>(xs + buf * C::XBUF + kw * C::XBOX, &p.tmX, bar_x + 8 * buf, 0, tx * TW + kw - 1, ty * TH - 1, n);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, (uint32_t)C::WBYTES);
+    for (int t = 0; t < 9; ++t) tma_load_4d<1>(ws + t * C::WTAP, &p.tmW, bar_w, t * CIN, 0, 0, 0);
+    if ((int)blockIdx.x < p.n_tiles) load_x(blockIdx.x, 0);
+  }
+  // statistics: thread owns 16-byte chunk (tid & 7) = channels 8j..8j+7 of rows (tid >> 3) + 16 i
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const uint32_t b = it & 1u;
+    if (tid == 0 && tile + (int)gridDim.x < p.n_tiles) load_x(tile + gridDim.x, b ^ 1u);    // buffer b^1: read by the
+                                                                                             // UMMAs of tile it-1, done
+    if (it == 0) mbar_wait(bar_w, 0);
+    mbar_wait(bar_x + 8 * b, (it >> 1) & 1u);
+    if (tid == 0) {
+      tcgen05_fence_after();
+      uint32_t acc = 0u;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int kh = t / 3, kw = t - kh * 3;
+        const uint64_t ad = make_smem_desc(xs + b * C::XBUF + kw * C::XBOX + kh * C::ATOM, 16, C::ATOM, C::LAYOUT);
+        const uint64_t bd = make_smem_desc(ws + t * C::WTAP, 16, C::ATOM, C::LAYOUT);
+#pragma unroll
+        for (int k = 0; k < CIN / 16; ++k) {
+          umma_bf16<1>(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), C::IDESC, acc);
+          acc = 1u;
+        }
+      }
+      tcgen05_commit<1>(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, it & 1u);
+    tcgen05_fence_after();
+    uint32_t lo[32], hi[32];
+    tmem_ld32_async(tmem + ((uint32_t)(warp * 32) << 16), lo);
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32, hi);
+    tcgen05_fence_before();
+    // pixel row m = tid: 128 bytes, chunk j at j ^ (m & 7) (128-byte swizzle, what the TMA store expects)
+    const uint32_t row = outs + tid * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(row + (((uint32_t)j ^ (tid & 7u)) << 4), pack2(__uint_as_float(lo[8 * j]), __uint_as_float(lo[8 * j + 1])),
+             pack2(__uint_as_float(lo[8 * j + 2]), __uint_as_float(lo[8 * j + 3])),
+             pack2(__uint_as_float(lo[8 * j + 4]), __uint_as_float(lo[8 * j + 5])),
+             pack2(__uint_as_float(lo[8 * j + 6]), __uint_as_float(lo[8 * j + 7])));
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(row + (((uint32_t)(j + 4) ^ (tid & 7u)) << 4), pack2(__uint_as_float(hi[8 * j]), __uint_as_float(hi[8 * j + 1])),
+             pack2(__uint_as_float(hi[8 * j + 2]), __uint_as_float(hi[8 * j + 3])),
+             pack2(__uint_as_float(hi[8 * j + 4]), __uint_as_float(hi[8 * j + 5])),
+             pack2(__uint_as_float(hi[8 * j + 6]), __uint_as_float(hi[8 * j + 7])));
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const int n = tile / per_img, r = tile - n * per_img, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      tma_store_4d(&p.tmZ, outs, 0, tx * TW, ty * TH, n);
+      tma_commit_group();
+    }
+    if (p.stats != nullptr) {
+      const uint32_t j = tid & 7u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t m = (uint32_t)(tid >> 3) + 16u * i;
+        const uint4 v = lds128(outs + m * 128 + ((j ^ (m & 7u)) << 4));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = __uint_as_float(w4[k] << 16), c2 = __uint_as_float(w4[k] & 0xFFFF0000u);
+          s1[2 * k] += a; s2[2 * k] = fmaf(a, a, s2[2 * k]);
+          s1[2 * k + 1] += c2; s2[2 * k + 1] = fmaf(c2, c2, s2[2 * k + 1]);
+        }
+      }
+    }
+    if (tid == 0) tma_wait_group_read<0>();              // the slab may be rewritten
+    __syncthreads();
+  }
+  if (p.stats != nullptr) {
+    // block reduction through the (now free) staging slab: [2][16 row groups][COUT] floats
+    float* s_red = reinterpret_cast<float*>(smem_raw + (outs - smem_u32(smem_raw)));
+    const int j = tid & 7, g = tid >> 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_red[g * COUT + j * 8 + k] = s1[k]; s_red[(16 + g) * COUT + j * 8 + k] = s2[k]; }
+    __syncthreads();
+    if (tid < 2 * COUT) {
+      const int which = tid / COUT, c = tid % COUT;
+      float a = 0.f;
+      for (int g2 = 0; g2 < 16; ++g2) a += s_red[(which * 16 + g2) * COUT + c];
+      atomicAdd(p.stats + which * COUT + c, (double)a);
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS) : "memory");
+}
+
+}  // namespace
+
+namespace avdn {
+
+bool conv3_halo_supported(int H, int W, int Cin, int Cout) {
+  return Cin == 32 && Cout == 64 && H % TH == 0 && W % TW == 0 && H >= TH && W >= TW;
+}
+
+int conv3_halo_fwd(const void* x, const void* wf, void* z, int N, int H, int W, int Cin, int Cout, double* stats,
+                   cudaStream_t s) {
+  if (!conv3_halo_supported(H, W, Cin, Cout))
+    return set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo: shape %dx%d, %d -> %d channels not covered", H, W, Cin, Cout);
+  using C = Cfg<32, 64>;
+  Params p;
+  const int64_t dx[4] = {Cin, W, H, N}, sx[4] = {1, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin};
+  const int32_t bx[4] = {Cin, TW, TH + 2, 1};
+  const int64_t K = 9ll * Cin;
+  const int64_t dw[4] = {K, Cout, 1, 1}, sw[4] = {1, K, K * Cout, K * Cout};
+  const int32_t bw[4] = {Cin, Cout, 1, 1};
+  const int64_t dz[4] = {Cout, W, H, N}, sz[4] = {1, Cout, (int64_t)W * Cout, (int64_t)H * W * Cout};
+  const int32_t bz[4] = {Cout, TW, TH, 1};
+  int r = encode_tensor_map_4d(x, 2, dx, sx, bx, &p.tmX);
+  if (!r) r = encode_tensor_map_4d(wf, 2, dw, sw, bw, &p.tmW);
+  if (!r) r = encode_tensor_map_4d(z, 2, dz, sz, bz, &p.tmZ);
+  if (r) return r;
+  p.tiles_x = W / TW;
+  p.tiles_y = H / TH;
+  const long long nt = (long long)N * p.tiles_x * p.tiles_y;
+  if (nt >= (1ll << 31)) return set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo: too many tiles");
+  p.n_tiles = (int32_t)nt;
+  p.stats = stats;
+  if (stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s) != cudaSuccess)
+    return check_launch("conv3_halo stats memset");
+  auto kfn = conv3_halo_kernel<32, 64>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess)
+      return check_launch("conv3_halo smem attribute");
+    attr = true;
+  }
+  const long long cap = (long long)sm_count() * 2;
+  kfn<<<(unsigned)(nt < cap ? nt : cap), THREADS, C::SMEM, s>>>(p);
+  return check_launch("conv3_halo_kernel");
+}
+
+}  // namespace avdn
+
+extern "C" int avdn_conv3x3_thin_fwd(const void* x_nhwc, const void* w_f, void* z, int N, int H, int W, int Cin,
+                                     int Cout, double* stats, avdn_stream_t stream) {
+  AVDN_REQUIRE(x_nhwc && w_f && z && N > 0, "avdn_conv3x3_thin_fwd: bad argument");
+  return avdn::conv3_halo_fwd(x_nhwc, w_f, z, N, H, W, Cin, Cout, stats, avdn::to_cuda(stream));
+}
+
+extern "C" int avdn_conv3x3_thin_supported(int H, int W, int Cin, int Cout) {
+  return avdn::conv3_halo_supported(H, W, Cin, Cout) ? 1 : 0;
+}

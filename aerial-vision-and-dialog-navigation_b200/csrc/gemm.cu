@@ -33,6 +33,7 @@
 //               HALF of B, so the L2->SM operand traffic per FLOP drops by a third.
 #include "common.cuh"
 #include "tcgen05.cuh"
+#include "conv3_halo.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -968,6 +969,15 @@ int encode_map(const void* ptr, int elem_bytes, const int64_t* dim, const int64_
   if (r != CUDA_SUCCESS) return avdn::set_err(AVDN_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return AVDN_OK;
 }
+
+}  // namespace
+
+int avdn::encode_tensor_map_4d(const void* ptr, int elem_bytes, const int64_t* dim, const int64_t* stride,
+                               const int32_t* boxdim, CUtensorMap* out) {
+  return encode_map(ptr, elem_bytes, dim, stride, boxdim, out);
+}
+
+namespace {
 
 int encode_operand(const avdn_operand& o, CUtensorMap* out) {
   return encode_map(o.ptr, 2, o.dim, o.stride, o.box, out);

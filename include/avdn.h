@@ -279,6 +279,15 @@ int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* da, const vo
                    const double* xs9, double* sums, float* gw, float* dw, float* dgamma, float* dbeta,
                    avdn_stream_t stream);
 
+/* 3x3 stride-1 pad-1 convolution of a THIN layer (nn.Conv2d, dark_net.py:22-28; e.g. module_list.3: 32 -> 64 channels
+ * at 112 x 112) with halo-tile reuse of the input (csrc/conv3_halo.cu): x [N,H,W,Cin] bf16, w_f [Cout, 9*Cin] bf16
+ * (tap-major, the layout avdn_pack_conv_weights writes), z [N,H,W,Cout] bf16, stats NULL or [2,Cout] f64 (BatchNorm
+ * batch statistics of the rounded z, zeroed by the call).  Same result as the avdn_gemm_* CONV launch of that layer.
+ * avdn_conv3x3_thin_supported returns 1 for the shapes it covers (Cin 32, Cout 64, H % 16 == 0, W % 8 == 0).      */
+int avdn_conv3x3_thin_fwd(const void* x_nhwc, const void* w_f, void* z, int N, int H, int W, int Cin, int Cout,
+                          double* stats, avdn_stream_t stream);
+int avdn_conv3x3_thin_supported(int H, int W, int Cin, int Cout);
+
 /* nn.BatchNorm2d in train mode (dark_net.py:31; eps 1e-5, momentum 0.1): batch
  * statistics of z [R,C] bf16 -> per-channel affine scale = gamma*rstd,
  * shift = beta - mean*scale, plus mean/rstd for the backward pass; updates the

@@ -202,3 +202,37 @@ def test_conv_dgrad_fused_bn_backward_sums(G, N, H, Cin, Cout, k, stride, acc):
             p.run()
         torch.cuda.synchronize()
         assert torch.allclose(sums.view(2, Cin), 2 * got, rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,W", [(1, 16, 8), (2, 32, 24), (3, 112, 112)])
+def test_conv3x3_thin_halo_matches_implicit_gemm(built_lib, N, H, W):
+    """avdn_conv3x3_thin_fwd (halo-tile reuse: three 8x18-pixel boxes per 8x16 output tile, resident filters) against the
+    general implicit-GEMM launch of the same 3x3 32->64 layer and against fp32 torch: same bf16 operands, fp32
+    accumulation, bf16 outputs, f64 statistics of the rounded outputs."""
+    from avdn_b200 import _lib, gemm as G
+    call, ptr = _lib.call, _lib.ptr
+    Cin, Cout = 32, 64
+    assert _lib.lib().avdn_conv3x3_thin_supported(H, W, Cin, Cout) == 1
+    assert _lib.lib().avdn_conv3x3_thin_supported(H + 1, W, Cin, Cout) == 0
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, 9 * Cin, device="cuda", generator=g) * 0.06).bfloat16()      # [co][tap][ci]
+    z_ref = torch.empty(N, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    st_ref = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    G.plan_conv_fwd(x, w, z_ref, N=N, H=H, W=W, Cin=Cin, Cout=Cout, k=3, stride=1, stats=st_ref).run()
+    z = torch.full_like(z_ref, float("nan"))
+    st = torch.full((2 * Cout,), 7.0, dtype=torch.float64, device="cuda")
+    call("avdn_conv3x3_thin_fwd", ptr(x), ptr(w), ptr(z), N, H, W, Cin, Cout, ptr(st))
+    torch.cuda.synchronize()
+    wt = w.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()
+    zt = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1)
+    assert torch.isfinite(z.float()).all()
+    d = (z.float() - zt).abs()
+    assert (d <= 2.0 ** -7 * zt.abs() + 1e-3).all(), d.max()          # one bf16 step of the fp32 result
+    assert (z.float() - z_ref.float()).abs().max() <= 2.0 ** -7 * zt.abs().max()
+    assert (z != z_ref).float().mean() < 1e-3                            # same operands, same accumulation depth
+    zs = z.double().view(-1, Cout)
+    assert torch.allclose(st[:Cout], zs.sum(0), rtol=1e-5, atol=1e-3 * (N * H * W) ** 0.5)
+    assert torch.allclose(st[Cout:], (zs * zs).sum(0), rtol=1e-4)
+    assert torch.allclose(st, st_ref, rtol=1e-4, atol=1e-2 * (N * H * W) ** 0.5)

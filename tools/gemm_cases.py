@@ -38,3 +38,18 @@ for name, p in cases:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); p.run(); e1.record(); torch.cuda.synchronize()
     print(f"{name}: {e0.elapsed_time(e1):.3f} ms  {p.flops / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
+
+# the same 3x3 32->64 layer at 112x112 through the halo-tile kernel (csrc/conv3_halo.cu)
+from avdn_b200 import _lib
+x = torch.randn(N, 112, 112, 32, device=dev).bfloat16()
+w = (torch.randn(64, 288, device=dev) * 0.05).bfloat16()
+z = torch.empty(N, 112, 112, 64, device=dev, dtype=torch.bfloat16)
+st = torch.zeros(128, dtype=torch.float64, device=dev)
+run = lambda: _lib.call("avdn_conv3x3_thin_fwd", _lib.ptr(x), _lib.ptr(w), _lib.ptr(z), N, 112, 112, 32, 64, _lib.ptr(st))
+for _ in range(reps):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(); e1.record(); torch.cuda.synchronize()
+fl = 2.0 * N * 112 * 112 * 64 * 288
+print(f"L3 fwd 3x3 32->64 @112 halo tiles: {e0.elapsed_time(e1):.3f} ms  {fl / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
