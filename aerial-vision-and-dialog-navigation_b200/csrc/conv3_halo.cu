@@ -25,7 +25,7 @@ using namespace avdn_tc;
 constexpr int TW = 8, TH = 16;            // output tile: 8 pixels x 16 rows = 128 = UMMA M
 constexpr int THREADS = 128;
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int XBUFS>
 struct Cfg {
   static constexpr int ROW = CIN * 2;                    // bytes per pixel = K-major row (64 or 128)
   static constexpr int ATOM = 8 * ROW;                   // 8 pixels = one box row = one swizzle atom
@@ -33,13 +33,14 @@ struct Cfg {
   static constexpr int XBUF = 3 * XBOX;                  // the three boxes of a tile
   static constexpr int WTAP = COUT * ROW;                // filters of one tap: COUT rows
   static constexpr int WBYTES = 9 * WTAP;
-  static constexpr int OUT_ROW = COUT * 2;               // bytes per output pixel (64 / 128 / 256)
-  static constexpr int OUT_SLABS = (OUT_ROW + 127) / 128;   // 128-byte-wide slabs of the staging tile
+  static constexpr int OUT_ROW = COUT * 2;               // bytes per output pixel (64 or 128)
   static constexpr int OUT_BYTES = 128 * OUT_ROW;
+  static constexpr int NCH = OUT_ROW / 16;               // 16-byte chunks per output pixel
   static constexpr uint32_t LAYOUT = (CIN == 64) ? 2u : 4u;  // SWIZZLE_128B / SWIZZLE_64B
-  static constexpr int SMEM = 2 * XBUF + WBYTES + OUT_BYTES + 1024;
+  static constexpr int SMEM = XBUFS * XBUF + WBYTES + OUT_BYTES + 1024;
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static constexpr uint32_t TMEM_COLS = COUT < 32 ? 32 : COUT;
+  static_assert((CIN == 32 || CIN == 64) && (COUT == 32 || COUT == 64), "thin layers only");
 };
 
 struct alignas(64) Params {
@@ -60,18 +61,27 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&b);
 }
+// byte offset of 16-byte chunk j of pixel row m in the staging slab, in the swizzle the TMA store expects
+// (128-byte rows: chunk ^ (m & 7); 64-byte rows: chunk ^ ((m >> 1) & 3))
+template <int OUT_ROW>
+__device__ __forceinline__ uint32_t out_chunk(uint32_t m, uint32_t j) {
+  return m * OUT_ROW + ((OUT_ROW == 128 ? (j ^ (m & 7u)) : (j ^ ((m >> 1) & 3u))) << 4);
+}
 
-template <int CIN, int COUT>
+// FLIP: tap (kh, kw) of the input patch multiplies filter tap 8 - (3 kh + kw) -- the data gradient of a stride-1
+// 3x3 convolution is that convolution of dz with the filters mirrored (and w_d = [ci][tap][co] as the B operand).
+// STATS: per-channel sum / sum of squares of the rounded outputs.  XBUFS: 2 = the next tile's boxes load under this
+// tile's UMMAs and epilogue; 1 = they load under the epilogue only (128-byte pixels: three boxes are 54 KB).
+template <int CIN, int COUT, bool FLIP, bool STATS, int XBUFS>
 __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_constant__ Params p) {
-  using C = Cfg<CIN, COUT>;
-  static_assert(COUT == 64, "the epilogue below is written for 128-byte output pixels");
+  using C = Cfg<CIN, COUT, XBUFS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t xs = base, ws = xs + 2 * C::XBUF, outs = ws + C::WBYTES;
+  const uint32_t xs = base, ws = xs + XBUFS * C::XBUF, outs = ws + C::WBYTES;
   __shared__ __align__(8) uint64_t bars[4];              // X buffer 0 / 1, filters, UMMAs done
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_x = smem_u32(&bars[0]), bar_w = bar_x + 16, bar_mma = bar_x + 24;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     mbar_init(bar_x, 1); mbar_init(bar_x + 8, 1); mbar_init(bar_w, 1); mbar_init(bar_mma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -100,18 +110,19 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
     for (int t = 0; t < 9; ++t) tma_load_4d<1>(ws + t * C::WTAP, &p.tmW, bar_w, t * CIN, 0, 0, 0);
     if ((int)blockIdx.x < p.n_tiles) load_x(blockIdx.x, 0);
   }
-  // statistics: thread owns 16-byte chunk (tid & 7) = channels 8j..8j+7 of rows (tid >> 3) + 16 i
+  // statistics: thread owns 16-byte chunk tid % NCH (8 channels) of the rows tid / NCH + (128 / NCH) i
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
 
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-    const uint32_t b = it & 1u;
-    if (tid == 0 && tile + (int)gridDim.x < p.n_tiles) load_x(tile + gridDim.x, b ^ 1u);    // buffer b^1: read by the
-                                                                                             // UMMAs of tile it-1, done
+    const uint32_t b = (XBUFS == 2) ? (it & 1u) : 0u;
+    const bool more = tile + (int)gridDim.x < p.n_tiles;
+    // two buffers: buffer b^1 was read by the UMMAs of tile it-1, which have completed
+    if (XBUFS == 2 && tid == 0 && more) load_x(tile + gridDim.x, b ^ 1u);
     if (it == 0) mbar_wait(bar_w, 0);
-    mbar_wait(bar_x + 8 * b, (it >> 1) & 1u);
+    mbar_wait(bar_x + 8 * b, (XBUFS == 2 ? (it >> 1) : it) & 1u);
     if (tid == 0) {
       tcgen05_fence_after();
       uint32_t acc = 0u;
@@ -119,7 +130,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
       for (int t = 0; t < 9; ++t) {
         const int kh = t / 3, kw = t - kh * 3;
         const uint64_t ad = make_smem_desc(xs + b * C::XBUF + kw * C::XBOX + kh * C::ATOM, 16, C::ATOM, C::LAYOUT);
-        const uint64_t bd = make_smem_desc(ws + t * C::WTAP, 16, C::ATOM, C::LAYOUT);
+        const uint64_t bd = make_smem_desc(ws + (FLIP ? 8 - t : t) * C::WTAP, 16, C::ATOM, C::LAYOUT);
 #pragma unroll
         for (int k = 0; k < CIN / 16; ++k) {
           umma_bf16<1>(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), C::IDESC, acc);
@@ -130,25 +141,21 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
     }
     __syncwarp();
     mbar_wait(bar_mma, it & 1u);
+    if (XBUFS == 1 && tid == 0 && more) load_x(tile + gridDim.x, 0);     // one buffer: reload under the epilogue
     tcgen05_fence_after();
-    uint32_t lo[32], hi[32];
-    tmem_ld32_async(tmem + ((uint32_t)(warp * 32) << 16), lo);
-    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32, hi);
+#pragma unroll
+    for (int h = 0; h < COUT / 32; ++h) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((warp * 32u) << 16) + 32 * h, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(outs + out_chunk<C::OUT_ROW>(tid, (uint32_t)(4 * h + j)),
+               pack2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+               pack2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+               pack2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+               pack2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+    }
     tcgen05_fence_before();
-    // pixel row m = tid: 128 bytes, chunk j at j ^ (m & 7) (128-byte swizzle, what the TMA store expects)
-    const uint32_t row = outs + tid * 128;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      sts128(row + (((uint32_t)j ^ (tid & 7u)) << 4), pack2(__uint_as_float(lo[8 * j]), __uint_as_float(lo[8 * j + 1])),
-             pack2(__uint_as_float(lo[8 * j + 2]), __uint_as_float(lo[8 * j + 3])),
-             pack2(__uint_as_float(lo[8 * j + 4]), __uint_as_float(lo[8 * j + 5])),
-             pack2(__uint_as_float(lo[8 * j + 6]), __uint_as_float(lo[8 * j + 7])));
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      sts128(row + (((uint32_t)(j + 4) ^ (tid & 7u)) << 4), pack2(__uint_as_float(hi[8 * j]), __uint_as_float(hi[8 * j + 1])),
-             pack2(__uint_as_float(hi[8 * j + 2]), __uint_as_float(hi[8 * j + 3])),
-             pack2(__uint_as_float(hi[8 * j + 4]), __uint_as_float(hi[8 * j + 5])),
-             pack2(__uint_as_float(hi[8 * j + 6]), __uint_as_float(hi[8 * j + 7])));
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -156,12 +163,12 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
       tma_store_4d(&p.tmZ, outs, 0, tx * TW, ty * TH, n);
       tma_commit_group();
     }
-    if (p.stats != nullptr) {
-      const uint32_t j = tid & 7u;
+    if (STATS) {
+      const uint32_t j = tid % C::NCH;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t m = (uint32_t)(tid >> 3) + 16u * i;
-        const uint4 v = lds128(outs + m * 128 + ((j ^ (m & 7u)) << 4));
+      for (int i = 0; i < C::NCH; ++i) {
+        const uint32_t m = tid / C::NCH + (128u / C::NCH) * i;
+        const uint4 v = lds128(outs + out_chunk<C::OUT_ROW>(m, j));
         const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -174,17 +181,18 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
     if (tid == 0) tma_wait_group_read<0>();              // the slab may be rewritten
     __syncthreads();
   }
-  if (p.stats != nullptr) {
-    // block reduction through the (now free) staging slab: [2][16 row groups][COUT] floats
+  if (STATS && p.stats != nullptr) {
+    // block reduction through the (now free) staging slab: [2][row groups][COUT] floats
+    constexpr int G = 128 / C::NCH;
     float* s_red = reinterpret_cast<float*>(smem_raw + (outs - smem_u32(smem_raw)));
-    const int j = tid & 7, g = tid >> 3;
+    const int j = tid % C::NCH, g = tid / C::NCH;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s_red[g * COUT + j * 8 + k] = s1[k]; s_red[(16 + g) * COUT + j * 8 + k] = s2[k]; }
+    for (int k = 0; k < 8; ++k) { s_red[g * COUT + j * 8 + k] = s1[k]; s_red[(G + g) * COUT + j * 8 + k] = s2[k]; }
     __syncthreads();
     if (tid < 2 * COUT) {
       const int which = tid / COUT, c = tid % COUT;
       float a = 0.f;
-      for (int g2 = 0; g2 < 16; ++g2) a += s_red[(which * 16 + g2) * COUT + c];
+      for (int g2 = 0; g2 < G; ++g2) a += s_red[(which * G + g2) * COUT + c];
       atomicAdd(p.stats + which * COUT + c, (double)a);
     }
   }
@@ -195,49 +203,64 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS) : "memory");
 }
 
+template <int CIN, int COUT, bool FLIP, bool STATS, int XBUFS>
+int launch(const void* x, const void* w, void* z, int N, int H, int W, double* stats, cudaStream_t s) {
+  using C = Cfg<CIN, COUT, XBUFS>;
+  Params p;
+  const int64_t dx[4] = {CIN, W, H, N}, sx[4] = {1, CIN, (int64_t)W * CIN, (int64_t)H * W * CIN};
+  const int32_t bx[4] = {CIN, TW, TH + 2, 1};
+  const int64_t K = 9ll * CIN;                           // w: [COUT rows][9 taps x CIN], tap-major
+  const int64_t dw[4] = {K, COUT, 1, 1}, sw[4] = {1, K, K * COUT, K * COUT};
+  const int32_t bw[4] = {CIN, COUT, 1, 1};
+  const int64_t dz[4] = {COUT, W, H, N}, sz[4] = {1, COUT, (int64_t)W * COUT, (int64_t)H * W * COUT};
+  const int32_t bz[4] = {COUT, TW, TH, 1};
+  int r = avdn::encode_tensor_map_4d(x, 2, dx, sx, bx, &p.tmX);
+  if (!r) r = avdn::encode_tensor_map_4d(w, 2, dw, sw, bw, &p.tmW);
+  if (!r) r = avdn::encode_tensor_map_4d(z, 2, dz, sz, bz, &p.tmZ);
+  if (r) return r;
+  p.tiles_x = W / TW;
+  p.tiles_y = H / TH;
+  const long long nt = (long long)N * p.tiles_x * p.tiles_y;
+  if (nt >= (1ll << 31)) return avdn::set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo: too many tiles");
+  p.n_tiles = (int32_t)nt;
+  p.stats = stats;
+  if (STATS && stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * COUT, s) != cudaSuccess)
+    return avdn::check_launch("conv3_halo stats memset");
+  auto kfn = conv3_halo_kernel<CIN, COUT, FLIP, STATS, XBUFS>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess)
+      return avdn::check_launch("conv3_halo smem attribute");
+    attr = true;
+  }
+  const long long cap = (long long)avdn::sm_count() * 2;
+  kfn<<<(unsigned)(nt < cap ? nt : cap), THREADS, C::SMEM, s>>>(p);
+  return avdn::check_launch("conv3_halo_kernel");
+}
+
 }  // namespace
 
 namespace avdn {
 
-bool conv3_halo_supported(int H, int W, int Cin, int Cout) {
-  return Cin == 32 && Cout == 64 && H % TH == 0 && W % TW == 0 && H >= TH && W >= TW;
-}
+static bool tile_ok(int H, int W) { return H % TH == 0 && W % TW == 0 && H >= TH && W >= TW; }
+
+bool conv3_halo_supported(int H, int W, int Cin, int Cout) { return Cin == 32 && Cout == 64 && tile_ok(H, W); }
+bool conv3_halo_dgrad_supported(int H, int W, int Cin, int Cout) { return Cin == 32 && Cout == 64 && tile_ok(H, W); }
 
 int conv3_halo_fwd(const void* x, const void* wf, void* z, int N, int H, int W, int Cin, int Cout, double* stats,
                    cudaStream_t s) {
   if (!conv3_halo_supported(H, W, Cin, Cout))
     return set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo: shape %dx%d, %d -> %d channels not covered", H, W, Cin, Cout);
-  using C = Cfg<32, 64>;
-  Params p;
-  const int64_t dx[4] = {Cin, W, H, N}, sx[4] = {1, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin};
-  const int32_t bx[4] = {Cin, TW, TH + 2, 1};
-  const int64_t K = 9ll * Cin;
-  const int64_t dw[4] = {K, Cout, 1, 1}, sw[4] = {1, K, K * Cout, K * Cout};
-  const int32_t bw[4] = {Cin, Cout, 1, 1};
-  const int64_t dz[4] = {Cout, W, H, N}, sz[4] = {1, Cout, (int64_t)W * Cout, (int64_t)H * W * Cout};
-  const int32_t bz[4] = {Cout, TW, TH, 1};
-  int r = encode_tensor_map_4d(x, 2, dx, sx, bx, &p.tmX);
-  if (!r) r = encode_tensor_map_4d(wf, 2, dw, sw, bw, &p.tmW);
-  if (!r) r = encode_tensor_map_4d(z, 2, dz, sz, bz, &p.tmZ);
-  if (r) return r;
-  p.tiles_x = W / TW;
-  p.tiles_y = H / TH;
-  const long long nt = (long long)N * p.tiles_x * p.tiles_y;
-  if (nt >= (1ll << 31)) return set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo: too many tiles");
-  p.n_tiles = (int32_t)nt;
-  p.stats = stats;
-  if (stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, s) != cudaSuccess)
-    return check_launch("conv3_halo stats memset");
-  auto kfn = conv3_halo_kernel<32, 64>;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess)
-      return check_launch("conv3_halo smem attribute");
-    attr = true;
-  }
-  const long long cap = (long long)sm_count() * 2;
-  kfn<<<(unsigned)(nt < cap ? nt : cap), THREADS, C::SMEM, s>>>(p);
-  return check_launch("conv3_halo_kernel");
+  return stats ? launch<32, 64, false, true, 2>(x, wf, z, N, H, W, stats, s)
+               : launch<32, 64, false, false, 2>(x, wf, z, N, H, W, nullptr, s);
+}
+
+// dx [N,H,W,Cin] = data gradient of the Cin -> Cout layer: a 3x3 convolution of dz [N,H,W,Cout] with the mirrored
+// filters w_d [Cin][9][Cout]
+int conv3_halo_dgrad(const void* dz, const void* wd, void* dx, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+  if (!conv3_halo_dgrad_supported(H, W, Cin, Cout))
+    return set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo dgrad: shape %dx%d, %d -> %d channels not covered", H, W, Cin, Cout);
+  return launch<64, 32, true, false, 1>(dz, wd, dx, N, H, W, nullptr, s);
 }
 
 }  // namespace avdn
@@ -246,6 +269,12 @@ extern "C" int avdn_conv3x3_thin_fwd(const void* x_nhwc, const void* w_f, void* 
                                      int Cout, double* stats, avdn_stream_t stream) {
   AVDN_REQUIRE(x_nhwc && w_f && z && N > 0, "avdn_conv3x3_thin_fwd: bad argument");
   return avdn::conv3_halo_fwd(x_nhwc, w_f, z, N, H, W, Cin, Cout, stats, avdn::to_cuda(stream));
+}
+
+extern "C" int avdn_conv3x3_thin_dgrad(const void* dz, const void* w_d, void* dx, int N, int H, int W, int Cin,
+                                       int Cout, avdn_stream_t stream) {
+  AVDN_REQUIRE(dz && w_d && dx && N > 0, "avdn_conv3x3_thin_dgrad: bad argument");
+  return avdn::conv3_halo_dgrad(dz, w_d, dx, N, H, W, Cin, Cout, avdn::to_cuda(stream));
 }
 
 extern "C" int avdn_conv3x3_thin_supported(int H, int W, int Cin, int Cout) {

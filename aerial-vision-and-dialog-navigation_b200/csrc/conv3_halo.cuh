@@ -14,5 +14,7 @@ int encode_tensor_map_4d(const void* ptr, int elem_bytes, const int64_t* dim, co
 bool conv3_halo_supported(int H, int W, int Cin, int Cout);
 int conv3_halo_fwd(const void* x, const void* wf, void* z, int N, int H, int W, int Cin, int Cout, double* stats,
                    cudaStream_t s);
+bool conv3_halo_dgrad_supported(int H, int W, int Cin, int Cout);
+int conv3_halo_dgrad(const void* dz, const void* wd, void* dx, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
 
 }  // namespace avdn

@@ -36,6 +36,9 @@ FUSE_BNB = os.environ.get("AVDN_FUSE_BNB", "0") == "1"
 # Block 0 in train mode: recompute path (avdn_conv0_fwd_stats / _fwd_apply / _bwd) -- its pre-activation z and its
 # gradient dz (2 GB each at 640 views) are never stored.  AVDN_CONV0_RECOMPUTE=0 keeps the stored-z path.
 CONV0_RECOMPUTE = os.environ.get("AVDN_CONV0_RECOMPUTE", "1") != "0"
+# Thin 3x3 stride-1 blocks (32 -> 64 channels: module_list.3 at 112 x 112) run their forward and data gradient on the
+# halo-tile kernel (csrc/conv3_halo.cu: three TMA boxes per tile instead of nine, resident filters) where it applies.
+CONV_HALO = os.environ.get("AVDN_CONV_HALO", "1") != "0"
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
@@ -135,6 +138,7 @@ class _Engine:
                 L.src = cur["layer"]           # producing layer of the input (None = image)
                 L.res = None                   # residual source layer (fused shortcut)
                 L.first = len(self.layers) == 0
+                L.halo = L.halo_dgrad = False
                 if L.first and not (L.Cin == 3 and L.Cout == 32 and k == 3 and s == 1):
                     raise NotImplementedError("first layer must be the 3->32 3x3 stride-1 conv of yolov3")
                 L.R = N * L.Hout * L.Wout
@@ -199,6 +203,8 @@ class _Engine:
                                           Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops)
                 L.p_fwd_stats = G.plan_conv_fwd(L.src.a, L.wf, L.z, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
                                                 Cout=L.Cout_p, k=L.k, stride=L.s, flops=L.flops, stats=L.sums)
+                L.halo = bool(CONV_HALO and L.k == 3 and L.s == 1 and
+                              _lib.lib().avdn_conv3x3_thin_supported(L.Hin, L.Win, L.Cin_p, L.Cout_p))
             self._fwd_plans = True
 
     def conv_table(self, net):
@@ -314,6 +320,7 @@ class _Engine:
                 P.bnb_fused = True
             L.p_dgrad = G.plan_conv_dgrad(dz, L.wd, L.src.g, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
                                           Cout=L.Cout_p, k=L.k, stride=L.s, accumulate=acc, flops=L.flops, bnb=bnb)
+            L.halo_dgrad = bool(getattr(L, "halo", False) and acc == 0 and bnb is None)     # overwrite only
             seen_as_input.add(id(L.src))
             if L.res is not None:
                 seen_as_input.add(id(L.res))
@@ -362,6 +369,10 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
             n += 2                  # kernels only (memsets / symbol copies inside the ABI calls are not counted)
         elif L.first:
             call("avdn_conv0_fwd", ptr(x_nhwc4), ptr(conv.weight), ptr(L.z), eng.N, L.Hin, L.Win, ptr(L.sums))
+            n += 1
+        elif L.halo:
+            call("avdn_conv3x3_thin_fwd", ptr(L.src.a), ptr(L.wf), ptr(L.z), eng.N, L.Hin, L.Win, L.Cin_p, L.Cout_p,
+                 ptr(L.sums))
             n += 1
         else:
             L.p_fwd_stats.run()
@@ -452,6 +463,10 @@ def _layer_backward(eng, L, unpack=True, zero=True):
             L.src.bsums.zero_()
             n += 1
         L.src.bnb_ready = True
+    if L.halo_dgrad:
+        call("avdn_conv3x3_thin_dgrad", ptr(L.dz), ptr(L.wd), ptr(L.src.g), eng.N, L.Hin, L.Win, L.Cin_p,
+             L.Cout_p)
+        return n + 1
     for p in L.p_dgrad:
         p.run()
     return n + len(L.p_dgrad)

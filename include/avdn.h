@@ -287,6 +287,10 @@ int avdn_conv0_bwd(const void* x_nhwc4, const float* w, const void* da, const vo
 int avdn_conv3x3_thin_fwd(const void* x_nhwc, const void* w_f, void* z, int N, int H, int W, int Cin, int Cout,
                           double* stats, avdn_stream_t stream);
 int avdn_conv3x3_thin_supported(int H, int W, int Cin, int Cout);
+/* Data gradient of the same layer: dx [N,H,W,Cin] bf16 = 3x3 convolution of dz [N,H,W,Cout] bf16 with the mirrored
+ * filters, w_d [Cin, 9*Cout] bf16 (avdn_pack_conv_weights' second output).  Overwrites dx.  Same shapes.       */
+int avdn_conv3x3_thin_dgrad(const void* dz, const void* w_d, void* dx, int N, int H, int W, int Cin, int Cout,
+                            avdn_stream_t stream);
 
 /* nn.BatchNorm2d in train mode (dark_net.py:31; eps 1e-5, momentum 0.1): batch
  * statistics of z [R,C] bf16 -> per-channel affine scale = gamma*rstd,

@@ -236,3 +236,30 @@ def test_conv3x3_thin_halo_matches_implicit_gemm(built_lib, N, H, W):
     assert torch.allclose(st[:Cout], zs.sum(0), rtol=1e-5, atol=1e-3 * (N * H * W) ** 0.5)
     assert torch.allclose(st[Cout:], (zs * zs).sum(0), rtol=1e-4)
     assert torch.allclose(st, st_ref, rtol=1e-4, atol=1e-2 * (N * H * W) ** 0.5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,W", [(1, 16, 8), (2, 32, 24), (2, 112, 112)])
+def test_conv3x3_thin_halo_dgrad_matches_implicit_gemm(built_lib, N, H, W):
+    """avdn_conv3x3_thin_dgrad (the data gradient of the 3x3 32->64 layer as a halo-tile convolution of dz with the
+    mirrored filters) against the implicit-GEMM dgrad launch and fp32 torch autograd."""
+    from avdn_b200 import _lib, gemm as G
+    call, ptr = _lib.call, _lib.ptr
+    Cin, Cout = 32, 64
+    g = torch.Generator(device="cuda").manual_seed(9)
+    dz = torch.randn(N, H, W, Cout, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * 0.06).bfloat16()
+    wd = w.permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).contiguous()                      # [ci][tap][co]
+    dx_ref = torch.empty(N, H, W, Cin, device="cuda", dtype=torch.bfloat16)
+    for pl in G.plan_conv_dgrad(dz, wd, dx_ref, N=N, H=H, W=W, Cin=Cin, Cout=Cout, k=3, stride=1):
+        pl.run()
+    dx = torch.full_like(dx_ref, float("nan"))
+    call("avdn_conv3x3_thin_dgrad", ptr(dz), ptr(wd), ptr(dx), N, H, W, Cin, Cout)
+    torch.cuda.synchronize()
+    xt = torch.zeros(N, Cin, H, W, device="cuda", requires_grad=True)
+    torch.nn.functional.conv2d(xt, w.float(), padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    ref = xt.grad.permute(0, 2, 3, 1)
+    assert torch.isfinite(dx.float()).all()
+    d = (dx.float() - ref).abs()
+    assert (d <= 2.0 ** -7 * ref.abs() + 2e-3).all(), d.max()
+    assert (dx != dx_ref).float().mean() < 1e-3
