@@ -37,7 +37,7 @@ struct Cfg {
   static constexpr int OUT_BYTES = 128 * OUT_ROW;
   static constexpr int NCH = OUT_ROW / 16;               // 16-byte chunks per output pixel
   static constexpr uint32_t LAYOUT = (CIN == 64) ? 2u : 4u;  // SWIZZLE_128B / SWIZZLE_64B
-  static constexpr int SMEM = XBUFS * XBUF + WBYTES + OUT_BYTES + 1024;
+  static constexpr int SMEM = XBUFS * XBUF + WBYTES + 2 * OUT_BYTES + 1024;     // two staging slabs
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static constexpr uint32_t TMEM_COLS = COUT < 32 ? 32 : COUT;
   static_assert((CIN == 32 || CIN == 64) && (COUT == 32 || COUT == 64), "thin layers only");
@@ -78,17 +78,17 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t xs = base, ws = xs + XBUFS * C::XBUF, outs = ws + C::WBYTES;
-  __shared__ __align__(8) uint64_t bars[4];              // X buffer 0 / 1, filters, UMMAs done
+  __shared__ __align__(8) uint64_t bars[5];              // X buffer 0 / 1, filters, UMMAs of accumulator 0 / 1 done
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_x = smem_u32(&bars[0]), bar_w = bar_x + 16, bar_mma = bar_x + 24;
   const uint32_t tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    mbar_init(bar_x, 1); mbar_init(bar_x + 8, 1); mbar_init(bar_w, 1); mbar_init(bar_mma, 1);
+    mbar_init(bar_x, 1); mbar_init(bar_x + 8, 1); mbar_init(bar_w, 1); mbar_init(bar_mma, 1); mbar_init(bar_mma + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                 "r"(C::TMEM_COLS)
+                 "r"(2 * C::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -105,26 +105,34 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
     for (int kw = 0; kw < 3; ++kw)
       tma_load_4d<1>(xs + buf * C::XBUF + kw * C::XBOX, &p.tmX, bar_x + 8 * buf, 0, tx * TW + kw - 1, ty * TH - 1, n);
   };
-  if (tid == 0) {
+  const int n_my = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (tid == 0 && n_my > 0) {
     mbar_expect_tx(bar_w, (uint32_t)C::WBYTES);
     for (int t = 0; t < 9; ++t) tma_load_4d<1>(ws + t * C::WTAP, &p.tmW, bar_w, t * CIN, 0, 0, 0);
-    if ((int)blockIdx.x < p.n_tiles) load_x(blockIdx.x, 0);
+    load_x(blockIdx.x, 0);
   }
   // statistics: thread owns 16-byte chunk tid % NCH (8 channels) of the rows tid / NCH + (128 / NCH) i
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
 
-  uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-    const uint32_t b = (XBUFS == 2) ? (it & 1u) : 0u;
-    const bool more = tile + (int)gridDim.x < p.n_tiles;
-    // two buffers: buffer b^1 was read by the UMMAs of tile it-1, which have completed
-    if (XBUFS == 2 && tid == 0 && more) load_x(tile + gridDim.x, b ^ 1u);
-    if (it == 0) mbar_wait(bar_w, 0);
-    mbar_wait(bar_x + 8 * b, (XBUFS == 2 ? (it >> 1) : it) & 1u);
-    if (tid == 0) {
+  // Software pipeline over the CTA's tiles: iteration `it` issues the UMMAs of tile it into accumulator it & 1 and
+  // then runs the epilogue of tile it-1 from the other accumulator while they execute; the boxes of tile it+1 are
+  // in flight throughout (two X buffers) or from the moment the UMMAs of tile it have read the single buffer.
+  for (int it = 0; it <= n_my; ++it) {
+    if (it < n_my && tid == 0) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const uint32_t b = (XBUFS == 2) ? ((uint32_t)it & 1u) : 0u;
+      const bool more = it + 1 < n_my;
+      if (XBUFS == 2 && more) {
+        // buffer (it+1) & 1 was read by the UMMAs of tile it-1
+        if (it >= 1) mbar_wait(bar_mma + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+        load_x(tile + (int)gridDim.x, b ^ 1u);
+      }
+      if (it == 0) mbar_wait(bar_w, 0);
+      mbar_wait(bar_x + 8 * b, (uint32_t)(XBUFS == 2 ? (it >> 1) : it) & 1u);
       tcgen05_fence_after();
+      const uint32_t tmem_d = tmem + (uint32_t)(it & 1) * C::TMEM_COLS;
       uint32_t acc = 0u;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
@@ -133,54 +141,66 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
         const uint64_t bd = make_smem_desc(ws + (FLIP ? 8 - t : t) * C::WTAP, 16, C::ATOM, C::LAYOUT);
 #pragma unroll
         for (int k = 0; k < CIN / 16; ++k) {
-          umma_bf16<1>(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), C::IDESC, acc);
+          umma_bf16<1>(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), C::IDESC, acc);
           acc = 1u;
         }
       }
-      tcgen05_commit<1>(bar_mma);
-    }
-    __syncwarp();
-    mbar_wait(bar_mma, it & 1u);
-    if (XBUFS == 1 && tid == 0 && more) load_x(tile + gridDim.x, 0);     // one buffer: reload under the epilogue
-    tcgen05_fence_after();
-#pragma unroll
-    for (int h = 0; h < COUT / 32; ++h) {
-      uint32_t v[32];
-      tmem_ld32(tmem + ((warp * 32u) << 16) + 32 * h, v);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        sts128(outs + out_chunk<C::OUT_ROW>(tid, (uint32_t)(4 * h + j)),
-               pack2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-               pack2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-               pack2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-               pack2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-    }
-    tcgen05_fence_before();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      const int n = tile / per_img, r = tile - n * per_img, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      tma_store_4d(&p.tmZ, outs, 0, tx * TW, ty * TH, n);
-      tma_commit_group();
-    }
-    if (STATS) {
-      const uint32_t j = tid % C::NCH;
-#pragma unroll
-      for (int i = 0; i < C::NCH; ++i) {
-        const uint32_t m = tid / C::NCH + (128u / C::NCH) * i;
-        const uint4 v = lds128(outs + out_chunk<C::OUT_ROW>(m, j));
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float a = __uint_as_float(w4[k] << 16), c2 = __uint_as_float(w4[k] & 0xFFFF0000u);
-          s1[2 * k] += a; s2[2 * k] = fmaf(a, a, s2[2 * k]);
-          s1[2 * k + 1] += c2; s2[2 * k + 1] = fmaf(c2, c2, s2[2 * k + 1]);
-        }
+      tcgen05_commit<1>(bar_mma + 8 * (it & 1));
+      if (XBUFS == 1 && more) {                          // one buffer: reload once these UMMAs have read it
+        mbar_wait(bar_mma + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
+        load_x(tile + (int)gridDim.x, 0);
       }
     }
-    if (tid == 0) tma_wait_group_read<0>();              // the slab may be rewritten
-    __syncthreads();
+    __syncwarp();
+    if (it >= 1) {
+      const int j = it - 1, tile = (int)blockIdx.x + j * (int)gridDim.x;
+      mbar_wait(bar_mma + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem + (uint32_t)(j & 1) * C::TMEM_COLS;
+      // slab j & 1: the TMA store of tile j-2 has finished reading it (wait_group.read 1 below); a bulk store takes
+      // ~2500 cycles until its source has been read, which one slab would put on every tile's critical path
+      const uint32_t slab = outs + (uint32_t)(j & 1) * C::OUT_BYTES;
+#pragma unroll
+      for (int h = 0; h < COUT / 32; ++h) {
+        uint32_t v[32];
+        tmem_ld32(tmem_d + ((warp * 32u) << 16) + 32 * h, v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts128(slab + out_chunk<C::OUT_ROW>(tid, (uint32_t)(4 * h + c)),
+                 pack2(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])),
+                 pack2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])),
+                 pack2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])),
+                 pack2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])));
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const int n = tile / per_img, r = tile - n * per_img, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        tma_store_4d(&p.tmZ, slab, 0, tx * TW, ty * TH, n);
+        tma_commit_group();
+      }
+      if (STATS) {
+        const uint32_t cj = tid % C::NCH;
+#pragma unroll
+        for (int i = 0; i < C::NCH; ++i) {
+          const uint32_t m = tid / C::NCH + (128u / C::NCH) * i;
+          const uint4 v = lds128(slab + out_chunk<C::OUT_ROW>(m, cj));
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float a = __uint_as_float(w4[k] << 16), c2 = __uint_as_float(w4[k] & 0xFFFF0000u);
+            s1[2 * k] += a; s2[2 * k] = fmaf(a, a, s2[2 * k]);
+            s1[2 * k + 1] += c2; s2[2 * k + 1] = fmaf(c2, c2, s2[2 * k + 1]);
+          }
+        }
+      }
+      if (tid == 0) tma_wait_group_read<1>();            // the OTHER slab (tile j-1's store) may be rewritten
+    }
+    __syncthreads();                                     // next slab free; accumulator (it-1) & 1 drained before tile it+1
   }
+  if (tid == 0) tma_wait_group_read<0>();
+  __syncthreads();
   if (STATS && p.stats != nullptr) {
     // block reduction through the (now free) staging slab: [2][row groups][COUT] floats
     constexpr int G = 128 / C::NCH;
@@ -200,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3_halo_kernel(const __grid_con
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * C::TMEM_COLS) : "memory");
 }
 
 template <int CIN, int COUT, bool FLIP, bool STATS, int XBUFS>
@@ -251,8 +271,8 @@ int conv3_halo_fwd(const void* x, const void* wf, void* z, int N, int H, int W, 
                    cudaStream_t s) {
   if (!conv3_halo_supported(H, W, Cin, Cout))
     return set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo: shape %dx%d, %d -> %d channels not covered", H, W, Cin, Cout);
-  return stats ? launch<32, 64, false, true, 2>(x, wf, z, N, H, W, stats, s)
-               : launch<32, 64, false, false, 2>(x, wf, z, N, H, W, nullptr, s);
+  return stats ? launch<32, 64, false, true, 1>(x, wf, z, N, H, W, stats, s)
+               : launch<32, 64, false, false, 1>(x, wf, z, N, H, W, nullptr, s);
 }
 
 // dx [N,H,W,Cin] = data gradient of the Cin -> Cout layer: a 3x3 convolution of dz [N,H,W,Cout] with the mirrored

@@ -53,3 +53,21 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
 fl = 2.0 * N * 112 * 112 * 64 * 288
 print(f"L3 fwd 3x3 32->64 @112 halo tiles: {e0.elapsed_time(e1):.3f} ms  {fl / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
+
+# its data gradient: implicit GEMM vs halo tiles
+from avdn_b200 import gemm as G2
+dzt = torch.randn(N, 112, 112, 64, device=dev).bfloat16()
+wdt = (torch.randn(32, 576, device=dev) * 0.05).bfloat16()
+dxt = torch.empty(N, 112, 112, 32, device=dev, dtype=torch.bfloat16)
+plans = G2.plan_conv_dgrad(dzt, wdt, dxt, N=N, H=112, W=112, Cin=32, Cout=64, k=3, stride=1)
+def run_g():
+    for pl in plans:
+        pl.run()
+run_h = lambda: _lib.call("avdn_conv3x3_thin_dgrad", _lib.ptr(dzt), _lib.ptr(wdt), _lib.ptr(dxt), N, 112, 112, 32, 64)
+for name, fn in (("L3 dgrad implicit GEMM", run_g), ("L3 dgrad halo tiles", run_h)):
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1):.3f} ms  {fl / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
