@@ -201,11 +201,12 @@ def profile_record(name, fn, flops=0, nbytes=0):
     PROFILE.append((name, ev0, ev1, flops, nbytes))
 
 
-def call(name, *args):
-    """Invoke an ABI function on torch's current stream; raise on error."""
+def call(name, *args, flops=0):
+    """Invoke an ABI function on torch's current stream; raise on error.  ``flops``: algorithmic FLOPs of the call,
+    recorded with its CUDA-event time when profiling is on (bench.py's roofline)."""
     fn = getattr(lib(), name)
     if PROFILE is not None:
-        profile_record(name, lambda: check(fn(*args, stream_ptr()), name))
+        profile_record(name, lambda: check(fn(*args, stream_ptr()), name), flops=flops)
         return
     check(fn(*args, stream_ptr()), name)
 

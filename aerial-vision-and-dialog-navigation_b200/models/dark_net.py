@@ -372,7 +372,7 @@ def _trunk_forward(net, eng, x_nhwc4, train, out=None, frozen=False):
             n += 1
         elif L.halo:
             call("avdn_conv3x3_thin_fwd", ptr(L.src.a), ptr(L.wf), ptr(L.z), eng.N, L.Hin, L.Win, L.Cin_p, L.Cout_p,
-                 ptr(L.sums))
+                 ptr(L.sums), flops=L.flops)
             n += 1
         else:
             L.p_fwd_stats.run()
@@ -465,7 +465,7 @@ def _layer_backward(eng, L, unpack=True, zero=True):
         L.src.bnb_ready = True
     if L.halo_dgrad:
         call("avdn_conv3x3_thin_dgrad", ptr(L.dz), ptr(L.wd), ptr(L.src.g), eng.N, L.Hin, L.Win, L.Cin_p,
-             L.Cout_p)
+             L.Cout_p, flops=L.flops)
         return n + 1
     for p in L.p_dgrad:
         p.run()

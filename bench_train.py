@@ -167,7 +167,7 @@ class TrainWorkload:
     def roofline(self, peaks, ms_per_step=None):
         if self.profile is None:
             self.profile_step()
-        g = {k: v for k, v in self.profile.items() if k.startswith("gemm")}
+        g = {k: v for k, v in self.profile.items() if k.startswith("gemm") or k.startswith("avdn_conv3x3_thin")}
         g_ms = sum(v[1] for v in g.values())
         g_fl = sum(v[2] for v in g.values())
         g_n = sum(v[0] for v in g.values())
@@ -179,7 +179,7 @@ class TrainWorkload:
         # DRAM traffic is not measurable from inside the run (it needs ncu): null here; the ncu capture of this
         # command is summarised under profiles/ (r02_*).
         traffic, traffic_src = None, "not measured in-run (ncu summaries under profiles/)"
-        return {"kernel": "gemm_kernel (tcgen05 implicit-GEMM conv fwd/dgrad/wgrad + transformer GEMMs)",
+        return {"kernel": "gemm_kernel + conv3_halo_kernel (tcgen05 conv fwd/dgrad/wgrad + transformer GEMMs)",
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peaks["source"] + " (sustained bf16 cuBLAS; kernel timed inside a long step)",
