@@ -52,6 +52,7 @@ _SIGNATURES = {
     "avdn_conv3x3_thin_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "avdn_conv3x3_thin_supported": [c_int, c_int, c_int, c_int],
     "avdn_conv3x3_thin_dgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "avdn_conv3x3_thin_wgrad": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "avdn_conv0_bwd": [c_void_p] * 8 + [c_f32, c_int, c_int, c_int] + [c_void_p] * 7 + [c_void_p],
     "avdn_bn_stats": [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_f32,
                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

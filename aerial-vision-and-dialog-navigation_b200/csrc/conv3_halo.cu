@@ -258,6 +258,107 @@ int launch(const void* x, const void* w, void* z, int N, int H, int W, double* s
   return avdn::check_launch("conv3_halo_kernel");
 }
 
+// ------------------------------------------------------------------ weight gradient
+// dW[co][ci][kh][kw] += sum over pixels dz[p][co] * x[p + (kh-1, kw-1)][ci]  for the 32 -> 64 block: the pixel
+// dimension is K.  Per 8 x 16-pixel tile: A = the dz tile, MN-major (one 128-byte row of 64 co per pixel, M = 64);
+// B = the three horizontal-tap boxes of x read MN-major (one 64-byte row of 32 ci per pixel, 64-byte swizzle) as ONE
+// N = 96 operand -- its three 32-wide MN atoms are the three boxes, LBO = one box apart -- advanced by kh whole atoms.
+// 3 filter rows x 8 K-steps = 24 UMMAs (M 64, N 96, K 16) per tile into three accumulators (288 TMEM columns) that
+// live for the whole kernel: no per-tile epilogue; a producer thread and an issuer thread run a 3-stage ring.
+constexpr int WG_STAGES = 3;
+struct alignas(64) WgParams {
+  CUtensorMap tmX, tmDz;
+  int32_t tiles_x, tiles_y, n_tiles;
+  float* dw;              // [64][32][3][3] fp32, accumulated
+};
+
+__global__ void __launch_bounds__(THREADS, 1) conv3_halo_wgrad_kernel(const __grid_constant__ WgParams p) {
+  constexpr int CIN = 32, COUT = 64;
+  constexpr int XBOX = (TH + 2) * 8 * CIN * 2;           // 9216
+  constexpr int XBUF = 3 * XBOX, DZ = 128 * COUT * 2;    // 27648 + 16384 per stage
+  constexpr int STAGE = XBUF + DZ;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_free = bar_full + 8 * WG_STAGES, bar_done = bar_free + 8 * WG_STAGES;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_free + 8 * s, 1); }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int n_my = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (tid == 0) {
+    // ---- producer: the dz tile and the three x boxes of every tile of this CTA ----
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % WG_STAGES, use = it / WG_STAGES;
+      if (use > 0) mbar_wait(bar_free + 8 * s, (uint32_t)(use - 1) & 1u);
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int n = tile / per_img, r = tile - n * per_img, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const uint32_t sx = base + s * STAGE, sd = sx + XBUF;
+      mbar_expect_tx(bar_full + 8 * s, (uint32_t)STAGE);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+        tma_load_4d<1>(sx + kw * XBOX, &p.tmX, bar_full + 8 * s, 0, tx * TW + kw - 1, ty * TH - 1, n);
+      tma_load_4d<1>(sd, &p.tmDz, bar_full + 8 * s, 0, tx * TW, ty * TH, n);
+    }
+  } else if (tid == 32) {
+    // ---- issuer ----
+    // D f32, A = B = bf16, both MN-major; N = 96, M = 64
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(96 >> 3) << 17) |
+                               ((uint32_t)(64 >> 4) << 24);
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % WG_STAGES, use = it / WG_STAGES;
+      mbar_wait(bar_full + 8 * s, (uint32_t)use & 1u);
+      tcgen05_fence_after();
+      const uint32_t sx = base + s * STAGE, sd = sx + XBUF;
+      const uint64_t ad = make_smem_desc(sd, 16384, 1024, 2);            // dz: 128-byte rows, 8-row groups 1 KB apart
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        // x: 64-byte rows, 8-row groups 512 B apart, the three 32-wide MN atoms (kw) one box apart
+        const uint64_t bd = make_smem_desc(sx + kh * 512, XBOX, 512, 4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16<1>(tmem + 96 * kh, ad + (uint64_t)(k * 128), bd + (uint64_t)(k * 64), IDESC, (it > 0 || k > 0) ? 1u : 0u);
+      }
+      tcgen05_commit<1>(bar_free + 8 * s);
+      if (it == n_my - 1) tcgen05_commit<1>(bar_done);
+    }
+  }
+  __syncwarp();
+  if (n_my > 0) {
+    mbar_wait(bar_done, 0);
+    tcgen05_fence_after();
+    // M = 64 accumulator: row co sits in lane (co % 16) + 32 * (co / 16); column 96 kh + 32 kw + ci
+    const int co = (int)warp * 16 + (int)lane;
+#pragma unroll
+    for (int h = 0; h < 9; ++h) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((warp * 32u) << 16) + 32 * h, v);
+      if (lane < 16) {
+        const int kh = h / 3, kw = h % 3;
+#pragma unroll
+        for (int ci = 0; ci < 32; ++ci) atomicAdd(p.dw + ((co * CIN + ci) * 3 + kh) * 3 + kw, __uint_as_float(v[ci]));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 }  // namespace
 
 namespace avdn {
@@ -283,7 +384,42 @@ int conv3_halo_dgrad(const void* dz, const void* wd, void* dx, int N, int H, int
   return launch<64, 32, true, false, 1>(dz, wd, dx, N, H, W, nullptr, s);
 }
 
+int conv3_halo_wgrad(const void* dz, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, cudaStream_t s) {
+  if (!conv3_halo_supported(H, W, Cin, Cout))
+    return set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo wgrad: shape %dx%d, %d -> %d channels not covered", H, W, Cin, Cout);
+  WgParams p;
+  const int64_t dx[4] = {Cin, W, H, N}, sx[4] = {1, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin};
+  const int32_t bx[4] = {Cin, TW, TH + 2, 1};
+  const int64_t dd[4] = {Cout, W, H, N}, sd[4] = {1, Cout, (int64_t)W * Cout, (int64_t)H * W * Cout};
+  const int32_t bd[4] = {Cout, TW, TH, 1};
+  int r = encode_tensor_map_4d(x, 2, dx, sx, bx, &p.tmX);
+  if (!r) r = encode_tensor_map_4d(dz, 2, dd, sd, bd, &p.tmDz);
+  if (r) return r;
+  p.tiles_x = W / TW;
+  p.tiles_y = H / TH;
+  const long long nt = (long long)N * p.tiles_x * p.tiles_y;
+  if (nt >= (1ll << 31)) return set_err(AVDN_ERR_UNSUPPORTED, "conv3_halo wgrad: too many tiles");
+  p.n_tiles = (int32_t)nt;
+  p.dw = dw;
+  const int smem = WG_STAGES * (3 * (TH + 2) * 8 * 64 + 128 * 128) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv3_halo_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return check_launch("conv3_halo wgrad smem attribute");
+    attr = true;
+  }
+  const long long cap = sm_count();
+  conv3_halo_wgrad_kernel<<<(unsigned)(nt < cap ? nt : cap), THREADS, smem, s>>>(p);
+  return check_launch("conv3_halo_wgrad_kernel");
+}
+
 }  // namespace avdn
+
+extern "C" int avdn_conv3x3_thin_wgrad(const void* dz, const void* x_nhwc, float* dw, int N, int H, int W, int Cin,
+                                       int Cout, avdn_stream_t stream) {
+  AVDN_REQUIRE(dz && x_nhwc && dw && N > 0, "avdn_conv3x3_thin_wgrad: bad argument");
+  return avdn::conv3_halo_wgrad(dz, x_nhwc, dw, N, H, W, Cin, Cout, avdn::to_cuda(stream));
+}
 
 extern "C" int avdn_conv3x3_thin_fwd(const void* x_nhwc, const void* w_f, void* z, int N, int H, int W, int Cin,
                                      int Cout, double* stats, avdn_stream_t stream) {

@@ -17,4 +17,6 @@ int conv3_halo_fwd(const void* x, const void* wf, void* z, int N, int H, int W, 
 bool conv3_halo_dgrad_supported(int H, int W, int Cin, int Cout);
 int conv3_halo_dgrad(const void* dz, const void* wd, void* dx, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
 
+int conv3_halo_wgrad(const void* dz, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, cudaStream_t s);
+
 }  // namespace avdn

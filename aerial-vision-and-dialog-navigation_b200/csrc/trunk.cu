@@ -408,6 +408,7 @@ __device__ __forceinline__ void unpack_tiles(const avdn_conv_item& it, float (*t
 __global__ void __launch_bounds__(256) unpack_conv_wgrads_kernel(const avdn_conv_item* __restrict__ items) {
   __shared__ float tile[9][32][33];
   const avdn_conv_item it = items[blockIdx.y];
+  if (it.dwf == nullptr) return;       // this block's weight gradient was accumulated into grad directly
   if (it.pairs) {
     unpack_conv_wgrad_pairs_body(it.dwf, it.Cout, it.Cin, it.k, it.stride, it.Cout_p, it.Cin_p, it.grad);
     return;

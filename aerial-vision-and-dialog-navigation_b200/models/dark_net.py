@@ -138,7 +138,7 @@ class _Engine:
                 L.src = cur["layer"]           # producing layer of the input (None = image)
                 L.res = None                   # residual source layer (fused shortcut)
                 L.first = len(self.layers) == 0
-                L.halo = L.halo_dgrad = False
+                L.halo = L.halo_dgrad = L.halo_wgrad = False
                 if L.first and not (L.Cin == 3 and L.Cout == 32 and k == 3 and s == 1):
                     raise NotImplementedError("first layer must be the 3->32 3x3 stride-1 conv of yolov3")
                 L.R = N * L.Hout * L.Wout
@@ -223,6 +223,8 @@ class _Engine:
                 it.w = net.module_list[L.idx][0].weight.data_ptr()
                 it.wf, it.wd = L.wf.data_ptr(), L.wd.data_ptr()
                 it.dwf, it.grad = sig[i][1] or None, sig[i][2] or None
+                if getattr(L, "halo_wgrad", False):
+                    it.dwf = None           # its weight gradient goes straight into grad (avdn_conv3x3_thin_wgrad)
                 it.Cout, it.Cin, it.k, it.stride = L.Cout, L.Cin, L.k, L.s
                 it.Cout_p, it.Cin_p = L.Cout_p, L.Cin_p
                 it.pairs = 1 if getattr(L, "pairs", False) else 0
@@ -321,6 +323,7 @@ class _Engine:
             L.p_dgrad = G.plan_conv_dgrad(dz, L.wd, L.src.g, N=self.N, H=L.Hin, W=L.Win, Cin=L.Cin_p,
                                           Cout=L.Cout_p, k=L.k, stride=L.s, accumulate=acc, flops=L.flops, bnb=bnb)
             L.halo_dgrad = bool(getattr(L, "halo", False) and acc == 0 and bnb is None)     # overwrite only
+            L.halo_wgrad = bool(getattr(L, "halo", False))
             seen_as_input.add(id(L.src))
             if L.res is not None:
                 seen_as_input.add(id(L.res))
@@ -447,11 +450,17 @@ def _layer_backward(eng, L, unpack=True, zero=True):
     if L.first:
         call("avdn_conv0_wgrad", ptr(L.dz), ptr(eng.x_in), ptr(L.dw), eng.N, L.Hin, L.Win)
         return n + 1
-    if zero:
-        L.dwf.zero_()
+    if L.halo_wgrad:
+        call("avdn_conv3x3_thin_wgrad", ptr(L.dz), ptr(L.src.a), ptr(L.dw), eng.N, L.Hin, L.Win, L.Cin_p, L.Cout_p,
+             flops=L.flops)
         n += 1
-    L.p_wgrad.run()
-    n += 1
+        unpack = False
+    else:
+        if zero:
+            L.dwf.zero_()
+            n += 1
+        L.p_wgrad.run()
+        n += 1
     if unpack:
         if L.pairs:
             call("avdn_unpack_conv_wgrad_pairs", ptr(L.dwf), L.Cout, L.Cin, L.k, L.s, L.Cout_p, L.Cin_p, ptr(L.dw))

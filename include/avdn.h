@@ -291,6 +291,9 @@ int avdn_conv3x3_thin_supported(int H, int W, int Cin, int Cout);
  * filters, w_d [Cin, 9*Cout] bf16 (avdn_pack_conv_weights' second output).  Overwrites dx.  Same shapes.       */
 int avdn_conv3x3_thin_dgrad(const void* dz, const void* w_d, void* dx, int N, int H, int W, int Cin, int Cout,
                             avdn_stream_t stream);
+/* Weight gradient of the same layer: dw [Cout,Cin,3,3] fp32 (nn.Conv2d layout) += sum over pixels dz * x.       */
+int avdn_conv3x3_thin_wgrad(const void* dz, const void* x_nhwc, float* dw, int N, int H, int W, int Cin, int Cout,
+                            avdn_stream_t stream);
 
 /* nn.BatchNorm2d in train mode (dark_net.py:31; eps 1e-5, momentum 0.1): batch
  * statistics of z [R,C] bf16 -> per-channel affine scale = gamma*rstd,
@@ -348,7 +351,7 @@ typedef struct avdn_conv_item {
   const float* w;   /* [Cout,Cin,k,k] fp32 master weight (pack) */
   void* wf;         /* bf16 [Cout_p][k*k][Cin_p] (pack) */
   void* wd;         /* bf16 [Cin_p][k*k][Cout_p] (pack) */
-  const float* dwf; /* WGRAD output (unpack) */
+  const float* dwf; /* WGRAD output (unpack); NULL: the entry is skipped by avdn_unpack_conv_wgrads */
   float* grad;      /* [Cout,Cin,k,k] fp32 gradient, accumulated (unpack) */
   int32_t Cout, Cin, k, stride, Cout_p, Cin_p;
   int32_t pairs;    /* 1: dwf is in the pixel-pair layout of avdn_unpack_conv_wgrad_pairs */

@@ -263,3 +263,23 @@ def test_conv3x3_thin_halo_dgrad_matches_implicit_gemm(built_lib, N, H, W):
     d = (dx.float() - ref).abs()
     assert (d <= 2.0 ** -7 * ref.abs() + 2e-3).all(), d.max()
     assert (dx != dx_ref).float().mean() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,W", [(1, 16, 8), (2, 32, 24), (2, 112, 112)])
+def test_conv3x3_thin_halo_wgrad_vs_torch(built_lib, N, H, W):
+    """avdn_conv3x3_thin_wgrad (pixels as K: the dz tile and the three horizontal-tap boxes of x read MN-major, the boxes
+    as ONE N = 96 operand, three accumulators alive for the whole kernel) against fp32 torch autograd; accumulates."""
+    from avdn_b200 import _lib
+    call, ptr = _lib.call, _lib.ptr
+    Cin, Cout = 32, 64
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    dz = torch.randn(N, H, W, Cout, device="cuda", generator=g).bfloat16()
+    dw = torch.full((Cout, Cin, 3, 3), 0.5, device="cuda")
+    call("avdn_conv3x3_thin_wgrad", ptr(dz), ptr(x), ptr(dw), N, H, W, Cin, Cout)
+    torch.cuda.synchronize()
+    wt = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+    torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=1).backward(dz.float().permute(0, 3, 1, 2))
+    err = ((dw - 0.5 - wt.grad).norm() / wt.grad.norm()).item()
+    assert err < 2e-3, err

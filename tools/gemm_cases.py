@@ -71,3 +71,22 @@ for name, fn in (("L3 dgrad implicit GEMM", run_g), ("L3 dgrad halo tiles", run_
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     print(f"{name}: {e0.elapsed_time(e1):.3f} ms  {fl / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
+
+# and its weight gradient: pixel-pair implicit GEMM vs halo tiles
+dwf = torch.zeros(2 * 64, 3 * 3 * 2 * 32, device=dev)          # the pixel-pair layout of the engine (dwf_shape)
+try:
+    pw = G2.plan_conv_wgrad_pairs(dzt, x, dwf, N=N, H=112, W=112, Cin=32, Cout=64, k=3, stride=1)
+    run_wg = pw.run
+except Exception as e:          # layout of the pair buffer is the engine's business; time the halo kernel alone then
+    print("pair-wgrad plan not built here:", e); run_wg = None
+dwt = torch.zeros(64, 32, 3, 3, device=dev)
+run_wh = lambda: _lib.call("avdn_conv3x3_thin_wgrad", _lib.ptr(dzt), _lib.ptr(x), _lib.ptr(dwt), N, 112, 112, 32, 64)
+for name, fn in (("L3 wgrad pixel-pair implicit GEMM", run_wg), ("L3 wgrad halo tiles", run_wh)):
+    if fn is None:
+        continue
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    print(f"{name}: {e0.elapsed_time(e1):.3f} ms  {fl / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
