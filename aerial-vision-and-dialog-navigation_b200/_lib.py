@@ -60,6 +60,7 @@ _SIGNATURES = {
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "avdn_bn_eval_coeffs": [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_f32, c_void_p, c_void_p,
                             c_void_p],
+    "avdn_bn_set_order": [c_int],
     "avdn_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_f32, c_void_p],
     "avdn_bn_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_f32,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

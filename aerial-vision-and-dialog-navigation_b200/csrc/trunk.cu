@@ -48,14 +48,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const uint4* __re
                                                                const float* __restrict__ scale,
                                                                const float* __restrict__ shift,
                                                                const float* __restrict__ mean, float slope,
-                                                               long long n8, int C, double* __restrict__ sums) {
+                                                               long long n8, int C, double* __restrict__ sums,
+                                                               int rev) {
   avdn_pdl_trigger();
   avdn_pdl_wait();
   extern __shared__ float sred[];           // [2][RY][C]
   const int C8 = C >> 3;
   const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
   const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8 (host guarantees)
-  const int cx = (int)(tid % C8);
+  // rev: walk the tensor back to front (element n8-1-k instead of k; n8 is a multiple of C8, so the
+  // thread's channel group becomes C8-1-cx) -- see bn_order() below
+  const int cx = rev ? C8 - 1 - (int)(tid % C8) : (int)(tid % C8);
+  const long long last = n8 - 1;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
@@ -70,8 +74,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const uint4* __re
     for (int u = 0; u < BN_UNROLL; ++u) {
       const long long k = i + u * stride;
       if (k < n8) {
-        zv[u] = __ldg(z + k);
-        if (BWD) gv[u] = __ldg(da + k);
+        const long long kk = rev ? last - k : k;
+        zv[u] = __ldg(z + kk);
+        if (BWD) gv[u] = __ldg(da + kk);
       }
     }
 #pragma unroll
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const uint4* __re
   const int RY = BN_THREADS / C8, ry = threadIdx.x / C8;
   float* a1 = sred;
   float* a2 = sred + RY * C;
-  // note: threadIdx.x % C8 == cx because BN_THREADS % C8 == 0
+  // note: threadIdx.x % C8 == cx (C8-1-cx when rev) because BN_THREADS % C8 == 0: a bijection per row lane either way
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a1[ry * C + cx * 8 + j] = s1[j]; a2[ry * C + cx * 8 + j] = s2[j]; }
   __syncthreads();
@@ -157,12 +162,13 @@ __global__ void bn_eval_coeffs_kernel(int C, int C_real, const float* __restrict
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               const uint4* __restrict__ residual, uint4* __restrict__ a,
-                                                              long long n8, int C8, float slope) {
+                                                              long long n8, int C8, float slope, int rev) {
   avdn_pdl_trigger();
   avdn_pdl_wait();
   const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
   const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8
-  const int cx = (int)(tid % C8);
+  const int cx = rev ? C8 - 1 - (int)(tid % C8) : (int)(tid % C8);
+  const long long last = n8 - 1;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = scale[cx * 8 + j]; sh[j] = shift[cx * 8 + j]; }
@@ -173,8 +179,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4* __res
     for (int u = 0; u < BN_UNROLL; ++u) {
       const long long k = i + u * stride;
       if (k < n8) {
-        zv[u] = __ldg(z + k);
-        if (has_res) rv[u] = __ldg(residual + k);
+        const long long kk = rev ? last - k : k;
+        zv[u] = __ldg(z + kk);
+        if (has_res) rv[u] = __ldg(residual + kk);
       }
     }
 #pragma unroll
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4* __res
           y = y > 0.f ? y : y * slope;
           f[j] = has_res ? y + r[j] : y;
         }
-        a[k] = pack8(f);
+        a[rev ? last - k : k] = pack8(f);
       }
     }
   }
@@ -224,13 +231,14 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double invR,
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ z,
                                                                   const float* __restrict__ coef,
                                                                   uint4* __restrict__ dz, long long n8, int C,
-                                                                  float slope) {
+                                                                  float slope, int rev) {
   avdn_pdl_trigger();
   avdn_pdl_wait();
   const int C8 = C >> 3;
   const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
   const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8
-  const int cx = (int)(tid % C8);
+  const int cx = rev ? C8 - 1 - (int)(tid % C8) : (int)(tid % C8);
+  const long long last = n8 - 1;
   float sc[8], sh[8], cA[8], cB[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -242,7 +250,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* _
 #pragma unroll
     for (int u = 0; u < BN_UNROLL; ++u) {
       const long long k = i + u * stride;
-      if (k < n8) { zv[u] = __ldg(z + k); gv[u] = __ldg(da + k); }
+      if (k < n8) {
+        const long long kk = rev ? last - k : k;
+        zv[u] = __ldg(z + kk);
+        gv[u] = __ldg(da + kk);
+      }
     }
 #pragma unroll
     for (int u = 0; u < BN_UNROLL; ++u) {
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* _
           const float gg = y > 0.f ? g[j] : g[j] * slope;
           f[j] = fmaf(sc[j], gg, fmaf(cA[j], f[j], cB[j]));
         }
-        dz[k] = pack8(f);
+        dz[rev ? last - k : k] = pack8(f);
       }
     }
   }
@@ -454,11 +466,43 @@ inline int grid_for(long long n, int block = 256, int waves = 8) {
 // ===================================================================== C ABI
 // grid of BN_THREADS-wide blocks whose total thread count is a multiple of C/8 (so that every
 // thread keeps its channel group) and that fills the machine without exceeding the work
+//
+// Traversal order (avdn_bn_set_order / AVDN_BN_ORDER, a bit mask, default 0 = every pass front to back in a
+// multi-wave grid).  The producer of a tensor leaves its TAIL in L2 (the convolutions walk their tiles front to
+// back) and the consumer of the pass's output starts at its HEAD, so a pass that walks back to front can take its
+// first ~L2-size bytes from L2 and leave the head of what it writes there:
+//   1 = forward apply back to front      2 = backward reduce back to front      4 = backward apply back to front
+//   8 = one-wave grids (co-resident CTAs only, so that the grid-stride sweep is monotone in time; implied by 1|2|4)
+static int& bn_order_flag() {
+  static int flag = [] {
+    const char* e = getenv("AVDN_BN_ORDER");
+    return e ? atoi(e) & 15 : 0;
+  }();
+  return flag;
+}
+extern "C" int avdn_bn_set_order(int mask) {
+  int& f = bn_order_flag();
+  const int old = f;
+  if (mask >= 0) f = mask & 15;
+  return old;
+}
+template <typename K>
+static int bn_resident_per_sm(K kernel, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, BN_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
 static int bn_grid(long long n8, int waves) {
   long long blocks = (n8 + (long long)BN_THREADS * BN_UNROLL - 1) / ((long long)BN_THREADS * BN_UNROLL);
   const long long cap = (long long)avdn::sm_count() * waves;
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
+}
+
+static int bn_bwd_apply_grid(long long n8) {
+  if (!bn_order_flag()) return bn_grid(n8, 16);
+  static const int occ = bn_resident_per_sm(bn_bwd_apply_kernel, 0);
+  return bn_grid(n8, occ);
 }
 
 static int bn_reduce_launch(bool bwd, const void* z, const void* da, const float* scale, const float* shift,
@@ -468,15 +512,22 @@ static int bn_reduce_launch(bool bwd, const void* z, const void* da, const float
   const int C8 = C / 8;
   const int RY = BN_THREADS / C8;
   const long long n8 = R * C8;
-  const int blocks = bn_grid(n8, 8);
   const size_t smem = (size_t)2 * RY * C * sizeof(float);      // = 2 * 256 * 8 * 4 = 16 KB
+  const int order = bn_order_flag();
+  const int rev = bwd && (order & 2) ? 1 : 0;
+  int waves = 8;
+  if (order && bwd) {      // the forward statistics (not on the training path: the convolutions produce them) keep their grid
+    static const int occ_b = bn_resident_per_sm(bn_reduce_kernel<true>, 16384);
+    waves = occ_b;
+  }
+  const int blocks = bn_grid(n8, waves);
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s) != cudaSuccess) return avdn::check_launch("bn reduce memset");
   if (bwd)
     avdn::launch_pdl(bn_reduce_kernel<true>, dim3(blocks), dim3(BN_THREADS), smem, s, reinterpret_cast<const uint4*>(z),
-                     reinterpret_cast<const uint4*>(da), scale, shift, mean, slope, n8, C, sums);
+                     reinterpret_cast<const uint4*>(da), scale, shift, mean, slope, n8, C, sums, rev);
   else
     avdn::launch_pdl(bn_reduce_kernel<false>, dim3(blocks), dim3(BN_THREADS), smem, s, reinterpret_cast<const uint4*>(z),
-                     nullptr, nullptr, nullptr, nullptr, slope, n8, C, sums);
+                     nullptr, nullptr, nullptr, nullptr, slope, n8, C, sums, 0);
   return avdn::check_launch("bn_reduce_kernel");
 }
 
@@ -516,9 +567,15 @@ extern "C" int avdn_bn_apply(const void* z, const float* scale, const float* shi
   AVDN_REQUIRE(z && scale && shift && a && R > 0 && C % 8 == 0 && BN_THREADS % (C / 8) == 0,
                "avdn_bn_apply: bad argument (C=%d)", C);
   const long long n8 = R * (C / 8);
-  avdn::launch_pdl(bn_apply_kernel, dim3(bn_grid(n8, 16)), dim3(BN_THREADS), 0, avdn::to_cuda(stream),
+  const int order = bn_order_flag();
+  int waves = 16;
+  if (order) {
+    static const int occ = bn_resident_per_sm(bn_apply_kernel, 0);
+    waves = occ;
+  }
+  avdn::launch_pdl(bn_apply_kernel, dim3(bn_grid(n8, waves)), dim3(BN_THREADS), 0, avdn::to_cuda(stream),
                    reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<const uint4*>(residual),
-                   reinterpret_cast<uint4*>(a), n8, C / 8, slope);
+                   reinterpret_cast<uint4*>(a), n8, C / 8, slope, order & 1);
   return avdn::check_launch("avdn_bn_apply");
 }
 
@@ -535,8 +592,9 @@ extern "C" int avdn_bn_backward(const void* da, const void* z, const float* scal
   r = avdn::check_launch("bn_bwd_coef_kernel");
   if (r) return r;
   const long long n8 = R * (C / 8);
-  avdn::launch_pdl(bn_bwd_apply_kernel, dim3(bn_grid(n8, 16)), dim3(BN_THREADS), 0, s, reinterpret_cast<const uint4*>(da),
-                   reinterpret_cast<const uint4*>(z), coef, reinterpret_cast<uint4*>(dz), n8, C, slope);
+  avdn::launch_pdl(bn_bwd_apply_kernel, dim3(bn_bwd_apply_grid(n8)), dim3(BN_THREADS), 0, s,
+                   reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(z), coef,
+                   reinterpret_cast<uint4*>(dz), n8, C, slope, (bn_order_flag() & 4) ? 1 : 0);
   return avdn::check_launch("bn_bwd_apply_kernel");
 }
 
@@ -554,8 +612,9 @@ extern "C" int avdn_bn_backward_apply(const void* da, const void* z, const float
   int r = avdn::check_launch("bn_bwd_coef_kernel");
   if (r) return r;
   const long long n8 = R * (C / 8);
-  avdn::launch_pdl(bn_bwd_apply_kernel, dim3(bn_grid(n8, 16)), dim3(BN_THREADS), 0, s, reinterpret_cast<const uint4*>(da),
-                   reinterpret_cast<const uint4*>(z), coef, reinterpret_cast<uint4*>(dz), n8, C, slope);
+  avdn::launch_pdl(bn_bwd_apply_kernel, dim3(bn_bwd_apply_grid(n8)), dim3(BN_THREADS), 0, s,
+                   reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(z), coef,
+                   reinterpret_cast<uint4*>(dz), n8, C, slope, (bn_order_flag() & 4) ? 1 : 0);
   return avdn::check_launch("bn_bwd_apply_kernel");
 }
 

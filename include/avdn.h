@@ -330,6 +330,13 @@ int avdn_bn_backward_apply(const void* da, const void* z, const float* scale, co
                            const double* sums, float* coef, void* dz, float* dgamma, float* dbeta,
                            avdn_stream_t stream);
 
+/* Traversal order of the three elementwise BatchNorm passes (a tuning knob, results are the same sums in another
+ * order): bit 0 = avdn_bn_apply walks the tensor back to front, bit 1 = the reduction of avdn_bn_backward does,
+ * bit 2 = its apply pass does, bit 3 = one-wave grids (implied by the others).  A producer leaves the tail of its
+ * output in L2 and a consumer starts at the head.  AVDN_BN_ORDER in the environment sets the initial value
+ * (default 0); the argument -1 only queries.  Returns the previous setting.                                    */
+int avdn_bn_set_order(int mask);
+
 /* nn.Conv2d weight [Cout,Cin,k,k] fp32 -> GEMM operands (bf16, zero padded):
  * wf [Cout_p][k*k][Cin_p] (forward / wgrad layout), wd [Cin_p][k*k][Cout_p] (dgrad). */
 int avdn_pack_conv_weight(const float* w, int Cout, int Cin, int k, int Cout_p, int Cin_p, void* wf, void* wd,

@@ -475,3 +475,65 @@ def test_conv0_tensor_path_vs_torch_fp64(built_lib, N, H, W):
         assert _rel2(dw, dw_ref.float()) < 1e-2, _rel2(dw, dw_ref.float())
     finally:
         h.avdn_conv0_set_tensor_path(old)
+
+
+@pytest.mark.parametrize("R,C,res", [(640 * 49, 1024, True), (3 * 56 * 56 + 5, 64, False), (2 * 7 * 7, 512, True),
+                                     (1000003, 32, False), (37, 2048, True)])
+def test_bn_traversal_orders(built_lib, R, C, res):
+    """avdn_bn_set_order: walking the tensor back to front / in one-wave grids changes only the ORDER of the sums.
+    The elementwise outputs (activation; dz for identical coefficients) are bit-identical to the default order, the
+    per-channel reductions (dgamma, dbeta) agree to fp32 summation noise, and against a torch fp64 restatement of
+    BatchNorm + LeakyReLU(0.01) (+ shortcut) backward within the bf16 storage error.  Shapes: whole tensors smaller
+    than one grid, ragged tails, every channel-group width from 4 to 256."""
+    from avdn_b200 import _lib
+    call, ptr = _lib.call, _lib.ptr
+    h = _lib.lib()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(R % 1000 + C)
+    z = (torch.randn(R, C, device=dev, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    da = torch.randn(R, C, device=dev, generator=g).to(torch.bfloat16)
+    r = torch.randn(R, C, device=dev, generator=g).to(torch.bfloat16) if res else None
+    gamma = torch.rand(C, device=dev, generator=g) + 0.5
+    beta = torch.randn(C, device=dev, generator=g) * 0.2
+    f32, f64 = torch.float32, torch.float64
+
+    def run(mask):
+        old = h.avdn_bn_set_order(mask)
+        try:
+            assert h.avdn_bn_set_order(-1) == mask
+            sums = torch.zeros(4 * C, dtype=f64, device=dev)
+            sc, sh, mu, rs = [torch.zeros(C, dtype=f32, device=dev) for _ in range(4)]
+            call("avdn_bn_stats", ptr(z), R, C, C, ptr(gamma), ptr(beta), None, None, 0.1, 1e-5, ptr(sums), ptr(sc),
+                 ptr(sh), ptr(mu), ptr(rs))
+            a = torch.empty_like(z)
+            call("avdn_bn_apply", ptr(z), ptr(sc), ptr(sh), ptr(r), ptr(a), R, C, 0.01)
+            dz = torch.empty_like(z)
+            dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+            call("avdn_bn_backward", ptr(da), ptr(z), ptr(sc), ptr(sh), ptr(mu), ptr(rs), R, C, C, 0.01, ptr(sums),
+                 ptr(dz), ptr(dg), ptr(db))
+            torch.cuda.synchronize()
+            return a, dz, dg, db, sc, sh
+        finally:
+            h.avdn_bn_set_order(old)
+
+    a0, dz0, dg0, db0, sc0, sh0 = run(0)
+    # fp64 restatement on the stored (bf16) z
+    zd = z.double()
+    m, v = zd.mean(0), zd.var(0, unbiased=False)
+    rstd = (v + 1e-5).rsqrt()
+    y = (zd - m) * rstd * gamma.double() + beta.double()
+    a_ref = torch.where(y > 0, y, 0.01 * y) + (r.double() if res else 0)
+    gg = da.double() * torch.where(y > 0, 1.0, 0.01)
+    db_ref, dg_ref = gg.sum(0), (gg * (zd - m) * rstd).sum(0)
+    dz_ref = gamma.double() * rstd * (gg - db_ref / R - (zd - m) * rstd * dg_ref / R)
+    assert _rel(a0, a_ref.float()) < 1e-2
+    assert _rel(dz0, dz_ref.float()) < 1e-2
+    assert _rel(db0, db_ref.float()) < 1e-3 and _rel(dg0, dg_ref.float()) < 1e-3
+    for mask in (8, 1, 2, 4, 9, 11, 13, 15):
+        a, dz, dg, db, sc, sh = run(mask)
+        assert torch.equal(sc, sc0) and torch.equal(sh, sh0), f"order {mask}: forward statistics changed"
+        assert torch.equal(a, a0), f"order {mask}: activation differs"
+        assert _rel(dg, dg0) < 1e-5 and _rel(db, db0) < 1e-5, f"order {mask}: reductions differ"
+        # dz depends on the reductions through two fp32 coefficients per channel: one bf16 step at most
+        assert (dz.float() - dz0.float()).abs().max().item() <= 2.0 ** -7 * dz0.float().abs().max().item(), mask
+        assert _rel(dz, dz_ref.float()) < 1e-2
