@@ -467,16 +467,22 @@ inline int grid_for(long long n, int block = 256, int waves = 8) {
 // grid of BN_THREADS-wide blocks whose total thread count is a multiple of C/8 (so that every
 // thread keeps its channel group) and that fills the machine without exceeding the work
 //
-// Traversal order (avdn_bn_set_order / AVDN_BN_ORDER, a bit mask, default 0 = every pass front to back in a
-// multi-wave grid).  The producer of a tensor leaves its TAIL in L2 (the convolutions walk their tiles front to
-// back) and the consumer of the pass's output starts at its HEAD, so a pass that walks back to front can take its
-// first ~L2-size bytes from L2 and leave the head of what it writes there:
+// Traversal order (avdn_bn_set_order / AVDN_BN_ORDER, a bit mask; 0 = every pass front to back in a multi-wave
+// grid, the round-1 behaviour).  Measured inside the config-2 training step on one B200 (tools/bn_order_ab.py,
+// profiles/r02_bn_order_ab.txt): one-wave grids (only co-resident CTAs, each thread looping over the tensor) take the
+// step's BatchNorm calls from 16.5 to 14.8 ms -- the backward passes ran 16 waves of CTAs that each loaded their
+// per-channel coefficients for ONE batch of four loads.  Direction: the producer of a tensor leaves its TAIL in L2
+// (the convolutions walk their tiles front to back) and the consumer of the pass's output starts at its HEAD, so a
+// pass that walks back to front takes its first bytes from L2 and leaves the head of what it writes there; that is
+// worth little inside the BatchNorm calls themselves (14.8 -> 14.6..14.8 ms) and ~0.5-1 ms of the step in the
+// convolutions that follow a reversed forward apply.  Default 9.
 //   1 = forward apply back to front      2 = backward reduce back to front      4 = backward apply back to front
-//   8 = one-wave grids (co-resident CTAs only, so that the grid-stride sweep is monotone in time; implied by 1|2|4)
+//   8 = one-wave grids (so that the grid-stride sweep is monotone in time; implied by 1|2|4)
+constexpr int BN_ORDER_DEFAULT = 9;
 static int& bn_order_flag() {
   static int flag = [] {
     const char* e = getenv("AVDN_BN_ORDER");
-    return e ? atoi(e) & 15 : 0;
+    return e ? atoi(e) & 15 : BN_ORDER_DEFAULT;
   }();
   return flag;
 }

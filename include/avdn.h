@@ -334,7 +334,8 @@ int avdn_bn_backward_apply(const void* da, const void* z, const float* scale, co
  * order): bit 0 = avdn_bn_apply walks the tensor back to front, bit 1 = the reduction of avdn_bn_backward does,
  * bit 2 = its apply pass does, bit 3 = one-wave grids (implied by the others).  A producer leaves the tail of its
  * output in L2 and a consumer starts at the head.  AVDN_BN_ORDER in the environment sets the initial value
- * (default 0); the argument -1 only queries.  Returns the previous setting.                                    */
+ * (default 9; 0 = the multi-wave front-to-back grids of ABI <= 7); the argument -1 only queries.  Returns the
+ * previous setting.                                                                                            */
 int avdn_bn_set_order(int mask);
 
 /* nn.Conv2d weight [Cout,Cin,k,k] fp32 -> GEMM operands (bf16, zero padded):

@@ -1,7 +1,7 @@
 """Experiment: traversal order of the elementwise BatchNorm passes (avdn_bn_set_order, csrc/trunk.cu) inside the
 config-2 training step.  One process, one box: the masks are timed interleaved, twice, so that clock drift under the
 power cap shows up as the spread between the two rounds rather than as a difference between masks.
-Usage (GPU box): python tools/bn_order_ab.py [steps]"""
+Usage (GPU box): python tools/bn_order_ab.py [steps] [rounds] [mask,mask,...]"""
 import json
 import os
 import sys
@@ -14,7 +14,8 @@ from bench_train import TrainWorkload          # noqa: E402
 from avdn_b200 import _lib                     # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-MASKS = [0, 8, 9, 11, 13, 15, 10, 12]
+ROUNDS = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+MASKS = [int(m) for m in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 8, 9, 11, 13, 15, 10, 12]
 dev = torch.device("cuda", 0)
 wl = TrainWorkload(0, 1)
 wl.setup_gpu(dev)
@@ -46,7 +47,7 @@ def bn_ms():
 
 
 res = {m: [] for m in MASKS}
-for rnd in range(2):
+for rnd in range(ROUNDS):
     for m in MASKS:
         h.avdn_bn_set_order(m)
         wl.step()                               # one untimed step under the new order
