@@ -43,8 +43,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 constexpr int BN_THREADS = 256;
 constexpr int BN_UNROLL = 4;
 
-template <bool BWD>
-__global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da,
+template <bool BWD, int UNR = BN_UNROLL>
+__global__ void __launch_bounds__(BN_THREADS, UNR > 4 ? 2 : 0) bn_reduce_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da,
                                                                const float* __restrict__ scale,
                                                                const float* __restrict__ shift,
                                                                const float* __restrict__ mean, float slope,
@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const uint4* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = scale[cx * 8 + j]; sh[j] = shift[cx * 8 + j]; mu[j] = mean[cx * 8 + j]; }
   }
-  for (long long i = tid; i < n8; i += stride * BN_UNROLL) {
-    uint4 zv[BN_UNROLL], gv[BN_UNROLL];
+  for (long long i = tid; i < n8; i += stride * UNR) {
+    uint4 zv[UNR], gv[UNR];
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const long long k = i + u * stride;
       if (k < n8) {
         const long long kk = rev ? last - k : k;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const uint4* __re
       }
     }
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       if (i + u * stride < n8) {
         float f[8];
         unpack8(zv[u], f);
@@ -159,7 +159,8 @@ __global__ void bn_eval_coeffs_kernel(int C, int C_real, const float* __restrict
 }
 
 // a = leaky(z*scale + shift) (+ residual)
-__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
+template <int UNR>
+__global__ void __launch_bounds__(BN_THREADS, UNR > 4 ? 2 : 0) bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               const uint4* __restrict__ residual, uint4* __restrict__ a,
                                                               long long n8, int C8, float slope, int rev) {
@@ -173,10 +174,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4* __res
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = scale[cx * 8 + j]; sh[j] = shift[cx * 8 + j]; }
   const bool has_res = residual != nullptr;
-  for (long long i = tid; i < n8; i += stride * BN_UNROLL) {
-    uint4 zv[BN_UNROLL], rv[BN_UNROLL];
+  for (long long i = tid; i < n8; i += stride * UNR) {
+    uint4 zv[UNR], rv[UNR];
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const long long k = i + u * stride;
       if (k < n8) {
         const long long kk = rev ? last - k : k;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4* __res
       }
     }
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const long long k = i + u * stride;
       if (k < n8) {
         float f[8], r[8];
@@ -228,7 +229,8 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, double invR,
   }
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ z,
+template <int UNR>
+__global__ void __launch_bounds__(BN_THREADS, UNR > 4 ? 2 : 0) bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ z,
                                                                   const float* __restrict__ coef,
                                                                   uint4* __restrict__ dz, long long n8, int C,
                                                                   float slope, int rev) {
@@ -245,10 +247,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* _
     sc[j] = coef[cx * 8 + j]; sh[j] = coef[C + cx * 8 + j];
     cA[j] = coef[2 * C + cx * 8 + j]; cB[j] = coef[3 * C + cx * 8 + j];
   }
-  for (long long i = tid; i < n8; i += stride * BN_UNROLL) {
-    uint4 zv[BN_UNROLL], gv[BN_UNROLL];
+  for (long long i = tid; i < n8; i += stride * UNR) {
+    uint4 zv[UNR], gv[UNR];
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const long long k = i + u * stride;
       if (k < n8) {
         const long long kk = rev ? last - k : k;
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4* _
       }
     }
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const long long k = i + u * stride;
       if (k < n8) {
         float f[8], g[8];
@@ -478,18 +480,19 @@ inline int grid_for(long long n, int block = 256, int waves = 8) {
 // convolutions that follow a reversed forward apply.  Default 9.
 //   1 = forward apply back to front      2 = backward reduce back to front      4 = backward apply back to front
 //   8 = one-wave grids (so that the grid-stride sweep is monotone in time; implied by 1|2|4)
+//  16 = eight instead of four 16-byte loads per tensor in flight per thread (one-wave grids; <= 128 registers)
 constexpr int BN_ORDER_DEFAULT = 9;
 static int& bn_order_flag() {
   static int flag = [] {
     const char* e = getenv("AVDN_BN_ORDER");
-    return e ? atoi(e) & 15 : BN_ORDER_DEFAULT;
+    return e ? atoi(e) & 31 : BN_ORDER_DEFAULT;
   }();
   return flag;
 }
 extern "C" int avdn_bn_set_order(int mask) {
   int& f = bn_order_flag();
   const int old = f;
-  if (mask >= 0) f = mask & 15;
+  if (mask >= 0) f = mask & 31;
   return old;
 }
 template <typename K>
@@ -498,17 +501,32 @@ static int bn_resident_per_sm(K kernel, size_t smem) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, BN_THREADS, smem) != cudaSuccess || n < 1) n = 1;
   return n;
 }
-static int bn_grid(long long n8, int waves) {
-  long long blocks = (n8 + (long long)BN_THREADS * BN_UNROLL - 1) / ((long long)BN_THREADS * BN_UNROLL);
+static int bn_grid(long long n8, int waves, int unroll = BN_UNROLL) {
+  long long blocks = (n8 + (long long)BN_THREADS * unroll - 1) / ((long long)BN_THREADS * unroll);
   const long long cap = (long long)avdn::sm_count() * waves;
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
-static int bn_bwd_apply_grid(long long n8) {
-  if (!bn_order_flag()) return bn_grid(n8, 16);
-  static const int occ = bn_resident_per_sm(bn_bwd_apply_kernel, 0);
-  return bn_grid(n8, occ);
+static void bn_bwd_apply_launch(const void* da, const void* z, const float* coef, void* dz, long long n8, int C,
+                                float slope, cudaStream_t s) {
+  const int order = bn_order_flag();
+  const int rev = (order & 4) ? 1 : 0;
+  if (order & 16) {
+    static const int occ = bn_resident_per_sm(bn_bwd_apply_kernel<8>, 0);
+    avdn::launch_pdl(bn_bwd_apply_kernel<8>, dim3(bn_grid(n8, occ, 8)), dim3(BN_THREADS), 0, s,
+                     reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(z), coef,
+                     reinterpret_cast<uint4*>(dz), n8, C, slope, rev);
+    return;
+  }
+  int waves = 16;
+  if (order) {
+    static const int occ = bn_resident_per_sm(bn_bwd_apply_kernel<BN_UNROLL>, 0);
+    waves = occ;
+  }
+  avdn::launch_pdl(bn_bwd_apply_kernel<BN_UNROLL>, dim3(bn_grid(n8, waves)), dim3(BN_THREADS), 0, s,
+                   reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(z), coef,
+                   reinterpret_cast<uint4*>(dz), n8, C, slope, rev);
 }
 
 static int bn_reduce_launch(bool bwd, const void* z, const void* da, const float* scale, const float* shift,
@@ -528,7 +546,12 @@ static int bn_reduce_launch(bool bwd, const void* z, const void* da, const float
   }
   const int blocks = bn_grid(n8, waves);
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s) != cudaSuccess) return avdn::check_launch("bn reduce memset");
-  if (bwd)
+  if (bwd && (order & 16)) {
+    static const int occ8 = bn_resident_per_sm(bn_reduce_kernel<true, 8>, 16384);
+    avdn::launch_pdl(bn_reduce_kernel<true, 8>, dim3(bn_grid(n8, occ8, 8)), dim3(BN_THREADS), smem, s,
+                     reinterpret_cast<const uint4*>(z), reinterpret_cast<const uint4*>(da), scale, shift, mean, slope,
+                     n8, C, sums, rev);
+  } else if (bwd)
     avdn::launch_pdl(bn_reduce_kernel<true>, dim3(blocks), dim3(BN_THREADS), smem, s, reinterpret_cast<const uint4*>(z),
                      reinterpret_cast<const uint4*>(da), scale, shift, mean, slope, n8, C, sums, rev);
   else
@@ -574,12 +597,19 @@ extern "C" int avdn_bn_apply(const void* z, const float* scale, const float* shi
                "avdn_bn_apply: bad argument (C=%d)", C);
   const long long n8 = R * (C / 8);
   const int order = bn_order_flag();
+  if (order & 16) {
+    static const int occ8 = bn_resident_per_sm(bn_apply_kernel<8>, 0);
+    avdn::launch_pdl(bn_apply_kernel<8>, dim3(bn_grid(n8, occ8, 8)), dim3(BN_THREADS), 0, avdn::to_cuda(stream),
+                     reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<const uint4*>(residual),
+                     reinterpret_cast<uint4*>(a), n8, C / 8, slope, order & 1);
+    return avdn::check_launch("avdn_bn_apply");
+  }
   int waves = 16;
   if (order) {
-    static const int occ = bn_resident_per_sm(bn_apply_kernel, 0);
+    static const int occ = bn_resident_per_sm(bn_apply_kernel<BN_UNROLL>, 0);
     waves = occ;
   }
-  avdn::launch_pdl(bn_apply_kernel, dim3(bn_grid(n8, waves)), dim3(BN_THREADS), 0, avdn::to_cuda(stream),
+  avdn::launch_pdl(bn_apply_kernel<BN_UNROLL>, dim3(bn_grid(n8, waves)), dim3(BN_THREADS), 0, avdn::to_cuda(stream),
                    reinterpret_cast<const uint4*>(z), scale, shift, reinterpret_cast<const uint4*>(residual),
                    reinterpret_cast<uint4*>(a), n8, C / 8, slope, order & 1);
   return avdn::check_launch("avdn_bn_apply");
@@ -598,9 +628,7 @@ extern "C" int avdn_bn_backward(const void* da, const void* z, const float* scal
   r = avdn::check_launch("bn_bwd_coef_kernel");
   if (r) return r;
   const long long n8 = R * (C / 8);
-  avdn::launch_pdl(bn_bwd_apply_kernel, dim3(bn_bwd_apply_grid(n8)), dim3(BN_THREADS), 0, s,
-                   reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(z), coef,
-                   reinterpret_cast<uint4*>(dz), n8, C, slope, (bn_order_flag() & 4) ? 1 : 0);
+  bn_bwd_apply_launch(da, z, coef, dz, n8, C, slope, s);
   return avdn::check_launch("bn_bwd_apply_kernel");
 }
 
@@ -618,9 +646,7 @@ extern "C" int avdn_bn_backward_apply(const void* da, const void* z, const float
   int r = avdn::check_launch("bn_bwd_coef_kernel");
   if (r) return r;
   const long long n8 = R * (C / 8);
-  avdn::launch_pdl(bn_bwd_apply_kernel, dim3(bn_bwd_apply_grid(n8)), dim3(BN_THREADS), 0, s,
-                   reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(z), coef,
-                   reinterpret_cast<uint4*>(dz), n8, C, slope, (bn_order_flag() & 4) ? 1 : 0);
+  bn_bwd_apply_launch(da, z, coef, dz, n8, C, slope, s);
   return avdn::check_launch("bn_bwd_apply_kernel");
 }
 

@@ -332,7 +332,8 @@ int avdn_bn_backward_apply(const void* da, const void* z, const float* scale, co
 
 /* Traversal order of the three elementwise BatchNorm passes (a tuning knob, results are the same sums in another
  * order): bit 0 = avdn_bn_apply walks the tensor back to front, bit 1 = the reduction of avdn_bn_backward does,
- * bit 2 = its apply pass does, bit 3 = one-wave grids (implied by the others).  A producer leaves the tail of its
+ * bit 2 = its apply pass does, bit 3 = one-wave grids (implied by the others), bit 4 = eight instead of four
+ * 16-byte loads per tensor in flight per thread.  A producer leaves the tail of its
  * output in L2 and a consumer starts at the head.  AVDN_BN_ORDER in the environment sets the initial value
  * (default 9; 0 = the multi-wave front-to-back grids of ABI <= 7); the argument -1 only queries.  Returns the
  * previous setting.                                                                                            */

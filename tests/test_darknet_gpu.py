@@ -529,7 +529,7 @@ def test_bn_traversal_orders(built_lib, R, C, res):
     assert _rel(a0, a_ref.float()) < 1e-2
     assert _rel(dz0, dz_ref.float()) < 1e-2
     assert _rel(db0, db_ref.float()) < 1e-3 and _rel(dg0, dg_ref.float()) < 1e-3
-    for mask in (8, 1, 2, 4, 9, 11, 13, 15):
+    for mask in (8, 1, 2, 4, 9, 11, 13, 15, 16, 24, 25, 31):
         a, dz, dg, db, sc, sh = run(mask)
         assert torch.equal(sc, sc0) and torch.equal(sh, sh0), f"order {mask}: forward statistics changed"
         assert torch.equal(a, a0), f"order {mask}: activation differs"
