@@ -477,11 +477,12 @@ inline int grid_for(long long n, int block = 256, int waves = 8) {
 // (the convolutions walk their tiles front to back) and the consumer of the pass's output starts at its HEAD, so a
 // pass that walks back to front takes its first bytes from L2 and leaves the head of what it writes there; that is
 // worth little inside the BatchNorm calls themselves (14.8 -> 14.6..14.8 ms) and ~0.5-1 ms of the step in the
-// convolutions that follow a reversed forward apply.  Default 9.
+// convolutions that follow a reversed forward apply.  Eight loads per tensor in flight per thread (bit 16, two CTAs of
+// <= 128 registers per SM) take the backward passes from 9.97 to 9.4 ms.  Default 25 = 16 | 8 | 1.
 //   1 = forward apply back to front      2 = backward reduce back to front      4 = backward apply back to front
 //   8 = one-wave grids (so that the grid-stride sweep is monotone in time; implied by 1|2|4)
 //  16 = eight instead of four 16-byte loads per tensor in flight per thread (one-wave grids; <= 128 registers)
-constexpr int BN_ORDER_DEFAULT = 9;
+constexpr int BN_ORDER_DEFAULT = 25;
 static int& bn_order_flag() {
   static int flag = [] {
     const char* e = getenv("AVDN_BN_ORDER");

@@ -335,7 +335,7 @@ int avdn_bn_backward_apply(const void* da, const void* z, const float* scale, co
  * bit 2 = its apply pass does, bit 3 = one-wave grids (implied by the others), bit 4 = eight instead of four
  * 16-byte loads per tensor in flight per thread.  A producer leaves the tail of its
  * output in L2 and a consumer starts at the head.  AVDN_BN_ORDER in the environment sets the initial value
- * (default 9; 0 = the multi-wave front-to-back grids of ABI <= 7); the argument -1 only queries.  Returns the
+ * (default 25; 0 = the multi-wave front-to-back grids of ABI <= 7); the argument -1 only queries.  Returns the
  * previous setting.                                                                                            */
 int avdn_bn_set_order(int mask);
 
