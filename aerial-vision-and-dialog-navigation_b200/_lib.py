@@ -110,6 +110,7 @@ _SIGNATURES = {
     "avdn_heads_fwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 + [c_void_p],
     "avdn_heads_bwd": [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 18 + [c_void_p],
     # ---- config 5: ViT_LSTM step + simulator update
+    "avdn_lstm_set_kernels": [c_int],
     "avdn_linear_f32": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int,
                         c_void_p],
     "avdn_lstm_cell": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_int, c_int, c_void_p],

@@ -77,6 +77,84 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
     }
 }
 
+// Second version for the rollout's shapes (M = 256 episodes, N = 4..2304, K = 32..1536, everything K-contiguous and
+// 16-byte aligned): 32 x 64 output tile per 128-thread CTA (2-3x the CTAs of the 64 x 64 tiling on these skinny
+// problems), k-steps of 32, operands fetched as float4 along k into REGISTERS one k-step ahead of the FMAs (the first
+// version waited for every k-step's loads between two barriers: ~1 us per 16 k), shared-memory reads as float4.
+// Every output is the same chain of fmaf over ascending k as in linear_f32_kernel, so the two agree bit for bit.
+constexpr int L2_BM = 32, L2_BN = 64, L2_BK = 32, L2_THREADS = 128;
+
+__global__ void __launch_bounds__(L2_THREADS) linear_f32_v2_kernel(const float* __restrict__ x, long long ldx,
+                                                                   const float* __restrict__ w, long long ldw,
+                                                                   const float* __restrict__ b, float* __restrict__ y,
+                                                                   long long ldy, int M, int N, int K, int act,
+                                                                   int accumulate) {
+  __shared__ __align__(16) float sx[L2_BK][L2_BM + 4];
+  __shared__ __align__(16) float sw[L2_BK][L2_BN + 4];
+  const int m0 = blockIdx.y * L2_BM, n0 = blockIdx.x * L2_BN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;      // 16 x 8 threads, 4 x 4 outputs each
+  // global -> register mapping: float4 number idx of a tile = (row idx >> 3, k-chunk idx & 7): eight consecutive
+  // lanes read 128 contiguous bytes of one row
+  float4 rx[2], rw[4];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * L2_THREADS, r = idx >> 3, k = k0 + (idx & 7) * 4, m = m0 + r;
+      rx[j] = (m < M && k < K) ? __ldg(reinterpret_cast<const float4*>(x + (long long)m * ldx + k)) : zero4;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = tid + j * L2_THREADS, r = idx >> 3, k = k0 + (idx & 7) * 4, n = n0 + r;
+      rw[j] = (n < N && k < K) ? __ldg(reinterpret_cast<const float4*>(w + (long long)n * ldw + k)) : zero4;
+    }
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += L2_BK) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * L2_THREADS, r = idx >> 3, kk = (idx & 7) * 4;
+      sx[kk][r] = rx[j].x; sx[kk + 1][r] = rx[j].y; sx[kk + 2][r] = rx[j].z; sx[kk + 3][r] = rx[j].w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = tid + j * L2_THREADS, r = idx >> 3, kk = (idx & 7) * 4;
+      sw[kk][r] = rw[j].x; sw[kk + 1][r] = rw[j].y; sw[kk + 2][r] = rw[j].z; sw[kk + 3][r] = rw[j].w;
+    }
+    __syncthreads();
+    if (k0 + L2_BK < K) fetch(k0 + L2_BK);         // in flight under the FMAs below
+#pragma unroll
+    for (int kk = 0; kk < L2_BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&sx[kk][ty * 4]);
+      const float4 c4 = *reinterpret_cast<const float4*>(&sw[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, c[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) {
+        float v = acc[i][j] + (b ? b[n] : 0.f);
+        if (accumulate) v += y[(long long)m * ldy + n];
+        if (act == 1) v = fmaxf(v, 0.f);
+        else if (act == 2) v = tanhf(v);
+        y[(long long)m * ldy + n] = v;
+      }
+    }
+}
+
 // ------------------------------------------------------------------ lstm_cell
 // gates [B,4H] = W_ih x + b_ih + W_hh h + b_hh (order i,f,g,o); c_prev may be NULL (zero state).
 __global__ void lstm_cell_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
@@ -145,6 +223,89 @@ __global__ void __launch_bounds__(256) lang_attn_kernel(const float* __restrict_
     float a = 0.f;
     for (int l = 0; l < L; ++l) a = fmaf(s_s[l], c[(size_t)l * D + d], a);
     weighted[(size_t)b * ldw + d] = a;
+  }
+}
+
+// Second version: the same sums in the same order (bit-identical results), with the loads of four rows (scores) or of
+// four rows x up to four columns (weighted sum) issued before they are used -- the first version had one dependent
+// load -> fma chain per thread, 250 deep, three times over.
+template <int ND>      // ND = ceil(D / 256) <= 4
+__global__ void __launch_bounds__(256) lang_attn_v2_kernel(const float* __restrict__ ctx, const float* __restrict__ target,
+                                                           int L, int D, float* __restrict__ attn_out,
+                                                           float* __restrict__ weighted, long long ldw) {
+  extern __shared__ float sm[];            // [D] target, [L] scores
+  float* s_t = sm;
+  float* s_s = sm + D;
+  __shared__ float s_max, s_sum;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* c = ctx + (size_t)b * L * D;
+  for (int d = tid; d < D; d += 256) s_t[d] = target[(size_t)b * D + d];
+  __syncthreads();
+  for (int l0 = warp; l0 < L; l0 += 32) {          // rows l0, l0+8, l0+16, l0+24 of this warp at once
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = lane; d < D; d += 32) {
+      const float t = s_t[d];
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[r] = (l0 + 8 * r < L) ? __ldg(c + (size_t)(l0 + 8 * r) * D + d) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = fmaf(v[r], t, a[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float t = warp_sum(a[r]);
+      if (lane == 0 && l0 + 8 * r < L) s_s[l0 + 8 * r] = t;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int l = lane; l < L; l += 32) m = fmaxf(m, s_s[l]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) s += expf(s_s[l] - m);
+    s = warp_sum(s);
+    if (lane == 0) { s_max = m; s_sum = s; }
+  }
+  __syncthreads();
+  for (int l = tid; l < L; l += 256) {
+    const float a = expf(s_s[l] - s_max) / s_sum;
+    s_s[l] = a;
+    if (attn_out) attn_out[(size_t)b * L + l] = a;
+  }
+  __syncthreads();
+  float acc[ND];
+#pragma unroll
+  for (int q = 0; q < ND; ++q) acc[q] = 0.f;
+  int l = 0;
+  for (; l + 4 <= L; l += 4) {
+    float v[4][ND];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < ND; ++q) {
+        const int d = tid + q * 256;
+        v[r][q] = d < D ? __ldg(c + (size_t)(l + r) * D + d) : 0.f;
+      }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float p = s_s[l + r];
+#pragma unroll
+      for (int q = 0; q < ND; ++q) acc[q] = fmaf(p, v[r][q], acc[q]);
+    }
+  }
+  for (; l < L; ++l) {
+    const float p = s_s[l];
+#pragma unroll
+    for (int q = 0; q < ND; ++q) {
+      const int d = tid + q * 256;
+      if (d < D) acc[q] = fmaf(p, __ldg(c + (size_t)l * D + d), acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < ND; ++q) {
+    const int d = tid + q * 256;
+    if (d < D) weighted[(size_t)b * ldw + d] = acc[q];
   }
 }
 
@@ -261,10 +422,35 @@ __global__ void waypoint_step_kernel(const float* __restrict__ output, double* _
 }  // namespace
 
 // ===================================================================== C ABI
+// Which kernels serve avdn_linear_f32 / avdn_lang_attn_fwd: 2 = the register-prefetching versions (default), 1 = the
+// first versions (kept: unaligned / K % 4 != 0 linears always use them, and the tests compare the two bit for bit).
+// AVDN_LSTM_KERNELS in the environment sets the initial value; the argument 0 only queries.
+static int& lstm_kernels_version() {
+  static int v = [] {
+    const char* e = getenv("AVDN_LSTM_KERNELS");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return v;
+}
+extern "C" int avdn_lstm_set_kernels(int version) {
+  int& v = lstm_kernels_version();
+  const int old = v;
+  if (version == 1 || version == 2) v = version;
+  return old;
+}
+
 extern "C" int avdn_linear_f32(const float* x, long long ldx, const float* w, long long ldw, const float* b, float* y,
                                long long ldy, int M, int N, int K, int act, int accumulate, avdn_stream_t stream) {
   AVDN_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, "avdn_linear_f32: bad argument");
   AVDN_REQUIRE(act >= 0 && act <= 2, "avdn_linear_f32: act must be 0 (none), 1 (relu) or 2 (tanh)");
+  const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (ldw % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(w) % 16 == 0);
+  if (lstm_kernels_version() >= 2 && vec) {
+    dim3 grid((N + L2_BN - 1) / L2_BN, (M + L2_BM - 1) / L2_BM);
+    linear_f32_v2_kernel<<<grid, L2_THREADS, 0, avdn::to_cuda(stream)>>>(x, ldx, w, ldw, b, y, ldy, M, N, K, act,
+                                                                        accumulate);
+    return avdn::check_launch("avdn_linear_f32 (v2)");
+  }
   dim3 grid((N + LT - 1) / LT, (M + LT - 1) / LT);
   linear_f32_kernel<<<grid, 256, 0, avdn::to_cuda(stream)>>>(x, ldx, w, ldw, b, y, ldy, M, N, K, act, accumulate);
   return avdn::check_launch("avdn_linear_f32");
@@ -289,7 +475,18 @@ extern "C" int avdn_lang_attn_fwd(const float* ctx, const float* target, int B, 
   AVDN_REQUIRE(ctx && target && weighted && B > 0 && L > 0 && D > 0 && ldw >= D, "avdn_lang_attn_fwd: bad argument");
   const size_t smem = (size_t)(D + L) * sizeof(float);
   AVDN_REQUIRE(smem <= 48 * 1024, "avdn_lang_attn_fwd: D + L = %d too large", D + L);
-  lang_attn_kernel<<<B, 256, smem, avdn::to_cuda(stream)>>>(ctx, target, L, D, attn, weighted, ldw);
+  cudaStream_t s = avdn::to_cuda(stream);
+  const int nd = (D + 255) / 256;
+  if (lstm_kernels_version() >= 2 && nd <= 4) {
+    switch (nd) {
+      case 1: lang_attn_v2_kernel<1><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
+      case 2: lang_attn_v2_kernel<2><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
+      case 3: lang_attn_v2_kernel<3><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
+      default: lang_attn_v2_kernel<4><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
+    }
+    return avdn::check_launch("avdn_lang_attn_fwd (v2)");
+  }
+  lang_attn_kernel<<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw);
   return avdn::check_launch("avdn_lang_attn_fwd");
 }
 

@@ -592,6 +592,12 @@ int avdn_adamw(float* p, const float* g, float* m, float* v, long long n, float 
  * fp32 CUDA-core kernels: ~3 MFLOP per sample and step next to 15.3 GFLOP of trunk.
  * ---------------------------------------------------------------------- */
 
+/* Which kernels serve avdn_linear_f32 and avdn_lang_attn_fwd: 2 (default) = 32 x 64 tiles with the operands of the
+ * next k-step fetched into registers as float4 under the FMAs (used when K, ldx, ldw are multiples of 4 and x, w
+ * are 16-byte aligned) / four rows of loads in flight in the attention; 1 = the first versions.  Both give the same
+ * sums in the same order (bit-identical results).  AVDN_LSTM_KERNELS=1 in the environment selects version 1
+ * initially; any other argument than 1 or 2 only queries.  Returns the previous setting.                       */
+int avdn_lstm_set_kernels(int version);
 /* y[M,N] (+)= act(x[M,K] w[N,K]^T + b[N]); ld* are row pitches in elements;
  * act: 0 none, 1 ReLU, 2 tanh; b may be NULL.  nn.Linear / the two halves of
  * nn.LSTMCell's gate pre-activations (vln_model.py:178-204,224-236).           */

@@ -180,3 +180,70 @@ def test_greedy_rollout_on_device_vs_oracle_pipeline(agent):
     assert eh[T - 1].all()
     traj = agent.trajectories(res)
     assert len(traj) == B and all(len(p) >= 1 for p in traj)
+
+
+@pytest.mark.parametrize("M,N,K,act,acc,pitch", [
+    (256, 2304, 576, 0, 1, 0), (256, 768, 1536, 2, 0, 0), (256, 768, 768, 1, 0, 768), (256, 768, 192, 0, 1, 0),
+    (256, 4, 32, 0, 0, 0), (3, 64, 256, 1, 0, 0), (37, 70, 100, 0, 0, 4), (1, 1, 4, 2, 1, 0), (65, 129, 36, 1, 1, 8)])
+def test_linear_f32_v2_bit_identical_to_v1(built_lib, M, N, K, act, acc, pitch):
+    """avdn_lstm_set_kernels: the register-prefetching 32 x 64-tile linear accumulates every output over ascending k
+    with fmaf exactly as the first kernel does -> bit-identical results; both against torch float64 (1e-5).  Shapes:
+    the rollout's own (256 episodes; K-offset views of wider buffers), ragged tiles in M and N, K not a multiple of
+    the k-step, a single output."""
+    from avdn_b200 import _lib
+    call, ptr = _lib.call, _lib.ptr
+    h = _lib.lib()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(M * 131 + N * 7 + K)
+    xbuf = torch.randn(M, K + pitch, device=dev, generator=g)
+    x = xbuf[:, pitch:]                                   # a view whose rows start `pitch` floats into a wider buffer
+    w = torch.randn(N, K, device=dev, generator=g) / K ** 0.5
+    b = torch.randn(N, device=dev, generator=g)
+    y0 = torch.randn(M, N, device=dev, generator=g)
+
+    def run(version):
+        old = h.avdn_lstm_set_kernels(version)
+        try:
+            assert h.avdn_lstm_set_kernels(0) == version
+            y = y0.clone()
+            call("avdn_linear_f32", ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(b), ptr(y), y.stride(0), M, N, K,
+                 act, acc)
+            torch.cuda.synchronize()
+            return y
+        finally:
+            h.avdn_lstm_set_kernels(old)
+
+    y1, y2 = run(1), run(2)
+    assert torch.equal(y1, y2)
+    ref = x.double() @ w.double().T + b.double() + (y0.double() if acc else 0)
+    ref = torch.relu(ref) if act == 1 else (torch.tanh(ref) if act == 2 else ref)
+    assert _rel(y2, ref) < 1e-5, _rel(y2, ref)
+
+
+@pytest.mark.parametrize("B,L,D", [(256, 250, 768), (3, 7, 49), (5, 33, 1000), (2, 250, 1024), (4, 1, 256)])
+def test_lang_attn_v2_bit_identical_to_v1(built_lib, B, L, D):
+    """The second SoftDotAttention kernel (loads of four rows in flight) keeps the summation order of the first."""
+    from avdn_b200 import _lib
+    call, ptr = _lib.call, _lib.ptr
+    h = _lib.lib()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(B + L + D)
+    ctx = torch.randn(B, L, D, device=dev, generator=g)
+    tgt = torch.randn(B, D, device=dev, generator=g) / D ** 0.5
+
+    def run(version):
+        old = h.avdn_lstm_set_kernels(version)
+        try:
+            attn = torch.zeros(B, L, device=dev)
+            out = torch.zeros(B, 2 * D, device=dev)
+            call("avdn_lang_attn_fwd", ptr(ctx), ptr(tgt), B, L, D, ptr(attn), ptr(out), out.stride(0))
+            torch.cuda.synchronize()
+            return attn, out[:, :D].clone()
+        finally:
+            h.avdn_lstm_set_kernels(old)
+
+    (a1, o1), (a2, o2) = run(1), run(2)
+    assert torch.equal(a1, a2) and torch.equal(o1, o2)
+    p = torch.softmax(torch.einsum("bld,bd->bl", ctx.double(), tgt.double()), dim=1)
+    assert _rel(a2, p) < 1e-5
+    assert _rel(o2, torch.einsum("bl,bld->bd", p, ctx.double())) < 1e-5
