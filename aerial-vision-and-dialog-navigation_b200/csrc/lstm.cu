@@ -226,35 +226,52 @@ __global__ void __launch_bounds__(256) lang_attn_kernel(const float* __restrict_
   }
 }
 
-// Second version: the same sums in the same order (bit-identical results), with the loads of four rows (scores) or of
-// four rows x up to four columns (weighted sum) issued before they are used -- the first version had one dependent
-// load -> fma chain per thread, 250 deep, three times over.
-template <int ND>      // ND = ceil(D / 256) <= 4
+// Second version, for D % 4 == 0 and D <= 1024 (the rollout's D = 768): the first version kept one 4-byte load per
+// lane in flight (8 warps x 128 B per CTA) while streaming 768 KB of context per sample twice.  Here every load is a
+// float4 and the loads of TWO rows x NQ float4 columns (scores) or EIGHT rows (weighted sum) are issued before they
+// are used: 48 KB / 24 KB in flight per CTA.  A lane now sums the columns 4q..4q+3 of q = lane, lane + 32, ... (not
+// d = lane, lane + 32, ...), so the results agree with the first version to fp32 summation order, not bit for bit.
+template <int NQ>      // NQ = ceil(D / 4 / 32) <= 8 float4 columns per lane
 __global__ void __launch_bounds__(256) lang_attn_v2_kernel(const float* __restrict__ ctx, const float* __restrict__ target,
                                                            int L, int D, float* __restrict__ attn_out,
                                                            float* __restrict__ weighted, long long ldw) {
-  extern __shared__ float sm[];            // [D] target, [L] scores
-  float* s_t = sm;
-  float* s_s = sm + D;
+  extern __shared__ float4 sm4[];          // [D] target, [L] scores
+  float* s_t = reinterpret_cast<float*>(sm4);
+  float* s_s = s_t + D;
   __shared__ float s_max, s_sum;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* c = ctx + (size_t)b * L * D;
+  const int D4 = D >> 2;
+  const float4* c4 = reinterpret_cast<const float4*>(ctx + (size_t)b * L * D);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int d = tid; d < D; d += 256) s_t[d] = target[(size_t)b * D + d];
   __syncthreads();
-  for (int l0 = warp; l0 < L; l0 += 32) {          // rows l0, l0+8, l0+16, l0+24 of this warp at once
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int d = lane; d < D; d += 32) {
-      const float t = s_t[d];
-      float v[4];
+  float4 t4[NQ];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) v[r] = (l0 + 8 * r < L) ? __ldg(c + (size_t)(l0 + 8 * r) * D + d) : 0.f;
+  for (int i = 0; i < NQ; ++i) {
+    const int q = lane + 32 * i;
+    t4[i] = q < D4 ? *reinterpret_cast<const float4*>(&s_t[4 * q]) : zero4;
+  }
+  for (int l0 = warp; l0 < L; l0 += 16) {          // rows l0 and l0 + 8 of this warp at once
+    float4 v[2][NQ];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = fmaf(v[r], t, a[r]);
-    }
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float t = warp_sum(a[r]);
-      if (lane == 0 && l0 + 8 * r < L) s_s[l0 + 8 * r] = t;
+      for (int i = 0; i < NQ; ++i) {
+        const int q = lane + 32 * i, l = l0 + 8 * r;
+        v[r][i] = (q < D4 && l < L) ? __ldg(c4 + (size_t)l * D4 + q) : zero4;
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        a = fmaf(v[r][i].x, t4[i].x, a);
+        a = fmaf(v[r][i].y, t4[i].y, a);
+        a = fmaf(v[r][i].z, t4[i].z, a);
+        a = fmaf(v[r][i].w, t4[i].w, a);
+      }
+      a = warp_sum(a);
+      if (lane == 0 && l0 + 8 * r < L) s_s[l0 + 8 * r] = a;
     }
   }
   __syncthreads();
@@ -274,38 +291,28 @@ __global__ void __launch_bounds__(256) lang_attn_v2_kernel(const float* __restri
     if (attn_out) attn_out[(size_t)b * L + l] = a;
   }
   __syncthreads();
-  float acc[ND];
+  if (tid < D4) {                                   // one float4 column per thread (D <= 1024)
+    float4 acc = zero4;
+    int l = 0;
+    for (; l + 8 <= L; l += 8) {
+      float4 u[8];
 #pragma unroll
-  for (int q = 0; q < ND; ++q) acc[q] = 0.f;
-  int l = 0;
-  for (; l + 4 <= L; l += 4) {
-    float v[4][ND];
+      for (int r = 0; r < 8; ++r) u[r] = __ldg(c4 + (size_t)(l + r) * D4 + tid);
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int q = 0; q < ND; ++q) {
-        const int d = tid + q * 256;
-        v[r][q] = d < D ? __ldg(c + (size_t)(l + r) * D + d) : 0.f;
+      for (int r = 0; r < 8; ++r) {
+        const float p = s_s[l + r];
+        acc.x = fmaf(p, u[r].x, acc.x); acc.y = fmaf(p, u[r].y, acc.y);
+        acc.z = fmaf(p, u[r].z, acc.z); acc.w = fmaf(p, u[r].w, acc.w);
       }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float p = s_s[l + r];
-#pragma unroll
-      for (int q = 0; q < ND; ++q) acc[q] = fmaf(p, v[r][q], acc[q]);
     }
-  }
-  for (; l < L; ++l) {
-    const float p = s_s[l];
-#pragma unroll
-    for (int q = 0; q < ND; ++q) {
-      const int d = tid + q * 256;
-      if (d < D) acc[q] = fmaf(p, __ldg(c + (size_t)l * D + d), acc[q]);
+    for (; l < L; ++l) {
+      const float p = s_s[l];
+      const float4 u = __ldg(c4 + (size_t)l * D4 + tid);
+      acc.x = fmaf(p, u.x, acc.x); acc.y = fmaf(p, u.y, acc.y);
+      acc.z = fmaf(p, u.z, acc.z); acc.w = fmaf(p, u.w, acc.w);
     }
-  }
-#pragma unroll
-  for (int q = 0; q < ND; ++q) {
-    const int d = tid + q * 256;
-    if (d < D) weighted[(size_t)b * ldw + d] = acc[q];
+    float* o = weighted + (size_t)b * ldw + 4 * tid;      // ldw need not be a multiple of 4: scalar stores
+    o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
   }
 }
 
@@ -422,8 +429,8 @@ __global__ void waypoint_step_kernel(const float* __restrict__ output, double* _
 }  // namespace
 
 // ===================================================================== C ABI
-// Which kernels serve avdn_linear_f32 / avdn_lang_attn_fwd: 2 = the register-prefetching versions (default), 1 = the
-// first versions (kept: unaligned / K % 4 != 0 linears always use them, and the tests compare the two bit for bit).
+// Which kernels serve avdn_linear_f32 / avdn_lang_attn_fwd: 2 = the register-prefetching / float4 versions (default),
+// 1 = the first versions (kept: unaligned or K % 4 != 0 / D % 4 != 0 shapes always use them, and the tests compare).
 // AVDN_LSTM_KERNELS in the environment sets the initial value; the argument 0 only queries.
 static int& lstm_kernels_version() {
   static int v = [] {
@@ -476,14 +483,15 @@ extern "C" int avdn_lang_attn_fwd(const float* ctx, const float* target, int B, 
   const size_t smem = (size_t)(D + L) * sizeof(float);
   AVDN_REQUIRE(smem <= 48 * 1024, "avdn_lang_attn_fwd: D + L = %d too large", D + L);
   cudaStream_t s = avdn::to_cuda(stream);
-  const int nd = (D + 255) / 256;
-  if (lstm_kernels_version() >= 2 && nd <= 4) {
-    switch (nd) {
-      case 1: lang_attn_v2_kernel<1><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
-      case 2: lang_attn_v2_kernel<2><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
-      case 3: lang_attn_v2_kernel<3><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
-      default: lang_attn_v2_kernel<4><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
+  const int nq = (D / 4 + 31) / 32;
+  if (lstm_kernels_version() >= 2 && D % 4 == 0 && nq <= 8 && reinterpret_cast<uintptr_t>(ctx) % 16 == 0) {
+#define AVDN_LANG_ATTN_CASE(NQ) \
+  case NQ: lang_attn_v2_kernel<NQ><<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw); break;
+    switch (nq) {
+      AVDN_LANG_ATTN_CASE(1) AVDN_LANG_ATTN_CASE(2) AVDN_LANG_ATTN_CASE(3) AVDN_LANG_ATTN_CASE(4)
+      AVDN_LANG_ATTN_CASE(5) AVDN_LANG_ATTN_CASE(6) AVDN_LANG_ATTN_CASE(7) AVDN_LANG_ATTN_CASE(8)
     }
+#undef AVDN_LANG_ATTN_CASE
     return avdn::check_launch("avdn_lang_attn_fwd (v2)");
   }
   lang_attn_kernel<<<B, 256, smem, s>>>(ctx, target, L, D, attn, weighted, ldw);

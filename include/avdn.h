@@ -594,8 +594,9 @@ int avdn_adamw(float* p, const float* g, float* m, float* v, long long n, float 
 
 /* Which kernels serve avdn_linear_f32 and avdn_lang_attn_fwd: 2 (default) = 32 x 64 tiles with the operands of the
  * next k-step fetched into registers as float4 under the FMAs (used when K, ldx, ldw are multiples of 4 and x, w
- * are 16-byte aligned) / four rows of loads in flight in the attention; 1 = the first versions.  Both give the same
- * sums in the same order (bit-identical results).  AVDN_LSTM_KERNELS=1 in the environment selects version 1
+ * are 16-byte aligned; the same sums in the same order as version 1, bit-identical) / float4 loads with two to eight
+ * rows in flight in the attention (D % 4 == 0, D <= 1024; agrees with version 1 to fp32 summation order); 1 = the
+ * first versions.  AVDN_LSTM_KERNELS=1 in the environment selects version 1
  * initially; any other argument than 1 or 2 only queries.  Returns the previous setting.                       */
 int avdn_lstm_set_kernels(int version);
 /* y[M,N] (+)= act(x[M,K] w[N,K]^T + b[N]); ld* are row pitches in elements;
