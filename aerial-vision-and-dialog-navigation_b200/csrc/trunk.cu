@@ -35,7 +35,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------ BN statistics
 // Per-channel reductions over the R rows of a [R,C] bf16 tensor.  Every thread owns ONE group of
 // 8 channels for its whole life (the grid stride is a multiple of C/8), so the per-channel
-// constants sit in registers; UNROLL independent 16-byte loads per tensor are in flight per
+// constants sit in registers; UNR (4 or 8) independent 16-byte loads per tensor are in flight per
 // thread.  Partial sums are fp32 per thread, reduced through shared memory per block and
 // committed with one fp64 atomic per channel per block.
 //   forward : sums[0][c] = sum z          sums[1][c] = sum z^2
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(BN_THREADS, UNR > 4 ? 2 : 0) bn_reduce_kernel(
   const long long tid = blockIdx.x * (long long)BN_THREADS + threadIdx.x;
   const long long stride = (long long)gridDim.x * BN_THREADS;      // multiple of C8 (host guarantees)
   // rev: walk the tensor back to front (element n8-1-k instead of k; n8 is a multiple of C8, so the
-  // thread's channel group becomes C8-1-cx) -- see bn_order() below
+  // thread's channel group becomes C8-1-cx) -- see bn_order_flag() below
   const int cx = rev ? C8 - 1 - (int)(tid % C8) : (int)(tid % C8);
   const long long last = n8 - 1;
   float s1[8], s2[8];
@@ -466,9 +466,6 @@ inline int grid_for(long long n, int block = 256, int waves = 8) {
 }  // namespace
 
 // ===================================================================== C ABI
-// grid of BN_THREADS-wide blocks whose total thread count is a multiple of C/8 (so that every
-// thread keeps its channel group) and that fills the machine without exceeding the work
-//
 // Traversal order (avdn_bn_set_order / AVDN_BN_ORDER, a bit mask; 0 = every pass front to back in a multi-wave
 // grid, the round-1 behaviour).  Measured inside the config-2 training step on one B200 (tools/bn_order_ab.py,
 // profiles/r02_bn_order_ab.txt): one-wave grids (only co-resident CTAs, each thread looping over the tensor) take the
@@ -502,6 +499,8 @@ static int bn_resident_per_sm(K kernel, size_t smem) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, BN_THREADS, smem) != cudaSuccess || n < 1) n = 1;
   return n;
 }
+// grid of BN_THREADS-wide blocks whose total thread count is a multiple of C/8 (so that every
+// thread keeps its channel group) and that fills the machine without exceeding the work
 static int bn_grid(long long n8, int waves, int unroll = BN_UNROLL) {
   long long blocks = (n8 + (long long)BN_THREADS * unroll - 1) / ((long long)BN_THREADS * unroll);
   const long long cap = (long long)avdn::sm_count() * waves;
