@@ -42,3 +42,22 @@ def test_gpu_arm_refuses_to_run_without_a_gpu():
     r = _run("--workload", "render", "--steps", "1", "--warmup", "0", "--no-cpu-baseline")
     assert r.returncode != 0                           # no silent CPU fallback
     assert not [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """N > 1: the driver launches the reference arm under torchrun like the GPU arm; rank 0 alone measures and prints,
+    the other rank exits 0 without work."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                        "--gpus", "2", "--impl", "reference", "--workload", "render", "--steps", "1", "--warmup", "0"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
