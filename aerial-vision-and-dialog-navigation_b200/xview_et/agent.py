@@ -12,7 +12,8 @@ What is here
 * ``NSS`` (agent.py:256-270), ``postprocess_waypoints`` (agent.py:637-653,745-752),
   ``move_view_corners`` / ``get_direction`` (agent.py:83-101,285-384: host float64,
   restated because the reference evaluates them on the host per sample),
-  ``save`` / ``load`` (agent.py:899-940; ``lang_model`` is outside the path).
+  ``save`` / ``load`` (agent.py:899-940; ``lang_model`` is written when one is attached, optimiser
+  moments in the flat-arena format).
 
 * ``rollout_greedy``: the student-feedback (inference / validation) loop of ``rollout``
   (agent.py:580-760) with the growing episode history: every step renders the B current views,
